@@ -1,0 +1,165 @@
+/*
+ * mraudio_b200 -- C-ABI of the B200-native (sm_100a) Q-Former / llm_proj / moment-scoring hot path of globc/mrAudio.
+ *
+ * The reference is pure Python and has no FFI of its own; each entry point below names the reference interface
+ * (file:line under /root/reference) whose arithmetic it replaces.  A maintainer binds this library with ctypes
+ * (see INTEGRATION.md); mraudio_b200/_lib.py is that binding.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; mra_last_error() returns a thread-local message.
+ *     Nothing throws or exits across the boundary.
+ *   - all data pointers are DEVICE pointers owned by the caller (PyTorch allocates inputs, outputs and workspace);
+ *     the library owns only its handle (TMA descriptors, launch configuration).
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises, the legacy default
+ *     stream is never used implicitly.  A handle is not thread-safe: one per rank/stream.
+ *   - activations / weights are bf16 (row-major, K contiguous); biases, LayerNorm parameters, the residual stream and
+ *     accumulators are fp32; ids and masks int32.
+ *   - there is NO CPU fallback: on a machine without an sm_100 device every compute entry returns an error.
+ */
+#ifndef MRAUDIO_B200_H
+#define MRAUDIO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRA_MAX_LAYERS 16
+#define MRA_NUM_IOU_THDS 10
+
+/* ---- library ------------------------------------------------------------------------------------------------ */
+const char* mra_last_error(void);
+int mra_version(void);
+/* 0 if the current CUDA device can run the kernels (compute capability 10.x), else an error. */
+int mra_device_check(void);
+
+/* ---- Q-Former handle ---------------------------------------------------------------------------------------- */
+/* Mirrors BertConfig as built by XInstructBLIP.init_Qformer (models/xinstructblip.py:615-623). */
+typedef struct mra_qformer_config {
+    int32_t hidden;      /* 768  */
+    int32_t layers;      /* 12   */
+    int32_t heads;       /* 12   (head_dim must be 64) */
+    int32_t inter;       /* 3072 */
+    int32_t enc_width;   /* encoder_width: 1408 video / 768 audio */
+    int32_t cross_freq;  /* cross_attention_freq: 2 */
+    int32_t num_query;   /* query_length: 32 */
+    int32_t llm_dim;     /* llm_proj out features: 4096 (0 = no projection) */
+    int32_t vocab;       /* 30523 */
+    int32_t max_pos;     /* 512 */
+    float ln_eps;        /* 1e-12 */
+} mra_qformer_config;
+
+/* One BertLayer.  Matrices bf16 [out, in]; vectors fp32.  Cross-attention members are NULL on layers without it. */
+typedef struct mra_qformer_layer_weights {
+    const void* w_qkv;  const float* b_qkv;          /* attention.self.{query,key,value} stacked: [3H, H], [3H] */
+    const void* w_ao;   const float* b_ao;           /* attention.output.dense */
+    const float* ln_a_g; const float* ln_a_b;        /* attention.output.LayerNorm */
+    const void* w_cq;   const float* b_cq;           /* crossattention.self.query */
+    const void* w_co;   const float* b_co;           /* crossattention.output.dense */
+    const float* ln_c_g; const float* ln_c_b;        /* crossattention.output.LayerNorm */
+    const void* w_fq1;  const float* b_fq1;          /* intermediate_query.dense [I, H] */
+    const void* w_fq2;  const float* b_fq2;          /* output_query.dense [H, I] */
+    const float* ln_fq_g; const float* ln_fq_b;      /* output_query.LayerNorm */
+    const void* w_ft1;  const float* b_ft1;          /* intermediate.dense */
+    const void* w_ft2;  const float* b_ft2;          /* output.dense */
+    const float* ln_ft_g; const float* ln_ft_b;      /* output.LayerNorm */
+} mra_qformer_layer_weights;
+
+typedef struct mra_qformer_weights {
+    const void* word_emb;   /* bf16 [vocab, H]    bert.embeddings.word_embeddings      (NULL for query-only) */
+    const void* pos_emb;    /* bf16 [max_pos, H]  bert.embeddings.position_embeddings  (NULL for query-only) */
+    const float* ln_e_g; const float* ln_e_b;        /* bert.embeddings.LayerNorm */
+    /* crossattention.self.{key,value} of ALL cross layers stacked so the encoder tokens are read once:
+       rows [c*2H, c*2H+H) = key of the c-th cross layer, [c*2H+H, (c+1)*2H) = its value.  bf16 [ncross*2H, W]. */
+    const void* w_ckv;  const float* b_ckv;
+    const void* w_proj; const float* b_proj;         /* {modality}_llm_proj: bf16 [D, H], fp32 [D] */
+    mra_qformer_layer_weights layer[MRA_MAX_LAYERS];
+} mra_qformer_weights;
+
+typedef struct mra_qformer mra_qformer_t;
+
+int mra_qformer_create(const mra_qformer_config* cfg, mra_qformer_t** out);
+int mra_qformer_set_weights(mra_qformer_t* h, const mra_qformer_weights* w);
+void mra_qformer_destroy(mra_qformer_t* h);
+
+/* flags for forward */
+#define MRA_FWD_SKIP_DEAD_TEXT_FFN 1u /* last layer's text FFN is never read by llm_proj (xinstructblip.py:303) */
+#define MRA_FWD_SAVE_FOR_BACKWARD  2u /* keep per-layer activations in the workspace for mra_qformer_backward */
+
+typedef struct mra_qformer_io {
+    /* inputs */
+    const void* enc;            /* bf16 [rows, Nk, W]   encoder_hidden_states (already through {modality}_ln) */
+    const int32_t* input_ids;   /* [rows, T] or NULL when T == 0 */
+    const int32_t* text_mask;   /* [rows, T] 1 = attend, 0 = padding; NULL = all ones */
+    const int32_t* enc_mask;    /* [rows, Nk] or NULL = all ones (the reference always passes ones, :266,275) */
+    const float* query_embeds;  /* fp32 [q_rows, Nq, H], q_rows == 1 (broadcast) or rows */
+    int32_t q_rows;
+    int32_t rows, T, Nk;
+    uint32_t flags;
+    /* outputs (either may be NULL) */
+    float* last_hidden;         /* fp32 [rows, Nq+T, H]  == Qformer.bert(...).last_hidden_state */
+    void* llm_out;              /* bf16 [rows*Nq, D]     == llm_proj(last_hidden_state[:, :Nq]) viewed [bs, F*Nq, D] */
+} mra_qformer_io;
+
+/* Replaces `{modality}_Qformer.bert(input_ids, attention_mask=, query_embeds=, encoder_hidden_states=,
+ * encoder_attention_mask=, return_dict=True)` (models/xinstructblip.py:286-293, 461-468) and the following
+ * `{modality}_llm_proj(last_hidden_state[:, :32, :])` (:303, :475). */
+size_t mra_qformer_workspace_bytes(const mra_qformer_t* h, int32_t rows, int32_t T, int32_t Nk, uint32_t flags);
+int mra_qformer_forward(mra_qformer_t* h, const mra_qformer_io* io, void* workspace, size_t workspace_bytes,
+                        void* stream);
+/* number of kernels the last forward call enqueued (for bench.py's gpu_launches) */
+int mra_qformer_last_launch_count(const mra_qformer_t* h);
+
+/* ---- building-block ops (each is also what the forward above launches; exposed for parity tests and backward) */
+
+/* C[M,N] = epilogue(A[M,K] . W[N,K]^T): tcgen05 tensor-core GEMM, TMA-fed, fp32 accumulation in TMEM.
+ *   A, W bf16 with row strides lda/ldw (elements, multiples of 8); bias fp32 [N] or NULL; residual fp32 [M,N] with
+ *   stride ldr or NULL; gelu != 0 applies erf-GELU after the bias; out_fp32 selects fp32 vs bf16 C (stride ldc).
+ *   Replaces torch.nn.Linear inside the Q-Former (LAVIS Qformer.py; HF port modeling_instructblip.py:499-509,549-553,
+ *   586-610) and `llm_proj` (models/xinstructblip.py:707-708). */
+#define MRA_GEMM_IMPL_TCGEN05 0
+#define MRA_GEMM_IMPL_SIMT_DEBUG 1 /* slow CUDA-core kernel, tests only: isolates tensor-core descriptor bugs */
+int mra_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const float* residual,
+                  int64_t ldr, void* C, int64_t ldc, int32_t M, int32_t N, int32_t K, int32_t gelu, int32_t out_fp32,
+                  int32_t impl, void* stream);
+
+/* Fused multi-head attention core, head_dim 64: O = softmax(Q K^T / 8 + mask) V, per (row, head).
+ *   q: bf16, row `qrow(r, i)` at q + qrow*ldq + head*64;  k, v likewise with ldk/ldv; o bf16 with ldo.
+ *   Row addressing: "split" layout used by the forward: query tokens of all rows first, then text tokens:
+ *     index(r, i) = i < nq_split ? r*nq_split + i : rows*nq_split + r*(S - nq_split) + (i - nq_split)
+ *   Self-attention: Sq = Sk = S, q/k/v share the index function.  Cross-attention: nq_split = Sq (dense), keys dense
+ *   (index r*Sk + j).  add_mask fp32 [rows, Sk] added to the scaled scores, or NULL.
+ *   Replaces BertSelfAttention core (HF port modeling_instructblip.py:512-536). */
+int mra_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
+                  int64_t ldo, const float* add_mask, int32_t rows, int32_t heads, int32_t Sq, int32_t Sk,
+                  int32_t nq_split, int32_t kv_dense, void* stream);
+
+/* y = LayerNorm(x) * gamma + beta over the last dim (n), fp32 statistics; writes fp32 and/or bf16 copies.
+ *   Replaces the LayerNorm in BertSelfOutput/BertOutput (HF port :549-553, :606-610), eps 1e-12. */
+int mra_layernorm(const float* x, const float* gamma, const float* beta, float* y32, void* y16, int32_t rows, int32_t n,
+                  float eps, void* stream);
+
+/* {modality}_ln: fp32-upcast LayerNorm of encoder tokens (models/xinstructblip.py:822-828, applied :265,274) fused
+ * with the frame fold + batch-major reorder of :280-285.  x: [F, bs, Nk, W] (frame_major != 0: the reference's list
+ * of per-frame tensors) or [bs*F, Nk, W]; in_dtype 0 = fp32, 1 = bf16, 2 = fp16.  out: bf16 [bs*F, Nk, W]. */
+int mra_modality_layernorm(const void* x, int32_t in_dtype, const float* gamma, const float* beta, void* out,
+                           int32_t bs, int32_t frames, int32_t Nk, int32_t W, int32_t frame_major, float eps,
+                           void* stream);
+
+/* ---- moment-retrieval scorer ----------------------------------------------------------------------------------
+ * One thread per query.  Replaces compute_average_precision_detection (eval/mr_utils.py:89-171), the per-query part
+ * of compute_mr_r1 (eval/mr_eval.py:97-131) and the IoU helpers (eval/mr_utils.py:16-67), in fp64 with numpy's
+ * operation order, nan semantics and argsort tie order.
+ *   pred [Q, Pmax, 2] f64, n_pred [Q] (>= 1); gt [Q, Gmax, 2] f64, n_gt [Q] (>= 1); thds [10] f64.
+ *   out_ap [Q, 10] f64; out_iou [Q] f64 (top-1 paired IoU); out_invalid [Q] u8 (-1 in top-1 window).
+ *   Limits: Pmax <= 256, Gmax <= 64. */
+int mra_mr_score(const double* pred, const int32_t* n_pred, const double* gt, const int32_t* n_gt, const double* thds,
+                 int32_t Q, int32_t Pmax, int32_t Gmax, double* out_ap, double* out_iou, uint8_t* out_invalid,
+                 void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRAUDIO_B200_H */

@@ -1,0 +1,100 @@
+"""ctypes binding of libmraudio_b200.so (C-ABI declared in include/mraudio_b200.h).
+
+There is no CPU fallback: importing this module without the built library raises, and every compute entry point
+returns an error on a machine without an sm_100 GPU (``MraError``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmraudio_b200.so")
+
+MRA_MAX_LAYERS = 16
+MRA_NUM_IOU_THDS = 10
+FWD_SKIP_DEAD_TEXT_FFN = 1
+FWD_SAVE_FOR_BACKWARD = 2
+GEMM_IMPL_TCGEN05 = 0
+GEMM_IMPL_SIMT_DEBUG = 1
+
+
+class MraError(RuntimeError):
+    pass
+
+
+class QFormerConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("hidden", "layers", "heads", "inter", "enc_width", "cross_freq", "num_query",
+                                         "llm_dim", "vocab", "max_pos")] + [("ln_eps", C.c_float)]
+
+
+_LAYER_FIELDS = ("w_qkv", "b_qkv", "w_ao", "b_ao", "ln_a_g", "ln_a_b", "w_cq", "b_cq", "w_co", "b_co", "ln_c_g", "ln_c_b",
+                 "w_fq1", "b_fq1", "w_fq2", "b_fq2", "ln_fq_g", "ln_fq_b", "w_ft1", "b_ft1", "w_ft2", "b_ft2", "ln_ft_g",
+                 "ln_ft_b")
+
+
+class QFormerLayerWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in _LAYER_FIELDS]
+
+
+class QFormerWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("word_emb", "pos_emb", "ln_e_g", "ln_e_b", "w_ckv", "b_ckv", "w_proj", "b_proj")] + \
+               [("layer", QFormerLayerWeights * MRA_MAX_LAYERS)]
+
+
+class QFormerIO(C.Structure):
+    _fields_ = [("enc", C.c_void_p), ("input_ids", C.c_void_p), ("text_mask", C.c_void_p), ("enc_mask", C.c_void_p),
+                ("query_embeds", C.c_void_p), ("q_rows", C.c_int32), ("rows", C.c_int32), ("T", C.c_int32),
+                ("Nk", C.c_int32), ("flags", C.c_uint32), ("last_hidden", C.c_void_p), ("llm_out", C.c_void_p)]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` or "
+            f"`make -C mraudio_b200/csrc`.  mraudio_b200 has no CPU / PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+    lib.mra_last_error.restype = C.c_char_p
+    lib.mra_last_error.argtypes = []
+    lib.mra_version.restype = C.c_int
+    lib.mra_device_check.restype = C.c_int
+    lib.mra_qformer_create.argtypes = [C.POINTER(QFormerConfig), C.POINTER(vp)]
+    lib.mra_qformer_set_weights.argtypes = [vp, C.POINTER(QFormerWeights)]
+    lib.mra_qformer_destroy.argtypes = [vp]
+    lib.mra_qformer_destroy.restype = None
+    lib.mra_qformer_workspace_bytes.argtypes = [vp, i32, i32, i32, C.c_uint32]
+    lib.mra_qformer_workspace_bytes.restype = C.c_size_t
+    lib.mra_qformer_forward.argtypes = [vp, C.POINTER(QFormerIO), vp, C.c_size_t, vp]
+    lib.mra_qformer_last_launch_count.argtypes = [vp]
+    lib.mra_gemm_bf16.argtypes = [vp, i64, vp, i64, vp, vp, i64, vp, i64, i32, i32, i32, i32, i32, i32, vp]
+    lib.mra_attention.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, vp, i32, i32, i32, i32, i32, i32, vp]
+    lib.mra_layernorm.argtypes = [vp, vp, vp, vp, vp, i32, i32, f32, vp]
+    lib.mra_modality_layernorm.argtypes = [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp]
+    lib.mra_mr_score.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]
+    return lib
+
+
+lib = _load()
+
+# every symbol include/mraudio_b200.h declares (checked by tests/test_capi_symbols.py)
+EXPORTED_SYMBOLS = (
+    "mra_last_error", "mra_version", "mra_device_check", "mra_qformer_create", "mra_qformer_set_weights",
+    "mra_qformer_destroy", "mra_qformer_workspace_bytes", "mra_qformer_forward", "mra_qformer_last_launch_count",
+    "mra_gemm_bf16", "mra_attention", "mra_layernorm", "mra_modality_layernorm", "mra_mr_score",
+)
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise MraError(lib.mra_last_error().decode("utf-8", "replace"))
+
+
+def ptr(t) -> int:
+    """device pointer of a torch tensor (None -> NULL)"""
+    return None if t is None else t.data_ptr()
+
+
+def current_stream() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream

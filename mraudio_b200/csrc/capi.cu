@@ -1,0 +1,103 @@
+// extern "C" surface of libmraudio_b200.so (see include/mraudio_b200.h) + process-wide helpers.
+#include <stdarg.h>
+
+#include "common.h"
+
+namespace mra {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int device_check() {
+    static int cached = -1;  // 0 ok, >0 error code
+    if (cached == 0) return 0;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        set_error("no CUDA device available (%s): mraudio_b200 has no CPU fallback", cudaGetErrorString(e));
+        return 3;
+    }
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, dev);
+    if (e != cudaSuccess) {
+        set_error("cudaGetDeviceProperties failed: %s", cudaGetErrorString(e));
+        return 3;
+    }
+    if (prop.major != 10) {
+        set_error("device '%s' is sm_%d%d; mraudio_b200 kernels are built for sm_100a (B200) only", prop.name, prop.major, prop.minor);
+        return 3;
+    }
+    cached = 0;
+    return 0;
+}
+
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+}  // namespace mra
+
+using namespace mra;
+
+extern "C" const char* mra_last_error(void) { return g_err; }
+extern "C" int mra_version(void) { return 100; }
+extern "C" int mra_device_check(void) { return device_check(); }
+
+extern "C" int mra_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const float* residual,
+                             int64_t ldr, void* C, int64_t ldc, int32_t M, int32_t N, int32_t K, int32_t gelu,
+                             int32_t out_fp32, int32_t impl, void* stream) {
+    MRA_REQUIRE(A && W && C, "mra_gemm_bf16: NULL operand");
+    if (int e = device_check()) return e;
+    GemmArgs a{A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K, gelu, out_fp32};
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (impl == MRA_GEMM_IMPL_SIMT_DEBUG) return launch_gemm_simt(a, s);
+    MRA_REQUIRE(impl == MRA_GEMM_IMPL_TCGEN05, "mra_gemm_bf16: unknown impl %d", impl);
+    return launch_gemm_tc(a, s);
+}
+
+extern "C" int mra_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
+                             int64_t ldo, const float* add_mask, int32_t rows, int32_t heads, int32_t Sq, int32_t Sk,
+                             int32_t nq_split, int32_t kv_dense, void* stream) {
+    MRA_REQUIRE(q && k && v && o, "mra_attention: NULL operand");
+    if (int e = device_check()) return e;
+    AttnArgs a{q, ldq, k, ldk, v, ldv, o, ldo, add_mask, rows, heads, Sq, Sk, nq_split, kv_dense};
+    return launch_attention(a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mra_layernorm(const float* x, const float* gamma, const float* beta, float* y32, void* y16, int32_t rows,
+                             int32_t n, float eps, void* stream) {
+    MRA_REQUIRE(x && gamma && beta && (y32 || y16), "mra_layernorm: NULL operand");
+    if (int e = device_check()) return e;
+    return launch_layernorm(x, gamma, beta, y32, y16, rows, n, eps, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mra_modality_layernorm(const void* x, int32_t in_dtype, const float* gamma, const float* beta, void* out,
+                                      int32_t bs, int32_t frames, int32_t Nk, int32_t W, int32_t frame_major, float eps,
+                                      void* stream) {
+    MRA_REQUIRE(x && gamma && beta && out, "mra_modality_layernorm: NULL operand");
+    if (int e = device_check()) return e;
+    return launch_modality_layernorm(x, in_dtype, gamma, beta, out, bs, frames, Nk, W, frame_major, eps,
+                                     reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mra_mr_score(const double* pred, const int32_t* n_pred, const double* gt, const int32_t* n_gt,
+                            const double* thds, int32_t Q, int32_t Pmax, int32_t Gmax, double* out_ap, double* out_iou,
+                            uint8_t* out_invalid, void* stream) {
+    MRA_REQUIRE(pred && n_pred && gt && n_gt && thds && out_ap && out_iou && out_invalid, "mra_mr_score: NULL operand");
+    if (int e = device_check()) return e;
+    return launch_mr_score(pred, n_pred, gt, n_gt, thds, Q, Pmax, Gmax, out_ap, out_iou, out_invalid,
+                           reinterpret_cast<cudaStream_t>(stream));
+}

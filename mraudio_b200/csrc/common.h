@@ -1,0 +1,76 @@
+// Internal declarations shared by the translation units of libmraudio_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/mraudio_b200.h"
+
+namespace mra {
+
+void set_error(const char* fmt, ...);
+
+#define MRA_CHECK_CUDA(expr)                                                                          \
+    do {                                                                                              \
+        cudaError_t _e = (expr);                                                                      \
+        if (_e != cudaSuccess) {                                                                      \
+            ::mra::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return 1;                                                                                 \
+        }                                                                                             \
+    } while (0)
+
+#define MRA_REQUIRE(cond, ...)          \
+    do {                                \
+        if (!(cond)) {                  \
+            ::mra::set_error(__VA_ARGS__); \
+            return 2;                   \
+        }                               \
+    } while (0)
+
+int device_check();
+int sm_count();
+
+// ---- launchers (each returns 0 / error and bumps *launches when non-null) ----
+struct GemmArgs {
+    const void* A; int64_t lda;
+    const void* W; int64_t ldw;
+    const float* bias;
+    const float* residual; int64_t ldr;
+    void* C; int64_t ldc;
+    int M, N, K;
+    int gelu;
+    int out_fp32;
+};
+int launch_gemm_tc(const GemmArgs& a, cudaStream_t s);
+int launch_gemm_simt(const GemmArgs& a, cudaStream_t s);
+
+struct AttnArgs {
+    const void* q; int64_t ldq;
+    const void* k; int64_t ldk;
+    const void* v; int64_t ldv;
+    void* o; int64_t ldo;
+    const float* add_mask;
+    int rows, heads, Sq, Sk, nq_split, kv_dense;
+};
+int launch_attention(const AttnArgs& a, cudaStream_t s);
+
+int launch_layernorm(const float* x, const float* g, const float* b, float* y32, void* y16, int rows, int n, float eps,
+                     cudaStream_t s);
+int launch_modality_layernorm(const void* x, int in_dtype, const float* g, const float* b, void* out, int bs, int frames,
+                              int Nk, int W, int frame_major, float eps, cudaStream_t s);
+// embeddings: LN(cat(query_embeds, word_emb[ids] + pos_emb[:T])) written in the split layout (queries first)
+int launch_embed_layernorm(const float* query_embeds, int q_rows, const int32_t* ids, const void* word_emb,
+                           const void* pos_emb, const float* g, const float* b, float* y32, void* y16, int rows, int Nq,
+                           int T, int H, int vocab, float eps, cudaStream_t s);
+// additive masks: out[r, j] = j < Nq ? 0 : (1 - text_mask[r, j-Nq]) * -10000
+int launch_build_self_mask(const int32_t* text_mask, float* out, int rows, int Nq, int T, cudaStream_t s);
+int launch_build_enc_mask(const int32_t* enc_mask, float* out, int rows, int Nk, cudaStream_t s);
+// split layout [queries ; text] fp32 -> interleaved [rows, Nq+T, H] fp32
+int launch_gather_last_hidden(const float* split, float* out, int rows, int Nq, int T, int H, cudaStream_t s);
+
+int launch_mr_score(const double* pred, const int32_t* n_pred, const double* gt, const int32_t* n_gt, const double* thds,
+                    int Q, int Pmax, int Gmax, double* out_ap, double* out_iou, uint8_t* out_invalid, cudaStream_t s);
+
+}  // namespace mra

@@ -1,0 +1,271 @@
+// HBM-bound row kernels of the Q-Former path: LayerNorm (fp32 residual stream in, fp32 + bf16 out), the embedding
+// gather + LayerNorm, the modality LayerNorm with the frame fold, additive-mask construction and the final re-layout.
+// One warp per row, 16-byte vectorised coalesced accesses, warp-shuffle reductions, two-pass (mean, then centred
+// variance) statistics in fp32 -- the same arithmetic as torch.nn.functional.layer_norm.
+#include <cuda_fp16.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace mra {
+namespace {
+
+constexpr int WARPS_PER_BLOCK = 8;
+constexpr int MAX_VEC = 8;  // supports row length up to 32 lanes * 8 vec * 8 elems = 2048
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// x[MAX_VEC][8] holds this lane's elements: vector i covers columns (i*32 + lane)*8 .. +7 (valid when < n).
+__device__ __forceinline__ void ln_normalise_store(float (&x)[MAX_VEC][8], int n, int lane, const float* __restrict__ g,
+                                                   const float* __restrict__ b, float eps, float* y32,
+                                                   __nv_bfloat16* y16) {
+    const int nvec = n >> 3;
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAX_VEC; ++i)
+        if (i * 32 + lane < nvec)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) sum += x[i][e];
+    const float mean = warp_sum(sum) / n;
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAX_VEC; ++i)
+        if (i * 32 + lane < nvec)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float d = x[i][e] - mean;
+                var = fmaf(d, d, var);
+            }
+    const float rstd = rsqrtf(warp_sum(var) / n + eps);
+#pragma unroll
+    for (int i = 0; i < MAX_VEC; ++i) {
+        const int vi = i * 32 + lane;
+        if (vi < nvec) {
+            const int c = vi * 8;
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(g + c)), g1 = __ldg(reinterpret_cast<const float4*>(g + c + 4));
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(b + c)), b1 = __ldg(reinterpret_cast<const float4*>(b + c + 4));
+            float y[8];
+            y[0] = (x[i][0] - mean) * rstd * g0.x + b0.x;
+            y[1] = (x[i][1] - mean) * rstd * g0.y + b0.y;
+            y[2] = (x[i][2] - mean) * rstd * g0.z + b0.z;
+            y[3] = (x[i][3] - mean) * rstd * g0.w + b0.w;
+            y[4] = (x[i][4] - mean) * rstd * g1.x + b1.x;
+            y[5] = (x[i][5] - mean) * rstd * g1.y + b1.y;
+            y[6] = (x[i][6] - mean) * rstd * g1.z + b1.z;
+            y[7] = (x[i][7] - mean) * rstd * g1.w + b1.w;
+            if (y32) {
+                *reinterpret_cast<float4*>(y32 + c) = make_float4(y[0], y[1], y[2], y[3]);
+                *reinterpret_cast<float4*>(y32 + c + 4) = make_float4(y[4], y[5], y[6], y[7]);
+            }
+            if (y16) {
+                uint4 o;
+                o.x = ptx::pack_bf16x2(y[0], y[1]);
+                o.y = ptx::pack_bf16x2(y[2], y[3]);
+                o.z = ptx::pack_bf16x2(y[4], y[5]);
+                o.w = ptx::pack_bf16x2(y[6], y[7]);
+                *reinterpret_cast<uint4*>(y16 + c) = o;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void load8_f32(const float* p, float (&x)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+}
+__device__ __forceinline__ void load8_bf16(const __nv_bfloat16* p, float (&x)[8]) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    x[0] = ptx::bf16lo(v.x); x[1] = ptx::bf16hi(v.x); x[2] = ptx::bf16lo(v.y); x[3] = ptx::bf16hi(v.y);
+    x[4] = ptx::bf16lo(v.z); x[5] = ptx::bf16hi(v.z); x[6] = ptx::bf16lo(v.w); x[7] = ptx::bf16hi(v.w);
+}
+__device__ __forceinline__ void load8_f16(const __half* p, float (&x)[8]) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(h[i]);
+        x[2 * i] = f.x; x[2 * i + 1] = f.y;
+    }
+}
+
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b,
+                 float* __restrict__ y32, __nv_bfloat16* __restrict__ y16, int rows, int n, float eps) {
+    const int row = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* xr = x + static_cast<int64_t>(row) * n;
+    float v[MAX_VEC][8];
+    const int nvec = n >> 3;
+#pragma unroll
+    for (int i = 0; i < MAX_VEC; ++i)
+        if (i * 32 + lane < nvec) load8_f32(xr + (i * 32 + lane) * 8, v[i]);
+    ln_normalise_store(v, n, lane, g, b, eps, y32 ? y32 + static_cast<int64_t>(row) * n : nullptr,
+                       y16 ? y16 + static_cast<int64_t>(row) * n : nullptr);
+}
+
+// out row (b*F + f) <- in row (frame_major ? f*bs + b : b*F + f), token tok.
+template <int DTYPE>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+modality_ln_kernel(const void* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b,
+                   __nv_bfloat16* __restrict__ out, int bs, int frames, int Nk, int W, int frame_major, float eps) {
+    const int64_t token = static_cast<int64_t>(blockIdx.x) * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int64_t total = static_cast<int64_t>(bs) * frames * Nk;
+    if (token >= total) return;
+    const int64_t orow = token / Nk;
+    const int tok = static_cast<int>(token % Nk);
+    const int bidx = static_cast<int>(orow / frames), f = static_cast<int>(orow % frames);
+    const int64_t irow = frame_major ? static_cast<int64_t>(f) * bs + bidx : orow;
+    const int64_t ioff = (irow * Nk + tok) * W;
+    float v[MAX_VEC][8];
+    const int nvec = W >> 3;
+#pragma unroll
+    for (int i = 0; i < MAX_VEC; ++i) {
+        const int vi = i * 32 + lane;
+        if (vi < nvec) {
+            if (DTYPE == 0) load8_f32(reinterpret_cast<const float*>(x) + ioff + vi * 8, v[i]);
+            if (DTYPE == 1) load8_bf16(reinterpret_cast<const __nv_bfloat16*>(x) + ioff + vi * 8, v[i]);
+            if (DTYPE == 2) load8_f16(reinterpret_cast<const __half*>(x) + ioff + vi * 8, v[i]);
+        }
+    }
+    ln_normalise_store(v, W, lane, g, b, eps, nullptr, out + token * W);
+}
+
+// rows of the split layout: [0, rows*Nq) query tokens (row r, token i), then [rows*Nq, rows*(Nq+T)) text tokens.
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+embed_ln_kernel(const float* __restrict__ query_embeds, int q_rows, const int32_t* __restrict__ ids,
+                const __nv_bfloat16* __restrict__ word_emb, const __nv_bfloat16* __restrict__ pos_emb,
+                const float* __restrict__ g, const float* __restrict__ b, float* __restrict__ y32,
+                __nv_bfloat16* __restrict__ y16, int rows, int Nq, int T, int H, int vocab, float eps) {
+    const int64_t orow = static_cast<int64_t>(blockIdx.x) * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int64_t nquery = static_cast<int64_t>(rows) * Nq;
+    if (orow >= nquery + static_cast<int64_t>(rows) * T) return;
+    float v[MAX_VEC][8];
+    const int nvec = H >> 3;
+    if (orow < nquery) {
+        const int r = static_cast<int>(orow / Nq), i = static_cast<int>(orow % Nq);
+        const float* src = query_embeds + (static_cast<int64_t>(q_rows == 1 ? 0 : r) * Nq + i) * H;
+#pragma unroll
+        for (int k = 0; k < MAX_VEC; ++k)
+            if (k * 32 + lane < nvec) load8_f32(src + (k * 32 + lane) * 8, v[k]);
+    } else {
+        const int64_t tt = orow - nquery;
+        const int r = static_cast<int>(tt / T), j = static_cast<int>(tt % T);
+        int id = ids[static_cast<int64_t>(r) * T + j];
+        id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+        const __nv_bfloat16* we = word_emb + static_cast<int64_t>(id) * H;
+        const __nv_bfloat16* pe = pos_emb + static_cast<int64_t>(j) * H;
+#pragma unroll
+        for (int k = 0; k < MAX_VEC; ++k)
+            if (k * 32 + lane < nvec) {
+                float a[8], c[8];
+                load8_bf16(we + (k * 32 + lane) * 8, a);
+                load8_bf16(pe + (k * 32 + lane) * 8, c);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[k][e] = a[e] + c[e];
+            }
+    }
+    ln_normalise_store(v, H, lane, g, b, eps, y32 + orow * H, y16 + orow * H);
+}
+
+__global__ void self_mask_kernel(const int32_t* __restrict__ text_mask, float* __restrict__ out, int rows, int Nq, int T) {
+    const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int S = Nq + T;
+    if (idx >= static_cast<int64_t>(rows) * S) return;
+    const int r = static_cast<int>(idx / S), j = static_cast<int>(idx % S);
+    float m = 0.f;
+    if (j >= Nq && text_mask != nullptr) m = (1.0f - static_cast<float>(text_mask[static_cast<int64_t>(r) * T + (j - Nq)])) * -10000.0f;
+    out[idx] = m;
+}
+
+__global__ void enc_mask_kernel(const int32_t* __restrict__ enc_mask, float* __restrict__ out, int64_t n) {
+    const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    out[idx] = (1.0f - static_cast<float>(enc_mask[idx])) * -10000.0f;
+}
+
+__global__ void gather_last_hidden_kernel(const float4* __restrict__ split, float4* __restrict__ out, int rows, int Nq, int T,
+                                          int H4) {
+    const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int S = Nq + T;
+    const int64_t total = static_cast<int64_t>(rows) * S * H4;
+    if (idx >= total) return;
+    const int c = static_cast<int>(idx % H4);
+    const int64_t tok = idx / H4;
+    const int r = static_cast<int>(tok / S), i = static_cast<int>(tok % S);
+    const int64_t srow = i < Nq ? static_cast<int64_t>(r) * Nq + i
+                                : static_cast<int64_t>(rows) * Nq + static_cast<int64_t>(r) * T + (i - Nq);
+    out[idx] = split[srow * H4 + c];
+}
+
+}  // namespace
+
+int launch_layernorm(const float* x, const float* g, const float* b, float* y32, void* y16, int rows, int n, float eps,
+                     cudaStream_t s) {
+    MRA_REQUIRE(rows > 0 && n > 0 && n % 8 == 0 && n <= 32 * MAX_VEC * 8, "layernorm width %d unsupported (multiple of 8, <= 2048)", n);
+    const int blocks = (rows + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    layernorm_kernel<<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, g, b, y32, reinterpret_cast<__nv_bfloat16*>(y16), rows, n, eps);
+    MRA_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_modality_layernorm(const void* x, int in_dtype, const float* g, const float* b, void* out, int bs, int frames,
+                              int Nk, int W, int frame_major, float eps, cudaStream_t s) {
+    MRA_REQUIRE(bs > 0 && frames > 0 && Nk > 0 && W > 0 && W % 8 == 0 && W <= 32 * MAX_VEC * 8,
+                "modality layernorm width %d unsupported (multiple of 8, <= 2048)", W);
+    MRA_REQUIRE(in_dtype >= 0 && in_dtype <= 2, "modality layernorm: unknown input dtype %d", in_dtype);
+    const int64_t tokens = static_cast<int64_t>(bs) * frames * Nk;
+    const unsigned blocks = static_cast<unsigned>((tokens + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+    if (in_dtype == 0) modality_ln_kernel<0><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, g, b, o, bs, frames, Nk, W, frame_major, eps);
+    if (in_dtype == 1) modality_ln_kernel<1><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, g, b, o, bs, frames, Nk, W, frame_major, eps);
+    if (in_dtype == 2) modality_ln_kernel<2><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, g, b, o, bs, frames, Nk, W, frame_major, eps);
+    MRA_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_embed_layernorm(const float* query_embeds, int q_rows, const int32_t* ids, const void* word_emb,
+                           const void* pos_emb, const float* g, const float* b, float* y32, void* y16, int rows, int Nq,
+                           int T, int H, int vocab, float eps, cudaStream_t s) {
+    MRA_REQUIRE(H % 8 == 0 && H <= 32 * MAX_VEC * 8, "embedding width %d unsupported", H);
+    MRA_REQUIRE(T == 0 || (ids && word_emb && pos_emb), "text tokens given but ids / embedding tables are NULL");
+    const int64_t total = static_cast<int64_t>(rows) * (Nq + T);
+    const unsigned blocks = static_cast<unsigned>((total + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+    embed_ln_kernel<<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(query_embeds, q_rows, ids,
+                                                           reinterpret_cast<const __nv_bfloat16*>(word_emb),
+                                                           reinterpret_cast<const __nv_bfloat16*>(pos_emb), g, b, y32,
+                                                           reinterpret_cast<__nv_bfloat16*>(y16), rows, Nq, T, H, vocab, eps);
+    MRA_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_build_self_mask(const int32_t* text_mask, float* out, int rows, int Nq, int T, cudaStream_t s) {
+    const int64_t n = static_cast<int64_t>(rows) * (Nq + T);
+    self_mask_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(text_mask, out, rows, Nq, T);
+    MRA_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_build_enc_mask(const int32_t* enc_mask, float* out, int rows, int Nk, cudaStream_t s) {
+    const int64_t n = static_cast<int64_t>(rows) * Nk;
+    enc_mask_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(enc_mask, out, n);
+    MRA_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_gather_last_hidden(const float* split, float* out, int rows, int Nq, int T, int H, cudaStream_t s) {
+    MRA_REQUIRE(H % 4 == 0, "hidden size must be a multiple of 4");
+    const int64_t n = static_cast<int64_t>(rows) * (Nq + T) * (H / 4);
+    gather_last_hidden_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(
+        reinterpret_cast<const float4*>(split), reinterpret_cast<float4*>(out), rows, Nq, T, H / 4);
+    MRA_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace mra

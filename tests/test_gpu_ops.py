@@ -1,0 +1,150 @@
+"""GPU parity of the building-block kernels, called through the C-ABI (mraudio_b200.ops -> libmraudio_b200.so)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-30)).item()
+
+
+GEMM_SHAPES = [
+    (128, 128, 64), (128, 256, 64), (256, 768, 768), (1000, 2304, 768), (257 * 3, 1536, 1408), (64, 4096, 768),
+    (8192, 3072, 768), (640, 768, 3072), (33, 8, 72), (129, 264, 200), (1, 768, 768),
+]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+@pytest.mark.parametrize("impl", [0, 1], ids=["tcgen05", "simt"])
+def test_gemm_matches_fp32_reference(M, N, K, impl):
+    from mraudio_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
+    x = torch.randn(M, K, generator=g).to(_dev(), torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) * 0.05).to(_dev(), torch.bfloat16)
+    b = torch.randn(N, generator=g).to(_dev())
+    ref = x.float() @ w.float().t() + b
+    y = ops.linear(x, w, b, out_fp32=True, impl=impl)
+    torch.cuda.synchronize()
+    assert _rel(y, ref) < 2e-5 * math.sqrt(K), "fp32-out GEMM must match an fp32 matmul of the same bf16 operands"
+    y16 = ops.linear(x, w, b, impl=impl)
+    assert _rel(y16, ref) < 6e-3
+
+
+@pytest.mark.parametrize("impl", [0, 1], ids=["tcgen05", "simt"])
+def test_gemm_epilogues(impl):
+    from mraudio_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    M, N, K = 300, 768, 3072
+    x = torch.randn(M, K, generator=g).to(_dev(), torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) * 0.02).to(_dev(), torch.bfloat16)
+    b = torch.randn(N, generator=g).to(_dev())
+    res = torch.randn(M, N, generator=g).to(_dev())
+    lin = x.float() @ w.float().t() + b
+    assert _rel(ops.linear(x, w, b, residual=res, out_fp32=True, impl=impl), lin + res) < 2e-3
+    assert _rel(ops.linear(x, w, b, gelu=True, out_fp32=True, impl=impl), torch.nn.functional.gelu(lin)) < 2e-3
+    assert _rel(ops.linear(x, w, None, out_fp32=True, impl=impl), lin - b) < 2e-3
+    # strided operands (a column slice of a wider matrix) and a strided output
+    big = torch.randn(M, 2 * K, generator=g).to(_dev(), torch.bfloat16)
+    xs = big[:, K:]
+    out = torch.zeros(M, 2 * N, device=_dev(), dtype=torch.bfloat16)
+    ops.linear(xs, w, b, impl=impl, out=out[:, N:])
+    assert _rel(out[:, N:], xs.float() @ w.float().t() + b) < 6e-3
+    assert out[:, :N].abs().max().item() == 0.0
+
+
+def test_gemm_tcgen05_equals_simt_bitwise_ordering_free():
+    """Same bf16 operands, fp32 accumulation: the two implementations agree to fp32 rounding noise."""
+    from mraudio_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(777, 1408, generator=g).to(_dev(), torch.bfloat16)
+    w = (torch.randn(1536, 1408, generator=g) * 0.02).to(_dev(), torch.bfloat16)
+    a = ops.linear(x, w, out_fp32=True, impl=0)
+    b = ops.linear(x, w, out_fp32=True, impl=1)
+    assert _rel(a, b) < 1e-5
+
+
+def _ref_attention(q, k, v, mask, heads):
+    R, Sq, H = q.shape
+    Sk = k.shape[1]
+    qh = q.float().view(R, Sq, heads, 64).permute(0, 2, 1, 3)
+    kh = k.float().view(R, Sk, heads, 64).permute(0, 2, 1, 3)
+    vh = v.float().view(R, Sk, heads, 64).permute(0, 2, 1, 3)
+    s = qh @ kh.transpose(-1, -2) / 8.0
+    if mask is not None:
+        s = s + mask[:, None, None, :]
+    return (torch.softmax(s, -1) @ vh).permute(0, 2, 1, 3).reshape(R, Sq, H)
+
+
+@pytest.mark.parametrize("rows,Sq,Sk,heads", [(3, 32, 257, 12), (2, 32, 256, 12), (5, 32, 8, 12), (2, 32, 1024, 12),
+                                               (1, 8, 8, 2), (4, 17, 100, 3)])
+def test_cross_attention(rows, Sq, Sk, heads):
+    from mraudio_b200 import ops
+    g = torch.Generator().manual_seed(rows * 100 + Sk)
+    H = heads * 64
+    q = torch.randn(rows, Sq, H, generator=g).to(_dev(), torch.bfloat16)
+    kv = torch.randn(rows, Sk, 2 * H, generator=g).to(_dev(), torch.bfloat16)
+    mask = torch.zeros(rows, Sk)
+    mask[0, Sk // 2:] = -10000.0
+    mask = mask.to(_dev())
+    kvf = kv.view(rows * Sk, 2 * H)
+    for m in (None, mask):
+        o = ops.attention(q.view(rows * Sq, H), kvf[:, :H], kvf[:, H:], rows, heads, Sq, Sk, Sq, True, m)
+        ref = _ref_attention(q, kv[..., :H], kv[..., H:], m, heads)
+        assert _rel(o.view(rows, Sq, H), ref) < 1.5e-2
+
+
+@pytest.mark.parametrize("rows,Nq,T", [(3, 32, 32), (2, 32, 0), (4, 32, 13), (2, 32, 128), (2, 8, 0)])
+def test_self_attention_split_layout(rows, Nq, T):
+    from mraudio_b200 import ops
+    heads, H = 12, 768
+    S = Nq + T
+    g = torch.Generator().manual_seed(rows + T)
+    qkv = torch.randn(rows, S, 3 * H, generator=g).to(_dev(), torch.bfloat16)
+    mask = torch.zeros(rows, S)
+    if T > 3:
+        mask[1, Nq + T // 2:] = -10000.0
+    mask = mask.to(_dev())
+    # split layout: all query tokens first, then all text tokens
+    split = torch.cat([qkv[:, :Nq].reshape(rows * Nq, 3 * H), qkv[:, Nq:].reshape(rows * T, 3 * H)], 0).contiguous()
+    o = ops.attention(split[:, :H], split[:, H:2 * H], split[:, 2 * H:], rows, heads, S, S, Nq, False, mask)
+    ref = _ref_attention(qkv[..., :H], qkv[..., H:2 * H], qkv[..., 2 * H:], mask, heads)
+    got = torch.cat([o[:rows * Nq].view(rows, Nq, H), o[rows * Nq:].view(rows, T, H)], 1)
+    assert _rel(got, ref) < 1.5e-2
+
+
+@pytest.mark.parametrize("rows,n", [(1, 768), (1000, 768), (77, 1408), (5, 1024), (9, 8)])
+def test_layernorm(rows, n):
+    from mraudio_b200 import ops
+    g = torch.Generator().manual_seed(n)
+    x = (torch.randn(rows, n, generator=g) * 3 + 1).to(_dev())
+    gam = torch.randn(n, generator=g).to(_dev())
+    bet = torch.randn(n, generator=g).to(_dev())
+    y32, y16 = ops.layernorm(x, gam, bet, 1e-12)
+    ref = torch.nn.functional.layer_norm(x, (n,), gam, bet, 1e-12)
+    assert (y32 - ref).abs().max().item() < 2e-5 * ref.abs().max().item() + 1e-6
+    assert torch.equal(y16, y32.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("frame_major", [False, True])
+def test_modality_layernorm_and_frame_fold(dtype, frame_major):
+    """models/xinstructblip.py:822-828 (fp32-upcast LN) + :280-285 (frame fold, batch-major reorder)."""
+    from mraudio_b200 import ops
+    bs, Fr, Nk, W = 3, 4, 17, 1408
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(bs, Fr, Nk, W, generator=g).to(dtype)
+    gam = (1 + 0.1 * torch.randn(W, generator=g)).to(_dev())
+    bet = (0.1 * torch.randn(W, generator=g)).to(_dev())
+    ref = torch.nn.functional.layer_norm(x.float().to(_dev()), (W,), gam, bet, 1e-5).reshape(bs * Fr, Nk, W)
+    xin = x.permute(1, 0, 2, 3).contiguous() if frame_major else x
+    y = ops.modality_layernorm(xin.to(_dev()), gam, bet, 1e-5, frame_major=frame_major)
+    assert y.shape == (bs * Fr, Nk, W) and y.dtype == torch.bfloat16
+    assert (y.float() - ref).abs().max().item() < 4e-2  # bf16 output rounding of values up to ~5
+    assert _rel(y, ref) < 5e-3

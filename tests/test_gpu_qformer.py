@@ -1,0 +1,143 @@
+"""GPU parity of the whole Q-Former + llm_proj forward (through mraudio_b200.qformer -> C-ABI) against the CPU oracle
+and the golden fixtures frozen from the HF port of the LAVIS Q-Former.
+
+Tolerance (BASELINE.json north_star): max|y - y_ref| / max|y_ref| <= 2e-2 against the fp32 reference.  Against the
+bf16-storage emulation of the oracle (same rounding points as the CUDA path) the bound is much tighter."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import qformer_oracle as qo
+
+pytestmark = pytest.mark.gpu
+TOL_FP32_REF = 2e-2
+TOL_EMULATED = 6e-3
+
+
+def _rel(a, b):
+    return ((a.float().cpu() - b.float()).abs().max() / b.float().abs().max()).item()
+
+
+def _build(cfg: qo.QFormerOracleConfig, w, llm_dim=4096):
+    from mraudio_b200 import BertConfig, BertLMHeadModel, LLMProjB200
+    bc = BertConfig.from_pretrained("bert-base-uncased")
+    bc.encoder_width = cfg.encoder_width
+    bc.add_cross_attention = True
+    bc.cross_attention_freq = cfg.cross_attention_freq
+    bc.query_length = cfg.query_length
+    bc.num_hidden_layers = cfg.num_hidden_layers
+    bc.vocab_size = cfg.vocab_size
+    model = BertLMHeadModel(bc)
+    sd = {k: v for k, v in w.items() if k.startswith("bert.")}
+    msg = model.load_state_dict(sd, strict=False)
+    assert not msg.missing_keys and not msg.unexpected_keys, msg
+    proj = LLMProjB200(cfg.hidden_size, llm_dim)
+    proj.load_state_dict({"weight": w["llm_proj.weight"], "bias": w["llm_proj.bias"]})
+    return model.cuda().eval(), proj.cuda().eval()
+
+
+@pytest.mark.parametrize("name,W,Nk", [("video", 1408, 257), ("audio", 768, 256)])
+def test_forward_matches_golden_and_oracle(name, W, Nk):
+    fx = np.load(os.path.join(GOLDEN, f"qformer_{name}.npz"))
+    cfg = qo.QFormerOracleConfig(encoder_width=W)
+    w = qo.init_qformer_weights(cfg, seed=int(fx["weight_seed"]), randomize_ln_and_bias=True)
+    g = torch.Generator().manual_seed(int(fx["input_seed"]))
+    ids = torch.randint(1000, 30000, (2, 32), generator=g)
+    enc = torch.randn(2, Nk, W, generator=g)
+    tmask = torch.from_numpy(fx["text_mask"])
+    atts = torch.cat([torch.ones(2, 32, dtype=torch.long), tmask], 1)
+    model, proj = _build(cfg, w)
+    qe = w["query_tokens"].expand(2, -1, -1).cuda()
+    with torch.no_grad():
+        out = model.bert(ids.cuda(), attention_mask=atts.cuda(), query_embeds=qe, encoder_hidden_states=enc.cuda(),
+                         encoder_attention_mask=torch.ones(2, Nk, dtype=torch.long).cuda(), return_dict=True)
+        hid = out.last_hidden_state
+        y = proj(hid[:, :32, :])
+    torch.cuda.synchronize()
+    assert hid.shape == (2, 64, 768) and y.shape == (2, 32, 4096)
+    ref = torch.from_numpy(fx["last_hidden_state"])
+    # padded text positions of row 1 are don't-care in the reference too (they only attend, nobody attends to them)
+    assert _rel(hid[:, :32], ref[:, :32]) < TOL_FP32_REF
+    assert _rel(hid[0], ref[0]) < TOL_FP32_REF
+    assert _rel(y[:, :, ::64], torch.from_numpy(fx["llm_proj_sample"])) < TOL_FP32_REF
+    with torch.no_grad():
+        emu = qo.qformer_bert(w, cfg, ids, atts, w["query_tokens"], enc.to(torch.bfloat16).float(), None, emulate_bf16=True)
+    assert _rel(hid[:, :32], emu[:, :32]) < TOL_EMULATED
+
+
+def test_query_only_two_layer_qformer_1024_keys():
+    """Video-LLaMA-v1-style video Q-Former shape (parity unpinned w.r.t. the reference; pinned to HF Blip2QFormerModel)."""
+    fx = np.load(os.path.join(GOLDEN, "qformer_queryonly.npz"))
+    cfg = qo.QFormerOracleConfig(encoder_width=768, num_hidden_layers=2, cross_attention_freq=1, has_text=False)
+    w = qo.init_qformer_weights(cfg, seed=int(fx["weight_seed"]), randomize_ln_and_bias=True)
+    g = torch.Generator().manual_seed(int(fx["input_seed"]))
+    enc = torch.randn(2, 1024, 768, generator=g)
+    model, _ = _build(cfg, w)
+    with torch.no_grad():
+        hid = model.bert(query_embeds=w["query_tokens"].cuda(), encoder_hidden_states=enc.cuda(), return_dict=True).last_hidden_state
+    assert _rel(hid, torch.from_numpy(fx["last_hidden_state"])) < TOL_FP32_REF
+
+
+@pytest.mark.parametrize("rows,T,Nk,W,layers", [(5, 32, 257, 1408, 4), (3, 0, 64, 768, 2), (7, 11, 19, 768, 3),
+                                                 (130, 32, 257, 1408, 2)])
+def test_forward_shapes_fused_projection_and_dead_ffn_skip(rows, T, Nk, W, layers):
+    cfg = qo.QFormerOracleConfig(encoder_width=W, num_hidden_layers=layers, has_text=T > 0)
+    w = qo.init_qformer_weights(cfg, seed=rows, randomize_ln_and_bias=True, llm_dim=512)
+    g = torch.Generator().manual_seed(rows + 1)
+    enc = torch.randn(rows, Nk, W, generator=g).to(torch.bfloat16)
+    ids = torch.randint(1000, 30000, (rows, T), generator=g) if T else None
+    atts = None
+    if T:
+        tmask = torch.ones(rows, T, dtype=torch.long)
+        tmask[0, T // 2:] = 0
+        atts = torch.cat([torch.ones(rows, 32, dtype=torch.long), tmask], 1)
+    model, proj = _build(cfg, w, llm_dim=512)
+    with torch.no_grad():
+        out = model.bert(ids.cuda() if T else None, attention_mask=atts.cuda() if T else None,
+                         query_embeds=w["query_tokens"].cuda(), encoder_hidden_states=enc.cuda(), return_dict=True,
+                         llm_proj=proj, skip_dead_text_ffn=True)
+        ref = qo.qformer_bert(w, cfg, ids, atts, w["query_tokens"], enc.float(), None, emulate_bf16=True,
+                              skip_dead_text_ffn=True)
+        ref32 = qo.qformer_bert(w, cfg, ids, atts, w["query_tokens"], enc.float(), None)
+        ref_y = qo.llm_proj(w, ref32[:, :32])
+    assert _rel(out.last_hidden_state[:, :32], ref[:, :32]) < TOL_EMULATED
+    assert _rel(out.last_hidden_state[:, :32], ref32[:, :32]) < TOL_FP32_REF
+    assert out.llm_inputs.shape == (rows, 32, 512)
+    assert _rel(out.llm_inputs, ref_y) < TOL_FP32_REF
+    # two-call form == fused form
+    with torch.no_grad():
+        y2 = proj(out.last_hidden_state[:, :32, :])
+    assert _rel(y2, ref_y) < TOL_FP32_REF
+
+
+def test_forward_is_deterministic_and_linear_in_projection():
+    cfg = qo.QFormerOracleConfig(encoder_width=768, num_hidden_layers=2)
+    w = qo.init_qformer_weights(cfg, seed=0, llm_dim=256)
+    model, proj = _build(cfg, w, llm_dim=256)
+    g = torch.Generator().manual_seed(0)
+    enc = torch.randn(4, 50, 768, generator=g).cuda()
+    ids = torch.randint(1000, 30000, (4, 8), generator=g).cuda()
+    kw = dict(query_embeds=w["query_tokens"].cuda(), encoder_hidden_states=enc, return_dict=True, llm_proj=proj)
+    with torch.no_grad():
+        a = model.bert(ids, **kw)
+        b = model.bert(ids, **kw)
+    assert torch.equal(a.last_hidden_state, b.last_hidden_state) and torch.equal(a.llm_inputs, b.llm_inputs)
+    # rows are independent: permuting the batch permutes the output (frames folded into the batch dimension)
+    perm = torch.tensor([2, 0, 3, 1]).cuda()
+    with torch.no_grad():
+        c = model.bert(ids[perm], **dict(kw, encoder_hidden_states=enc[perm]))
+    assert torch.equal(c.last_hidden_state, a.last_hidden_state[perm])
+
+
+def test_errors_are_loud():
+    from mraudio_b200 import MraError
+    cfg = qo.QFormerOracleConfig(encoder_width=768, num_hidden_layers=1)
+    w = qo.init_qformer_weights(cfg, seed=0, llm_dim=64)
+    model, _ = _build(cfg, w, llm_dim=64)
+    with pytest.raises(MraError):
+        model.bert(query_embeds=w["query_tokens"], encoder_hidden_states=torch.zeros(1, 4, 768))  # CPU tensors
+    with pytest.raises(ValueError):
+        model.bert(query_embeds=w["query_tokens"].cuda(), encoder_hidden_states=torch.zeros(1, 4, 1408).cuda())

@@ -1,0 +1,90 @@
+"""GPU parity of the moment-retrieval scorer (mra_mr_score through mraudio_b200.mr_eval) -- bit-exact against the
+oracle (itself pinned to fixtures frozen from the reference's eval/mr_eval.py) and against those fixtures directly."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from oracle import mr_eval_oracle as mo
+
+pytestmark = pytest.mark.gpu
+CASES = sorted(p for p in glob.glob(os.path.join(GOLDEN, "mr_eval_*.json")) if "docstring" not in p)
+
+
+def _eq(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return a.shape == b.shape and bool(np.all((a == b) | (np.isnan(a) & np.isnan(b))))
+
+
+def _same_tree(a, b):
+    if isinstance(a, dict):
+        assert set(map(str, a)) == set(map(str, b)), (a.keys(), b.keys())
+        bb = {str(k): v for k, v in b.items()}
+        for k, v in a.items():
+            _same_tree(v, bb[str(k)])
+    else:
+        assert _eq(a, b), (a, b)
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[8:-5] for p in CASES])
+def test_records_and_metrics_match_reference_fixture(path):
+    from mraudio_b200 import mr_eval
+    fx = json.load(open(path))
+    sub, gt = fx["submission"], fx["ground_truth"]
+    rec = mr_eval.score_records(sub, gt)
+    ora = mo.score_records(sub, gt)
+    assert _eq(rec["ap"], ora["ap"]) and _eq(rec["iou"], ora["iou"]) and np.array_equal(rec["invalid"], ora["invalid"])
+    got = mr_eval.eval_submission(sub, gt, verbose=False)
+    exp = fx["eval_submission"] if "eval_submission" in fx else mo.eval_submission(sub, gt)
+    _same_tree(dict(got["brief"]), dict(exp["brief"]))
+    _same_tree(got["full"], exp["full"])
+
+
+@pytest.mark.parametrize("Q,seed,flt", [(1, 1, False), (257, 2, False), (5000, 7, False), (3000, 9, True)])
+def test_synthetic_sweep_exact(Q, seed, flt):
+    from mraudio_b200 import mr_eval
+    sub, gt = mo.synth_submission(Q, seed=seed, float_windows=flt)
+    rec = mr_eval.score_records(sub, gt)
+    ora = mo.score_records(sub, gt)
+    assert _eq(rec["ap"], ora["ap"])
+    assert _eq(rec["iou"], ora["iou"])
+    assert np.array_equal(rec["invalid"], ora["invalid"])
+    _same_tree(dict(mr_eval.eval_submission(sub, gt, verbose=False)["brief"]), dict(mo.eval_submission(sub, gt)["brief"]))
+
+
+def test_full_size_properties():
+    """cfg5 size (128 videos x k queries): size-independent properties instead of the slow oracle."""
+    from mraudio_b200 import mr_eval
+    Q = 128 * 400
+    sub, gt = mo.synth_submission(Q, seed=11)
+    rec = mr_eval.score_records(sub, gt)
+    assert rec["ap"].shape == (Q, 10)
+    assert np.all((rec["ap"] >= 0) & (rec["ap"] <= 1))
+    assert np.all(np.diff(rec["ap"], axis=1) <= 1e-15), "AP is non-increasing in the IoU threshold"
+    # perfect predictions score 1 everywhere; scoring is permutation-equivariant over queries
+    perfect = [{"qid": d["qid"], "pred_relevant_windows": [list(w) for w in g["relevant_windows"]]} for d, g in zip(sub, gt)]
+    uniq = [i for i, g in enumerate(gt) if len({tuple(w) for w in g["relevant_windows"]}) == len(g["relevant_windows"])]
+    recp = mr_eval.score_records(perfect, gt)
+    assert np.all(recp["ap"][uniq] == 1.0) and np.all(recp["iou"] == 1.0)
+    perm = np.random.default_rng(0).permutation(Q)
+    recq = mr_eval.score_records([sub[i] for i in perm], gt)
+    assert _eq(recq["ap"], rec["ap"][perm]) and _eq(recq["iou"], rec["iou"][perm])
+
+
+def test_edge_cases():
+    from mraudio_b200 import mr_eval
+    sub = [{"qid": 1, "pred_relevant_windows": [[-1, -1]]}, {"qid": 2, "pred_relevant_windows": [[10, 20, 0.9], [30, 40, 0.1]]}]
+    gt = [{"qid": 1, "relevant_windows": [[0, 0]]}, {"qid": 2, "relevant_windows": [[12, 20], [30, 41]]}]
+    rec = mr_eval.score_records(sub, gt)
+    ora = mo.score_records(sub, gt)
+    assert _eq(rec["ap"], ora["ap"]) and _eq(rec["iou"], ora["iou"])
+    assert rec["ap"][1].tolist() == [1, 1, 1, 1, 1, 1, 1, 0.25, 0.25, 0]
+    with pytest.raises(IndexError):
+        mr_eval.score_records([{"qid": 1, "pred_relevant_windows": []}], gt[:1])
+    with pytest.raises(AssertionError):
+        mr_eval.eval_submission(sub[:1], gt, verbose=False)
+    out = mr_eval.eval_submission(sub[:1], gt, verbose=False, match_number=False)
+    assert out["brief"]["MR-full-invalid_pred_num"] == 1
