@@ -92,7 +92,7 @@ typedef struct mra_qformer_io {
     /* inputs */
     const void* enc;            /* bf16 [rows, Nk, W]   encoder_hidden_states (already through {modality}_ln) */
     const int32_t* input_ids;   /* [rows, T] or NULL when T == 0 */
-    const int32_t* text_mask;   /* [rows, T] 1 = attend, 0 = padding; NULL = all ones */
+    const int32_t* attn_mask;   /* [rows, Nq+T] attention_mask over queries||text: 1 = attend, 0 = padding; NULL = ones */
     const int32_t* enc_mask;    /* [rows, Nk] or NULL = all ones (the reference always passes ones, :266,275) */
     const float* query_embeds;  /* fp32 [q_rows, Nq, H], q_rows == 1 (broadcast) or rows */
     int32_t q_rows;
@@ -111,6 +111,22 @@ int mra_qformer_forward(mra_qformer_t* h, const mra_qformer_io* io, void* worksp
                         void* stream);
 /* number of kernels the last forward call enqueued (for bench.py's gpu_launches) */
 int mra_qformer_last_launch_count(const mra_qformer_t* h);
+
+/* Device-side timing of the launches of mra_qformer_forward with CUDA events recorded on the caller's stream.
+ *   MRA_PROFILE_DOMINANT brackets only the tensor-core GEMM launches (the dominant kernel: bench.py's roofline),
+ *   MRA_PROFILE_ALL every launch.  mra_qformer_profile_read synchronises on the recorded events, returns the summed
+ *   milliseconds and launch counts per category since the previous read, and clears them. */
+#define MRA_PROFILE_OFF 0
+#define MRA_PROFILE_DOMINANT 1
+#define MRA_PROFILE_ALL 2
+#define MRA_CAT_GEMM_CROSS_KV 0 /* cross-attention K/V projection of all cross layers (one GEMM) */
+#define MRA_CAT_GEMM 1          /* every other Linear */
+#define MRA_CAT_ATTENTION 2
+#define MRA_CAT_LAYERNORM 3
+#define MRA_CAT_OTHER 4
+#define MRA_NUM_CATS 5
+int mra_qformer_profile_mode(mra_qformer_t* h, int32_t mode);
+int mra_qformer_profile_read(mra_qformer_t* h, double* ms_by_cat, int64_t* launches_by_cat);
 
 /* ---- building-block ops (each is also what the forward above launches; exposed for parity tests and backward) */
 

@@ -17,6 +17,8 @@ FWD_SKIP_DEAD_TEXT_FFN = 1
 FWD_SAVE_FOR_BACKWARD = 2
 GEMM_IMPL_TCGEN05 = 0
 GEMM_IMPL_SIMT_DEBUG = 1
+PROFILE_OFF, PROFILE_DOMINANT, PROFILE_ALL = 0, 1, 2
+PROFILE_CATS = ("gemm_cross_kv", "gemm", "attention", "layernorm", "other")
 
 
 class MraError(RuntimeError):
@@ -43,7 +45,7 @@ class QFormerWeights(C.Structure):
 
 
 class QFormerIO(C.Structure):
-    _fields_ = [("enc", C.c_void_p), ("input_ids", C.c_void_p), ("text_mask", C.c_void_p), ("enc_mask", C.c_void_p),
+    _fields_ = [("enc", C.c_void_p), ("input_ids", C.c_void_p), ("attn_mask", C.c_void_p), ("enc_mask", C.c_void_p),
                 ("query_embeds", C.c_void_p), ("q_rows", C.c_int32), ("rows", C.c_int32), ("T", C.c_int32),
                 ("Nk", C.c_int32), ("flags", C.c_uint32), ("last_hidden", C.c_void_p), ("llm_out", C.c_void_p)]
 
@@ -67,6 +69,8 @@ def _load():
     lib.mra_qformer_workspace_bytes.restype = C.c_size_t
     lib.mra_qformer_forward.argtypes = [vp, C.POINTER(QFormerIO), vp, C.c_size_t, vp]
     lib.mra_qformer_last_launch_count.argtypes = [vp]
+    lib.mra_qformer_profile_mode.argtypes = [vp, i32]
+    lib.mra_qformer_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.mra_gemm_bf16.argtypes = [vp, i64, vp, i64, vp, vp, i64, vp, i64, i32, i32, i32, i32, i32, i32, vp]
     lib.mra_attention.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.mra_layernorm.argtypes = [vp, vp, vp, vp, vp, i32, i32, f32, vp]
@@ -81,6 +85,7 @@ lib = _load()
 EXPORTED_SYMBOLS = (
     "mra_last_error", "mra_version", "mra_device_check", "mra_qformer_create", "mra_qformer_set_weights",
     "mra_qformer_destroy", "mra_qformer_workspace_bytes", "mra_qformer_forward", "mra_qformer_last_launch_count",
+    "mra_qformer_profile_mode", "mra_qformer_profile_read",
     "mra_gemm_bf16", "mra_attention", "mra_layernorm", "mra_modality_layernorm", "mra_mr_score",
 )
 

@@ -64,8 +64,7 @@ int launch_modality_layernorm(const void* x, int in_dtype, const float* g, const
 int launch_embed_layernorm(const float* query_embeds, int q_rows, const int32_t* ids, const void* word_emb,
                            const void* pos_emb, const float* g, const float* b, float* y32, void* y16, int rows, int Nq,
                            int T, int H, int vocab, float eps, cudaStream_t s);
-// additive masks: out[r, j] = j < Nq ? 0 : (1 - text_mask[r, j-Nq]) * -10000
-int launch_build_self_mask(const int32_t* text_mask, float* out, int rows, int Nq, int T, cudaStream_t s);
+// additive masks (LAVIS get_extended_attention_mask): out[r, j] = (1 - mask[r, j]) * -10000
 int launch_build_enc_mask(const int32_t* enc_mask, float* out, int rows, int Nk, cudaStream_t s);
 // split layout [queries ; text] fp32 -> interleaved [rows, Nq+T, H] fp32
 int launch_gather_last_hidden(const float* split, float* out, int rows, int Nq, int T, int H, cudaStream_t s);

@@ -174,16 +174,6 @@ embed_ln_kernel(const float* __restrict__ query_embeds, int q_rows, const int32_
     ln_normalise_store(v, H, lane, g, b, eps, y32 + orow * H, y16 + orow * H);
 }
 
-__global__ void self_mask_kernel(const int32_t* __restrict__ text_mask, float* __restrict__ out, int rows, int Nq, int T) {
-    const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const int S = Nq + T;
-    if (idx >= static_cast<int64_t>(rows) * S) return;
-    const int r = static_cast<int>(idx / S), j = static_cast<int>(idx % S);
-    float m = 0.f;
-    if (j >= Nq && text_mask != nullptr) m = (1.0f - static_cast<float>(text_mask[static_cast<int64_t>(r) * T + (j - Nq)])) * -10000.0f;
-    out[idx] = m;
-}
-
 __global__ void enc_mask_kernel(const int32_t* __restrict__ enc_mask, float* __restrict__ out, int64_t n) {
     const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (idx >= n) return;
@@ -241,13 +231,6 @@ int launch_embed_layernorm(const float* query_embeds, int q_rows, const int32_t*
                                                            reinterpret_cast<const __nv_bfloat16*>(word_emb),
                                                            reinterpret_cast<const __nv_bfloat16*>(pos_emb), g, b, y32,
                                                            reinterpret_cast<__nv_bfloat16*>(y16), rows, Nq, T, H, vocab, eps);
-    MRA_CHECK_CUDA(cudaGetLastError());
-    return 0;
-}
-
-int launch_build_self_mask(const int32_t* text_mask, float* out, int rows, int Nq, int T, cudaStream_t s) {
-    const int64_t n = static_cast<int64_t>(rows) * (Nq + T);
-    self_mask_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(text_mask, out, rows, Nq, T);
     MRA_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -19,6 +19,17 @@ struct mra_qformer {
     int cross_slot[MRA_MAX_LAYERS];  // index of the layer's K/V block inside w_ckv, or -1
     int last_launches = 0;
     int gemm_impl = MRA_GEMM_IMPL_TCGEN05;
+    // optional per-category device timing (CUDA events on the caller's stream), see mra_qformer_profile_*
+    int profile_mode = MRA_PROFILE_OFF;
+    struct Span { int cat; cudaEvent_t a, b; };
+    std::vector<Span> spans;          // recorded since the last read
+    std::vector<cudaEvent_t> pool;    // recycled events
+    cudaEvent_t get_event() {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        return e;
+    }
 };
 
 namespace mra {
@@ -105,11 +116,39 @@ extern "C" int mra_qformer_set_weights(mra_qformer_t* h, const mra_qformer_weigh
     return 0;
 }
 
-extern "C" void mra_qformer_destroy(mra_qformer_t* h) { delete h; }
+extern "C" void mra_qformer_destroy(mra_qformer_t* h) {
+    if (!h) return;
+    for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    for (auto e : h->pool) cudaEventDestroy(e);
+    delete h;
+}
 
 extern "C" size_t mra_qformer_workspace_bytes(const mra_qformer_t* h, int32_t rows, int32_t T, int32_t Nk, uint32_t) {
     if (!h || rows <= 0 || T < 0 || Nk <= 0) return 0;
     return carve(h, rows, T, Nk, nullptr).total;
+}
+
+extern "C" int mra_qformer_profile_mode(mra_qformer_t* h, int32_t mode) {
+    MRA_REQUIRE(h, "mra_qformer_profile_mode: NULL handle");
+    MRA_REQUIRE(mode >= MRA_PROFILE_OFF && mode <= MRA_PROFILE_ALL, "unknown profile mode %d", mode);
+    h->profile_mode = mode;
+    return 0;
+}
+
+extern "C" int mra_qformer_profile_read(mra_qformer_t* h, double* ms_by_cat, int64_t* launches_by_cat) {
+    MRA_REQUIRE(h && ms_by_cat && launches_by_cat, "mra_qformer_profile_read: NULL argument");
+    for (int i = 0; i < MRA_NUM_CATS; ++i) { ms_by_cat[i] = 0.0; launches_by_cat[i] = 0; }
+    for (auto& sp : h->spans) {
+        MRA_CHECK_CUDA(cudaEventSynchronize(sp.b));
+        float ms = 0.f;
+        MRA_CHECK_CUDA(cudaEventElapsedTime(&ms, sp.a, sp.b));
+        ms_by_cat[sp.cat] += ms;
+        launches_by_cat[sp.cat] += 1;
+        h->pool.push_back(sp.a);
+        h->pool.push_back(sp.b);
+    }
+    h->spans.clear();
+    return 0;
 }
 
 extern "C" int mra_qformer_last_launch_count(const mra_qformer_t* h) { return h ? h->last_launches : 0; }
@@ -138,11 +177,33 @@ extern "C" int mra_qformer_forward(mra_qformer_t* h, const mra_qformer_io* io, v
     const int Mq = rows * Nq, Mt = rows * T, Mtot = Mq + Mt;
     const int kv_ld = h->n_cross * 2 * H;
     int launches = 0;
+    // profiling spans: MRA_PROFILE_DOMINANT brackets only GEMM launches, MRA_PROFILE_ALL every launch
+    int cur_cat = -1;
+    cudaEvent_t cur_ev = nullptr;
+    auto span_begin = [&](int cat) {
+        cur_cat = -1;
+        if (h->profile_mode == MRA_PROFILE_OFF) return;
+        if (h->profile_mode == MRA_PROFILE_DOMINANT && cat > MRA_CAT_GEMM) return;
+        cur_cat = cat;
+        cur_ev = h->get_event();
+        cudaEventRecord(cur_ev, s);
+    };
+    auto span_end = [&]() {
+        if (cur_cat < 0) return;
+        cudaEvent_t b = h->get_event();
+        cudaEventRecord(b, s);
+        h->spans.push_back({cur_cat, cur_ev, b});
+        cur_cat = -1;
+    };
+    int gemm_cat = MRA_CAT_GEMM;
     auto gemm = [&](const void* A, int64_t lda, const void* Wt, int64_t ldw, const float* bias, const float* res,
                     int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int gelu, int f32) -> int {
         GemmArgs a{A, lda, Wt, ldw, bias, res, ldr, C, ldc, M, N, K, gelu, f32};
         ++launches;
-        return h->gemm_impl == MRA_GEMM_IMPL_SIMT_DEBUG ? launch_gemm_simt(a, s) : launch_gemm_tc(a, s);
+        span_begin(gemm_cat);
+        int e = h->gemm_impl == MRA_GEMM_IMPL_SIMT_DEBUG ? launch_gemm_simt(a, s) : launch_gemm_tc(a, s);
+        span_end();
+        return e;
     };
 #define MRA_TRY(expr)            \
     do {                         \
@@ -150,12 +211,14 @@ extern "C" int mra_qformer_forward(mra_qformer_t* h, const mra_qformer_io* io, v
     } while (0)
 
     // ---- embeddings + masks
+    span_begin(MRA_CAT_OTHER);
     MRA_TRY(launch_embed_layernorm(io->query_embeds, io->q_rows, io->input_ids, W.word_emb, W.pos_emb, W.ln_e_g, W.ln_e_b,
                                    ws.x32, ws.xb, rows, Nq, T, H, c.vocab, c.ln_eps, s));
+    span_end();
     ++launches;
     const float* self_mask = nullptr;
-    if (T > 0 && io->text_mask) {
-        MRA_TRY(launch_build_self_mask(io->text_mask, ws.self_mask, rows, Nq, T, s));
+    if (io->attn_mask) {
+        MRA_TRY(launch_build_enc_mask(io->attn_mask, ws.self_mask, rows, Nq + T, s));
         ++launches;
         self_mask = ws.self_mask;
     }
@@ -166,8 +229,10 @@ extern "C" int mra_qformer_forward(mra_qformer_t* h, const mra_qformer_io* io, v
         enc_mask = ws.enc_mask;
     }
     // ---- cross-attention keys / values of ALL cross layers in one GEMM: the encoder tokens are read once
+    gemm_cat = MRA_CAT_GEMM_CROSS_KV;
     MRA_TRY(gemm(io->enc, c.enc_width, W.w_ckv, c.enc_width, W.b_ckv, nullptr, 0, ws.kv, kv_ld, rows * Nk, kv_ld,
                  c.enc_width, 0, 0));
+    gemm_cat = MRA_CAT_GEMM;
 
     for (int l = 0; l < c.layers; ++l) {
         const auto& L = W.layer[l];
@@ -176,27 +241,37 @@ extern "C" int mra_qformer_forward(mra_qformer_t* h, const mra_qformer_io* io, v
         MRA_TRY(gemm(ws.xb, H, L.w_qkv, H, L.b_qkv, nullptr, 0, ws.qkv, 3 * H, Mtot, 3 * H, H, 0, 0));
         {
             AttnArgs a{ws.qkv, 3 * H, ws.qkv + H, 3 * H, ws.qkv + 2 * H, 3 * H, ws.ctx, H, self_mask, rows, c.heads, S, S, Nq, 0};
+            span_begin(MRA_CAT_ATTENTION);
             MRA_TRY(launch_attention(a, s));
+            span_end();
             ++launches;
         }
         MRA_TRY(gemm(ws.ctx, H, L.w_ao, H, L.b_ao, ws.x32, H, ws.pre, H, Mtot, H, H, 0, 1));
+        span_begin(MRA_CAT_LAYERNORM);
         MRA_TRY(launch_layernorm(ws.pre, L.ln_a_g, L.ln_a_b, ws.a32, ws.ab, Mtot, H, c.ln_eps, s));
+        span_end();
         ++launches;
         // cross-attention of the query tokens onto this row's encoder tokens
         if (h->cross_slot[l] >= 0) {
             const __nv_bfloat16* kbase = ws.kv + static_cast<size_t>(h->cross_slot[l]) * 2 * H;
             MRA_TRY(gemm(ws.ab, H, L.w_cq, H, L.b_cq, nullptr, 0, ws.cq, H, Mq, H, H, 0, 0));
             AttnArgs a{ws.cq, H, kbase, kv_ld, kbase + H, kv_ld, ws.ctx, H, enc_mask, rows, c.heads, Nq, Nk, Nq, 1};
+            span_begin(MRA_CAT_ATTENTION);
             MRA_TRY(launch_attention(a, s));
+            span_end();
             ++launches;
             MRA_TRY(gemm(ws.ctx, H, L.w_co, H, L.b_co, ws.a32, H, ws.pre, H, Mq, H, H, 0, 1));
+            span_begin(MRA_CAT_LAYERNORM);
             MRA_TRY(launch_layernorm(ws.pre, L.ln_c_g, L.ln_c_b, ws.a32, ws.ab, Mq, H, c.ln_eps, s));
+            span_end();
             ++launches;
         }
         // FFN_query on the query rows
         MRA_TRY(gemm(ws.ab, H, L.w_fq1, H, L.b_fq1, nullptr, 0, ws.inter, I, Mq, I, H, 1, 0));
         MRA_TRY(gemm(ws.inter, I, L.w_fq2, I, L.b_fq2, ws.a32, H, ws.pre, H, Mq, H, I, 0, 1));
+        span_begin(MRA_CAT_LAYERNORM);
         MRA_TRY(launch_layernorm(ws.pre, L.ln_fq_g, L.ln_fq_b, ws.x32, ws.xb, Mq, H, c.ln_eps, s));
+        span_end();
         ++launches;
         // FFN_text on the text rows
         if (T > 0) {
@@ -213,14 +288,18 @@ extern "C" int mra_qformer_forward(mra_qformer_t* h, const mra_qformer_io* io, v
                 const size_t oi = static_cast<size_t>(Mq) * I;
                 MRA_TRY(gemm(ws.ab + o, H, L.w_ft1, H, L.b_ft1, nullptr, 0, ws.inter + oi, I, Mt, I, H, 1, 0));
                 MRA_TRY(gemm(ws.inter + oi, I, L.w_ft2, I, L.b_ft2, ws.a32 + o, H, ws.pre + o, H, Mt, H, I, 0, 1));
+                span_begin(MRA_CAT_LAYERNORM);
                 MRA_TRY(launch_layernorm(ws.pre + o, L.ln_ft_g, L.ln_ft_b, ws.x32 + o, ws.xb + o, Mt, H, c.ln_eps, s));
+                span_end();
                 ++launches;
             }
         }
     }
     // ---- outputs
     if (io->last_hidden) {
+        span_begin(MRA_CAT_OTHER);
         MRA_TRY(launch_gather_last_hidden(ws.x32, io->last_hidden, rows, Nq, T, H, s));
+        span_end();
         ++launches;
     }
     if (io->llm_out) {

@@ -165,6 +165,7 @@ class BertModelB200(nn.Module):
         self._pack_applied = set()
         self._workspace = None
         self.last_launches = 0
+        self._profile_mode = _lib.PROFILE_OFF
         self._init_weights()
 
     # BERT _init_weights: Linear / Embedding N(0, initializer_range), bias 0, LayerNorm (1, 0)
@@ -200,7 +201,26 @@ class BertModelB200(nn.Module):
             check(lib.mra_qformer_create(C.byref(cc), C.byref(hp)))
             h = hp
             self._handles[llm_dim] = h
+            check(lib.mra_qformer_profile_mode(h, self._profile_mode))
         return h
+
+    # ------------------------------------------------------------------------------------------- device-side timing
+    def set_profile_mode(self, mode: int) -> None:
+        """CUDA-event timing of the forward's launches (``_lib.PROFILE_OFF / PROFILE_DOMINANT / PROFILE_ALL``)."""
+        self._profile_mode = mode
+        for h in self._handles.values():
+            check(lib.mra_qformer_profile_mode(h, mode))
+
+    def read_profile(self):
+        """(ms per category, launches per category) accumulated since the last read; synchronises on the events."""
+        ms_tot, n_tot = [0.0] * len(_lib.PROFILE_CATS), [0] * len(_lib.PROFILE_CATS)
+        for h in self._handles.values():
+            ms = (C.c_double * len(_lib.PROFILE_CATS))()
+            n = (C.c_int64 * len(_lib.PROFILE_CATS))()
+            check(lib.mra_qformer_profile_read(h, ms, n))
+            ms_tot = [a + b for a, b in zip(ms_tot, ms)]
+            n_tot = [a + int(b) for a, b in zip(n_tot, n)]
+        return ms_tot, n_tot
 
     def _packed(self, proj: Optional[nn.Linear]):
         ver = (_param_version(self), _param_version(proj) if proj is not None else None)
@@ -208,11 +228,11 @@ class BertModelB200(nn.Module):
             return self._pack[2]
         bf = lambda t: t.detach().to(torch.bfloat16).contiguous()
         f32 = lambda t: t.detach().float().contiguous()
-        keep = {}
+        keep = []   # packed tensors must outlive the handle's use of their device pointers
         W = _lib.QFormerWeights()
 
         def put(struct, field, tensor):
-            keep[(id(struct), field)] = tensor
+            keep.append(tensor)
             setattr(struct, field, tensor.data_ptr())
 
         e = self.embeddings
@@ -286,15 +306,14 @@ class BertModelB200(nn.Module):
                 raise ValueError(f"input_ids batch {input_ids.shape[0]} does not match encoder rows {rows}")
             T = input_ids.shape[1]
             ids = input_ids.to(device=dev, dtype=torch.int32).contiguous()
-        if attention_mask is not None and T > 0:
+        # masks go to the device as they are (no host-side inspection: that would synchronise the stream)
+        if attention_mask is not None:
             if attention_mask.shape != (rows, Nq + T):
                 raise ValueError(f"attention_mask shape {tuple(attention_mask.shape)} != {(rows, Nq + T)}")
-            if not bool((attention_mask[:, :Nq] != 0).all()):
-                raise NotImplementedError("masked query tokens are not supported (the reference passes ones, :246-250)")
-            tm = attention_mask[:, Nq:]
-            if not bool((tm != 0).all()):
-                tmask = tm.to(device=dev, dtype=torch.int32).contiguous()
-        if encoder_attention_mask is not None and not bool((encoder_attention_mask != 0).all()):
+            tmask = attention_mask.to(device=dev, dtype=torch.int32).contiguous()
+        if encoder_attention_mask is not None:
+            if encoder_attention_mask.shape != (rows, Nk):
+                raise ValueError(f"encoder_attention_mask shape {tuple(encoder_attention_mask.shape)} != {(rows, Nk)}")
             emask = encoder_attention_mask.to(device=dev, dtype=torch.int32).contiguous()
 
         llm_dim = llm_proj.weight.shape[0] if llm_proj is not None else 0
@@ -310,7 +329,7 @@ class BertModelB200(nn.Module):
             self._workspace = torch.empty(need, device=dev, dtype=torch.uint8)
         last_hidden = torch.empty(rows, Nq + T, cfg.hidden_size, device=dev, dtype=torch.float32) if need_last_hidden else None
         llm_out = torch.empty(rows * Nq, llm_dim, device=dev, dtype=torch.bfloat16) if llm_proj is not None else None
-        io = _lib.QFormerIO(enc=enc_b.data_ptr(), input_ids=_lib.ptr(ids), text_mask=_lib.ptr(tmask), enc_mask=_lib.ptr(emask),
+        io = _lib.QFormerIO(enc=enc_b.data_ptr(), input_ids=_lib.ptr(ids), attn_mask=_lib.ptr(tmask), enc_mask=_lib.ptr(emask),
                             query_embeds=qe.data_ptr(), q_rows=q_rows, rows=rows, T=T, Nk=Nk, flags=flags,
                             last_hidden=_lib.ptr(last_hidden), llm_out=_lib.ptr(llm_out))
         check(lib.mra_qformer_forward(h, C.byref(io), self._workspace.data_ptr(), self._workspace.numel(), current_stream()))
