@@ -223,6 +223,9 @@ def run_b200(args):
 
     for _ in range(args.warmup):
         device_step()
+    if args.device_only:
+        print(json.dumps({"ms_per_step": timed(device_step, args.steps), "launches_per_step": model.last_launches}))
+        return
     sampler = ClockSampler(local) if rank == 0 else None
     t_clock0 = time.time()
     # ---- value: device-resident inputs
@@ -315,6 +318,7 @@ def main():
     ap.add_argument("--videos", type=int, default=32, help="videos per GPU per step (config 2: 32)")
     ap.add_argument("--frames", type=int, default=8)
     ap.add_argument("--text-len", type=int, default=32)
+    ap.add_argument("--device-only", action="store_true", help="run warm-up + timed device steps and exit (for ncu)")
     ap.add_argument("--ref-videos", type=int, default=1, help="videos per step of the CPU reference arm (bounded sample)")
     args = ap.parse_args()
     if args.impl == "reference":
