@@ -141,6 +141,9 @@ int mra_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const 
                   int64_t ldr, void* C, int64_t ldc, int32_t M, int32_t N, int32_t K, int32_t gelu, int32_t out_fp32,
                   int32_t impl, void* stream);
 
+/* Tuning aid: force the output-tile width of the tcgen05 GEMM (128, 192 or 256; 0 = automatic choice). */
+int mra_gemm_tile_override(int32_t bn);
+
 /* Fused multi-head attention core, head_dim 64: O = softmax(Q K^T / 8 + mask) V, per (row, head).
  *   q: bf16, row `qrow(r, i)` at q + qrow*ldq + head*64;  k, v likewise with ldk/ldv; o bf16 with ldo.
  *   Row addressing: "split" layout used by the forward: query tokens of all rows first, then text tokens:

@@ -68,6 +68,12 @@ extern "C" int mra_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t 
     return launch_gemm_tc(a, s);
 }
 
+extern "C" int mra_gemm_tile_override(int32_t bn) {
+    MRA_REQUIRE(bn == 0 || bn == 128 || bn == 192 || bn == 256, "tile width override must be 0 (auto), 128, 192 or 256");
+    set_gemm_tile_override(bn);
+    return 0;
+}
+
 extern "C" int mra_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
                              int64_t ldo, const float* add_mask, int32_t rows, int32_t heads, int32_t Sq, int32_t Sk,
                              int32_t nq_split, int32_t kv_dense, void* stream) {

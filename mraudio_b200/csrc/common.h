@@ -45,6 +45,7 @@ struct GemmArgs {
 };
 int launch_gemm_tc(const GemmArgs& a, cudaStream_t s);
 int launch_gemm_simt(const GemmArgs& a, cudaStream_t s);
+void set_gemm_tile_override(int bn);
 
 struct AttnArgs {
     const void* q; int64_t ldq;

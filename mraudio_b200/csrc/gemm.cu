@@ -5,8 +5,12 @@
 //     running concurrently share the same A rows through L2);
 //   * warp 0 = TMA producer (cp.async.bulk.tensor, 128B-swizzled 64-wide K slabs, STAGES-deep mbarrier ring),
 //     warp 1 = MMA issuer (one thread, tcgen05.mma kind::f16, M=128, N=BN, K=16, fp32 accumulators in TMEM),
-//     warps 2..5 = epilogue (tcgen05.ld 32x32b, bias / erf-GELU / fp32 residual fused, vectorised stores);
-//   * two TMEM accumulator stages (2*BN columns) so the epilogue of tile i overlaps the main loop of tile i+1.
+//     warps 2..5 = epilogue: tcgen05.ld 32x32b -> registers -> bias / erf-GELU / fp32 residual -> 128B-swizzled
+//     shared-memory staging -> TMA bulk tensor STORE (each warp streams its own 32-row slab in 128-byte-wide column
+//     chunks, double-buffered); the fp32 residual arrives by TMA LOAD into the same kind of per-warp chunk buffers,
+//     prefetched two chunks ahead (the first two while the tile's main loop is still running).  All global traffic
+//     of the epilogue is therefore asynchronous, fully coalesced and clipped at the M / N edges by the TMA unit;
+//   * two TMEM accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1.
 // Reference arithmetic replaced: torch.nn.Linear (+ GELU, + residual add) in LAVIS Qformer.py / HF port
 // modeling_instructblip.py:499-509,549-553,586-610 and llm_proj (models/xinstructblip.py:707-708).
 #include <cuda.h>
@@ -25,32 +29,61 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
 constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 4;
+constexpr int CHUNK_BYTES = 32 * 128;       // one epilogue chunk of one warp: 32 rows x 128 bytes
 
 struct EpiParams {
     const float* bias;
-    const float* residual;
-    int64_t ldr;
-    void* C;
-    int64_t ldc;
     int M, N, K;
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool RES>
 struct SmemLayout {
     static constexpr int B_STAGE_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-    static constexpr int NUM_BARS = 2 * STAGES + 4;
+    static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int EPI_BUFS_PER_WARP = RES ? 4 : 2;   // 2 output chunks (+ 2 residual chunks)
+    static constexpr int EPI_BYTES = EPI_WARPS * EPI_BUFS_PER_WARP * CHUNK_BYTES;
+    static constexpr int BAR_OFFSET = EPI_OFFSET + EPI_BYTES;
+    static constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * EPI_WARPS;
     static constexpr int TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;  // + tmem ptr + 1024B alignment slack
+    static_assert(TOTAL <= 227 * 1024, "shared memory budget exceeded");
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// erf-GELU: 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the
+// bf16 rounding of the result) -- 2 MUFU + ~12 FMA-pipe instructions per element instead of erff()'s ~30, which matters
+// because the GELU epilogue is issue-bound (128 x BN elements per tile against a 6144-cycle main loop at BN = 256).
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float u = x * 0.70710678118654752f;
+    const float a = fabsf(u);
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, a, 1.0f)));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    p *= t;
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a * a * -1.4426950408889634f));
+    const float erf_abs = fmaf(-p, e, 1.0f);
+    const float erf_u = copysignf(erf_abs, u);
+    const float h = 0.5f * x;
+    return fmaf(h, erf_u, h);
+}
 
-template <int BN, int STAGES, bool GELU, bool OUT_F32>
+// byte offset of 16-byte unit `j` of row `r` inside a 32-row x 128-byte chunk buffer with the TMA 128-byte swizzle
+__device__ __forceinline__ uint32_t swz(int r, int j) { return static_cast<uint32_t>(r * 128 + ((j ^ (r & 7)) << 4)); }
+
+template <int BN, int STAGES, bool GELU, bool OUT_F32, bool RES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const EpiParams p) {
-    using L = SmemLayout<BN, STAGES>;
-    constexpr uint32_t TMEM_COLS = 2 * BN;  // 256 or 512: power of two >= 32
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const EpiParams p) {
+    using L = SmemLayout<BN, STAGES, RES>;
+    constexpr uint32_t TMEM_COLS = BN <= 128 ? 256 : 512;  // two accumulator stages, power of two
+    constexpr int ACC_STRIDE = BN <= 128 ? 128 : 256;
+    constexpr int CH = OUT_F32 ? 32 : 64;                  // columns per epilogue chunk (128 bytes of output per row)
+    constexpr int NCH = BN / CH;
+    static_assert(BN % CH == 0 && (!OUT_F32 || NCH % 2 == 0), "tile width must be a whole (fp32: even) number of chunks");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
@@ -59,7 +92,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    uint64_t* res_bar = tempty_bar + 2;                    // [EPI_WARPS][2]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + 2 * EPI_WARPS);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -71,14 +105,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmA);
         ptx::prefetch_tensormap(&tmB);
+        ptx::prefetch_tensormap(&tmC);
+        if (RES) ptx::prefetch_tensormap(&tmR);
         for (int i = 0; i < STAGES; ++i) {
             ptx::mbar_init(&full_bar[i], 1);
             ptx::mbar_init(&empty_bar[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tfull_bar[i], 1);
-            ptx::mbar_init(&tempty_bar[i], 4);  // one arrival per epilogue warp
+            ptx::mbar_init(&tempty_bar[i], EPI_WARPS);  // one arrival per epilogue warp
         }
+        for (int i = 0; i < 2 * EPI_WARPS; ++i) ptx::mbar_init(&res_bar[i], 1);
         ptx::fence_mbar_init();
     }
     if (warp == 1) {
@@ -118,7 +155,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t acc_phase = (iter >> 1) & 1;
                 ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
                 ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
+                const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     ptx::mbar_wait(&full_bar[stage], phase);
                     ptx::tc_fence_after();
@@ -137,33 +174,55 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else {
         // ------------------------------------------------------------------ epilogue warps 2..5
-        const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32) are the ones this warp may read
+        const int quad = warp & 3;      // TMEM lanes [32*quad, 32*quad+32) are the ones this warp may read
+        const int ew = warp - 2;        // private staging buffers / residual barriers
+        uint8_t* my = smem + L::EPI_OFFSET + ew * L::EPI_BUFS_PER_WARP * CHUNK_BYTES;
+        // staging layout per warp: [out 0][out 1]([residual 0][residual 1] when RES)
+        uint64_t* rbar = res_bar + 2 * ew;
+        uint32_t rphase = 0;            // bit b = parity to wait for on rbar[b]
+        int oc = 0;                     // running output-chunk counter: selects the staging buffer across tiles
         int iter = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
             const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
             const int acc = iter & 1;
             const uint32_t acc_phase = (iter >> 1) & 1;
+            const int row0 = m_blk * BM + quad * 32;   // first row of this warp's slab
+            const int col_base = n_blk * BN;
+            if (RES && lane == 0) {
+                // residual chunks 0 and 1 of this tile: issued before the accumulator is ready (overlaps the main loop)
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    ptx::mbar_arrive_expect_tx(&rbar[b], CHUNK_BYTES);
+                    ptx::tma_load_2d(my + (2 + b) * CHUNK_BYTES, &tmR, &rbar[b], col_base + b * 32, row0);
+                }
+            }
             ptx::mbar_wait(&tfull_bar[acc], acc_phase);
             ptx::tc_fence_after();
-            const int row = m_blk * BM + quad * 32 + lane;
-            const bool row_ok = row < p.M;
-            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * ACC_STRIDE;
 #pragma unroll 1
-            for (int c = 0; c < BN; c += 32) {
-                uint32_t r[32];
-                ptx::tmem_ld_32x32b_x32(t_row + c, r);
-                ptx::tmem_ld_wait();
-                const int col0 = n_blk * BN + c;
-                if (row_ok && col0 < p.N) {
+            for (int c = 0; c < NCH; ++c, ++oc) {
+                const int b = c & 1;        // residual buffer (fp32 output: NCH is even, so this alternates across tiles too)
+                const int ob = oc & 1;      // output staging buffer
+                const int col0 = col_base + c * CH;
+                uint8_t* odst = my + ob * CHUNK_BYTES;
+                // the TMA store that last read obuf[ob] (two chunks ago) must have finished reading shared memory
+                if (lane == 0) ptx::tma_store_wait_read<1>();
+                __syncwarp();
+#pragma unroll
+                for (int half = 0; half < CH / 32; ++half) {
+                    uint32_t r[32];
+                    ptx::tmem_ld_32x32b_x32(t_row + c * CH + half * 32, r);
+                    ptx::tmem_ld_wait();
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    const int cc = col0 + half * 32;
                     if (p.bias != nullptr) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
-                            if (col0 + j < p.N) {
-                                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                            if (cc + j < p.N) {
+                                const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + cc + j));
+                                v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
                             }
                         }
                     }
@@ -171,43 +230,65 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
                     }
-                    if (p.residual != nullptr) {
-                        const float* rp = p.residual + static_cast<int64_t>(row) * p.ldr + col0;
+                    if (RES) {
+                        // OUT_F32: CH == 32, one residual chunk per output chunk.  (bf16 out + residual: two per chunk)
+                        const int rb = OUT_F32 ? b : half;
+                        ptx::mbar_wait(&rbar[rb], (rphase >> rb) & 1u);
+                        rphase ^= 1u << rb;
+                        const uint8_t* rsrc = my + (2 + rb) * CHUNK_BYTES;
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            if (col0 + j < p.N) {
-                                const float4 x = *reinterpret_cast<const float4*>(rp + j);
-                                v[j] += x.x; v[j + 1] += x.y; v[j + 2] += x.z; v[j + 3] += x.w;
-                            }
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 x = *reinterpret_cast<const float4*>(rsrc + swz(lane, j));
+                            v[4 * j] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
                         }
                     }
                     if (OUT_F32) {
-                        float* cp = reinterpret_cast<float*>(p.C) + static_cast<int64_t>(row) * p.ldc + col0;
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            if (col0 + j < p.N)
-                                *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                        }
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<float4*>(odst + swz(lane, j)) =
+                                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                     } else {
-                        __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<int64_t>(row) * p.ldc + col0;
 #pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            if (col0 + j < p.N) {
-                                uint4 o;
-                                o.x = ptx::pack_bf16x2(v[j], v[j + 1]);
-                                o.y = ptx::pack_bf16x2(v[j + 2], v[j + 3]);
-                                o.z = ptx::pack_bf16x2(v[j + 4], v[j + 5]);
-                                o.w = ptx::pack_bf16x2(v[j + 6], v[j + 7]);
-                                *reinterpret_cast<uint4*>(cp + j) = o;
+                        for (int j = 0; j < 4; ++j) {
+                            uint4 o;
+                            o.x = ptx::pack_bf16x2(v[8 * j], v[8 * j + 1]);
+                            o.y = ptx::pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                            o.z = ptx::pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+                            o.w = ptx::pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                            *reinterpret_cast<uint4*>(odst + swz(lane, half * 4 + j)) = o;
+                        }
+                    }
+                }
+                if (c == NCH - 1) {
+                    // all tcgen05.ld of this tile are done: hand the accumulator back to the MMA warp
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+                }
+                ptx::fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA (async proxy)
+                __syncwarp();               // ... of every lane; also: every lane is done reading rbuf
+                if (lane == 0) {
+                    if (col0 < p.N && row0 < p.M) ptx::tma_store_2d(&tmC, odst, col0, row0);  // edges clipped by TMA
+                    ptx::tma_store_commit();
+                    if (RES) {
+                        // prefetch the residual chunk(s) that will land in the buffer(s) just consumed
+                        if (OUT_F32) {
+                            if (c + 2 < NCH) {
+                                ptx::mbar_arrive_expect_tx(&rbar[b], CHUNK_BYTES);
+                                ptx::tma_load_2d(my + (2 + b) * CHUNK_BYTES, &tmR, &rbar[b], col_base + (c + 2) * 32, row0);
+                            }
+                        } else if (c + 1 < NCH) {
+#pragma unroll
+                            for (int hb = 0; hb < 2; ++hb) {
+                                ptx::mbar_arrive_expect_tx(&rbar[hb], CHUNK_BYTES);
+                                ptx::tma_load_2d(my + (2 + hb) * CHUNK_BYTES, &tmR, &rbar[hb], col_base + (c + 1) * CH + hb * 32, row0);
                             }
                         }
                     }
                 }
             }
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
         }
+        if (lane == 0) ptx::tma_store_wait<0>();
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -219,9 +300,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 // ---------------------------------------------------------------------------------------------------------------
 // Debug / test-only CUDA-core kernel with the same contract (isolates descriptor bugs in the tensor-core path).
+struct SimtParams {
+    const float* bias;
+    const float* residual;
+    int64_t ldr;
+    void* C;
+    int64_t ldc;
+    int M, N, K;
+};
+
 template <bool GELU, bool OUT_F32>
 __global__ void gemm_simt_kernel(const __nv_bfloat16* __restrict__ A, int64_t lda, const __nv_bfloat16* __restrict__ W,
-                                 int64_t ldw, const EpiParams p) {
+                                 int64_t ldw, const SimtParams p) {
     __shared__ float sa[16][17];
     __shared__ float sw[16][17];
     const int tx = threadIdx.x, ty = threadIdx.y;
@@ -240,7 +330,7 @@ __global__ void gemm_simt_kernel(const __nv_bfloat16* __restrict__ A, int64_t ld
     }
     if (row < p.M && col < p.N) {
         if (p.bias) acc += p.bias[col];
-        if (GELU) acc = gelu_erf(acc);
+        if (GELU) acc = 0.5f * acc * (1.0f + erff(acc * 0.70710678118654752f));  // library erf: independent of gelu_erf
         if (p.residual) acc += p.residual[static_cast<int64_t>(row) * p.ldr + col];
         if (OUT_F32)
             reinterpret_cast<float*>(p.C)[static_cast<int64_t>(row) * p.ldc + col] = acc;
@@ -271,9 +361,10 @@ EncodeTiledFn get_encode_fn() {
 struct MapKey {
     const void* ptr;
     int64_t rows, cols, ld;
-    int box_rows;
+    int box_rows, box_cols, elem_bytes;
     bool operator==(const MapKey& o) const {
-        return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+        return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows &&
+               box_cols == o.box_cols && elem_bytes == o.elem_bytes;
     }
 };
 struct MapKeyHash {
@@ -282,16 +373,18 @@ struct MapKeyHash {
         h = h * 1000003u ^ static_cast<size_t>(k.rows);
         h = h * 1000003u ^ static_cast<size_t>(k.cols);
         h = h * 1000003u ^ static_cast<size_t>(k.ld);
-        h = h * 1000003u ^ static_cast<size_t>(k.box_rows);
+        h = h * 1000003u ^ static_cast<size_t>(k.box_rows * 131 + k.box_cols * 7 + k.elem_bytes);
         return h;
     }
 };
 
-// bf16 row-major [rows, cols] with row stride ld (elements); box = {64 cols, box_rows rows}; 128B swizzle; OOB -> 0.
-int get_tensor_map(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, CUtensorMap* out) {
+// Row-major [rows, cols] matrix of 2-byte (bf16) or 4-byte (fp32) elements with row stride ld (elements);
+// box = {box_cols, box_rows} with box_cols * elem_bytes == 128; 128B swizzle; out-of-bounds reads -> 0, writes clipped.
+int get_tensor_map(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols, int elem_bytes,
+                   CUtensorMap* out) {
     static std::mutex mu;
     static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-    MapKey key{ptr, rows, cols, ld, box_rows};
+    MapKey key{ptr, rows, cols, ld, box_rows, box_cols, elem_bytes};
     {
         std::lock_guard<std::mutex> g(mu);
         auto it = cache.find(key);
@@ -303,15 +396,16 @@ int get_tensor_map(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int 
     EncodeTiledFn enc = get_encode_fn();
     MRA_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
     MRA_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "GEMM operand pointer must be 16-byte aligned");
-    MRA_REQUIRE(ld % 8 == 0, "GEMM operand row stride must be a multiple of 8 elements (16 bytes), got %lld", (long long)ld);
+    MRA_REQUIRE((ld * elem_bytes) % 16 == 0, "GEMM operand row stride must be a multiple of 16 bytes, got %lld elements of %d bytes",
+                (long long)ld, elem_bytes);
     cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-    cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
-    cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+    cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * elem_bytes};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
     cuuint32_t estr[2] = {1, 1};
     CUtensorMap m;
-    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(&m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                     const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MRA_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld)", (int)r,
                 (long long)rows, (long long)cols, (long long)ld);
     {
@@ -323,42 +417,54 @@ int get_tensor_map(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int 
     return 0;
 }
 
-template <int BN, int STAGES, bool GELU, bool OUT_F32>
+template <int BN, int STAGES, bool GELU, bool OUT_F32, bool RES>
 int launch_tc_variant(const GemmArgs& a, cudaStream_t s) {
-    using L = SmemLayout<BN, STAGES>;
-    auto kern = gemm_tc_kernel<BN, STAGES, GELU, OUT_F32>;
+    using L = SmemLayout<BN, STAGES, RES>;
+    auto kern = gemm_tc_kernel<BN, STAGES, GELU, OUT_F32, RES>;
     static bool attr_set = false;
     if (!attr_set) {
         MRA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         attr_set = true;
     }
-    CUtensorMap tmA, tmB;
-    if (int e = get_tensor_map(a.A, a.M, a.K, a.lda, BM, &tmA)) return e;
-    if (int e = get_tensor_map(a.W, a.N, a.K, a.ldw, BN, &tmB)) return e;
-    EpiParams p{a.bias, a.residual, a.ldr, a.C, a.ldc, a.M, a.N, a.K};
+    CUtensorMap tmA, tmB, tmC, tmR;
+    if (int e = get_tensor_map(a.A, a.M, a.K, a.lda, BM, BK, 2, &tmA)) return e;
+    if (int e = get_tensor_map(a.W, a.N, a.K, a.ldw, BN, BK, 2, &tmB)) return e;
+    if (int e = get_tensor_map(a.C, a.M, a.N, a.ldc, 32, OUT_F32 ? 32 : 64, OUT_F32 ? 4 : 2, &tmC)) return e;
+    if (RES) {
+        if (int e = get_tensor_map(a.residual, a.M, a.N, a.ldr, 32, 32, 4, &tmR)) return e;
+    } else {
+        tmR = tmC;
+    }
+    EpiParams p{a.bias, a.M, a.N, a.K};
     const int m_tiles = (a.M + BM - 1) / BM, n_tiles = (a.N + BN - 1) / BN;
     const int total = m_tiles * n_tiles;
     const int grid = total < sm_count() ? total : sm_count();
-    kern<<<grid, NUM_THREADS, L::TOTAL, s>>>(tmA, tmB, p);
+    kern<<<grid, NUM_THREADS, L::TOTAL, s>>>(tmA, tmB, tmC, tmR, p);
     MRA_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
-template <int BN, int STAGES>
+template <int BN, int ST_PLAIN, int ST_RES>
 int dispatch_epi(const GemmArgs& a, cudaStream_t s) {
-    if (a.gelu) {
-        if (a.out_fp32) return launch_tc_variant<BN, STAGES, true, true>(a, s);
-        return launch_tc_variant<BN, STAGES, true, false>(a, s);
+    const int code = (a.gelu ? 4 : 0) | (a.out_fp32 ? 2 : 0) | (a.residual ? 1 : 0);
+    switch (code) {
+        case 0: return launch_tc_variant<BN, ST_PLAIN, false, false, false>(a, s);
+        case 1: return launch_tc_variant<BN, ST_RES, false, false, true>(a, s);
+        case 2: return launch_tc_variant<BN, ST_PLAIN, false, true, false>(a, s);
+        case 3: return launch_tc_variant<BN, ST_RES, false, true, true>(a, s);
+        case 4: return launch_tc_variant<BN, ST_PLAIN, true, false, false>(a, s);
+        case 5: return launch_tc_variant<BN, ST_RES, true, false, true>(a, s);
+        case 6: return launch_tc_variant<BN, ST_PLAIN, true, true, false>(a, s);
+        default: return launch_tc_variant<BN, ST_RES, true, true, true>(a, s);
     }
-    if (a.out_fp32) return launch_tc_variant<BN, STAGES, false, true>(a, s);
-    return launch_tc_variant<BN, STAGES, false, false>(a, s);
 }
 
 int check_args(const GemmArgs& a) {
     MRA_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "GEMM with empty dimension M=%d N=%d K=%d", a.M, a.N, a.K);
     MRA_REQUIRE(a.N % 8 == 0, "GEMM N must be a multiple of 8, got %d", a.N);
     MRA_REQUIRE(a.K % 8 == 0, "GEMM K must be a multiple of 8, got %d", a.K);
-    MRA_REQUIRE(a.ldc % 8 == 0, "GEMM ldc must be a multiple of 8, got %lld", (long long)a.ldc);
+    MRA_REQUIRE((a.ldc * (a.out_fp32 ? 4 : 2)) % 16 == 0, "GEMM output row stride must be a multiple of 16 bytes, got ldc=%lld",
+                (long long)a.ldc);
     MRA_REQUIRE((reinterpret_cast<uintptr_t>(a.C) & 15) == 0, "GEMM output pointer must be 16-byte aligned");
     if (a.residual) {
         MRA_REQUIRE(a.ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(a.residual) & 15) == 0,
@@ -370,23 +476,36 @@ int check_args(const GemmArgs& a) {
 
 }  // namespace
 
+static int g_forced_bn = [] { const char* e = getenv("MRA_GEMM_BN"); return e ? atoi(e) : 0; }();
+void set_gemm_tile_override(int bn) { g_forced_bn = bn; }
+
 int launch_gemm_tc(const GemmArgs& a, cudaStream_t s) {
     if (int e = check_args(a)) return e;
-    // Tile-width choice: 128x256 tiles run the tensor pipe at full rate (smem operand traffic 96 B/clk/SM); 128x128
-    // tiles are smem-bound (128 B/clk) but quantise better when there are few tiles.  Pick the cheaper estimate.
+    // Tile-width choice by a wave-quantisation estimate: cost = waves x (tile width) x (a factor for how well that
+    // width feeds the tensor pipe: 128-wide tiles are shared-memory-bandwidth bound).  MRA_GEMM_BN overrides (tuning).
     const int sms = sm_count();
     const long m_tiles = (a.M + BM - 1) / BM;
-    const long t256 = m_tiles * ((a.N + 255) / 256), t128 = m_tiles * ((a.N + 127) / 128);
-    const double c256 = double((t256 + sms - 1) / sms) * 2.0;
-    const double c128 = double((t128 + sms - 1) / sms) * 1.15;
-    if (a.N % 256 == 0 && c256 <= c128) return dispatch_epi<256, 4>(a, s);
-    return dispatch_epi<128, 6>(a, s);
+    const int forced = g_forced_bn;
+    int best_bn = 128;
+    double best = 1e30;
+    const int cand[3] = {256, 192, 128};
+    const double factor[3] = {1.0, 1.05, 1.15};
+    for (int i = 0; i < 3; ++i) {
+        const int bn = cand[i];
+        if (forced ? bn != forced : false) continue;
+        const long tiles = m_tiles * ((a.N + bn - 1) / bn);
+        const double cost = double((tiles + sms - 1) / sms) * bn * factor[i];
+        if (cost < best) { best = cost; best_bn = bn; }
+    }
+    if (best_bn == 256) return dispatch_epi<256, 4, 3>(a, s);
+    if (best_bn == 192) return dispatch_epi<192, 4, 4>(a, s);
+    return dispatch_epi<128, 6, 5>(a, s);
 }
 
 int launch_gemm_simt(const GemmArgs& a, cudaStream_t s) {
     if (int e = check_args(a)) return e;
     dim3 block(16, 16), grid((a.N + 15) / 16, (a.M + 15) / 16);
-    EpiParams p{a.bias, a.residual, a.ldr, a.C, a.ldc, a.M, a.N, a.K};
+    SimtParams p{a.bias, a.residual, a.ldr, a.C, a.ldc, a.M, a.N, a.K};
     const __nv_bfloat16* A = reinterpret_cast<const __nv_bfloat16*>(a.A);
     const __nv_bfloat16* W = reinterpret_cast<const __nv_bfloat16*>(a.W);
     if (a.gelu) {

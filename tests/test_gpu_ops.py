@@ -50,6 +50,15 @@ def test_gemm_epilogues(impl):
     assert _rel(ops.linear(x, w, b, residual=res, out_fp32=True, impl=impl), lin + res) < 2e-3
     assert _rel(ops.linear(x, w, b, gelu=True, out_fp32=True, impl=impl), torch.nn.functional.gelu(lin)) < 2e-3
     assert _rel(ops.linear(x, w, None, out_fp32=True, impl=impl), lin - b) < 2e-3
+    # every epilogue combination incl. bf16 output + residual and GELU + residual
+    for gelu in (False, True):
+        for f32 in (False, True):
+            ref = torch.nn.functional.gelu(lin) if gelu else lin
+            got = ops.linear(x, w, b, residual=res, gelu=gelu, out_fp32=f32, impl=impl)
+            assert _rel(got, ref + res) < (2e-3 if f32 else 6e-3), (gelu, f32)
+    # the fast erf of the tensor-core epilogue is accurate far below bf16 resolution
+    y = ops.linear(x, w, b, gelu=True, out_fp32=True, impl=impl)
+    assert (y - torch.nn.functional.gelu(ops.linear(x, w, b, out_fp32=True, impl=impl))).abs().max().item() < 2e-6
     # strided operands (a column slice of a wider matrix) and a strided output
     big = torch.randn(M, 2 * K, generator=g).to(_dev(), torch.bfloat16)
     xs = big[:, K:]
@@ -57,6 +66,25 @@ def test_gemm_epilogues(impl):
     ops.linear(xs, w, b, impl=impl, out=out[:, N:])
     assert _rel(out[:, N:], xs.float() @ w.float().t() + b) < 6e-3
     assert out[:, :N].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("bn", [128, 192, 256])
+@pytest.mark.parametrize("M,N,K", [(300, 768, 768), (1000, 2304, 768), (129, 264, 200), (4096, 3072, 768)])
+def test_gemm_every_tile_width(bn, M, N, K):
+    from mraudio_b200 import ops, _lib
+    g = torch.Generator().manual_seed(bn + M)
+    x = torch.randn(M, K, generator=g).to(_dev(), torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) * 0.05).to(_dev(), torch.bfloat16)
+    b = torch.randn(N, generator=g).to(_dev())
+    res = torch.randn(M, N, generator=g).to(_dev())
+    ref = x.float() @ w.float().t() + b
+    try:
+        _lib.check(_lib.lib.mra_gemm_tile_override(bn))
+        assert _rel(ops.linear(x, w, b, residual=res, out_fp32=True), ref + res) < 1e-4
+        assert _rel(ops.linear(x, w, b, gelu=True), torch.nn.functional.gelu(ref)) < 6e-3
+        assert _rel(ops.linear(x, w, b), ref) < 6e-3
+    finally:
+        _lib.lib.mra_gemm_tile_override(0)
 
 
 def test_gemm_tcgen05_equals_simt_bitwise_ordering_free():
