@@ -155,6 +155,10 @@ int mra_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const 
                   int64_t ldo, const float* add_mask, int32_t rows, int32_t heads, int32_t Sq, int32_t Sk,
                   int32_t nq_split, int32_t kv_dense, void* stream);
 
+/* Test aid: generic != 0 forces the register-staged generic attention kernel instead of the TMA-pipelined one (which
+ * covers Sq <= 256, Sk <= 4096 and split points that are multiples of 32; other shapes always use the generic one). */
+int mra_attention_impl_override(int32_t generic);
+
 /* y = LayerNorm(x) * gamma + beta over the last dim (n), fp32 statistics; writes fp32 and/or bf16 copies.
  *   Replaces the LayerNorm in BertSelfOutput/BertOutput (HF port :549-553, :606-610), eps 1e-12. */
 int mra_layernorm(const float* x, const float* gamma, const float* beta, float* y32, void* y16, int32_t rows, int32_t n,

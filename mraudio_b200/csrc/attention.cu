@@ -6,6 +6,11 @@
 // materialises (HF port modeling_instructblip.py:512-536) never exists in HBM.  Tensor-core work uses
 // mma.sync.m16n8k16 bf16 (fp32 accumulate): at 1.6 % of the path's FLOPs these tiles are too small for tcgen05's
 // 128-row atoms to pay off.
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -220,7 +225,349 @@ __global__ void __launch_bounds__(NWARPS * 32) attention_kernel(const Params p) 
     }
 }
 
+
+// =====================================================================================================================
+// TMA-pipelined variant (the one the forward uses): same math, but Q / K / V tiles arrive as 128B-swizzled 32 x 64 boxes
+// through cp.async.bulk.tensor (3-D tensor maps [row][token][column], so tokens past the end of a row are zero-filled
+// by the TMA unit and never fetched), K/V chunks of 64 keys flow through a STAGES-deep mbarrier ring, and fragments are
+// read with ldmatrix from the swizzled tiles (bank-conflict free).  One CTA per (row, head), one warp per 16 queries.
+// The token axis may consist of two segments ("split" layout: query tokens of all rows first, text tokens after them).
+struct TmaParams {
+    __nv_bfloat16* o; int64_t ldo;
+    const float* add_mask;
+    int rows, heads, Sq, Sk;
+    int q_n0, q_n1;   // query tokens per row in segment 0 / 1
+    int k_n0, k_n1;   // key tokens per row in segment 0 / 1
+    int nchunks;      // ceil(Sk / 64)
+};
+
+constexpr int TMA_STAGES = 2;
+constexpr int BOX_BYTES = 32 * 128;          // 32 tokens x 64 bf16
+constexpr int STAGE_BYTES_ATT = 4 * BOX_BYTES;  // K lo, K hi, V lo, V hi
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* desc, uint64_t* bar, int32_t c0, int32_t c1, int32_t c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            ptx::smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(desc)), "r"(ptx::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_t(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+// address of 16-byte unit `u` of token row `row` inside a tile made of consecutive 32-row swizzled boxes
+__device__ __forceinline__ uint32_t tile_addr(uint32_t base, int row, int u) {
+    return base + row * 128 + ((u ^ (row & 7)) << 4);
+}
+
+template <int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32)
+attention_tma_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ CUtensorMap tmQ1,
+                     const __grid_constant__ CUtensorMap tmK0, const __grid_constant__ CUtensorMap tmK1,
+                     const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmV1, const TmaParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int QBOXES = (NWARPS * 16 + 31) / 32;
+    uint8_t* sQ = smem;                                         // QBOXES boxes
+    uint8_t* sKV = smem + QBOXES * BOX_BYTES;                   // TMA_STAGES x (K 64x64, V 64x64)
+    float* sMask = reinterpret_cast<float*>(sKV + TMA_STAGES * STAGE_BYTES_ATT);   // [nchunks * 64]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sMask + p.nchunks * 64);          // q_full, full[TMA_STAGES]
+
+    const int head = blockIdx.x % p.heads;
+    const int r = blockIdx.x / p.heads;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    constexpr int NT = NWARPS * 32;
+
+    auto load_kv_chunk = [&](int kc, int stage) {
+        uint8_t* dst = sKV + stage * STAGE_BYTES_ATT;
+        ptx::mbar_arrive_expect_tx(&bars[1 + stage], STAGE_BYTES_ATT);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int key0 = kc * 64 + h * 32;
+            const bool seg1 = p.k_n1 > 0 && key0 >= p.k_n0;
+            const int tok = seg1 ? key0 - p.k_n0 : key0;   // past the end -> zero fill
+            tma_load_3d(dst + h * BOX_BYTES, seg1 ? &tmK1 : &tmK0, &bars[1 + stage], head * HD, tok, r);
+            tma_load_3d(dst + (2 + h) * BOX_BYTES, seg1 ? &tmV1 : &tmV0, &bars[1 + stage], head * HD, tok, r);
+        }
+    };
+
+    if (tid == 0) {
+        ptx::prefetch_tensormap(&tmQ0);
+        ptx::prefetch_tensormap(&tmK0);
+        ptx::prefetch_tensormap(&tmV0);
+        for (int i = 0; i < 1 + TMA_STAGES; ++i) ptx::mbar_init(&bars[i], 1);
+        ptx::fence_mbar_init();
+        ptx::mbar_arrive_expect_tx(&bars[0], QBOXES * BOX_BYTES);
+#pragma unroll
+        for (int b = 0; b < QBOXES; ++b) {
+            const int q0 = b * 32;
+            const bool seg1 = p.q_n1 > 0 && q0 >= p.q_n0;
+            tma_load_3d(sQ + b * BOX_BYTES, seg1 ? &tmQ1 : &tmQ0, &bars[0], head * HD, seg1 ? q0 - p.q_n0 : q0, r);
+        }
+        for (int s = 0; s < TMA_STAGES && s < p.nchunks; ++s) load_kv_chunk(s, s);
+    }
+    // additive mask (log2 domain); -inf past the last key
+    for (int j = tid; j < p.nchunks * 64; j += NT) {
+        float mv = -INFINITY;
+        if (j < p.Sk) mv = p.add_mask ? p.add_mask[static_cast<int64_t>(r) * p.Sk + j] * LOG2E : 0.f;
+        sMask[j] = mv;
+    }
+    __syncthreads();   // barrier inits + mask visible to everyone
+
+    const float scale_log2 = 0.125f * LOG2E;
+    const int qr0 = warp * 16;
+    const bool active = qr0 < p.Sq;
+    uint32_t qf[4][4];
+    ptx::mbar_wait(&bars[0], 0);
+    {
+        const uint32_t qb = ptx::smem_u32(sQ);
+        const int row = qr0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) ldmatrix_x4(qf[ks], tile_addr(qb, row, ks * 2 + (lane >> 4)));
+    }
+    float o_acc[8][4];
+    float m_run[2] = {-INFINITY, -INFINITY};
+    float l_run[2] = {0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.f; }
+
+    for (int kc = 0; kc < p.nchunks; ++kc) {
+        const int stage = kc % TMA_STAGES;
+        ptx::mbar_wait(&bars[1 + stage], (kc / TMA_STAGES) & 1);
+        if (active) {
+            const uint32_t kb = ptx::smem_u32(sKV + stage * STAGE_BYTES_ATT);
+            const uint32_t vb = kb + 2 * BOX_BYTES;
+            const float* mk = sMask + kc * 64;
+            // ---- S = Q K^T for 16 rows x 64 keys
+            float s[8][4];
+#pragma unroll
+            for (int np = 0; np < 4; ++np) {    // pairs of 8-key tiles
+                s[2 * np][0] = s[2 * np][1] = s[2 * np][2] = s[2 * np][3] = 0.f;
+                s[2 * np + 1][0] = s[2 * np + 1][1] = s[2 * np + 1][2] = s[2 * np + 1][3] = 0.f;
+                const int key = np * 16 + (lane & 7) + (lane >> 4) * 8;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    uint32_t kf[4];
+                    ldmatrix_x4(kf, tile_addr(kb, key, ks * 2 + ((lane >> 3) & 1)));
+                    mma_bf16_16816(s[2 * np], qf[ks], kf[0], kf[1]);
+                    mma_bf16_16816(s[2 * np + 1], qf[ks], kf[2], kf[3]);
+                }
+            }
+            // ---- scale + mask (log2 domain), chunk row max
+            float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const float2 mm = *reinterpret_cast<const float2*>(mk + nt * 8 + 2 * t);
+                s[nt][0] = fmaf(s[nt][0], scale_log2, mm.x);
+                s[nt][1] = fmaf(s[nt][1], scale_log2, mm.y);
+                s[nt][2] = fmaf(s[nt][2], scale_log2, mm.x);
+                s[nt][3] = fmaf(s[nt][3], scale_log2, mm.y);
+                mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+                mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
+            }
+            float corr[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
+                mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
+                const float m_new = fmaxf(m_run[h], mx[h]);
+                corr[h] = (m_run[h] == -INFINITY) ? 0.f : exp2f(m_run[h] - m_new);
+                m_run[h] = m_new;
+                l_run[h] *= corr[h];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                o_acc[i][0] *= corr[0]; o_acc[i][1] *= corr[0];
+                o_acc[i][2] *= corr[1]; o_acc[i][3] *= corr[1];
+            }
+            // ---- P = exp2(S - m), row sums, pack to bf16 A fragments
+            uint32_t pf[4][4];
+            float ls[2] = {0.f, 0.f};
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const float p0 = exp2f(s[nt][0] - m_run[0]);
+                const float p1 = exp2f(s[nt][1] - m_run[0]);
+                const float p2 = exp2f(s[nt][2] - m_run[1]);
+                const float p3 = exp2f(s[nt][3] - m_run[1]);
+                ls[0] += p0 + p1;
+                ls[1] += p2 + p3;
+                const int j = nt >> 1;
+                if ((nt & 1) == 0) {
+                    pf[j][0] = ptx::pack_bf16x2(p0, p1);
+                    pf[j][1] = ptx::pack_bf16x2(p2, p3);
+                } else {
+                    pf[j][2] = ptx::pack_bf16x2(p0, p1);
+                    pf[j][3] = ptx::pack_bf16x2(p2, p3);
+                }
+            }
+            l_run[0] += ls[0];
+            l_run[1] += ls[1];
+            // ---- O += P V   (V^T fragments through ldmatrix.trans from the row-major [key][dim] tile)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {          // 16 keys per step
+                const int key = j * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+                for (int dp = 0; dp < 4; ++dp) {   // pairs of 8-wide dim tiles
+                    uint32_t vf[4];
+                    ldmatrix_x4_t(vf, tile_addr(vb, key, dp * 2 + (lane >> 4)));
+                    mma_bf16_16816(o_acc[2 * dp], pf[j], vf[0], vf[1]);
+                    mma_bf16_16816(o_acc[2 * dp + 1], pf[j], vf[2], vf[3]);
+                }
+            }
+        }
+        __syncthreads();   // every warp is done with this stage
+        if (tid == 0 && kc + TMA_STAGES < p.nchunks) load_kv_chunk(kc + TMA_STAGES, stage);
+    }
+    if (active) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            l_run[h] += __shfl_xor_sync(0xffffffffu, l_run[h], 1);
+            l_run[h] += __shfl_xor_sync(0xffffffffu, l_run[h], 2);
+        }
+        const float inv[2] = {1.f / l_run[0], 1.f / l_run[1]};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int i = qr0 + g + h * 8;
+            if (i < p.Sq) {
+                const int64_t grow = (p.q_n1 > 0 && i >= p.q_n0)
+                                         ? static_cast<int64_t>(p.rows) * p.q_n0 + static_cast<int64_t>(r) * p.q_n1 + (i - p.q_n0)
+                                         : static_cast<int64_t>(r) * p.q_n0 + i;
+                __nv_bfloat16* op = p.o + grow * p.ldo + head * HD + 2 * t;
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt)
+                    *reinterpret_cast<uint32_t*>(op + nt * 8) =
+                        ptx::pack_bf16x2(o_acc[nt][2 * h] * inv[h], o_acc[nt][2 * h + 1] * inv[h]);
+            }
+        }
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn attn_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* q = nullptr;
+        cudaDriverEntryPointQueryResult res;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &res) == cudaSuccess &&
+            res == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(q);
+    });
+    return fn;
+}
+
+struct Map3Key {
+    const void* ptr; int64_t ld; int width, ntok, rows;
+    bool operator==(const Map3Key& o) const { return ptr == o.ptr && ld == o.ld && width == o.width && ntok == o.ntok && rows == o.rows; }
+};
+struct Map3Hash {
+    size_t operator()(const Map3Key& k) const {
+        size_t h = reinterpret_cast<size_t>(k.ptr);
+        h = h * 1000003u ^ static_cast<size_t>(k.ld);
+        h = h * 1000003u ^ static_cast<size_t>(k.width * 31 + k.ntok);
+        h = h * 1000003u ^ static_cast<size_t>(k.rows);
+        return h;
+    }
+};
+
+// bf16 [rows][ntok][width] view with token stride ld (elements) and row stride ntok*ld; box {64, 32, 1}, 128B swizzle.
+int get_map3(const void* ptr, int64_t ld, int width, int ntok, int rows, CUtensorMap* out) {
+    static std::mutex mu;
+    static std::unordered_map<Map3Key, CUtensorMap, Map3Hash> cache;
+    Map3Key key{ptr, ld, width, ntok, rows};
+    {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) { *out = it->second; return 0; }
+    }
+    EncodeTiledFn enc = attn_encode_fn();
+    MRA_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t gdim[3] = {static_cast<cuuint64_t>(width), static_cast<cuuint64_t>(ntok), static_cast<cuuint64_t>(rows)};
+    cuuint64_t gstride[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(ld) * 2 * ntok};
+    cuuint32_t box[3] = {64, 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUtensorMap m;
+    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MRA_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (attention) failed with CUresult %d", (int)r);
+    {
+        std::lock_guard<std::mutex> g(mu);
+        if (cache.size() > 8192) cache.clear();
+        cache[key] = m;
+    }
+    *out = m;
+    return 0;
+}
+
+template <int NWARPS>
+int launch_tma_variant(const AttnArgs& a, const TmaParams& p, const CUtensorMap* maps, size_t smem, cudaStream_t s) {
+    auto kern = attention_tma_kernel<NWARPS>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MRA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr_set = true;
+    }
+    kern<<<static_cast<unsigned>(a.rows) * a.heads, NWARPS * 32, smem, s>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
+    MRA_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// returns -1 when the shape is outside what the TMA kernel covers (the caller then uses the generic kernel)
+int try_launch_attention_tma(const AttnArgs& a, cudaStream_t s) {
+    const bool split_q = a.nq_split < a.Sq;                  // queries in two segments
+    const bool split_k = !a.kv_dense && a.nq_split < a.Sk;   // keys in two segments
+    if (a.Sq > 256 || a.Sk > 4096) return -1;
+    if ((split_q || split_k) && a.nq_split % 32 != 0) return -1;
+    if (a.ldo % 2 != 0) return -1;
+    TmaParams p;
+    p.o = reinterpret_cast<__nv_bfloat16*>(a.o); p.ldo = a.ldo; p.add_mask = a.add_mask;
+    p.rows = a.rows; p.heads = a.heads; p.Sq = a.Sq; p.Sk = a.Sk;
+    p.q_n0 = split_q ? a.nq_split : a.Sq; p.q_n1 = split_q ? a.Sq - a.nq_split : 0;
+    p.k_n0 = split_k ? a.nq_split : a.Sk; p.k_n1 = split_k ? a.Sk - a.nq_split : 0;
+    p.nchunks = (a.Sk + 63) / 64;
+    const int width = a.heads * HD;
+    const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(a.q);
+    const __nv_bfloat16* k = reinterpret_cast<const __nv_bfloat16*>(a.k);
+    const __nv_bfloat16* v = reinterpret_cast<const __nv_bfloat16*>(a.v);
+    CUtensorMap maps[6];
+    if (int e = get_map3(q, a.ldq, width, p.q_n0, a.rows, &maps[0])) return e;
+    maps[1] = maps[0];
+    if (p.q_n1 > 0)
+        if (int e = get_map3(q + static_cast<int64_t>(a.rows) * p.q_n0 * a.ldq, a.ldq, width, p.q_n1, a.rows, &maps[1])) return e;
+    if (int e = get_map3(k, a.ldk, width, p.k_n0, a.rows, &maps[2])) return e;
+    maps[3] = maps[2];
+    if (p.k_n1 > 0)
+        if (int e = get_map3(k + static_cast<int64_t>(a.rows) * p.k_n0 * a.ldk, a.ldk, width, p.k_n1, a.rows, &maps[3])) return e;
+    if (int e = get_map3(v, a.ldv, width, p.k_n0, a.rows, &maps[4])) return e;
+    maps[5] = maps[4];
+    if (p.k_n1 > 0)
+        if (int e = get_map3(v + static_cast<int64_t>(a.rows) * p.k_n0 * a.ldv, a.ldv, width, p.k_n1, a.rows, &maps[5])) return e;
+    const int nw = (a.Sq + 15) / 16;
+    auto smem_for = [&](int nwarps) {
+        const int qboxes = (nwarps * 16 + 31) / 32;
+        return static_cast<size_t>(qboxes) * BOX_BYTES + TMA_STAGES * STAGE_BYTES_ATT + static_cast<size_t>(p.nchunks) * 64 * 4 +
+               (1 + TMA_STAGES) * 8 + 1024;
+    };
+    if (nw <= 2) return launch_tma_variant<2>(a, p, maps, smem_for(2), s);
+    if (nw <= 4) return launch_tma_variant<4>(a, p, maps, smem_for(4), s);
+    if (nw <= 8) return launch_tma_variant<8>(a, p, maps, smem_for(8), s);
+    return launch_tma_variant<16>(a, p, maps, smem_for(16), s);
+}
+
 }  // namespace
+
+static bool g_force_generic = getenv("MRA_ATTN_GENERIC") != nullptr;
+void set_attention_impl_override(int generic) { g_force_generic = generic != 0; }
 
 int launch_attention(const AttnArgs& a, cudaStream_t s) {
     MRA_REQUIRE(a.rows > 0 && a.heads > 0 && a.Sq > 0 && a.Sk > 0, "attention with empty dimension");
@@ -230,6 +577,10 @@ int launch_attention(const AttnArgs& a, cudaStream_t s) {
                     (reinterpret_cast<uintptr_t>(a.o) & 3) == 0,
                 "attention operands must be 16-byte aligned");
     MRA_REQUIRE(static_cast<int64_t>(a.rows) * a.heads < (1ll << 31), "attention grid too large");
+    if (!g_force_generic) {
+        const int e = try_launch_attention_tma(a, s);
+        if (e >= 0) return e;
+    }
     Params p{reinterpret_cast<const __nv_bfloat16*>(a.q), a.ldq, reinterpret_cast<const __nv_bfloat16*>(a.k), a.ldk,
              reinterpret_cast<const __nv_bfloat16*>(a.v), a.ldv, reinterpret_cast<__nv_bfloat16*>(a.o), a.ldo,
              a.add_mask, a.rows, a.heads, a.Sq, a.Sk, a.nq_split, a.kv_dense};

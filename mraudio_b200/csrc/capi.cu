@@ -83,6 +83,11 @@ extern "C" int mra_attention(const void* q, int64_t ldq, const void* k, int64_t 
     return launch_attention(a, reinterpret_cast<cudaStream_t>(stream));
 }
 
+extern "C" int mra_attention_impl_override(int32_t generic) {
+    set_attention_impl_override(generic);
+    return 0;
+}
+
 extern "C" int mra_layernorm(const float* x, const float* gamma, const float* beta, float* y32, void* y16, int32_t rows,
                              int32_t n, float eps, void* stream) {
     MRA_REQUIRE(x && gamma && beta && (y32 || y16), "mra_layernorm: NULL operand");

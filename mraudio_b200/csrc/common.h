@@ -56,6 +56,7 @@ struct AttnArgs {
     int rows, heads, Sq, Sk, nq_split, kv_dense;
 };
 int launch_attention(const AttnArgs& a, cudaStream_t s);
+void set_attention_impl_override(int generic);
 
 int launch_layernorm(const float* x, const float* g, const float* b, float* y32, void* y16, int rows, int n, float eps,
                      cudaStream_t s);

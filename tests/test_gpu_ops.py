@@ -98,6 +98,14 @@ def test_gemm_tcgen05_equals_simt_bitwise_ordering_free():
     assert _rel(a, b) < 1e-5
 
 
+@pytest.fixture(params=["tma", "generic"])
+def attn_impl(request):
+    from mraudio_b200 import _lib
+    _lib.lib.mra_attention_impl_override(1 if request.param == "generic" else 0)
+    yield request.param
+    _lib.lib.mra_attention_impl_override(0)
+
+
 def _ref_attention(q, k, v, mask, heads):
     R, Sq, H = q.shape
     Sk = k.shape[1]
@@ -111,8 +119,8 @@ def _ref_attention(q, k, v, mask, heads):
 
 
 @pytest.mark.parametrize("rows,Sq,Sk,heads", [(3, 32, 257, 12), (2, 32, 256, 12), (5, 32, 8, 12), (2, 32, 1024, 12),
-                                               (1, 8, 8, 2), (4, 17, 100, 3)])
-def test_cross_attention(rows, Sq, Sk, heads):
+                                               (1, 8, 8, 2), (4, 17, 100, 3), (2, 64, 300, 4), (2, 200, 70, 2)])
+def test_cross_attention(rows, Sq, Sk, heads, attn_impl):
     from mraudio_b200 import ops
     g = torch.Generator().manual_seed(rows * 100 + Sk)
     H = heads * 64
@@ -128,8 +136,8 @@ def test_cross_attention(rows, Sq, Sk, heads):
         assert _rel(o.view(rows, Sq, H), ref) < 1.5e-2
 
 
-@pytest.mark.parametrize("rows,Nq,T", [(3, 32, 32), (2, 32, 0), (4, 32, 13), (2, 32, 128), (2, 8, 0)])
-def test_self_attention_split_layout(rows, Nq, T):
+@pytest.mark.parametrize("rows,Nq,T", [(3, 32, 32), (2, 32, 0), (4, 32, 13), (2, 32, 128), (2, 8, 0), (3, 64, 40), (2, 8, 5)])
+def test_self_attention_split_layout(rows, Nq, T, attn_impl):
     from mraudio_b200 import ops
     heads, H = 12, 768
     S = Nq + T
