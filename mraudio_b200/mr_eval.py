@@ -78,15 +78,15 @@ def score_records(submission: List[dict], ground_truth: List[dict], device=None)
     return {"ap": ap.cpu().numpy(), "iou": iou.cpu().numpy(), "invalid": inv.cpu().numpy().astype(bool)}
 
 
-def score_records_distributed(submission: List[dict], ground_truth: List[dict], group=None, device=None):
-    """Each rank scores ITS shard of queries; fixed-width records ``[ap(10), iou, invalid, order]`` are gathered to rank 0
-    (the one exchange step of the scoring path).  ``submission`` entries may carry ``"_order"`` (global
-    position) to restore the global submission order on rank 0; rank != 0 returns None."""
+def gather_records(rec: Dict[str, np.ndarray], order: np.ndarray, group=None, device=None):
+    """The one exchange step of the scoring path: every rank contributes fixed-width records
+    ``[ap(10), iou, invalid, order]`` (13 x f64 per query) of ITS shard; rank 0 receives them (``dist.gather``, NCCL
+    over NVLink on the GPU box, gloo in the CPU tests), restores the global submission order given by ``order`` and
+    returns the merged records; other ranks return None.  Reducing on rank 0 in submission order keeps every metric
+    bit-identical to the single-process result."""
     import torch.distributed as dist
-    rec = score_records(submission, ground_truth, device=device) if len(submission) else \
-        {"ap": np.zeros((0, 10)), "iou": np.zeros(0), "invalid": np.zeros(0, dtype=bool)}
-    order = np.array([d.get("_order", i) for i, d in enumerate(submission)], dtype=np.float64)
-    local = np.concatenate([rec["ap"], rec["iou"][:, None], rec["invalid"][:, None].astype(np.float64), order[:, None]], 1)
+    local = np.concatenate([rec["ap"].reshape(-1, 10), rec["iou"].reshape(-1, 1),
+                            rec["invalid"].reshape(-1, 1).astype(np.float64), np.asarray(order, dtype=np.float64).reshape(-1, 1)], 1)
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         allrec = local
     else:
@@ -106,6 +106,15 @@ def score_records_distributed(submission: List[dict], ground_truth: List[dict], 
         allrec = np.concatenate([g[: int(c.item())].cpu().numpy() for g, c in zip(gathered, counts)], 0)
     allrec = allrec[np.argsort(allrec[:, 12], kind="stable")]
     return {"ap": allrec[:, :10], "iou": allrec[:, 10], "invalid": allrec[:, 11].astype(bool)}
+
+
+def score_records_distributed(submission: List[dict], ground_truth: List[dict], group=None, device=None):
+    """Each rank scores ITS shard of queries on its GPU, then ``gather_records``.  ``submission`` entries may carry
+    ``"_order"`` (global position) to restore the global submission order on rank 0; rank != 0 returns None."""
+    rec = score_records(submission, ground_truth, device=device) if len(submission) else \
+        {"ap": np.zeros((0, 10)), "iou": np.zeros(0), "invalid": np.zeros(0, dtype=bool)}
+    order = np.array([d.get("_order", i) for i, d in enumerate(submission)], dtype=np.float64)
+    return gather_records(rec, order, group=group, device=device)
 
 
 def _mr_ap_from_records(rec) -> dict:
