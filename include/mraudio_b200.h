@@ -112,6 +112,38 @@ int mra_qformer_forward(mra_qformer_t* h, const mra_qformer_io* io, void* worksp
 /* number of kernels the last forward call enqueued (for bench.py's gpu_launches) */
 int mra_qformer_last_launch_count(const mra_qformer_t* h);
 
+/* ---- fine-tuning: backward of the Q-Former / projection parameters + optimizer ---------------------------------
+ * Replaces the autograd + optimizer the reference runs in utils/trainer.py:129-140 for the trainable parameters (here
+ * the Q-Former, query tokens and llm_proj; encoders and LLM frozen: no gradient flows into `enc`).
+ *   1. mra_qformer_forward(io with MRA_FWD_SAVE_FOR_BACKWARD) keeps per-layer activations in `workspace`;
+ *   2. mra_qformer_backward(same io, same workspace, d_llm = dL/d(llm_out) bf16 [rows*Nq, D]) ACCUMULATES fp32
+ *      gradients into `g` (same packed layout as mra_qformer_weights: stacked q,k,v / stacked cross k,v);
+ *      `wT` holds the bf16 weights transposed ([in, out] row-major; w_ckv / embeddings unused) for the dgrad GEMMs;
+ *   3. mra_adam_step: torch.optim.Adam semantics on flat fp32 buffers (utils/trainer.py:65), grads pre-multiplied by
+ *      grad_scale (1 / (accum_grad_iters * world_size) after a sum all-reduce);  mra_cast_bf16 refreshes bf16 copies. */
+typedef struct mra_qformer_layer_grads {
+    float* w_qkv;  float* b_qkv;  float* w_ao;   float* b_ao;   float* ln_a_g;  float* ln_a_b;
+    float* w_cq;   float* b_cq;   float* w_co;   float* b_co;   float* ln_c_g;  float* ln_c_b;
+    float* w_fq1;  float* b_fq1;  float* w_fq2;  float* b_fq2;  float* ln_fq_g; float* ln_fq_b;
+    float* w_ft1;  float* b_ft1;  float* w_ft2;  float* b_ft2;  float* ln_ft_g; float* ln_ft_b;
+} mra_qformer_layer_grads;
+typedef struct mra_qformer_grads {
+    float* word_emb; float* pos_emb;   /* may be NULL (frozen embeddings) */
+    float* ln_e_g; float* ln_e_b;
+    float* w_ckv; float* b_ckv;
+    float* w_proj; float* b_proj;
+    float* query_tokens;               /* fp32 [q_rows, Nq, H]; may be NULL */
+    mra_qformer_layer_grads layer[MRA_MAX_LAYERS];
+} mra_qformer_grads;
+
+size_t mra_qformer_backward_workspace_bytes(const mra_qformer_t* h, int32_t rows, int32_t T, int32_t Nk);
+int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, const void* d_llm, const mra_qformer_weights* wT,
+                         const mra_qformer_grads* g, void* workspace, size_t workspace_bytes, void* bwd_workspace,
+                         size_t bwd_bytes, void* stream);
+int mra_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int32_t step, float grad_scale, void* stream);
+int mra_cast_bf16(const float* in, void* out, int64_t n, void* stream);
+
 /* Device-side timing of the launches of mra_qformer_forward with CUDA events recorded on the caller's stream.
  *   MRA_PROFILE_DOMINANT brackets only the tensor-core GEMM launches (the dominant kernel: bench.py's roofline),
  *   MRA_PROFILE_ALL every launch.  mra_qformer_profile_read synchronises on the recorded events, returns the summed

@@ -44,6 +44,15 @@ class QFormerWeights(C.Structure):
                [("layer", QFormerLayerWeights * MRA_MAX_LAYERS)]
 
 
+class QFormerLayerGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in _LAYER_FIELDS]
+
+
+class QFormerGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("word_emb", "pos_emb", "ln_e_g", "ln_e_b", "w_ckv", "b_ckv", "w_proj", "b_proj",
+                                          "query_tokens")] + [("layer", QFormerLayerGrads * MRA_MAX_LAYERS)]
+
+
 class QFormerIO(C.Structure):
     _fields_ = [("enc", C.c_void_p), ("input_ids", C.c_void_p), ("attn_mask", C.c_void_p), ("enc_mask", C.c_void_p),
                 ("query_embeds", C.c_void_p), ("q_rows", C.c_int32), ("rows", C.c_int32), ("T", C.c_int32),
@@ -69,6 +78,12 @@ def _load():
     lib.mra_qformer_workspace_bytes.restype = C.c_size_t
     lib.mra_qformer_forward.argtypes = [vp, C.POINTER(QFormerIO), vp, C.c_size_t, vp]
     lib.mra_qformer_last_launch_count.argtypes = [vp]
+    lib.mra_qformer_backward_workspace_bytes.argtypes = [vp, i32, i32, i32]
+    lib.mra_qformer_backward_workspace_bytes.restype = C.c_size_t
+    lib.mra_qformer_backward.argtypes = [vp, C.POINTER(QFormerIO), vp, C.POINTER(QFormerWeights), C.POINTER(QFormerGrads), vp,
+                                         C.c_size_t, vp, C.c_size_t, vp]
+    lib.mra_adam_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, vp]
+    lib.mra_cast_bf16.argtypes = [vp, vp, i64, vp]
     lib.mra_qformer_profile_mode.argtypes = [vp, i32]
     lib.mra_qformer_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.mra_gemm_bf16.argtypes = [vp, i64, vp, i64, vp, vp, i64, vp, i64, i32, i32, i32, i32, i32, i32, vp]
@@ -86,7 +101,8 @@ lib = _load()
 # every symbol include/mraudio_b200.h declares (checked by tests/test_capi_symbols.py)
 EXPORTED_SYMBOLS = (
     "mra_last_error", "mra_version", "mra_device_check", "mra_qformer_create", "mra_qformer_set_weights",
-    "mra_qformer_destroy", "mra_qformer_workspace_bytes", "mra_qformer_forward", "mra_qformer_last_launch_count",
+    "mra_qformer_destroy", "mra_qformer_workspace_bytes", "mra_qformer_forward", "mra_qformer_last_launch_count", "mra_qformer_backward_workspace_bytes", "mra_qformer_backward", "mra_adam_step",
+    "mra_cast_bf16",
     "mra_qformer_profile_mode", "mra_qformer_profile_read",
     "mra_gemm_bf16", "mra_gemm_tile_override", "mra_attention", "mra_attention_impl_override", "mra_layernorm", "mra_modality_layernorm", "mra_mr_score",
 )

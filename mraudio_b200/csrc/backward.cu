@@ -1,0 +1,457 @@
+// Backward-pass kernels of the Q-Former / llm_proj fine-tuning step (the autograd the reference runs through
+// utils/trainer.py:129-140 for the trainable parameters; here: Q-Former + projection, encoders and LLM frozen).
+// The tensor-core work of the backward (dgrad / wgrad) reuses gemm_tc_kernel; this file holds the HBM-bound pieces:
+//   transpose (+ column sums = bias gradients), LayerNorm backward, GELU forward/backward, attention backward,
+//   embedding backward, Adam, fp32 -> bf16 casts.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace mra {
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------ transpose (+colsum)
+// in: bf16 [R, C] (row stride ld_in)  ->  out: bf16 [C, ld_out] with out[c, r] = in[r, c] and zeros for r in [R, ld_out).
+// colsum (optional, fp32 [C]) += sum_r in[r, c]   (bias gradient of a Linear whose output gradient is `in`).
+__global__ void __launch_bounds__(256)
+transpose_kernel(const __nv_bfloat16* __restrict__ in, int64_t ld_in, __nv_bfloat16* __restrict__ out, int64_t ld_out, int R,
+                 int C, float* __restrict__ colsum) {
+    __shared__ float tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = r0 + ty + i * 8, c = c0 + tx;
+        tile[ty + i * 8][tx] = (r < R && c < C) ? __bfloat162float(in[static_cast<int64_t>(r) * ld_in + c]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = c0 + ty + i * 8, r = r0 + tx;
+        if (c < C && r < ld_out) out[static_cast<int64_t>(c) * ld_out + r] = __float2bfloat16_rn(tile[tx][ty + i * 8]);
+    }
+    if (colsum != nullptr) {
+        // warp ty sums column (c0 + lane?) -- each warp reduces 4 columns of the tile over its 32 rows
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int cc = ty + i * 8;
+            float v = tile[tx][cc];
+            v = warp_sum(v);
+            if (tx == 0 && c0 + cc < C) atomicAdd(&colsum[c0 + cc], v);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm backward
+constexpr int LNB_WARPS = 8;
+constexpr int LNB_MAXV = 8;   // columns per lane = 8 * LNB_MAXV  (n <= 2048)
+
+// dx = rstd * (dyg - mean(dyg) - xhat * mean(dyg * xhat)),  dyg = dy * gamma, statistics recomputed from `pre`.
+// dgamma += sum_rows dy * xhat, dbeta += sum_rows dy.   One warp per row, grid-stride over rows.
+__global__ void __launch_bounds__(LNB_WARPS * 32)
+ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ pre, const float* __restrict__ gamma,
+              float* __restrict__ dx32, __nv_bfloat16* __restrict__ dx16, float* __restrict__ dgamma,
+              float* __restrict__ dbeta, int rows, int n, float eps) {
+    __shared__ float red[LNB_WARPS][256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nvec = n >> 3;
+    float ag[LNB_MAXV][8], ab[LNB_MAXV][8];
+#pragma unroll
+    for (int i = 0; i < LNB_MAXV; ++i)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ag[i][e] = ab[i][e] = 0.f;
+
+    for (int row = blockIdx.x * LNB_WARPS + warp; row < rows; row += gridDim.x * LNB_WARPS) {
+        const float* pr = pre + static_cast<int64_t>(row) * n;
+        const float* dr = dy + static_cast<int64_t>(row) * n;
+        float x[LNB_MAXV][8], d[LNB_MAXV][8];
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < LNB_MAXV; ++i) {
+            const int vi = i * 32 + lane;
+            if (vi < nvec) {
+                const float4 a = *reinterpret_cast<const float4*>(pr + vi * 8), b = *reinterpret_cast<const float4*>(pr + vi * 8 + 4);
+                x[i][0] = a.x; x[i][1] = a.y; x[i][2] = a.z; x[i][3] = a.w; x[i][4] = b.x; x[i][5] = b.y; x[i][6] = b.z; x[i][7] = b.w;
+                const float4 c = *reinterpret_cast<const float4*>(dr + vi * 8), e4 = *reinterpret_cast<const float4*>(dr + vi * 8 + 4);
+                d[i][0] = c.x; d[i][1] = c.y; d[i][2] = c.z; d[i][3] = c.w; d[i][4] = e4.x; d[i][5] = e4.y; d[i][6] = e4.z; d[i][7] = e4.w;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) sum += x[i][e];
+            }
+        }
+        const float mean = warp_sum(sum) / n;
+        float var = 0.f;
+#pragma unroll
+        for (int i = 0; i < LNB_MAXV; ++i)
+            if (i * 32 + lane < nvec)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { const float t = x[i][e] - mean; var = fmaf(t, t, var); }
+        const float rstd = rsqrtf(warp_sum(var) / n + eps);
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < LNB_MAXV; ++i) {
+            const int vi = i * 32 + lane;
+            if (vi < nvec) {
+                const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
+                const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float xh = (x[i][e] - mean) * rstd;
+                    ag[i][e] = fmaf(d[i][e], xh, ag[i][e]);
+                    ab[i][e] += d[i][e];
+                    const float dg = d[i][e] * g[e];
+                    x[i][e] = xh;
+                    d[i][e] = dg;
+                    s1 += dg;
+                    s2 = fmaf(dg, xh, s2);
+                }
+            }
+        }
+        const float c1 = warp_sum(s1) / n, c2 = warp_sum(s2) / n;
+#pragma unroll
+        for (int i = 0; i < LNB_MAXV; ++i) {
+            const int vi = i * 32 + lane;
+            if (vi < nvec) {
+                float o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = rstd * (d[i][e] - c1 - x[i][e] * c2);
+                if (dx32) {
+                    float* p = dx32 + static_cast<int64_t>(row) * n + vi * 8;
+                    *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<float4*>(p + 4) = make_float4(o[4], o[5], o[6], o[7]);
+                }
+                if (dx16) {
+                    uint4 u;
+                    u.x = ptx::pack_bf16x2(o[0], o[1]); u.y = ptx::pack_bf16x2(o[2], o[3]);
+                    u.z = ptx::pack_bf16x2(o[4], o[5]); u.w = ptx::pack_bf16x2(o[6], o[7]);
+                    *reinterpret_cast<uint4*>(dx16 + static_cast<int64_t>(row) * n + vi * 8) = u;
+                }
+            }
+        }
+    }
+    // block reduction of the gamma / beta partial sums: lane's vector slot i covers columns i*256 + lane*8 + e
+    if (dgamma == nullptr) return;
+#pragma unroll
+    for (int i = 0; i < LNB_MAXV; ++i) {
+        if (i * 256 < n) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                __syncthreads();
+#pragma unroll
+                for (int e = 0; e < 8; ++e) red[warp][lane * 8 + e] = half == 0 ? ag[i][e] : ab[i][e];
+                __syncthreads();
+                float v = 0.f;
+#pragma unroll
+                for (int w = 0; w < LNB_WARPS; ++w) v += red[w][threadIdx.x];
+                const int col = i * 256 + threadIdx.x;
+                if (col < n) atomicAdd((half == 0 ? dgamma : dbeta) + col, v);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ GELU
+__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad(float x) {
+    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+    const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+    return fmaf(x, pdf, cdf);
+}
+// y = gelu(z)  (training forward keeps z for the backward);  dz = dy * gelu'(z)
+template <bool BWD>
+__global__ void __launch_bounds__(256)
+gelu_kernel(const __nv_bfloat16* __restrict__ z, const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ out, int64_t n8) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n8) return;
+    const uint4 zv = reinterpret_cast<const uint4*>(z)[i];
+    uint4 dv = make_uint4(0, 0, 0, 0);
+    if (BWD) dv = reinterpret_cast<const uint4*>(dy)[i];
+    const uint32_t zz[4] = {zv.x, zv.y, zv.z, zv.w}, dd[4] = {dv.x, dv.y, dv.z, dv.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float a = ptx::bf16lo(zz[k]), b = ptx::bf16hi(zz[k]);
+        if (BWD) o[k] = ptx::pack_bf16x2(ptx::bf16lo(dd[k]) * gelu_grad(a), ptx::bf16hi(dd[k]) * gelu_grad(b));
+        else o[k] = ptx::pack_bf16x2(gelu_exact(a), gelu_exact(b));
+    }
+    reinterpret_cast<uint4*>(out)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// ------------------------------------------------------------------------------------------------ attention backward
+// One CTA per (row, head), head_dim 64.  Recomputes P = softmax(Q K^T / 8 + mask) (fp32), then
+//   dV = P^T dO,  dP = dO V^T,  dS = P o (dP - rowsum(dP o P)),  dQ = dS K / 8,  dK = dS^T Q / 8.
+// Q, K, V, dO tiles live in shared memory as bf16 (row stride 66 elements: conflict-free for "lane = row" and
+// "lane = column pair" access), P and dS as fp32 [Sq][Sk].  Token addressing as in the forward (split / dense).
+struct AttnBwdParams {
+    const __nv_bfloat16* q; int64_t ldq;
+    const __nv_bfloat16* k; int64_t ldk;
+    const __nv_bfloat16* v; int64_t ldv;
+    const __nv_bfloat16* d_o; int64_t ldo;
+    __nv_bfloat16* dq; int64_t lddq;
+    __nv_bfloat16* dk; int64_t lddk;
+    __nv_bfloat16* dv; int64_t lddv;
+    const float* add_mask;
+    int rows, heads, Sq, Sk, nq_split, kv_dense;
+};
+constexpr int AB_LD = 66;
+
+__device__ __forceinline__ int64_t tok_index(int r, int i, int rows, int nsplit, int S, bool dense) {
+    if (dense) return static_cast<int64_t>(r) * S + i;
+    return i < nsplit ? static_cast<int64_t>(r) * nsplit + i
+                      : static_cast<int64_t>(rows) * nsplit + static_cast<int64_t>(r) * (S - nsplit) + (i - nsplit);
+}
+
+__global__ void __launch_bounds__(256)
+attn_bwd_kernel(const AttnBwdParams p) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_raw);   // [Sq][66]
+    __nv_bfloat16* sDO = sQ + p.Sq * AB_LD;                           // [Sq][66]
+    __nv_bfloat16* sK = sDO + p.Sq * AB_LD;                           // [Sk][66]
+    __nv_bfloat16* sV = sK + p.Sk * AB_LD;                            // [Sk][66]
+    float* sP = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sV + p.Sk * AB_LD) + 15) & ~uintptr_t(15));
+    float* sDS = sP + static_cast<size_t>(p.Sq) * p.Sk;               // [Sq][Sk]
+    const int head = blockIdx.x % p.heads, r = blockIdx.x / p.heads;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool q_dense = p.nq_split >= p.Sq;
+
+    for (int idx = tid; idx < p.Sq * 32; idx += 256) {
+        const int i = idx >> 5, c = idx & 31;
+        const int64_t gi = tok_index(r, i, p.rows, p.nq_split, p.Sq, q_dense);
+        *reinterpret_cast<uint32_t*>(sQ + i * AB_LD + 2 * c) = *reinterpret_cast<const uint32_t*>(p.q + gi * p.ldq + head * 64 + 2 * c);
+        *reinterpret_cast<uint32_t*>(sDO + i * AB_LD + 2 * c) = *reinterpret_cast<const uint32_t*>(p.d_o + gi * p.ldo + head * 64 + 2 * c);
+    }
+    for (int idx = tid; idx < p.Sk * 32; idx += 256) {
+        const int j = idx >> 5, c = idx & 31;
+        const int64_t gj = tok_index(r, j, p.rows, p.nq_split, p.Sk, p.kv_dense != 0);
+        *reinterpret_cast<uint32_t*>(sK + j * AB_LD + 2 * c) = *reinterpret_cast<const uint32_t*>(p.k + gj * p.ldk + head * 64 + 2 * c);
+        *reinterpret_cast<uint32_t*>(sV + j * AB_LD + 2 * c) = *reinterpret_cast<const uint32_t*>(p.v + gj * p.ldv + head * 64 + 2 * c);
+    }
+    __syncthreads();
+
+    // ---- phase 1: one warp per query row: P row, dS row, dQ row
+    for (int i = warp; i < p.Sq; i += 8) {
+        float* Pi = sP + static_cast<size_t>(i) * p.Sk;
+        float* dSi = sDS + static_cast<size_t>(i) * p.Sk;
+        float mx = -INFINITY;
+        for (int j = lane; j < p.Sk; j += 32) {
+            float s = 0.f, dp = 0.f;
+#pragma unroll 8
+            for (int d = 0; d < 64; d += 2) {
+                const float2 qv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sQ + i * AB_LD + d));
+                const float2 kv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sK + j * AB_LD + d));
+                const float2 ov = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sDO + i * AB_LD + d));
+                const float2 vv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sV + j * AB_LD + d));
+                s = fmaf(qv.x, kv.x, fmaf(qv.y, kv.y, s));
+                dp = fmaf(ov.x, vv.x, fmaf(ov.y, vv.y, dp));
+            }
+            s = s * 0.125f + (p.add_mask ? p.add_mask[static_cast<int64_t>(r) * p.Sk + j] : 0.f);
+            Pi[j] = s;
+            dSi[j] = dp;
+            mx = fmaxf(mx, s);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.f;
+        for (int j = lane; j < p.Sk; j += 32) {
+            const float e = __expf(Pi[j] - mx);
+            Pi[j] = e;
+            sum += e;
+        }
+        const float inv = 1.f / warp_sum(sum);
+        float dsum = 0.f;
+        for (int j = lane; j < p.Sk; j += 32) {
+            const float pj = Pi[j] * inv;
+            Pi[j] = pj;
+            dsum = fmaf(pj, dSi[j], dsum);
+        }
+        dsum = warp_sum(dsum);
+        for (int j = lane; j < p.Sk; j += 32) dSi[j] = Pi[j] * (dSi[j] - dsum);
+        __syncwarp();
+        // dQ_i[d] = sum_j dS_ij K_j[d] / 8 : lane owns dims 2*lane, 2*lane+1
+        float a0 = 0.f, a1 = 0.f;
+        for (int j = 0; j < p.Sk; ++j) {
+            const float ds = dSi[j];
+            const float2 kv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sK + j * AB_LD + 2 * lane));
+            a0 = fmaf(ds, kv.x, a0);
+            a1 = fmaf(ds, kv.y, a1);
+        }
+        const int64_t gi = tok_index(r, i, p.rows, p.nq_split, p.Sq, q_dense);
+        *reinterpret_cast<uint32_t*>(p.dq + gi * p.lddq + head * 64 + 2 * lane) = ptx::pack_bf16x2(a0 * 0.125f, a1 * 0.125f);
+    }
+    __syncthreads();
+    // ---- phase 2: one warp per key: dK_j = sum_i dS_ij Q_i / 8, dV_j = sum_i P_ij dO_i
+    for (int j = warp; j < p.Sk; j += 8) {
+        float k0 = 0.f, k1 = 0.f, v0 = 0.f, v1 = 0.f;
+        for (int i = 0; i < p.Sq; ++i) {
+            const float ds = sDS[static_cast<size_t>(i) * p.Sk + j], pj = sP[static_cast<size_t>(i) * p.Sk + j];
+            const float2 qv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sQ + i * AB_LD + 2 * lane));
+            const float2 ov = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sDO + i * AB_LD + 2 * lane));
+            k0 = fmaf(ds, qv.x, k0); k1 = fmaf(ds, qv.y, k1);
+            v0 = fmaf(pj, ov.x, v0); v1 = fmaf(pj, ov.y, v1);
+        }
+        const int64_t gj = tok_index(r, j, p.rows, p.nq_split, p.Sk, p.kv_dense != 0);
+        *reinterpret_cast<uint32_t*>(p.dk + gj * p.lddk + head * 64 + 2 * lane) = ptx::pack_bf16x2(k0 * 0.125f, k1 * 0.125f);
+        *reinterpret_cast<uint32_t*>(p.dv + gj * p.lddv + head * 64 + 2 * lane) = ptx::pack_bf16x2(v0, v1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ embedding backward
+// d_emb: fp32 [rows*Nq + rows*T, H] (split layout).  query rows -> d_query[q_rows, Nq, H]; text rows -> scatter-add into
+// the word / position embedding gradients.
+__global__ void __launch_bounds__(256)
+embed_bwd_query_kernel(const float* __restrict__ d_emb, float* __restrict__ d_query, int q_rows, int rows, int Nq, int H) {
+    const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;   // over Nq*H (q_rows==1) or rows*Nq*H
+    const int64_t per = static_cast<int64_t>(Nq) * H;
+    if (q_rows == 1) {
+        if (idx >= per) return;
+        float s = 0.f;
+        for (int r = 0; r < rows; ++r) s += d_emb[static_cast<int64_t>(r) * per + idx];
+        d_query[idx] += s;
+    } else {
+        if (idx >= per * rows) return;
+        d_query[idx] += d_emb[idx];
+    }
+}
+__global__ void __launch_bounds__(256)
+embed_bwd_text_kernel(const float* __restrict__ d_emb_text, const int32_t* __restrict__ ids, float* __restrict__ d_word,
+                      float* __restrict__ d_pos, int rows, int T, int H, int vocab) {
+    const int tok = blockIdx.x;   // r*T + j
+    const int j = tok % T;
+    int id = ids[tok];
+    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+    for (int c = threadIdx.x; c < H; c += blockDim.x) {
+        const float g = d_emb_text[static_cast<int64_t>(tok) * H + c];
+        atomicAdd(&d_word[static_cast<int64_t>(id) * H + c], g);
+        atomicAdd(&d_pos[static_cast<int64_t>(j) * H + c], g);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ optimizer / casts
+// torch.optim.Adam semantics (utils/trainer.py:65: Adam(lr) with default betas / eps, L2 weight decay added to the grad).
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
+            float lr, float beta1, float beta2, float eps, float weight_decay, float bc1, float bc2_sqrt, float grad_scale) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float gi = g[i] * grad_scale;
+    const float pi = p[i];
+    if (weight_decay != 0.f) gi = fmaf(weight_decay, pi, gi);
+    const float mi = fmaf(beta1, m[i], (1.f - beta1) * gi);
+    const float vi = fmaf(beta2, v[i], (1.f - beta2) * gi * gi);
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+}
+
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t n) {
+    const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n) {
+        const float4 x = *reinterpret_cast<const float4*>(in + i);
+        uint2 o;
+        o.x = ptx::pack_bf16x2(x.x, x.y);
+        o.y = ptx::pack_bf16x2(x.z, x.w);
+        *reinterpret_cast<uint2*>(out + i) = o;
+    } else {
+        for (int64_t k = i; k < n; ++k) out[k] = __float2bfloat16_rn(in[k]);
+    }
+}
+
+}  // namespace
+
+int launch_transpose(const void* in, int64_t ld_in, void* out, int64_t ld_out, int R, int C, float* colsum, cudaStream_t s) {
+    MRA_REQUIRE(R > 0 && C > 0 && ld_out >= R, "transpose: bad shape R=%d C=%d ld_out=%lld", R, C, (long long)ld_out);
+    dim3 grid((C + 31) / 32, static_cast<unsigned>((ld_out + 31) / 32));
+    transpose_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(in), ld_in, reinterpret_cast<__nv_bfloat16*>(out),
+                                          ld_out, R, C, colsum);
+    MRA_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_ln_bwd(const float* dy, const float* pre, const float* gamma, float* dx32, void* dx16, float* dgamma, float* dbeta,
+                  int rows, int n, float eps, cudaStream_t s) {
+    MRA_REQUIRE(rows > 0 && n % 8 == 0 && n <= 32 * LNB_MAXV * 8, "layernorm backward width %d unsupported", n);
+    int blocks = (rows + LNB_WARPS - 1) / LNB_WARPS;
+    const int cap = sm_count() * 4;
+    if (blocks > cap) blocks = cap;
+    ln_bwd_kernel<<<blocks, LNB_WARPS * 32, 0, s>>>(dy, pre, gamma, dx32, reinterpret_cast<__nv_bfloat16*>(dx16), dgamma, dbeta,
+                                                    rows, n, eps);
+    MRA_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_gelu_fwd(const void* z, void* out, int64_t n, cudaStream_t s) {
+    MRA_REQUIRE(n % 8 == 0, "gelu: element count must be a multiple of 8");
+    const int64_t n8 = n / 8;
+    gelu_kernel<false><<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(z), nullptr,
+                                                                             reinterpret_cast<__nv_bfloat16*>(out), n8);
+    MRA_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+int launch_gelu_bwd(const void* z, const void* dy, void* dz, int64_t n, cudaStream_t s) {
+    MRA_REQUIRE(n % 8 == 0, "gelu: element count must be a multiple of 8");
+    const int64_t n8 = n / 8;
+    gelu_kernel<true><<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(z),
+                                                                            reinterpret_cast<const __nv_bfloat16*>(dy),
+                                                                            reinterpret_cast<__nv_bfloat16*>(dz), n8);
+    MRA_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_attention_bwd(const AttnBwdArgs& a, cudaStream_t s) {
+    MRA_REQUIRE(a.rows > 0 && a.heads > 0 && a.Sq > 0 && a.Sk > 0, "attention backward with empty dimension");
+    const size_t smem = static_cast<size_t>(2 * a.Sq + 2 * a.Sk) * AB_LD * 2 + 16 + static_cast<size_t>(a.Sq) * a.Sk * 8;
+    MRA_REQUIRE(smem <= 220 * 1024, "attention backward: Sq=%d x Sk=%d needs %zu bytes of shared memory (max 220 KiB)", a.Sq, a.Sk, smem);
+    static bool attr_set = false;
+    if (!attr_set) {
+        MRA_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr_set = true;
+    }
+    AttnBwdParams p{reinterpret_cast<const __nv_bfloat16*>(a.q), a.ldq, reinterpret_cast<const __nv_bfloat16*>(a.k), a.ldk,
+                    reinterpret_cast<const __nv_bfloat16*>(a.v), a.ldv, reinterpret_cast<const __nv_bfloat16*>(a.d_o), a.ldo,
+                    reinterpret_cast<__nv_bfloat16*>(a.dq), a.lddq, reinterpret_cast<__nv_bfloat16*>(a.dk), a.lddk,
+                    reinterpret_cast<__nv_bfloat16*>(a.dv), a.lddv, a.add_mask, a.rows, a.heads, a.Sq, a.Sk, a.nq_split, a.kv_dense};
+    attn_bwd_kernel<<<static_cast<unsigned>(a.rows) * a.heads, 256, smem, s>>>(p);
+    MRA_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_embed_bwd(const float* d_emb, const int32_t* ids, float* d_query, int q_rows, float* d_word, float* d_pos, int rows,
+                     int Nq, int T, int H, int vocab, cudaStream_t s) {
+    if (d_query) {
+        const int64_t n = static_cast<int64_t>(Nq) * H * (q_rows == 1 ? 1 : rows);
+        embed_bwd_query_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(d_emb, d_query, q_rows, rows, Nq, H);
+        MRA_CHECK_CUDA(cudaGetLastError());
+    }
+    if (T > 0 && d_word && d_pos) {
+        embed_bwd_text_kernel<<<static_cast<unsigned>(rows) * T, 256, 0, s>>>(d_emb + static_cast<int64_t>(rows) * Nq * H, ids, d_word,
+                                                                          d_pos, rows, T, H, vocab);
+        MRA_CHECK_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                float weight_decay, int step, float grad_scale, cudaStream_t s) {
+    MRA_REQUIRE(n > 0 && step >= 1, "adam: bad arguments");
+    const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
+    const float bc2 = sqrtf(1.f - powf(beta2, static_cast<float>(step)));
+    adam_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2,
+                                                                      grad_scale);
+    MRA_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_cast_bf16(const float* in, void* out, int64_t n, cudaStream_t s) {
+    MRA_REQUIRE(n > 0, "cast: empty");
+    const int64_t n4 = (n + 3) / 4;
+    cast_bf16_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, s>>>(in, reinterpret_cast<__nv_bfloat16*>(out), n);
+    MRA_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace mra

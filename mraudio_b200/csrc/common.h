@@ -64,12 +64,36 @@ int launch_modality_layernorm(const void* x, int in_dtype, const float* g, const
                               int Nk, int W, int frame_major, float eps, cudaStream_t s);
 // embeddings: LN(cat(query_embeds, word_emb[ids] + pos_emb[:T])) written in the split layout (queries first)
 int launch_embed_layernorm(const float* query_embeds, int q_rows, const int32_t* ids, const void* word_emb,
-                           const void* pos_emb, const float* g, const float* b, float* y32, void* y16, int rows, int Nq,
-                           int T, int H, int vocab, float eps, cudaStream_t s);
+                           const void* pos_emb, const float* g, const float* b, float* y32, void* y16, float* pre_out, int rows,
+                           int Nq, int T, int H, int vocab, float eps, cudaStream_t s);
 // additive masks (LAVIS get_extended_attention_mask): out[r, j] = (1 - mask[r, j]) * -10000
 int launch_build_enc_mask(const int32_t* enc_mask, float* out, int rows, int Nk, cudaStream_t s);
 // split layout [queries ; text] fp32 -> interleaved [rows, Nq+T, H] fp32
 int launch_gather_last_hidden(const float* split, float* out, int rows, int Nq, int T, int H, cudaStream_t s);
+
+// ---- backward / optimizer (backward.cu)
+struct AttnBwdArgs {
+    const void* q; int64_t ldq;
+    const void* k; int64_t ldk;
+    const void* v; int64_t ldv;
+    const void* d_o; int64_t ldo;
+    void* dq; int64_t lddq;
+    void* dk; int64_t lddk;
+    void* dv; int64_t lddv;
+    const float* add_mask;
+    int rows, heads, Sq, Sk, nq_split, kv_dense;
+};
+int launch_attention_bwd(const AttnBwdArgs& a, cudaStream_t s);
+int launch_transpose(const void* in, int64_t ld_in, void* out, int64_t ld_out, int R, int C, float* colsum, cudaStream_t s);
+int launch_ln_bwd(const float* dy, const float* pre, const float* gamma, float* dx32, void* dx16, float* dgamma, float* dbeta,
+                  int rows, int n, float eps, cudaStream_t s);
+int launch_gelu_fwd(const void* z, void* out, int64_t n, cudaStream_t s);
+int launch_gelu_bwd(const void* z, const void* dy, void* dz, int64_t n, cudaStream_t s);
+int launch_embed_bwd(const float* d_emb, const int32_t* ids, float* d_query, int q_rows, float* d_word, float* d_pos, int rows,
+                     int Nq, int T, int H, int vocab, cudaStream_t s);
+int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                float weight_decay, int step, float grad_scale, cudaStream_t s);
+int launch_cast_bf16(const float* in, void* out, int64_t n, cudaStream_t s);
 
 int launch_mr_score(const double* pred, const int32_t* n_pred, const double* gt, const int32_t* n_gt, const double* thds,
                     int Q, int Pmax, int Gmax, double* out_ap, double* out_iou, uint8_t* out_invalid, cudaStream_t s);

@@ -141,7 +141,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 embed_ln_kernel(const float* __restrict__ query_embeds, int q_rows, const int32_t* __restrict__ ids,
                 const __nv_bfloat16* __restrict__ word_emb, const __nv_bfloat16* __restrict__ pos_emb,
                 const float* __restrict__ g, const float* __restrict__ b, float* __restrict__ y32,
-                __nv_bfloat16* __restrict__ y16, int rows, int Nq, int T, int H, int vocab, float eps) {
+                __nv_bfloat16* __restrict__ y16, float* __restrict__ pre_out, int rows, int Nq, int T, int H, int vocab,
+                float eps) {
     const int64_t orow = static_cast<int64_t>(blockIdx.x) * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     const int64_t nquery = static_cast<int64_t>(rows) * Nq;
@@ -169,6 +170,15 @@ embed_ln_kernel(const float* __restrict__ query_embeds, int q_rows, const int32_
                 load8_bf16(pe + (k * 32 + lane) * 8, c);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) v[k][e] = a[e] + c[e];
+            }
+    }
+    if (pre_out != nullptr) {   // saved for the backward of the embedding LayerNorm
+#pragma unroll
+        for (int k = 0; k < MAX_VEC; ++k)
+            if (k * 32 + lane < nvec) {
+                float* pp = pre_out + orow * H + (k * 32 + lane) * 8;
+                *reinterpret_cast<float4*>(pp) = make_float4(v[k][0], v[k][1], v[k][2], v[k][3]);
+                *reinterpret_cast<float4*>(pp + 4) = make_float4(v[k][4], v[k][5], v[k][6], v[k][7]);
             }
     }
     ln_normalise_store(v, H, lane, g, b, eps, y32 + orow * H, y16 + orow * H);
@@ -221,8 +231,8 @@ int launch_modality_layernorm(const void* x, int in_dtype, const float* g, const
 }
 
 int launch_embed_layernorm(const float* query_embeds, int q_rows, const int32_t* ids, const void* word_emb,
-                           const void* pos_emb, const float* g, const float* b, float* y32, void* y16, int rows, int Nq,
-                           int T, int H, int vocab, float eps, cudaStream_t s) {
+                           const void* pos_emb, const float* g, const float* b, float* y32, void* y16, float* pre_out, int rows,
+                           int Nq, int T, int H, int vocab, float eps, cudaStream_t s) {
     MRA_REQUIRE(H % 8 == 0 && H <= 32 * MAX_VEC * 8, "embedding width %d unsupported", H);
     MRA_REQUIRE(T == 0 || (ids && word_emb && pos_emb), "text tokens given but ids / embedding tables are NULL");
     const int64_t total = static_cast<int64_t>(rows) * (Nq + T);
@@ -230,7 +240,7 @@ int launch_embed_layernorm(const float* query_embeds, int q_rows, const int32_t*
     embed_ln_kernel<<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(query_embeds, q_rows, ids,
                                                            reinterpret_cast<const __nv_bfloat16*>(word_emb),
                                                            reinterpret_cast<const __nv_bfloat16*>(pos_emb), g, b, y32,
-                                                           reinterpret_cast<__nv_bfloat16*>(y16), rows, Nq, T, H, vocab, eps);
+                                                           reinterpret_cast<__nv_bfloat16*>(y16), pre_out, rows, Nq, T, H, vocab, eps);
     MRA_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -36,23 +36,39 @@ namespace mra {
 namespace {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+inline int pad8(int v) { return (v + 7) & ~7; }
+
+// Per-layer activation buffers.  Inference: every layer aliases ONE set (activations are dead after the layer).
+// MRA_FWD_SAVE_FOR_BACKWARD: every layer has its own set, kept for mra_qformer_backward.
+struct LayerBufs {
+    __nv_bfloat16* xb;      // [Mtot, H]   layer input (bf16 GEMM operand); slot `layers` = output of the last layer
+    __nv_bfloat16* qkv;     // [Mtot, 3H]
+    __nv_bfloat16* ctx;     // [Mtot, H]   self-attention context
+    float* pre_a;           // [Mtot, H]   pre-LayerNorm sum of the self-attention block
+    __nv_bfloat16* ab;      // [Mtot, H]   LN_a output
+    __nv_bfloat16* cq;      // [Mq, H]     cross-attention queries
+    __nv_bfloat16* cctx;    // [Mq, H]     cross-attention context
+    float* pre_c;           // [Mq, H]
+    __nv_bfloat16* ab2;     // [Mq, H]     LN_c output (== ab rows [0, Mq) when not saving)
+    __nv_bfloat16* z;       // [Mtot, I]   pre-GELU activations (saved only)
+    __nv_bfloat16* inter;   // [Mtot, I]   GELU output
+    float* pre_f;           // [Mtot, H]   pre-LayerNorm sums of FFN_query (rows < Mq) / FFN_text
+};
 
 struct Workspace {
-    float* x32; __nv_bfloat16* xb;     // layer input  (residual stream + bf16 operand copy)
-    float* a32; __nv_bfloat16* ab;     // attention output
-    float* pre;                        // pre-LayerNorm sums (fp32)
-    __nv_bfloat16* qkv;                // [Mtot, 3H]
-    __nv_bfloat16* ctx;                // [Mtot, H]
-    __nv_bfloat16* inter;              // [Mtot, I]
-    __nv_bfloat16* cq;                 // [Mq, H]
-    __nv_bfloat16* kv;                 // [rows*Nk, ncross*2H]
-    float* self_mask;                  // [rows, S]
-    float* enc_mask;                   // [rows, Nk]
+    float* x32;             // residual stream: layer input (fp32)
+    float* a32;             // residual stream: attention output (fp32)
+    float* pre_e;           // embedding sums before the embedding LayerNorm (saved only)
+    __nv_bfloat16* kv;      // [rows*Nk, ncross*2H]
+    float* self_mask;       // [rows, S]
+    float* enc_mask;        // [rows, Nk]
+    LayerBufs layer[MRA_MAX_LAYERS + 1];
     size_t total;
 };
 
-Workspace carve(const mra_qformer* h, int rows, int T, int Nk, void* base) {
+Workspace carve(const mra_qformer* h, int rows, int T, int Nk, uint32_t flags, void* base) {
     const auto& c = h->cfg;
+    const bool save = (flags & MRA_FWD_SAVE_FOR_BACKWARD) != 0;
     const size_t H = c.hidden, I = c.inter;
     const size_t Mq = static_cast<size_t>(rows) * c.num_query, Mtot = Mq + static_cast<size_t>(rows) * T;
     size_t off = 0;
@@ -63,19 +79,87 @@ Workspace carve(const mra_qformer* h, int rows, int T, int Nk, void* base) {
     };
     Workspace w;
     w.x32 = reinterpret_cast<float*>(take(Mtot * H * 4));
-    w.xb = reinterpret_cast<__nv_bfloat16*>(take(Mtot * H * 2));
     w.a32 = reinterpret_cast<float*>(take(Mtot * H * 4));
-    w.ab = reinterpret_cast<__nv_bfloat16*>(take(Mtot * H * 2));
-    w.pre = reinterpret_cast<float*>(take(Mtot * H * 4));
-    w.qkv = reinterpret_cast<__nv_bfloat16*>(take(Mtot * 3 * H * 2));
-    w.ctx = reinterpret_cast<__nv_bfloat16*>(take(Mtot * H * 2));
-    w.inter = reinterpret_cast<__nv_bfloat16*>(take(Mtot * I * 2));
-    w.cq = reinterpret_cast<__nv_bfloat16*>(take(Mq * H * 2));
+    w.pre_e = save ? reinterpret_cast<float*>(take(Mtot * H * 4)) : nullptr;
     w.kv = reinterpret_cast<__nv_bfloat16*>(take(static_cast<size_t>(rows) * Nk * h->n_cross * 2 * H * 2));
     w.self_mask = reinterpret_cast<float*>(take(static_cast<size_t>(rows) * (c.num_query + T) * 4));
     w.enc_mask = reinterpret_cast<float*>(take(static_cast<size_t>(rows) * Nk * 4));
+    const int nsets = save ? c.layers : 1;
+    for (int l = 0; l < nsets; ++l) {
+        LayerBufs& b = w.layer[l];
+        b.xb = reinterpret_cast<__nv_bfloat16*>(take(Mtot * H * 2));
+        b.qkv = reinterpret_cast<__nv_bfloat16*>(take(Mtot * 3 * H * 2));
+        b.ctx = reinterpret_cast<__nv_bfloat16*>(take(Mtot * H * 2));
+        b.pre_a = reinterpret_cast<float*>(take(Mtot * H * 4));
+        b.ab = reinterpret_cast<__nv_bfloat16*>(take(Mtot * H * 2));
+        b.cq = reinterpret_cast<__nv_bfloat16*>(take(Mq * H * 2));
+        b.inter = reinterpret_cast<__nv_bfloat16*>(take(Mtot * I * 2));
+        if (save) {
+            b.cctx = reinterpret_cast<__nv_bfloat16*>(take(Mq * H * 2));
+            b.pre_c = reinterpret_cast<float*>(take(Mq * H * 4));
+            b.ab2 = reinterpret_cast<__nv_bfloat16*>(take(Mq * H * 2));
+            b.z = reinterpret_cast<__nv_bfloat16*>(take(Mtot * I * 2));
+            b.pre_f = reinterpret_cast<float*>(take(Mtot * H * 4));
+        } else {
+            b.cctx = b.ctx;
+            b.pre_c = b.pre_a;
+            b.ab2 = b.ab;
+            b.z = nullptr;
+            b.pre_f = b.pre_a;
+        }
+    }
+    if (save) {
+        w.layer[c.layers] = w.layer[0];
+        w.layer[c.layers].xb = reinterpret_cast<__nv_bfloat16*>(take(Mtot * H * 2));
+    } else {
+        for (int l = 1; l <= c.layers; ++l) w.layer[l] = w.layer[0];
+    }
     w.total = off;
     return w;
+}
+
+// scratch of the backward pass (caller-owned, see mra_qformer_backward_workspace_bytes)
+struct BwdWorkspace {
+    float* g_x; float* g_a; float* g_pre32;      // [Mtot, H] fp32
+    __nv_bfloat16* g_pre16; __nv_bfloat16* g_ctx16;   // [Mtot, H]
+    __nv_bfloat16* g_cq16;                        // [Mq, H]
+    __nv_bfloat16* g_big16; __nv_bfloat16* g_big2;    // [Mtot, max(I, 3H)]
+    __nv_bfloat16* g_kv16;                        // [rows*Nk, 2H]
+    __nv_bfloat16* t1; __nv_bfloat16* t2;         // transposed operands of the wgrad GEMMs
+    __nv_bfloat16* encT;                          // [W, pad8(rows*Nk)]
+    size_t total;
+};
+
+BwdWorkspace carve_bwd(const mra_qformer* h, int rows, int T, int Nk, void* base) {
+    const auto& c = h->cfg;
+    const size_t H = c.hidden, I = c.inter, D = c.llm_dim, W = c.enc_width;
+    const size_t Mq = static_cast<size_t>(rows) * c.num_query, Mtot = Mq + static_cast<size_t>(rows) * T;
+    const size_t Mqp = pad8(static_cast<int>(Mq)), Mtp = pad8(static_cast<int>(Mtot)), NKp = pad8(rows * Nk);
+    const size_t big = I > 3 * H ? I : 3 * H;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off = align_up(off + bytes, 1024);
+        return reinterpret_cast<uint8_t*>(base) + o;
+    };
+    BwdWorkspace b;
+    b.g_x = reinterpret_cast<float*>(take(Mtot * H * 4));
+    b.g_a = reinterpret_cast<float*>(take(Mtot * H * 4));
+    b.g_pre32 = reinterpret_cast<float*>(take(Mtot * H * 4));
+    b.g_pre16 = reinterpret_cast<__nv_bfloat16*>(take(Mtot * H * 2));
+    b.g_ctx16 = reinterpret_cast<__nv_bfloat16*>(take(Mtot * H * 2));
+    b.g_cq16 = reinterpret_cast<__nv_bfloat16*>(take(Mq * H * 2));
+    b.g_big16 = reinterpret_cast<__nv_bfloat16*>(take(Mtot * big * 2));
+    b.g_big2 = reinterpret_cast<__nv_bfloat16*>(take(Mtot * big * 2));
+    b.g_kv16 = reinterpret_cast<__nv_bfloat16*>(take(static_cast<size_t>(rows) * Nk * 2 * H * 2));
+    size_t t1 = big * Mtp;
+    if (D * Mqp > t1) t1 = D * Mqp;
+    if (2 * H * NKp > t1) t1 = 2 * H * NKp;
+    b.t1 = reinterpret_cast<__nv_bfloat16*>(take(t1 * 2));
+    b.t2 = reinterpret_cast<__nv_bfloat16*>(take((I > H ? I : H) * Mtp * 2));
+    b.encT = reinterpret_cast<__nv_bfloat16*>(take(W * NKp * 2));
+    b.total = off;
+    return b;
 }
 
 }  // namespace
@@ -123,9 +207,14 @@ extern "C" void mra_qformer_destroy(mra_qformer_t* h) {
     delete h;
 }
 
-extern "C" size_t mra_qformer_workspace_bytes(const mra_qformer_t* h, int32_t rows, int32_t T, int32_t Nk, uint32_t) {
+extern "C" size_t mra_qformer_workspace_bytes(const mra_qformer_t* h, int32_t rows, int32_t T, int32_t Nk, uint32_t flags) {
     if (!h || rows <= 0 || T < 0 || Nk <= 0) return 0;
-    return carve(h, rows, T, Nk, nullptr).total;
+    return carve(h, rows, T, Nk, flags, nullptr).total;
+}
+
+extern "C" size_t mra_qformer_backward_workspace_bytes(const mra_qformer_t* h, int32_t rows, int32_t T, int32_t Nk) {
+    if (!h || rows <= 0 || T < 0 || Nk <= 0) return 0;
+    return carve_bwd(h, rows, T, Nk, nullptr).total;
 }
 
 extern "C" int mra_qformer_profile_mode(mra_qformer_t* h, int32_t mode) {
@@ -169,7 +258,8 @@ extern "C" int mra_qformer_forward(mra_qformer_t* h, const mra_qformer_io* io, v
     MRA_REQUIRE(T == 0 || (io->input_ids && W.word_emb && W.pos_emb), "text tokens need input_ids and embedding tables");
     MRA_REQUIRE(T == 0 || W.layer[0].w_ft1, "text tokens need the text FFN weights");
     MRA_REQUIRE(!io->llm_out || (W.w_proj && W.b_proj && c.llm_dim > 0), "llm_out requested but no projection weights");
-    Workspace ws = carve(h, rows, T, Nk, workspace);
+    const bool save = (io->flags & MRA_FWD_SAVE_FOR_BACKWARD) != 0;
+    Workspace ws = carve(h, rows, T, Nk, io->flags, workspace);
     MRA_REQUIRE(workspace_bytes >= ws.total, "workspace too small: %zu < %zu bytes", workspace_bytes, ws.total);
     MRA_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
 
@@ -205,6 +295,13 @@ extern "C" int mra_qformer_forward(mra_qformer_t* h, const mra_qformer_io* io, v
         span_end();
         return e;
     };
+    auto layernorm = [&](const float* pre, const float* g, const float* b, float* y32, void* y16, int M) -> int {
+        span_begin(MRA_CAT_LAYERNORM);
+        int e = launch_layernorm(pre, g, b, y32, y16, M, H, c.ln_eps, s);
+        span_end();
+        ++launches;
+        return e;
+    };
 #define MRA_TRY(expr)            \
     do {                         \
         if (int _e = (expr)) return _e; \
@@ -213,7 +310,7 @@ extern "C" int mra_qformer_forward(mra_qformer_t* h, const mra_qformer_io* io, v
     // ---- embeddings + masks
     span_begin(MRA_CAT_OTHER);
     MRA_TRY(launch_embed_layernorm(io->query_embeds, io->q_rows, io->input_ids, W.word_emb, W.pos_emb, W.ln_e_g, W.ln_e_b,
-                                   ws.x32, ws.xb, rows, Nq, T, H, c.vocab, c.ln_eps, s));
+                                   ws.x32, ws.layer[0].xb, ws.pre_e, rows, Nq, T, H, c.vocab, c.ln_eps, s));
     span_end();
     ++launches;
     const float* self_mask = nullptr;
@@ -234,45 +331,55 @@ extern "C" int mra_qformer_forward(mra_qformer_t* h, const mra_qformer_io* io, v
                  c.enc_width, 0, 0));
     gemm_cat = MRA_CAT_GEMM;
 
+    // FFN over the row range [r0, r0 + n): y = LN(x + W2 gelu(W1 x)), x = a32 / in16, output -> x32 / out16
+    auto ffn = [&](const LayerBufs& B, const __nv_bfloat16* in16, __nv_bfloat16* out16, size_t r0, int n, const void* w1,
+                   const float* b1, const void* w2, const float* b2, const float* g, const float* be) -> int {
+        const size_t o = r0 * H, oi = r0 * I;
+        if (save) {
+            MRA_TRY(gemm(in16 + o, H, w1, H, b1, nullptr, 0, B.z + oi, I, n, I, H, 0, 0));
+            span_begin(MRA_CAT_OTHER);
+            MRA_TRY(launch_gelu_fwd(B.z + oi, B.inter + oi, static_cast<int64_t>(n) * I, s));
+            span_end();
+            ++launches;
+        } else {
+            MRA_TRY(gemm(in16 + o, H, w1, H, b1, nullptr, 0, B.inter + oi, I, n, I, H, 1, 0));
+        }
+        MRA_TRY(gemm(B.inter + oi, I, w2, I, b2, ws.a32 + o, H, B.pre_f + o, H, n, H, I, 0, 1));
+        return layernorm(B.pre_f + o, g, be, ws.x32 + o, out16 + o, n);
+    };
+
     for (int l = 0; l < c.layers; ++l) {
         const auto& L = W.layer[l];
+        const LayerBufs& B = ws.layer[l];
+        __nv_bfloat16* xb_next = ws.layer[l + 1].xb;
         const bool last = l == c.layers - 1;
         // self-attention over queries || text
-        MRA_TRY(gemm(ws.xb, H, L.w_qkv, H, L.b_qkv, nullptr, 0, ws.qkv, 3 * H, Mtot, 3 * H, H, 0, 0));
+        MRA_TRY(gemm(B.xb, H, L.w_qkv, H, L.b_qkv, nullptr, 0, B.qkv, 3 * H, Mtot, 3 * H, H, 0, 0));
         {
-            AttnArgs a{ws.qkv, 3 * H, ws.qkv + H, 3 * H, ws.qkv + 2 * H, 3 * H, ws.ctx, H, self_mask, rows, c.heads, S, S, Nq, 0};
+            AttnArgs a{B.qkv, 3 * H, B.qkv + H, 3 * H, B.qkv + 2 * H, 3 * H, B.ctx, H, self_mask, rows, c.heads, S, S, Nq, 0};
             span_begin(MRA_CAT_ATTENTION);
             MRA_TRY(launch_attention(a, s));
             span_end();
             ++launches;
         }
-        MRA_TRY(gemm(ws.ctx, H, L.w_ao, H, L.b_ao, ws.x32, H, ws.pre, H, Mtot, H, H, 0, 1));
-        span_begin(MRA_CAT_LAYERNORM);
-        MRA_TRY(launch_layernorm(ws.pre, L.ln_a_g, L.ln_a_b, ws.a32, ws.ab, Mtot, H, c.ln_eps, s));
-        span_end();
-        ++launches;
+        MRA_TRY(gemm(B.ctx, H, L.w_ao, H, L.b_ao, ws.x32, H, B.pre_a, H, Mtot, H, H, 0, 1));
+        MRA_TRY(layernorm(B.pre_a, L.ln_a_g, L.ln_a_b, ws.a32, B.ab, Mtot));
         // cross-attention of the query tokens onto this row's encoder tokens
+        const __nv_bfloat16* fq_in = B.ab;
         if (h->cross_slot[l] >= 0) {
             const __nv_bfloat16* kbase = ws.kv + static_cast<size_t>(h->cross_slot[l]) * 2 * H;
-            MRA_TRY(gemm(ws.ab, H, L.w_cq, H, L.b_cq, nullptr, 0, ws.cq, H, Mq, H, H, 0, 0));
-            AttnArgs a{ws.cq, H, kbase, kv_ld, kbase + H, kv_ld, ws.ctx, H, enc_mask, rows, c.heads, Nq, Nk, Nq, 1};
+            MRA_TRY(gemm(B.ab, H, L.w_cq, H, L.b_cq, nullptr, 0, B.cq, H, Mq, H, H, 0, 0));
+            AttnArgs a{B.cq, H, kbase, kv_ld, kbase + H, kv_ld, B.cctx, H, enc_mask, rows, c.heads, Nq, Nk, Nq, 1};
             span_begin(MRA_CAT_ATTENTION);
             MRA_TRY(launch_attention(a, s));
             span_end();
             ++launches;
-            MRA_TRY(gemm(ws.ctx, H, L.w_co, H, L.b_co, ws.a32, H, ws.pre, H, Mq, H, H, 0, 1));
-            span_begin(MRA_CAT_LAYERNORM);
-            MRA_TRY(launch_layernorm(ws.pre, L.ln_c_g, L.ln_c_b, ws.a32, ws.ab, Mq, H, c.ln_eps, s));
-            span_end();
-            ++launches;
+            MRA_TRY(gemm(B.cctx, H, L.w_co, H, L.b_co, ws.a32, H, B.pre_c, H, Mq, H, H, 0, 1));
+            MRA_TRY(layernorm(B.pre_c, L.ln_c_g, L.ln_c_b, ws.a32, B.ab2, Mq));
+            fq_in = B.ab2;
         }
         // FFN_query on the query rows
-        MRA_TRY(gemm(ws.ab, H, L.w_fq1, H, L.b_fq1, nullptr, 0, ws.inter, I, Mq, I, H, 1, 0));
-        MRA_TRY(gemm(ws.inter, I, L.w_fq2, I, L.b_fq2, ws.a32, H, ws.pre, H, Mq, H, I, 0, 1));
-        span_begin(MRA_CAT_LAYERNORM);
-        MRA_TRY(launch_layernorm(ws.pre, L.ln_fq_g, L.ln_fq_b, ws.x32, ws.xb, Mq, H, c.ln_eps, s));
-        span_end();
-        ++launches;
+        MRA_TRY(ffn(B, fq_in, xb_next, 0, Mq, L.w_fq1, L.b_fq1, L.w_fq2, L.b_fq2, L.ln_fq_g, L.ln_fq_b));
         // FFN_text on the text rows
         if (T > 0) {
             const size_t o = static_cast<size_t>(Mq) * H;
@@ -285,16 +392,11 @@ extern "C" int mra_qformer_forward(mra_qformer_t* h, const mra_qformer_io* io, v
                 }
             } else {
                 MRA_REQUIRE(L.w_ft1 && L.b_ft1 && L.w_ft2 && L.b_ft2 && L.ln_ft_g && L.ln_ft_b, "layer %d: text FFN weights missing", l);
-                const size_t oi = static_cast<size_t>(Mq) * I;
-                MRA_TRY(gemm(ws.ab + o, H, L.w_ft1, H, L.b_ft1, nullptr, 0, ws.inter + oi, I, Mt, I, H, 1, 0));
-                MRA_TRY(gemm(ws.inter + oi, I, L.w_ft2, I, L.b_ft2, ws.a32 + o, H, ws.pre + o, H, Mt, H, I, 0, 1));
-                span_begin(MRA_CAT_LAYERNORM);
-                MRA_TRY(launch_layernorm(ws.pre + o, L.ln_ft_g, L.ln_ft_b, ws.x32 + o, ws.xb + o, Mt, H, c.ln_eps, s));
-                span_end();
-                ++launches;
+                MRA_TRY(ffn(B, B.ab, xb_next, Mq, Mt, L.w_ft1, L.b_ft1, L.w_ft2, L.b_ft2, L.ln_ft_g, L.ln_ft_b));
             }
         }
     }
+    const __nv_bfloat16* xb_final = ws.layer[c.layers].xb;
     // ---- outputs
     if (io->last_hidden) {
         span_begin(MRA_CAT_OTHER);
@@ -303,9 +405,160 @@ extern "C" int mra_qformer_forward(mra_qformer_t* h, const mra_qformer_io* io, v
         ++launches;
     }
     if (io->llm_out) {
-        MRA_TRY(gemm(ws.xb, H, W.w_proj, H, W.b_proj, nullptr, 0, io->llm_out, c.llm_dim, Mq, c.llm_dim, H, 0, 0));
+        MRA_TRY(gemm(xb_final, H, W.w_proj, H, W.b_proj, nullptr, 0, io->llm_out, c.llm_dim, Mq, c.llm_dim, H, 0, 0));
     }
 #undef MRA_TRY
     h->last_launches = launches;
     return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Backward of mra_qformer_forward(flags | MRA_FWD_SAVE_FOR_BACKWARD) for the Q-Former / projection parameters
+// (encoders frozen: no gradient flows into `enc`).  Gradients are ACCUMULATED into `g` (zero them for a fresh step).
+extern "C" int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, const void* d_llm,
+                                    const mra_qformer_weights* wT, const mra_qformer_grads* g, void* workspace,
+                                    size_t workspace_bytes, void* bwd_workspace, size_t bwd_bytes, void* stream_) {
+    MRA_REQUIRE(h && io && d_llm && wT && g && workspace && bwd_workspace, "mra_qformer_backward: NULL argument");
+    MRA_REQUIRE(h->has_weights, "mra_qformer_backward: weights not set");
+    MRA_REQUIRE(io->flags & MRA_FWD_SAVE_FOR_BACKWARD, "mra_qformer_backward: the forward must run with MRA_FWD_SAVE_FOR_BACKWARD");
+    if (int e = device_check()) return e;
+    const auto& c = h->cfg;
+    const auto& W = h->w;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+    const int rows = io->rows, T = io->T, Nk = io->Nk, Nq = c.num_query, H = c.hidden, I = c.inter, D = c.llm_dim;
+    MRA_REQUIRE(D > 0 && wT->w_proj && g->w_proj && g->b_proj, "mra_qformer_backward needs the projection (llm_dim > 0)");
+    Workspace ws = carve(h, rows, T, Nk, io->flags, workspace);
+    MRA_REQUIRE(workspace_bytes >= ws.total, "workspace too small: %zu < %zu bytes", workspace_bytes, ws.total);
+    BwdWorkspace bw = carve_bwd(h, rows, T, Nk, bwd_workspace);
+    MRA_REQUIRE(bwd_bytes >= bw.total, "backward workspace too small: %zu < %zu bytes", bwd_bytes, bw.total);
+    MRA_REQUIRE((reinterpret_cast<uintptr_t>(bwd_workspace) & 255) == 0, "backward workspace must be 256-byte aligned");
+    const int S = Nq + T;
+    const int Mq = rows * Nq, Mt = rows * T, Mtot = Mq + Mt;
+    const int kv_ld = h->n_cross * 2 * H;
+    const int NK = rows * Nk, NKp = pad8(NK);
+    const bool skip_dead = (io->flags & MRA_FWD_SKIP_DEAD_TEXT_FFN) != 0;
+    int launches = 0;
+#define MRA_TRY(expr)            \
+    do {                         \
+        if (int _e = (expr)) return _e; \
+        ++launches;              \
+    } while (0)
+    auto gemm = [&](const void* A, int64_t lda, const void* Wt, int64_t ldw, const float* res, int64_t ldr, void* C, int64_t ldc,
+                    int M, int N, int K, int f32) -> int {
+        GemmArgs a{A, lda, Wt, ldw, nullptr, res, ldr, C, ldc, M, N, K, 0, f32};
+        return h->gemm_impl == MRA_GEMM_IMPL_SIMT_DEBUG ? launch_gemm_simt(a, s) : launch_gemm_tc(a, s);
+    };
+    // dW[N_out, K_in] += dY^T X  (+ db += colsum dY):  dY bf16 [n, N_out] (ld ldy), X bf16 [n, K_in] (ld ldx)
+    auto wgrad = [&](const __nv_bfloat16* dY, int64_t ldy, const __nv_bfloat16* X, int64_t ldx, int n, int N_out, int K_in,
+                     float* gW, int64_t ldg, float* gB, const __nv_bfloat16* XT /* pre-transposed X or nullptr */) -> int {
+        const int np = pad8(n);
+        MRA_TRY(launch_transpose(dY, ldy, bw.t1, np, n, N_out, gB, s));
+        if (XT == nullptr) {
+            MRA_TRY(launch_transpose(X, ldx, bw.t2, np, n, K_in, nullptr, s));
+            XT = bw.t2;
+        }
+        MRA_TRY(gemm(bw.t1, np, XT, np, gW, ldg, gW, ldg, N_out, K_in, np, 1));
+        return 0;
+    };
+    auto ln_bwd = [&](const float* dy, const float* pre, const float* gamma, float* dgam, float* dbet, size_t r0, int n) -> int {
+        const size_t o = r0 * H;
+        MRA_TRY(launch_ln_bwd(dy + o, pre + o, gamma, bw.g_pre32 + o, bw.g_pre16 + o, dgam, dbet, n, H, c.ln_eps, s));
+        return 0;
+    };
+    // FFN backward over rows [r0, r0+n): g_out = bw.g_x rows -> g_in accumulated into bw.g_a rows
+    auto ffn_bwd = [&](const LayerBufs& B, const __nv_bfloat16* in16, size_t r0, int n, const void* w1T, const void* w2T,
+                       const float* gamma, float* g_w1, float* g_b1, float* g_w2, float* g_b2, float* g_gam, float* g_bet) -> int {
+        const size_t o = r0 * H, oi = r0 * I;
+        if (int e = ln_bwd(bw.g_x, B.pre_f, gamma, g_gam, g_bet, r0, n)) return e;
+        if (int e = wgrad(bw.g_pre16 + o, H, B.inter + oi, I, n, H, I, g_w2, I, g_b2, nullptr)) return e;
+        MRA_TRY(gemm(bw.g_pre16 + o, H, w2T, H, nullptr, 0, bw.g_big16, I, n, I, H, 0));          // d_inter
+        MRA_TRY(launch_gelu_bwd(B.z + oi, bw.g_big16, bw.g_big2, static_cast<int64_t>(n) * I, s)); // dz
+        if (int e = wgrad(bw.g_big2, I, in16 + o, H, n, I, H, g_w1, H, g_b1, nullptr)) return e;
+        MRA_TRY(gemm(bw.g_big2, I, w1T, I, bw.g_pre32 + o, H, bw.g_a + o, H, n, H, I, 1));          // + residual path
+        return 0;
+    };
+
+    // ---- llm_proj
+    const __nv_bfloat16* dl = reinterpret_cast<const __nv_bfloat16*>(d_llm);
+    if (int e = wgrad(dl, D, ws.layer[c.layers].xb, H, Mq, D, H, g->w_proj, H, g->b_proj, nullptr)) return e;
+    MRA_TRY(gemm(dl, D, wT->w_proj, D, nullptr, 0, bw.g_x, H, Mq, H, D, 1));
+    if (Mt > 0) {
+        MRA_CHECK_CUDA(cudaMemsetAsync(bw.g_x + static_cast<size_t>(Mq) * H, 0, static_cast<size_t>(Mt) * H * 4, s));
+        ++launches;
+    }
+    // enc^T once for the wgrad of all cross K/V projections
+    MRA_TRY(launch_transpose(io->enc, c.enc_width, bw.encT, NKp, NK, c.enc_width, nullptr, s));
+
+    for (int l = c.layers - 1; l >= 0; --l) {
+        const auto& L = W.layer[l];
+        const auto& LT = wT->layer[l];
+        const auto& G = g->layer[l];
+        const LayerBufs& B = ws.layer[l];
+        const bool last = l == c.layers - 1;
+        const bool cross = h->cross_slot[l] >= 0;
+        // ---- FFN_query (rows < Mq) and FFN_text
+        if (int e = ffn_bwd(B, cross ? B.ab2 : B.ab, 0, Mq, LT.w_fq1, LT.w_fq2, L.ln_fq_g, G.w_fq1, G.b_fq1, G.w_fq2, G.b_fq2,
+                            G.ln_fq_g, G.ln_fq_b)) return e;
+        if (Mt > 0) {
+            const size_t o = static_cast<size_t>(Mq) * H;
+            if (last && skip_dead) {
+                MRA_CHECK_CUDA(cudaMemcpyAsync(bw.g_a + o, bw.g_x + o, static_cast<size_t>(Mt) * H * 4, cudaMemcpyDeviceToDevice, s));
+                ++launches;
+            } else {
+                MRA_REQUIRE(LT.w_ft1 && LT.w_ft2 && G.w_ft1 && G.w_ft2, "layer %d: text FFN transposed weights / grads missing", l);
+                if (int e = ffn_bwd(B, B.ab, Mq, Mt, LT.w_ft1, LT.w_ft2, L.ln_ft_g, G.w_ft1, G.b_ft1, G.w_ft2, G.b_ft2,
+                                    G.ln_ft_g, G.ln_ft_b)) return e;
+            }
+        }
+        // ---- cross-attention block (query rows): g_a[:Mq] is the gradient w.r.t. LN_c's output
+        if (cross) {
+            const int slot = h->cross_slot[l];
+            const __nv_bfloat16* kbase = ws.kv + static_cast<size_t>(slot) * 2 * H;
+            if (int e = ln_bwd(bw.g_a, B.pre_c, L.ln_c_g, G.ln_c_g, G.ln_c_b, 0, Mq)) return e;
+            if (int e = wgrad(bw.g_pre16, H, B.cctx, H, Mq, H, H, G.w_co, H, G.b_co, nullptr)) return e;
+            MRA_TRY(gemm(bw.g_pre16, H, LT.w_co, H, nullptr, 0, bw.g_ctx16, H, Mq, H, H, 0));      // d_cctx
+            AttnBwdArgs a{B.cq, H, kbase, kv_ld, kbase + H, kv_ld, bw.g_ctx16, H, bw.g_cq16, H, bw.g_kv16, 2 * H,
+                          bw.g_kv16 + H, 2 * H, io->enc_mask ? ws.enc_mask : nullptr, rows, c.heads, Nq, Nk, Nq, 1};
+            MRA_TRY(launch_attention_bwd(a, s));
+            if (int e = wgrad(bw.g_cq16, H, B.ab, H, Mq, H, H, G.w_cq, H, G.b_cq, nullptr)) return e;
+            MRA_TRY(gemm(bw.g_cq16, H, LT.w_cq, H, bw.g_pre32, H, bw.g_a, H, Mq, H, H, 1));         // -> grad of LN_a out (query rows)
+            if (int e = wgrad(bw.g_kv16, 2 * H, nullptr, 0, NK, 2 * H, c.enc_width,
+                              g->w_ckv + static_cast<size_t>(slot) * 2 * H * c.enc_width, c.enc_width,
+                              g->b_ckv + static_cast<size_t>(slot) * 2 * H, bw.encT)) return e;
+        }
+        // ---- self-attention block (all rows)
+        if (int e = ln_bwd(bw.g_a, B.pre_a, L.ln_a_g, G.ln_a_g, G.ln_a_b, 0, Mtot)) return e;
+        if (int e = wgrad(bw.g_pre16, H, B.ctx, H, Mtot, H, H, G.w_ao, H, G.b_ao, nullptr)) return e;
+        MRA_TRY(gemm(bw.g_pre16, H, LT.w_ao, H, nullptr, 0, bw.g_ctx16, H, Mtot, H, H, 0));         // d_ctx
+        {
+            AttnBwdArgs a{B.qkv, 3 * H, B.qkv + H, 3 * H, B.qkv + 2 * H, 3 * H, bw.g_ctx16, H, bw.g_big16, 3 * H,
+                          bw.g_big16 + H, 3 * H, bw.g_big16 + 2 * H, 3 * H, io->attn_mask ? ws.self_mask : nullptr,
+                          rows, c.heads, S, S, Nq, 0};
+            MRA_TRY(launch_attention_bwd(a, s));
+        }
+        if (int e = wgrad(bw.g_big16, 3 * H, B.xb, H, Mtot, 3 * H, H, G.w_qkv, H, G.b_qkv, nullptr)) return e;
+        MRA_TRY(gemm(bw.g_big16, 3 * H, LT.w_qkv, 3 * H, bw.g_pre32, H, bw.g_x, H, Mtot, H, 3 * H, 1));  // grad of the layer input
+    }
+    // ---- embeddings
+    if (int e = ln_bwd(bw.g_x, ws.pre_e, W.ln_e_g, g->ln_e_g, g->ln_e_b, 0, Mtot)) return e;
+    MRA_TRY(launch_embed_bwd(bw.g_pre32, io->input_ids, g->query_tokens, io->q_rows, g->word_emb, g->pos_emb, rows, Nq, T, H,
+                             c.vocab, s));
+#undef MRA_TRY
+    h->last_launches = launches;
+    return 0;
+}
+
+extern "C" int mra_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                             float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
+                             void* stream) {
+    MRA_REQUIRE(params && grads && exp_avg && exp_avg_sq, "mra_adam_step: NULL argument");
+    if (int e = device_check()) return e;
+    return launch_adam(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale,
+                       reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mra_cast_bf16(const float* in, void* out, int64_t n, void* stream) {
+    MRA_REQUIRE(in && out, "mra_cast_bf16: NULL argument");
+    if (int e = device_check()) return e;
+    return launch_cast_bf16(in, out, n, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -1,0 +1,325 @@
+"""Fine-tuning of the Q-Former / query tokens / llm_proj on cached encoder features (LLM and encoders frozen).
+
+Mirrors the slice of ``utils/trainer.py`` that touches the hot path (file:line under /root/reference):
+
+* ``Trainer.train_epoch`` inner loop ``:124-140`` -- forward, ``loss / accum_grad_iters``, backward, optimizer step every
+  ``accum_grad_iters`` iterations, ``zero_grad``;
+* ``optim.Adam(model.parameters(), lr=3e-4)`` ``:65`` and ``LinearWarmupCosineLRScheduler(max_epoch, min_lr=0,
+  init_lr=3e-4, warmup_steps=1000, warmup_start_lr=1e-8)`` ``:66`` stepped per iteration ``:127``;
+* ``DistributedDataParallel`` ``:69``: gradients are averaged over ranks -- here by ONE NCCL all-reduce per optimizer
+  step over the flat gradient buffer of each modality (the reference all-reduces on every backward, also on
+  non-stepping accumulation iterations);
+* ``_save_checkpoint`` ``:184-210``: only ``requires_grad`` parameters + optimizer state + epoch.
+
+As shipped the reference freezes these parameters (``models/xinstructblip.py:196-204``) and trains LoRA adapters of the
+LLM; un-freezing them is the training configuration BASELINE.json's north_star names.  bf16 tensor-core math with fp32
+master weights replaces the reference's fp16 autocast + GradScaler (no loss scaling is needed with bf16 exponents).
+
+Memory layout: all trainable tensors of one modality live in ONE flat fp32 buffer in the packed order the C-ABI wants
+(q,k,v stacked; cross k,v of all layers stacked); the ``nn.Parameter``s of the module become views into it, ``.grad``s
+are views into a second flat buffer, Adam state two more.  One cast kernel refreshes the bf16 operand copy.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from typing import Dict, List, Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import _lib
+from ._lib import check, current_stream, lib
+from .qformer import BertLMHeadModel
+
+_ALIGN = 64  # elements
+
+
+def _layer_segments(H, I, W, cross):
+    seg = [("w_qkv", (3 * H, H)), ("b_qkv", (3 * H,)), ("w_ao", (H, H)), ("b_ao", (H,)), ("ln_a_g", (H,)), ("ln_a_b", (H,))]
+    if cross:
+        seg += [("w_cq", (H, H)), ("b_cq", (H,)), ("w_co", (H, H)), ("b_co", (H,)), ("ln_c_g", (H,)), ("ln_c_b", (H,))]
+    seg += [("w_fq1", (I, H)), ("b_fq1", (I,)), ("w_fq2", (H, I)), ("b_fq2", (H,)), ("ln_fq_g", (H,)), ("ln_fq_b", (H,)),
+            ("w_ft1", (I, H)), ("b_ft1", (I,)), ("w_ft2", (H, I)), ("b_ft2", (H,)), ("ln_ft_g", (H,)), ("ln_ft_b", (H,))]
+    return seg
+
+
+class TrainableQFormer:
+    """Flat-buffer training state of one modality: ``{modality}_Qformer`` + ``{modality}_query_tokens`` +
+    ``{modality}_llm_proj``.  After construction the module's parameters alias ``self.flat`` (fp32 master weights)."""
+
+    def __init__(self, qformer: BertLMHeadModel, query_tokens: nn.Parameter, llm_proj: nn.Linear):
+        bert = qformer.bert
+        dev = query_tokens.device
+        if dev.type != "cuda":
+            raise _lib.MraError("TrainableQFormer needs the module on a CUDA device (no CPU fallback)")
+        self.qformer, self.bert, self.query_tokens, self.llm_proj = qformer, bert, query_tokens, llm_proj
+        cfg = bert.config
+        self.cfg = cfg
+        H, I, W, D = cfg.hidden_size, cfg.intermediate_size, cfg.encoder_width, llm_proj.weight.shape[0]
+        self.H, self.I, self.W, self.D = H, I, W, D
+        layers = bert.encoder.layer
+        self.cross = [bool(L.has_cross_attention) for L in layers]
+        nc = sum(self.cross)
+        # ---- segment table (name -> offset, shape) in the packed order
+        segs: List[Tuple[str, tuple]] = [("word_emb", tuple(bert.embeddings.word_embeddings.weight.shape)),
+                                         ("pos_emb", tuple(bert.embeddings.position_embeddings.weight.shape)),
+                                         ("ln_e_g", (H,)), ("ln_e_b", (H,)), ("w_ckv", (nc * 2 * H, W)), ("b_ckv", (nc * 2 * H,)),
+                                         ("w_proj", (D, H)), ("b_proj", (D,)), ("query_tokens", tuple(query_tokens.shape))]
+        for l, c in enumerate(self.cross):
+            segs += [(f"L{l}.{n}", shp) for n, shp in _layer_segments(H, I, W, c)]
+        self.seg: Dict[str, Tuple[int, tuple]] = {}
+        off = 0
+        for name, shp in segs:
+            self.seg[name] = (off, shp)
+            off += (math.prod(shp) + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.numel = off
+        self.flat = torch.zeros(off, device=dev, dtype=torch.float32)
+        self.grad = torch.zeros(off, device=dev, dtype=torch.float32)
+        self.exp_avg = torch.zeros(off, device=dev, dtype=torch.float32)
+        self.exp_avg_sq = torch.zeros(off, device=dev, dtype=torch.float32)
+        self.flat16 = torch.zeros(off, device=dev, dtype=torch.bfloat16)
+        # ---- re-home every parameter into the flat buffer (and its .grad into the flat gradient buffer)
+        e = bert.embeddings
+        self._bind(e.word_embeddings.weight, "word_emb")
+        self._bind(e.position_embeddings.weight, "pos_emb")
+        self._bind(e.LayerNorm.weight, "ln_e_g")
+        self._bind(e.LayerNorm.bias, "ln_e_b")
+        self._bind(llm_proj.weight, "w_proj")
+        self._bind(llm_proj.bias, "b_proj")
+        self._bind(query_tokens, "query_tokens")
+        slot = 0
+        for l, L in enumerate(layers):
+            p = f"L{l}."
+            a = L.attention
+            for i, n in enumerate(("query", "key", "value")):
+                self._bind(getattr(a.self, n).weight, p + "w_qkv", i * H, H)
+                self._bind(getattr(a.self, n).bias, p + "b_qkv", i * H, H)
+            self._bind(a.output.dense.weight, p + "w_ao"); self._bind(a.output.dense.bias, p + "b_ao")
+            self._bind(a.output.LayerNorm.weight, p + "ln_a_g"); self._bind(a.output.LayerNorm.bias, p + "ln_a_b")
+            if self.cross[l]:
+                c = L.crossattention
+                self._bind(c.self.query.weight, p + "w_cq"); self._bind(c.self.query.bias, p + "b_cq")
+                self._bind(c.output.dense.weight, p + "w_co"); self._bind(c.output.dense.bias, p + "b_co")
+                self._bind(c.output.LayerNorm.weight, p + "ln_c_g"); self._bind(c.output.LayerNorm.bias, p + "ln_c_b")
+                self._bind(c.self.key.weight, "w_ckv", slot * 2 * H, H); self._bind(c.self.key.bias, "b_ckv", slot * 2 * H, H)
+                self._bind(c.self.value.weight, "w_ckv", slot * 2 * H + H, H); self._bind(c.self.value.bias, "b_ckv", slot * 2 * H + H, H)
+                slot += 1
+            self._bind(L.intermediate_query.dense.weight, p + "w_fq1"); self._bind(L.intermediate_query.dense.bias, p + "b_fq1")
+            self._bind(L.output_query.dense.weight, p + "w_fq2"); self._bind(L.output_query.dense.bias, p + "b_fq2")
+            self._bind(L.output_query.LayerNorm.weight, p + "ln_fq_g"); self._bind(L.output_query.LayerNorm.bias, p + "ln_fq_b")
+            self._bind(L.intermediate.dense.weight, p + "w_ft1"); self._bind(L.intermediate.dense.bias, p + "b_ft1")
+            self._bind(L.output.dense.weight, p + "w_ft2"); self._bind(L.output.dense.bias, p + "b_ft2")
+            self._bind(L.output.LayerNorm.weight, p + "ln_ft_g"); self._bind(L.output.LayerNorm.bias, p + "ln_ft_b")
+        # ---- transposed bf16 copies for the dgrad GEMMs: name -> tensor [in, out]
+        self._t_names = ["w_proj"] + [f"L{l}.{n}" for l, c in enumerate(self.cross)
+                                      for n in (["w_qkv", "w_ao"] + (["w_cq", "w_co"] if c else []) + ["w_fq1", "w_fq2", "w_ft1", "w_ft2"])]
+        self.wT = {n: torch.empty(self.seg[n][1][1], self.seg[n][1][0], device=dev, dtype=torch.bfloat16) for n in self._t_names}
+        self._handle = bert._handle(D)
+        self._structs = None
+        self._ws = self._bws = None
+        self._saved = None
+        self.step_count = 0
+        self.refresh_operands()
+        bert._pack = None            # the inference path must re-pack from the (moved) parameters
+        bert._pack_applied = set()
+
+    # ------------------------------------------------------------------------------------------------ flat views
+    def _view(self, buf, name, row0=0, nrows=None):
+        off, shp = self.seg[name]
+        if nrows is None:
+            return buf[off:off + math.prod(shp)].view(shp)
+        inner = math.prod(shp[1:]) if len(shp) > 1 else 1
+        return buf[off + row0 * inner: off + (row0 + nrows) * inner].view((nrows,) + tuple(shp[1:]))
+
+    def _bind(self, param: nn.Parameter, name, row0=0, nrows=None):
+        v = self._view(self.flat, name, row0, nrows)
+        assert v.shape == param.shape, (name, v.shape, param.shape)
+        v.copy_(param.data)
+        param.data = v
+        param.grad = self._view(self.grad, name, row0, nrows)
+
+    def _ptr(self, buf, name, esize):
+        return buf.data_ptr() + self.seg[name][0] * esize
+
+    def refresh_operands(self):
+        """bf16 operand copy of the master weights (one cast kernel) + transposed copies for dgrad."""
+        check(lib.mra_cast_bf16(self.flat.data_ptr(), self.flat16.data_ptr(), self.numel, current_stream()))
+        for n, t in self.wT.items():
+            t.copy_(self._view(self.flat16, n).t())
+        if self._structs is None:
+            self._structs = self._build_structs()
+            check(lib.mra_qformer_set_weights(self._handle, C.byref(self._structs[0])))
+
+    def _build_structs(self):
+        W, WT, G = _lib.QFormerWeights(), _lib.QFormerWeights(), _lib.QFormerGrads()
+        for f in ("word_emb", "pos_emb", "w_ckv", "w_proj"):
+            setattr(W, f, self._ptr(self.flat16, f, 2))
+        for f in ("ln_e_g", "ln_e_b", "b_ckv", "b_proj"):
+            setattr(W, f, self._ptr(self.flat, f, 4))
+        WT.w_proj = self.wT["w_proj"].data_ptr()
+        for f in ("word_emb", "pos_emb", "ln_e_g", "ln_e_b", "w_ckv", "b_ckv", "w_proj", "b_proj", "query_tokens"):
+            setattr(G, f, self._ptr(self.grad, f, 4))
+        for l, c in enumerate(self.cross):
+            for n, shp in _layer_segments(self.H, self.I, self.W, c):
+                key = f"L{l}.{n}"
+                is_mat = len(shp) == 2
+                setattr(W.layer[l], n, self._ptr(self.flat16, key, 2) if is_mat else self._ptr(self.flat, key, 4))
+                setattr(G.layer[l], n, self._ptr(self.grad, key, 4))
+                if key in self.wT:
+                    setattr(WT.layer[l], n, self.wT[key].data_ptr())
+        return W, WT, G
+
+    # ------------------------------------------------------------------------------------------------ forward / backward
+    def forward(self, enc: torch.Tensor, input_ids: Optional[torch.Tensor], attention_mask: Optional[torch.Tensor]) -> torch.Tensor:
+        """Training forward (activations kept): returns ``llm_proj(Qformer.bert(...).last_hidden_state[:, :Nq])`` as
+        bf16 ``[rows, Nq, D]`` attached to autograd; ``.backward()`` accumulates into the flat gradient buffer."""
+        return _QFormerTrainFn.apply(self, enc, input_ids, attention_mask, self.query_tokens)
+
+    def _forward_impl(self, enc, input_ids, attention_mask):
+        cfg = self.cfg
+        dev = enc.device
+        rows, Nk, Wd = enc.shape
+        if Wd != cfg.encoder_width:
+            raise ValueError(f"encoder_hidden_states width {Wd} != config.encoder_width {cfg.encoder_width}")
+        Nq = cfg.query_length
+        enc_b = enc.to(torch.bfloat16).contiguous()
+        T, ids, amask = 0, None, None
+        if input_ids is not None:
+            T = input_ids.shape[1]
+            ids = input_ids.to(device=dev, dtype=torch.int32).contiguous()
+        if attention_mask is not None:
+            amask = attention_mask.to(device=dev, dtype=torch.int32).contiguous()
+        flags = _lib.FWD_SAVE_FOR_BACKWARD | _lib.FWD_SKIP_DEAD_TEXT_FFN
+        need = lib.mra_qformer_workspace_bytes(self._handle, rows, T, Nk, flags)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, device=dev, dtype=torch.uint8)
+        out = torch.empty(rows * Nq, self.D, device=dev, dtype=torch.bfloat16)
+        io = _lib.QFormerIO(enc=enc_b.data_ptr(), input_ids=_lib.ptr(ids), attn_mask=_lib.ptr(amask), enc_mask=None,
+                            query_embeds=self._ptr(self.flat, "query_tokens", 4), q_rows=self.query_tokens.shape[0],
+                            rows=rows, T=T, Nk=Nk, flags=flags, last_hidden=None, llm_out=out.data_ptr())
+        check(lib.mra_qformer_forward(self._handle, C.byref(io), self._ws.data_ptr(), self._ws.numel(), current_stream()))
+        self._saved = (io, enc_b, ids, amask, rows, T, Nk)
+        return out.view(rows, Nq, self.D)
+
+    def _backward_impl(self, d_out: torch.Tensor):
+        io, enc_b, ids, amask, rows, T, Nk = self._saved
+        d = d_out.reshape(rows * self.cfg.query_length, self.D).to(torch.bfloat16).contiguous()
+        need = lib.mra_qformer_backward_workspace_bytes(self._handle, rows, T, Nk)
+        if self._bws is None or self._bws.numel() < need:
+            self._bws = torch.empty(need, device=d.device, dtype=torch.uint8)
+        W, WT, G = self._structs
+        check(lib.mra_qformer_backward(self._handle, C.byref(io), d.data_ptr(), C.byref(WT), C.byref(G), self._ws.data_ptr(),
+                                       self._ws.numel(), self._bws.data_ptr(), self._bws.numel(), current_stream()))
+        self.last_backward_launches = lib.mra_qformer_last_launch_count(self._handle)
+        self._saved = None
+
+    # ------------------------------------------------------------------------------------------------ optimizer
+    def zero_grad(self):
+        self.grad.zero_()
+
+    def adam_step(self, lr: float, grad_scale: float = 1.0, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0):
+        self.step_count += 1
+        check(lib.mra_adam_step(self.flat.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                                self.numel, lr, betas[0], betas[1], eps, weight_decay, self.step_count, grad_scale,
+                                current_stream()))
+        self.refresh_operands()
+
+
+class _QFormerTrainFn(torch.autograd.Function):
+    """Autograd node of one modality's Q-Former + projection.  The parameter gradients are accumulated by the CUDA
+    backward directly into ``TrainableQFormer.grad`` (which the parameters' ``.grad`` alias), so ``None`` is returned for
+    them; ``query_tokens`` is an input only to make autograd schedule the node."""
+
+    @staticmethod
+    def forward(ctx, state: TrainableQFormer, enc, input_ids, attention_mask, query_tokens):
+        ctx.state = state
+        return state._forward_impl(enc, input_ids, attention_mask)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        ctx.state._backward_impl(d_out)
+        return None, None, None, None, None
+
+
+def warmup_cosine_lr(cur_epoch: int, cur_step: int, max_epoch: int, init_lr: float = 3e-4, min_lr: float = 0.0,
+                     warmup_steps: int = 1000, warmup_start_lr: float = 1e-8) -> float:
+    """LAVIS ``LinearWarmupCosineLRScheduler.step`` (utils/trainer.py:66,127): linear warm-up over the first
+    ``warmup_steps`` iterations of epoch 0, then a per-epoch cosine."""
+    if cur_epoch == 0 and cur_step < warmup_steps:
+        return min(init_lr, warmup_start_lr + (init_lr - warmup_start_lr) * cur_step / max(warmup_steps, 1))
+    return (init_lr - min_lr) * 0.5 * (1.0 + math.cos(math.pi * cur_epoch / max_epoch)) + min_lr
+
+
+class QFormerTrainer:
+    """The hot-path slice of ``utils/trainer.py::Trainer`` for ``XInstructBLIPQFormers``: ``train_step`` = one iteration of
+    ``train_epoch`` (:124-140).  ``loss_fn(inputs_llm, atts_llm, samples) -> scalar`` stands in for the frozen LLM's loss
+    (out of scope); the default is the surrogate ``sum(inputs_llm * G)`` used by the parity tests and the benchmark."""
+
+    def __init__(self, model, max_epoch: int = 1, accum_grad_iters: int = 2, init_lr: float = 3e-4, warmup_steps: int = 1000,
+                 loss_fn=None, group=None):
+        self.model = model
+        model.freeze_qformers(False)
+        self.states = {m: TrainableQFormer(getattr(model, f"{m}_Qformer"), getattr(model, f"{m}_query_tokens"),
+                                           getattr(model, f"{m}_llm_proj")) for m in model.modalities}
+        self.accum_grad_iters, self.max_epoch, self.init_lr, self.warmup_steps = accum_grad_iters, max_epoch, init_lr, warmup_steps
+        self.loss_fn = loss_fn
+        self.group = group
+        self.iter = 0
+        self.lr = init_lr
+
+    def _world(self):
+        import torch.distributed as dist
+        return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+
+    def forward_modalities(self, feats, input_ids, attention_mask):
+        """Training-mode ``encode_modalities`` (models/xinstructblip.py:456-477) -> (inputs_llm, atts_llm)."""
+        model = self.model
+        inputs_llm, atts_llm = {}, {}
+        for m in model.modalities:
+            if m not in feats:
+                continue
+            enc = model.fold_frames(m, feats[m], apply_ln=False)
+            bs = input_ids.shape[0]
+            num = enc.shape[0] // bs
+            ids = input_ids.repeat(num, 1)                      # reference tiling (:463)
+            tmask = attention_mask.repeat(num, 1)
+            q_atts = torch.ones(enc.shape[0], model.num_query_token, dtype=tmask.dtype, device=tmask.device)
+            y = self.states[m].forward(enc, ids, torch.cat([q_atts, tmask], 1))
+            inputs_llm[m] = y.reshape(bs, num, model.num_query_token, -1).view(bs, num * model.num_query_token, -1)
+            atts_llm[m] = torch.ones(inputs_llm[m].size()[:-1], dtype=torch.long, device=y.device)
+        return inputs_llm, atts_llm
+
+    def train_step(self, feats, input_ids, attention_mask, samples=None, cur_epoch: int = 0, surrogate: Optional[Dict[str, torch.Tensor]] = None):
+        """One iteration of the reference's inner loop.  Returns the (unscaled) loss tensor."""
+        import torch.distributed as dist
+        self.lr = warmup_cosine_lr(cur_epoch, self.iter, self.max_epoch, self.init_lr, 0.0, self.warmup_steps)   # :127
+        inputs_llm, atts_llm = self.forward_modalities(feats, input_ids, attention_mask)
+        if self.loss_fn is not None:
+            loss = self.loss_fn(inputs_llm, atts_llm, samples)
+        else:
+            loss = sum((inputs_llm[m].float() * surrogate[m]).sum() for m in inputs_llm)
+        (loss / self.accum_grad_iters).backward()                                                                  # :131-133
+        self.iter += 1
+        if self.iter % self.accum_grad_iters == 0:                                                                  # :137
+            world = self._world()
+            if world > 1:
+                for st in self.states.values():       # DDP's gradient averaging: one flat all-reduce per modality
+                    dist.all_reduce(st.grad, op=dist.ReduceOp.SUM, group=self.group)
+            for st in self.states.values():
+                st.adam_step(self.lr, grad_scale=1.0 / world)
+                st.zero_grad()
+        return loss.detach()
+
+    def state_dict_trainable(self):
+        """``_save_checkpoint`` payload (utils/trainer.py:184-199): only parameters that require grad."""
+        grad = {k: v.requires_grad for k, v in self.model.named_parameters()}
+        return {k: v for k, v in self.model.state_dict().items() if grad.get(k, False)}
+
+    def save_checkpoint(self, path: str, cur_epoch: int):
+        os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+        torch.save({"model": self.state_dict_trainable(),
+                    "optimizer": {m: {"exp_avg": s.exp_avg, "exp_avg_sq": s.exp_avg_sq, "step": s.step_count}
+                                  for m, s in self.states.items()},
+                    "scaler": None, "epoch": cur_epoch}, path)

@@ -68,3 +68,15 @@ def test_shard_range_partitions_like_a_contiguous_sampler(n, world):
     assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
     sizes = [hi - lo for lo, hi in spans]
     assert max(sizes) - min(sizes) <= 1
+
+
+def test_warmup_cosine_schedule_matches_lavis_formula():
+    """LinearWarmupCosineLRScheduler(max_epoch, min_lr=0, init_lr=3e-4, warmup_steps=1000, warmup_start_lr=1e-8)
+    stepped per iteration (utils/trainer.py:66,127)."""
+    import math
+    from mraudio_b200.training import warmup_cosine_lr
+    assert warmup_cosine_lr(0, 0, 10) == pytest.approx(1e-8)
+    assert warmup_cosine_lr(0, 500, 10) == pytest.approx(1e-8 + (3e-4 - 1e-8) * 0.5)
+    assert warmup_cosine_lr(0, 1000, 10) == pytest.approx(3e-4)            # warm-up over: cosine at epoch 0 = init_lr
+    assert warmup_cosine_lr(5, 3, 10) == pytest.approx(3e-4 * 0.5 * (1 + math.cos(math.pi * 0.5)))
+    assert warmup_cosine_lr(9, 0, 10) == pytest.approx(3e-4 * 0.5 * (1 + math.cos(math.pi * 0.9)))
