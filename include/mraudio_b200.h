@@ -203,6 +203,13 @@ int mra_modality_layernorm(const void* x, int32_t in_dtype, const float* gamma, 
                            int32_t bs, int32_t frames, int32_t Nk, int32_t W, int32_t frame_major, float eps,
                            void* stream);
 
+/* Video-LLaMA-v1-style frame position embedding: out[b,f,t,:] = bf16(x[b,f,t,:] + pos[f,:]), x: [bs, frames, n, W]
+ * (in_dtype as above), pos fp32 [frames, W].  The result viewed [bs, frames*n, W] is the key/value input of the video
+ * Q-Former.  (models/videollama.py:1-25 only wraps the `videollama2` package; this arithmetic is the public
+ * Video-LLaMA v1 design named by BASELINE.json config 3 -- parity unpinned, see DESIGN.md.) */
+int mra_add_frame_position(const void* x, int32_t in_dtype, const float* pos, void* out, int32_t bs, int32_t frames,
+                           int32_t n, int32_t W, void* stream);
+
 /* ---- moment-retrieval scorer ----------------------------------------------------------------------------------
  * One thread per query.  Replaces compute_average_precision_detection (eval/mr_utils.py:89-171), the per-query part
  * of compute_mr_r1 (eval/mr_eval.py:97-131) and the IoU helpers (eval/mr_utils.py:16-67), in fp64 with numpy's

@@ -104,6 +104,13 @@ extern "C" int mra_modality_layernorm(const void* x, int32_t in_dtype, const flo
                                      reinterpret_cast<cudaStream_t>(stream));
 }
 
+extern "C" int mra_add_frame_position(const void* x, int32_t in_dtype, const float* pos, void* out, int32_t bs, int32_t frames,
+                                      int32_t n, int32_t W, void* stream) {
+    MRA_REQUIRE(x && pos && out, "mra_add_frame_position: NULL operand");
+    if (int e = device_check()) return e;
+    return launch_add_frame_pos(x, in_dtype, pos, out, bs, frames, n, W, reinterpret_cast<cudaStream_t>(stream));
+}
+
 extern "C" int mra_mr_score(const double* pred, const int32_t* n_pred, const double* gt, const int32_t* n_gt,
                             const double* thds, int32_t Q, int32_t Pmax, int32_t Gmax, double* out_ap, double* out_iou,
                             uint8_t* out_invalid, void* stream) {

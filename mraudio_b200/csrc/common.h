@@ -62,6 +62,8 @@ int launch_layernorm(const float* x, const float* g, const float* b, float* y32,
                      cudaStream_t s);
 int launch_modality_layernorm(const void* x, int in_dtype, const float* g, const float* b, void* out, int bs, int frames,
                               int Nk, int W, int frame_major, float eps, cudaStream_t s);
+int launch_add_frame_pos(const void* x, int in_dtype, const float* pos, void* out, int bs, int frames, int n, int W,
+                         cudaStream_t s);
 // embeddings: LN(cat(query_embeds, word_emb[ids] + pos_emb[:T])) written in the split layout (queries first)
 int launch_embed_layernorm(const float* query_embeds, int q_rows, const int32_t* ids, const void* word_emb,
                            const void* pos_emb, const float* g, const float* b, float* y32, void* y16, float* pre_out, int rows,

@@ -136,6 +136,32 @@ modality_ln_kernel(const void* __restrict__ x, const float* __restrict__ g, cons
     ln_normalise_store(v, W, lane, g, b, eps, nullptr, out + token * W);
 }
 
+// out[b, f, t, :] = bf16(x[b, f, t, :] + pos[f, :])  -- Video-LLaMA-v1 frame position embedding (broadcast over tokens)
+template <int DTYPE>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+add_frame_pos_kernel(const void* __restrict__ x, const float* __restrict__ pos, __nv_bfloat16* __restrict__ out, int64_t tokens,
+                     int frames, int n, int W) {
+    const int64_t token = static_cast<int64_t>(blockIdx.x) * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (token >= tokens) return;
+    const int f = static_cast<int>((token / n) % frames);
+    const int nvec = W >> 3;
+    for (int vi = lane; vi < nvec; vi += 32) {
+        float v[8], pe[8];
+        const int64_t off = token * W + vi * 8;
+        if (DTYPE == 0) load8_f32(reinterpret_cast<const float*>(x) + off, v);
+        if (DTYPE == 1) load8_bf16(reinterpret_cast<const __nv_bfloat16*>(x) + off, v);
+        if (DTYPE == 2) load8_f16(reinterpret_cast<const __half*>(x) + off, v);
+        load8_f32(pos + static_cast<int64_t>(f) * W + vi * 8, pe);
+        uint4 o;
+        o.x = ptx::pack_bf16x2(v[0] + pe[0], v[1] + pe[1]);
+        o.y = ptx::pack_bf16x2(v[2] + pe[2], v[3] + pe[3]);
+        o.z = ptx::pack_bf16x2(v[4] + pe[4], v[5] + pe[5]);
+        o.w = ptx::pack_bf16x2(v[6] + pe[6], v[7] + pe[7]);
+        *reinterpret_cast<uint4*>(out + off) = o;
+    }
+}
+
 // rows of the split layout: [0, rows*Nq) query tokens (row r, token i), then [rows*Nq, rows*(Nq+T)) text tokens.
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 embed_ln_kernel(const float* __restrict__ query_embeds, int q_rows, const int32_t* __restrict__ ids,
@@ -226,6 +252,20 @@ int launch_modality_layernorm(const void* x, int in_dtype, const float* g, const
     if (in_dtype == 0) modality_ln_kernel<0><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, g, b, o, bs, frames, Nk, W, frame_major, eps);
     if (in_dtype == 1) modality_ln_kernel<1><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, g, b, o, bs, frames, Nk, W, frame_major, eps);
     if (in_dtype == 2) modality_ln_kernel<2><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, g, b, o, bs, frames, Nk, W, frame_major, eps);
+    MRA_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_add_frame_pos(const void* x, int in_dtype, const float* pos, void* out, int bs, int frames, int n, int W,
+                         cudaStream_t s) {
+    MRA_REQUIRE(bs > 0 && frames > 0 && n > 0 && W > 0 && W % 8 == 0, "frame position embedding: bad shape");
+    MRA_REQUIRE(in_dtype >= 0 && in_dtype <= 2, "frame position embedding: unknown input dtype %d", in_dtype);
+    const int64_t tokens = static_cast<int64_t>(bs) * frames * n;
+    const unsigned blocks = static_cast<unsigned>((tokens + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+    if (in_dtype == 0) add_frame_pos_kernel<0><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, pos, o, tokens, frames, n, W);
+    if (in_dtype == 1) add_frame_pos_kernel<1><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, pos, o, tokens, frames, n, W);
+    if (in_dtype == 2) add_frame_pos_kernel<2><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, pos, o, tokens, frames, n, W);
     MRA_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

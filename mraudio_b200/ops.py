@@ -84,6 +84,17 @@ def modality_layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
     return out
 
 
+def add_frame_position(x: torch.Tensor, pos: torch.Tensor) -> torch.Tensor:
+    """x [bs, F, n, W] (fp32 / bf16 / fp16) + pos fp32 [>=F, W] broadcast over the n tokens -> bf16 [bs, F*n, W]."""
+    _need_cuda(x, pos)
+    assert x.dim() == 4 and x.is_contiguous() and x.dtype in _DTYPE_CODE
+    bs, Fr, n, W = x.shape
+    assert pos.dtype == torch.float32 and pos.is_contiguous() and pos.shape[0] >= Fr and pos.shape[1] == W
+    out = torch.empty(bs, Fr * n, W, device=x.device, dtype=torch.bfloat16)
+    check(lib.mra_add_frame_position(ptr(x), _DTYPE_CODE[x.dtype], ptr(pos), ptr(out), bs, Fr, n, W, current_stream()))
+    return out
+
+
 def mr_score(pred: torch.Tensor, n_pred: torch.Tensor, gt: torch.Tensor, n_gt: torch.Tensor, thds: torch.Tensor):
     """pred f64 [Q, Pmax, 2], n_pred i32 [Q], gt f64 [Q, Gmax, 2], n_gt i32 [Q], thds f64 [10]
     -> (ap f64 [Q, 10], iou f64 [Q], invalid u8 [Q])."""
