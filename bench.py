@@ -231,17 +231,13 @@ def run_b200(args):
     # ---- value: device-resident inputs
     ms_dev = timed(device_step, args.steps)
     launches = model.last_launches * args.steps
-    # ---- roofline: same K steps with events around every GEMM launch; the modalities run back to back on one stream
-    #      here so that a launch's event span holds that launch only (not a kernel of the other Q-Former)
-    model.concurrent_modalities = False
-    ms_serial = timed(device_step, args.steps)
+    # ---- roofline: same K steps with events around every GEMM launch
     set_profile(_lib.PROFILE_DOMINANT)
     ms_instr = timed(device_step, args.steps)
     prof_ms, prof_n = read_profile()
     # ---- e2e: host buffers through the public host API
     pipe = model.host_pipeline(B, F, {m: v[0] for m, v in MODAL.items()}, T, slots=2)
     set_profile(_lib.PROFILE_OFF)
-    model.concurrent_modalities = False
 
     def e2e_steps(n):
         for i in range(n):
@@ -259,7 +255,6 @@ def run_b200(args):
     t_clock1 = time.time()
     clocks = sampler.stop(t_clock0, t_clock1) if sampler else None
     # ---- per-category breakdown (not part of any headline number)
-    model.concurrent_modalities = False
     set_profile(_lib.PROFILE_ALL)
     for _ in range(2):
         device_step()
@@ -296,7 +291,7 @@ def run_b200(args):
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src + ", sustained figure (kernel timed inside a long step)",
                      "kernel": "gemm_tc_kernel (tcgen05 Linear; all launches of a step, flops-weighted)",
-                     "launches_per_step": gemm_n, "ms_per_step_in_kernel": gemm_ms, "ms_per_step_instrumented": ms_instr, "ms_per_step_single_stream": ms_serial,
+                     "launches_per_step": gemm_n, "ms_per_step_in_kernel": gemm_ms, "ms_per_step_instrumented": ms_instr,
                      "algorithmic_tflop_per_step": lin / 1e12,
                      "cross_kv_launch": {"tflop": kv / 1e12, "ms": kv_ms, "achieved": kv / (kv_ms * 1e-3) / 1e12 if kv_ms else 0.0}},
         "cpu_baseline": {"value": cpu_v, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},

@@ -109,6 +109,12 @@ typedef struct mra_qformer_io {
 size_t mra_qformer_workspace_bytes(const mra_qformer_t* h, int32_t rows, int32_t T, int32_t Nk, uint32_t flags);
 int mra_qformer_forward(mra_qformer_t* h, const mra_qformer_io* io, void* workspace, size_t workspace_bytes,
                         void* stream);
+/* Same for up to two Q-Formers of one batch (video + audio) in lockstep: each Linear of a layer is ONE grouped GEMM launch
+ * over both (FFN_query / FFN_text are further problems of the same launch).  The handles must share the layer geometry
+ * (hidden, heads, layers, intermediate, queries, cross frequency, llm_dim); encoder width, rows, T, Nk may differ.
+ * The launch count / profile of the call is reported on hs[0]. */
+int mra_qformer_forward_multi(int32_t n, mra_qformer_t* const* hs, const mra_qformer_io* const* ios, void* const* workspaces,
+                              const size_t* workspace_bytes, void* stream);
 /* number of kernels the last forward call enqueued (for bench.py's gpu_launches) */
 int mra_qformer_last_launch_count(const mra_qformer_t* h);
 

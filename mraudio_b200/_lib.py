@@ -77,6 +77,8 @@ def _load():
     lib.mra_qformer_workspace_bytes.argtypes = [vp, i32, i32, i32, C.c_uint32]
     lib.mra_qformer_workspace_bytes.restype = C.c_size_t
     lib.mra_qformer_forward.argtypes = [vp, C.POINTER(QFormerIO), vp, C.c_size_t, vp]
+    lib.mra_qformer_forward_multi.argtypes = [i32, C.POINTER(vp), C.POINTER(C.POINTER(QFormerIO)), C.POINTER(vp),
+                                              C.POINTER(C.c_size_t), vp]
     lib.mra_qformer_last_launch_count.argtypes = [vp]
     lib.mra_qformer_backward_workspace_bytes.argtypes = [vp, i32, i32, i32]
     lib.mra_qformer_backward_workspace_bytes.restype = C.c_size_t
@@ -102,7 +104,7 @@ lib = _load()
 # every symbol include/mraudio_b200.h declares (checked by tests/test_capi_symbols.py)
 EXPORTED_SYMBOLS = (
     "mra_last_error", "mra_version", "mra_device_check", "mra_qformer_create", "mra_qformer_set_weights",
-    "mra_qformer_destroy", "mra_qformer_workspace_bytes", "mra_qformer_forward", "mra_qformer_last_launch_count", "mra_qformer_backward_workspace_bytes", "mra_qformer_backward", "mra_adam_step",
+    "mra_qformer_destroy", "mra_qformer_workspace_bytes", "mra_qformer_forward", "mra_qformer_forward_multi", "mra_qformer_last_launch_count", "mra_qformer_backward_workspace_bytes", "mra_qformer_backward", "mra_adam_step",
     "mra_cast_bf16",
     "mra_qformer_profile_mode", "mra_qformer_profile_read",
     "mra_gemm_bf16", "mra_gemm_tile_override", "mra_attention", "mra_attention_impl_override", "mra_layernorm", "mra_modality_layernorm", "mra_add_frame_position", "mra_mr_score",

@@ -44,6 +44,7 @@ struct GemmArgs {
     int out_fp32;
 };
 int launch_gemm_tc(const GemmArgs& a, cudaStream_t s);
+int launch_gemm_tc_grouped(const GemmArgs* a, int n, cudaStream_t s);   // n <= 4 problems sharing N, K, epilogue kind
 int launch_gemm_simt(const GemmArgs& a, cudaStream_t s);
 void set_gemm_tile_override(int bn);
 
@@ -60,6 +61,12 @@ void set_attention_impl_override(int generic);
 
 int launch_layernorm(const float* x, const float* g, const float* b, float* y32, void* y16, int rows, int n, float eps,
                      cudaStream_t s);
+struct LnSegment {
+    const float* x; const float* gamma; const float* beta;
+    float* y32; void* y16;
+    int rows;
+};
+int launch_layernorm_grouped(const LnSegment* segs, int nseg, int n, float eps, cudaStream_t s);
 int launch_modality_layernorm(const void* x, int in_dtype, const float* g, const float* b, void* out, int bs, int frames,
                               int Nk, int W, int frame_major, float eps, cudaStream_t s);
 int launch_add_frame_pos(const void* x, int in_dtype, const float* pos, void* out, int bs, int frames, int n, int W,

@@ -108,6 +108,33 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g, const
                        y16 ? y16 + static_cast<int64_t>(row) * n : nullptr);
 }
 
+// up to 4 independent row ranges (same width) in one launch: warp w of the grid handles global row w
+struct LnGroup {
+    LnSegment seg[4];
+    int start[5];
+    int n;
+};
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+layernorm_grouped_kernel(const LnGroup grp, int n, float eps) {
+    const int grow = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (grow >= grp.start[grp.n]) return;
+    int g = 0;
+#pragma unroll
+    for (int i = 1; i < 4; ++i)
+        if (i < grp.n && grow >= grp.start[i]) g = i;
+    const LnSegment& sg = grp.seg[g];
+    const int row = grow - grp.start[g];
+    const float* xr = sg.x + static_cast<int64_t>(row) * n;
+    float v[MAX_VEC][8];
+    const int nvec = n >> 3;
+#pragma unroll
+    for (int i = 0; i < MAX_VEC; ++i)
+        if (i * 32 + lane < nvec) load8_f32(xr + (i * 32 + lane) * 8, v[i]);
+    ln_normalise_store(v, n, lane, sg.gamma, sg.beta, eps, sg.y32 ? sg.y32 + static_cast<int64_t>(row) * n : nullptr,
+                       sg.y16 ? reinterpret_cast<__nv_bfloat16*>(sg.y16) + static_cast<int64_t>(row) * n : nullptr);
+}
+
 // out row (b*F + f) <- in row (frame_major ? f*bs + b : b*F + f), token tok.
 template <int DTYPE>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
@@ -237,6 +264,25 @@ int launch_layernorm(const float* x, const float* g, const float* b, float* y32,
     MRA_REQUIRE(rows > 0 && n > 0 && n % 8 == 0 && n <= 32 * MAX_VEC * 8, "layernorm width %d unsupported (multiple of 8, <= 2048)", n);
     const int blocks = (rows + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     layernorm_kernel<<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, g, b, y32, reinterpret_cast<__nv_bfloat16*>(y16), rows, n, eps);
+    MRA_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_layernorm_grouped(const LnSegment* segs, int nseg, int n, float eps, cudaStream_t s) {
+    MRA_REQUIRE(nseg >= 1 && nseg <= 4, "grouped layernorm takes 1..4 row ranges");
+    MRA_REQUIRE(n > 0 && n % 8 == 0 && n <= 32 * MAX_VEC * 8, "layernorm width %d unsupported (multiple of 8, <= 2048)", n);
+    LnGroup grp;
+    int total = 0;
+    for (int i = 0; i < 4; ++i) {
+        grp.seg[i] = segs[i < nseg ? i : 0];
+        grp.start[i] = total;
+        if (i < nseg) total += segs[i].rows;
+    }
+    grp.start[4] = total;
+    for (int i = nseg; i <= 4; ++i) grp.start[i] = total;
+    grp.n = nseg;
+    const int blocks = (total + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    layernorm_grouped_kernel<<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(grp, n, eps);
     MRA_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

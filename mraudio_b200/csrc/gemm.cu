@@ -5,10 +5,10 @@
 //     running concurrently share the same A rows through L2);
 //   * warp 0 = TMA producer (cp.async.bulk.tensor, 128B-swizzled 64-wide K slabs, STAGES-deep mbarrier ring),
 //     warp 1 = MMA issuer (one thread, tcgen05.mma kind::f16, M=128, N=BN, K=16, fp32 accumulators in TMEM),
-//     warps 2..5 = epilogue: tcgen05.ld 32x32b -> registers -> bias / erf-GELU / fp32 residual -> 128B-swizzled
-//     shared-memory staging -> TMA bulk tensor STORE (each warp streams its own 32-row slab in 128-byte-wide column
-//     chunks, double-buffered); the fp32 residual arrives by TMA LOAD into the same kind of per-warp chunk buffers,
-//     prefetched two chunks ahead (the first two while the tile's main loop is still running).  All global traffic
+//     warps 2..9 = epilogue (two per TMEM lane quadrant, alternating over 128-byte-wide column chunks): tcgen05.ld
+//     32x32b -> registers -> bias / erf-GELU / fp32 residual -> 128B-swizzled shared-memory staging -> TMA bulk tensor
+//     STORE; the fp32 residual arrives by TMA LOAD into a per-warp chunk buffer, prefetched one chunk ahead (the
+//     first one while the tile's main loop is still running).  All global traffic
 //     of the epilogue is therefore asynchronous, fully coalesced and clipped at the M / N edges by the TMA unit;
 //   * two TMEM accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1.
 // Reference arithmetic replaced: torch.nn.Linear (+ GELU, + residual add) in LAVIS Qformer.py / HF port
@@ -28,24 +28,45 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
-constexpr int NUM_THREADS = 192;
-constexpr int EPI_WARPS = 4;
+constexpr int EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int CHUNK_BYTES = 32 * 128;       // one epilogue chunk of one warp: 32 rows x 128 bytes
 
-struct EpiParams {
-    const float* bias;
-    int M, N, K;
+constexpr int MAX_GROUPS = 4;
+
+// A launch processes up to MAX_GROUPS independent problems that share N, K and the epilogue kind but have their own
+// A / W / C / residual matrices, bias and M (grouped GEMM: e.g. FFN_query + FFN_text of both modalities in one launch,
+// so that the persistent grid sees 4x the tiles and the wave-quantisation tail shrinks accordingly).
+struct GroupMaps {
+    CUtensorMap a[MAX_GROUPS], b[MAX_GROUPS], c[MAX_GROUPS], r[MAX_GROUPS];
 };
+struct EpiParams {
+    const float* bias[MAX_GROUPS];
+    int M[MAX_GROUPS];
+    int tile_start[MAX_GROUPS + 1];   // first tile index of each group (tiles of a group: m-block major, n fastest)
+    int groups;
+    int N, K;
+};
+
+__device__ __forceinline__ void decode_tile(const EpiParams& p, int tile, int n_tiles, int& g, int& m_blk, int& n_blk) {
+    g = 0;
+#pragma unroll
+    for (int i = 1; i < MAX_GROUPS; ++i)
+        if (i < p.groups && tile >= p.tile_start[i]) g = i;
+    const int t = tile - p.tile_start[g];
+    m_blk = t / n_tiles;
+    n_blk = t - m_blk * n_tiles;
+}
 
 template <int BN, int STAGES, bool RES>
 struct SmemLayout {
     static constexpr int B_STAGE_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;
-    static constexpr int EPI_BUFS_PER_WARP = RES ? 4 : 2;   // 2 output chunks (+ 2 residual chunks)
+    static constexpr int EPI_BUFS_PER_WARP = RES ? 2 : 1;   // 1 output chunk (+ 1 residual chunk) of 4 KiB
     static constexpr int EPI_BYTES = EPI_WARPS * EPI_BUFS_PER_WARP * CHUNK_BYTES;
     static constexpr int BAR_OFFSET = EPI_OFFSET + EPI_BYTES;
-    static constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * EPI_WARPS;
+    static constexpr int NUM_BARS = 2 * STAGES + 4 + EPI_WARPS;
     static constexpr int TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;  // + tmem ptr + 1024B alignment slack
     static_assert(TOTAL <= 227 * 1024, "shared memory budget exceeded");
 };
@@ -76,14 +97,13 @@ __device__ __forceinline__ uint32_t swz(int r, int j) { return static_cast<uint3
 
 template <int BN, int STAGES, bool GELU, bool OUT_F32, bool RES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const EpiParams p) {
+gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ EpiParams p) {
     using L = SmemLayout<BN, STAGES, RES>;
     constexpr uint32_t TMEM_COLS = BN <= 128 ? 256 : 512;  // two accumulator stages, power of two
     constexpr int ACC_STRIDE = BN <= 128 ? 128 : 256;
     constexpr int CH = OUT_F32 ? 32 : 64;                  // columns per epilogue chunk (128 bytes of output per row)
     constexpr int NCH = BN / CH;
-    static_assert(BN % CH == 0 && (!OUT_F32 || NCH % 2 == 0), "tile width must be a whole (fp32: even) number of chunks");
+    static_assert(BN % CH == 0, "tile width must be a whole number of chunks");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
@@ -92,21 +112,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
-    uint64_t* res_bar = tempty_bar + 2;                    // [EPI_WARPS][2]
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + 2 * EPI_WARPS);
+    uint64_t* res_bar = tempty_bar + 2;                    // [EPI_WARPS]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + EPI_WARPS);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int m_tiles = (p.M + BM - 1) / BM;
     const int n_tiles = (p.N + BN - 1) / BN;
-    const int total_tiles = m_tiles * n_tiles;
+    const int total_tiles = p.tile_start[p.groups];
     const int k_blocks = (p.K + BK - 1) / BK;
 
     if (warp == 0 && lane == 0) {
-        ptx::prefetch_tensormap(&tmA);
-        ptx::prefetch_tensormap(&tmB);
-        ptx::prefetch_tensormap(&tmC);
-        if (RES) ptx::prefetch_tensormap(&tmR);
+        for (int g = 0; g < p.groups; ++g) {
+            ptx::prefetch_tensormap(&maps.a[g]);
+            ptx::prefetch_tensormap(&maps.b[g]);
+            ptx::prefetch_tensormap(&maps.c[g]);
+            if (RES) ptx::prefetch_tensormap(&maps.r[g]);
+        }
         for (int i = 0; i < STAGES; ++i) {
             ptx::mbar_init(&full_bar[i], 1);
             ptx::mbar_init(&empty_bar[i], 1);
@@ -115,7 +136,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ptx::mbar_init(&tfull_bar[i], 1);
             ptx::mbar_init(&tempty_bar[i], EPI_WARPS);  // one arrival per epilogue warp
         }
-        for (int i = 0; i < 2 * EPI_WARPS; ++i) ptx::mbar_init(&res_bar[i], 1);
+        for (int i = 0; i < EPI_WARPS; ++i) ptx::mbar_init(&res_bar[i], 1);
         ptx::fence_mbar_init();
     }
     if (warp == 1) {
@@ -133,12 +154,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+                int g, m_blk, n_blk;
+                decode_tile(p, tile, n_tiles, g, m_blk, n_blk);
+                const CUtensorMap* tmA = &maps.a[g];
+                const CUtensorMap* tmB = &maps.b[g];
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     ptx::mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-                    ptx::tma_load_2d(sA + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
-                    ptx::tma_load_2d(sB + stage * L::B_STAGE_BYTES, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+                    ptx::tma_load_2d(sA + stage * A_STAGE_BYTES, tmA, &full_bar[stage], kb * BK, m_blk * BM);
+                    ptx::tma_load_2d(sB + stage * L::B_STAGE_BYTES, tmB, &full_bar[stage], kb * BK, n_blk * BN);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -173,43 +197,46 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue warps 2..5
+        // ------------------------------------------------------------------ epilogue warps 2..9
+        // Two warps share each TMEM lane quadrant (32 rows) and alternate over the tile's column chunks, so that every
+        // SM sub-partition has two epilogue warps to hide TMEM / shared-memory / MUFU latencies behind each other.
         const int quad = warp & 3;      // TMEM lanes [32*quad, 32*quad+32) are the ones this warp may read
-        const int ew = warp - 2;        // private staging buffers / residual barriers
-        uint8_t* my = smem + L::EPI_OFFSET + ew * L::EPI_BUFS_PER_WARP * CHUNK_BYTES;
-        // staging layout per warp: [out 0][out 1]([residual 0][residual 1] when RES)
-        uint64_t* rbar = res_bar + 2 * ew;
-        uint32_t rphase = 0;            // bit b = parity to wait for on rbar[b]
-        int oc = 0;                     // running output-chunk counter: selects the staging buffer across tiles
+        const int ew = warp - 2;        // private staging buffers / residual barrier
+        const int member = ew >> 2;     // 0 / 1: takes the chunks c == member (mod 2)
+        uint8_t* my = smem + L::EPI_OFFSET + ew * L::EPI_BUFS_PER_WARP * CHUNK_BYTES;   // [out]([residual] when RES)
+        uint8_t* odst = my;
+        uint8_t* rsrc = my + CHUNK_BYTES;
+        uint64_t* rbar = res_bar + ew;
+        uint32_t rphase = 0;
+        constexpr int RSUB = CH / 32;   // 32-column residual sub-chunks per output chunk
         int iter = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
-            const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+            int g, m_blk, n_blk;
+            decode_tile(p, tile, n_tiles, g, m_blk, n_blk);
+            const CUtensorMap* tmC = &maps.c[g];
+            const CUtensorMap* tmR = &maps.r[g];
+            const float* bias = p.bias[g];
+            const int Mg = p.M[g];
             const int acc = iter & 1;
             const uint32_t acc_phase = (iter >> 1) & 1;
             const int row0 = m_blk * BM + quad * 32;   // first row of this warp's slab
             const int col_base = n_blk * BN;
-            if (RES && lane == 0) {
-                // residual chunks 0 and 1 of this tile: issued before the accumulator is ready (overlaps the main loop)
-#pragma unroll
-                for (int b = 0; b < 2; ++b) {
-                    ptx::mbar_arrive_expect_tx(&rbar[b], CHUNK_BYTES);
-                    ptx::tma_load_2d(my + (2 + b) * CHUNK_BYTES, &tmR, &rbar[b], col_base + b * 32, row0);
-                }
+            if (RES && lane == 0 && member < NCH) {
+                // first residual sub-chunk of this tile: issued before the accumulator is ready (overlaps the main loop)
+                ptx::mbar_arrive_expect_tx(rbar, CHUNK_BYTES);
+                ptx::tma_load_2d(rsrc, tmR, rbar, col_base + member * CH, row0);
             }
             ptx::mbar_wait(&tfull_bar[acc], acc_phase);
             ptx::tc_fence_after();
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * ACC_STRIDE;
 #pragma unroll 1
-            for (int c = 0; c < NCH; ++c, ++oc) {
-                const int b = c & 1;        // residual buffer (fp32 output: NCH is even, so this alternates across tiles too)
-                const int ob = oc & 1;      // output staging buffer
+            for (int c = member; c < NCH; c += 2) {
                 const int col0 = col_base + c * CH;
-                uint8_t* odst = my + ob * CHUNK_BYTES;
-                // the TMA store that last read obuf[ob] (two chunks ago) must have finished reading shared memory
-                if (lane == 0) ptx::tma_store_wait_read<1>();
+                // the TMA store that last read this warp's staging buffer must have finished reading shared memory
+                if (lane == 0) ptx::tma_store_wait_read<0>();
                 __syncwarp();
 #pragma unroll
-                for (int half = 0; half < CH / 32; ++half) {
+                for (int half = 0; half < RSUB; ++half) {
                     uint32_t r[32];
                     ptx::tmem_ld_32x32b_x32(t_row + c * CH + half * 32, r);
                     ptx::tmem_ld_wait();
@@ -217,11 +244,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
                     const int cc = col0 + half * 32;
-                    if (p.bias != nullptr) {
+                    if (bias != nullptr) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
                             if (cc + j < p.N) {
-                                const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + cc + j));
+                                const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + cc + j));
                                 v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
                             }
                         }
@@ -231,15 +258,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
                     }
                     if (RES) {
-                        // OUT_F32: CH == 32, one residual chunk per output chunk.  (bf16 out + residual: two per chunk)
-                        const int rb = OUT_F32 ? b : half;
-                        ptx::mbar_wait(&rbar[rb], (rphase >> rb) & 1u);
-                        rphase ^= 1u << rb;
-                        const uint8_t* rsrc = my + (2 + rb) * CHUNK_BYTES;
+                        ptx::mbar_wait(rbar, rphase);
+                        rphase ^= 1;
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const float4 x = *reinterpret_cast<const float4*>(rsrc + swz(lane, j));
                             v[4 * j] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
+                        }
+                        __syncwarp();   // every lane has read the residual buffer: refill it with the next sub-chunk
+                        if (lane == 0) {
+                            int nc = c, nh = half + 1;
+                            if (nh == RSUB) { nh = 0; nc += 2; }
+                            if (nc < NCH) {
+                                ptx::mbar_arrive_expect_tx(rbar, CHUNK_BYTES);
+                                ptx::tma_load_2d(rsrc, tmR, rbar, col_base + nc * CH + nh * 32, row0);
+                            }
                         }
                     }
                     if (OUT_F32) {
@@ -259,33 +292,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                 }
-                if (c == NCH - 1) {
-                    // all tcgen05.ld of this tile are done: hand the accumulator back to the MMA warp
+                if (c + 2 >= NCH) {
+                    // this warp's tcgen05.ld of the tile are done: hand the accumulator back to the MMA warp
                     ptx::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
                 }
                 ptx::fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA (async proxy)
-                __syncwarp();               // ... of every lane; also: every lane is done reading rbuf
+                __syncwarp();
                 if (lane == 0) {
-                    if (col0 < p.N && row0 < p.M) ptx::tma_store_2d(&tmC, odst, col0, row0);  // edges clipped by TMA
+                    if (col0 < p.N && row0 < Mg) ptx::tma_store_2d(tmC, odst, col0, row0);  // edges clipped by TMA
                     ptx::tma_store_commit();
-                    if (RES) {
-                        // prefetch the residual chunk(s) that will land in the buffer(s) just consumed
-                        if (OUT_F32) {
-                            if (c + 2 < NCH) {
-                                ptx::mbar_arrive_expect_tx(&rbar[b], CHUNK_BYTES);
-                                ptx::tma_load_2d(my + (2 + b) * CHUNK_BYTES, &tmR, &rbar[b], col_base + (c + 2) * 32, row0);
-                            }
-                        } else if (c + 1 < NCH) {
-#pragma unroll
-                            for (int hb = 0; hb < 2; ++hb) {
-                                ptx::mbar_arrive_expect_tx(&rbar[hb], CHUNK_BYTES);
-                                ptx::tma_load_2d(my + (2 + hb) * CHUNK_BYTES, &tmR, &rbar[hb], col_base + (c + 1) * CH + hb * 32, row0);
-                            }
-                        }
-                    }
                 }
+            }
+            if (member >= NCH) {   // (only when a tile has a single chunk) nothing to read: release immediately
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
             }
         }
         if (lane == 0) ptx::tma_store_wait<0>();
@@ -418,7 +441,7 @@ int get_tensor_map(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int 
 }
 
 template <int BN, int STAGES, bool GELU, bool OUT_F32, bool RES>
-int launch_tc_variant(const GemmArgs& a, cudaStream_t s) {
+int launch_tc_variant(const GemmArgs* ga, int n, cudaStream_t s) {
     using L = SmemLayout<BN, STAGES, RES>;
     auto kern = gemm_tc_kernel<BN, STAGES, GELU, OUT_F32, RES>;
     static bool attr_set = false;
@@ -426,36 +449,55 @@ int launch_tc_variant(const GemmArgs& a, cudaStream_t s) {
         MRA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         attr_set = true;
     }
-    CUtensorMap tmA, tmB, tmC, tmR;
-    if (int e = get_tensor_map(a.A, a.M, a.K, a.lda, BM, BK, 2, &tmA)) return e;
-    if (int e = get_tensor_map(a.W, a.N, a.K, a.ldw, BN, BK, 2, &tmB)) return e;
-    if (int e = get_tensor_map(a.C, a.M, a.N, a.ldc, 32, OUT_F32 ? 32 : 64, OUT_F32 ? 4 : 2, &tmC)) return e;
-    if (RES) {
-        if (int e = get_tensor_map(a.residual, a.M, a.N, a.ldr, 32, 32, 4, &tmR)) return e;
-    } else {
-        tmR = tmC;
+    GroupMaps maps;
+    EpiParams p;
+    p.groups = n;
+    p.N = ga[0].N;
+    p.K = ga[0].K;
+    const int n_tiles = (p.N + BN - 1) / BN;
+    int total = 0;
+    for (int g = 0; g < MAX_GROUPS; ++g) {
+        const GemmArgs& a = ga[g < n ? g : 0];
+        if (g < n) {
+            if (int e = get_tensor_map(a.A, a.M, a.K, a.lda, BM, BK, 2, &maps.a[g])) return e;
+            if (int e = get_tensor_map(a.W, a.N, a.K, a.ldw, BN, BK, 2, &maps.b[g])) return e;
+            if (int e = get_tensor_map(a.C, a.M, a.N, a.ldc, 32, OUT_F32 ? 32 : 64, OUT_F32 ? 4 : 2, &maps.c[g])) return e;
+            if (RES) {
+                if (int e = get_tensor_map(a.residual, a.M, a.N, a.ldr, 32, 32, 4, &maps.r[g])) return e;
+            } else {
+                maps.r[g] = maps.c[g];
+            }
+            p.bias[g] = a.bias;
+            p.M[g] = a.M;
+            p.tile_start[g] = total;
+            total += ((a.M + BM - 1) / BM) * n_tiles;
+        } else {
+            maps.a[g] = maps.a[0]; maps.b[g] = maps.b[0]; maps.c[g] = maps.c[0]; maps.r[g] = maps.r[0];
+            p.bias[g] = nullptr;
+            p.M[g] = 0;
+            p.tile_start[g] = total;
+        }
     }
-    EpiParams p{a.bias, a.M, a.N, a.K};
-    const int m_tiles = (a.M + BM - 1) / BM, n_tiles = (a.N + BN - 1) / BN;
-    const int total = m_tiles * n_tiles;
+    p.tile_start[MAX_GROUPS] = total;
+    for (int g = n; g <= MAX_GROUPS; ++g) p.tile_start[g] = total;
     const int grid = total < sm_count() ? total : sm_count();
-    kern<<<grid, NUM_THREADS, L::TOTAL, s>>>(tmA, tmB, tmC, tmR, p);
+    kern<<<grid, NUM_THREADS, L::TOTAL, s>>>(maps, p);
     MRA_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
 template <int BN, int ST_PLAIN, int ST_RES>
-int dispatch_epi(const GemmArgs& a, cudaStream_t s) {
-    const int code = (a.gelu ? 4 : 0) | (a.out_fp32 ? 2 : 0) | (a.residual ? 1 : 0);
+int dispatch_epi(const GemmArgs* a, int n, cudaStream_t s) {
+    const int code = (a[0].gelu ? 4 : 0) | (a[0].out_fp32 ? 2 : 0) | (a[0].residual ? 1 : 0);
     switch (code) {
-        case 0: return launch_tc_variant<BN, ST_PLAIN, false, false, false>(a, s);
-        case 1: return launch_tc_variant<BN, ST_RES, false, false, true>(a, s);
-        case 2: return launch_tc_variant<BN, ST_PLAIN, false, true, false>(a, s);
-        case 3: return launch_tc_variant<BN, ST_RES, false, true, true>(a, s);
-        case 4: return launch_tc_variant<BN, ST_PLAIN, true, false, false>(a, s);
-        case 5: return launch_tc_variant<BN, ST_RES, true, false, true>(a, s);
-        case 6: return launch_tc_variant<BN, ST_PLAIN, true, true, false>(a, s);
-        default: return launch_tc_variant<BN, ST_RES, true, true, true>(a, s);
+        case 0: return launch_tc_variant<BN, ST_PLAIN, false, false, false>(a, n, s);
+        case 1: return launch_tc_variant<BN, ST_RES, false, false, true>(a, n, s);
+        case 2: return launch_tc_variant<BN, ST_PLAIN, false, true, false>(a, n, s);
+        case 3: return launch_tc_variant<BN, ST_RES, false, true, true>(a, n, s);
+        case 4: return launch_tc_variant<BN, ST_PLAIN, true, false, false>(a, n, s);
+        case 5: return launch_tc_variant<BN, ST_RES, true, false, true>(a, n, s);
+        case 6: return launch_tc_variant<BN, ST_PLAIN, true, true, false>(a, n, s);
+        default: return launch_tc_variant<BN, ST_RES, true, true, true>(a, n, s);
     }
 }
 
@@ -479,12 +521,19 @@ int check_args(const GemmArgs& a) {
 static int g_forced_bn = [] { const char* e = getenv("MRA_GEMM_BN"); return e ? atoi(e) : 0; }();
 void set_gemm_tile_override(int bn) { g_forced_bn = bn; }
 
-int launch_gemm_tc(const GemmArgs& a, cudaStream_t s) {
-    if (int e = check_args(a)) return e;
+int launch_gemm_tc_grouped(const GemmArgs* a, int n, cudaStream_t s) {
+    MRA_REQUIRE(n >= 1 && n <= MAX_GROUPS, "grouped GEMM takes 1..%d problems, got %d", MAX_GROUPS, n);
+    for (int g = 0; g < n; ++g) {
+        if (int e = check_args(a[g])) return e;
+        MRA_REQUIRE(a[g].N == a[0].N && a[g].K == a[0].K && a[g].gelu == a[0].gelu && a[g].out_fp32 == a[0].out_fp32 &&
+                        (a[g].residual != nullptr) == (a[0].residual != nullptr),
+                    "grouped GEMM problems must share N, K and the epilogue kind");
+    }
     // Tile-width choice by a wave-quantisation estimate: cost = waves x (tile width) x (a factor for how well that
     // width feeds the tensor pipe: 128-wide tiles are shared-memory-bandwidth bound).  MRA_GEMM_BN overrides (tuning).
     const int sms = sm_count();
-    const long m_tiles = (a.M + BM - 1) / BM;
+    long m_tiles = 0;
+    for (int g = 0; g < n; ++g) m_tiles += (a[g].M + BM - 1) / BM;
     const int forced = g_forced_bn;
     int best_bn = 128;
     double best = 1e30;
@@ -493,14 +542,16 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t s) {
     for (int i = 0; i < 3; ++i) {
         const int bn = cand[i];
         if (forced ? bn != forced : false) continue;
-        const long tiles = m_tiles * ((a.N + bn - 1) / bn);
+        const long tiles = m_tiles * ((a[0].N + bn - 1) / bn);
         const double cost = double((tiles + sms - 1) / sms) * bn * factor[i];
         if (cost < best) { best = cost; best_bn = bn; }
     }
-    if (best_bn == 256) return dispatch_epi<256, 4, 3>(a, s);
-    if (best_bn == 192) return dispatch_epi<192, 4, 4>(a, s);
-    return dispatch_epi<128, 6, 5>(a, s);
+    if (best_bn == 256) return dispatch_epi<256, 4, 3>(a, n, s);
+    if (best_bn == 192) return dispatch_epi<192, 4, 4>(a, n, s);
+    return dispatch_epi<128, 6, 5>(a, n, s);
 }
+
+int launch_gemm_tc(const GemmArgs& a, cudaStream_t s) { return launch_gemm_tc_grouped(&a, 1, s); }
 
 int launch_gemm_simt(const GemmArgs& a, cudaStream_t s) {
     if (int e = check_args(a)) return e;

@@ -242,64 +242,119 @@ extern "C" int mra_qformer_profile_read(mra_qformer_t* h, double* ms_by_cat, int
 
 extern "C" int mra_qformer_last_launch_count(const mra_qformer_t* h) { return h ? h->last_launches : 0; }
 
-extern "C" int mra_qformer_forward(mra_qformer_t* h, const mra_qformer_io* io, void* workspace, size_t workspace_bytes,
-                                   void* stream_) {
-    MRA_REQUIRE(h && io && workspace, "mra_qformer_forward: NULL argument");
-    MRA_REQUIRE(h->has_weights, "mra_qformer_forward: weights not set");
-    if (int e = device_check()) return e;
-    const auto& c = h->cfg;
-    const auto& W = h->w;
-    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
-    const int rows = io->rows, T = io->T, Nk = io->Nk, Nq = c.num_query, H = c.hidden, I = c.inter;
-    MRA_REQUIRE(rows > 0 && Nk > 0 && T >= 0, "bad shape rows=%d T=%d Nk=%d", rows, T, Nk);
-    MRA_REQUIRE(T <= c.max_pos, "T=%d exceeds max_position_embeddings=%d", T, c.max_pos);
-    MRA_REQUIRE(io->enc && io->query_embeds, "enc / query_embeds must not be NULL");
-    MRA_REQUIRE(io->q_rows == 1 || io->q_rows == rows, "query_embeds rows must be 1 or %d, got %d", rows, io->q_rows);
-    MRA_REQUIRE(T == 0 || (io->input_ids && W.word_emb && W.pos_emb), "text tokens need input_ids and embedding tables");
-    MRA_REQUIRE(T == 0 || W.layer[0].w_ft1, "text tokens need the text FFN weights");
-    MRA_REQUIRE(!io->llm_out || (W.w_proj && W.b_proj && c.llm_dim > 0), "llm_out requested but no projection weights");
-    const bool save = (io->flags & MRA_FWD_SAVE_FOR_BACKWARD) != 0;
-    Workspace ws = carve(h, rows, T, Nk, io->flags, workspace);
-    MRA_REQUIRE(workspace_bytes >= ws.total, "workspace too small: %zu < %zu bytes", workspace_bytes, ws.total);
-    MRA_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
+// Forward of up to two Q-Formers in lockstep (e.g. the video and the audio Q-Former of one batch): every Linear of a layer
+// is ONE grouped GEMM launch over all contexts -- and FFN_query / FFN_text are further problems of the same launch -- so
+// the persistent GEMM grid sees 2-4x the tiles (smaller wave-quantisation tails) at half the launch count.  The
+// contexts must agree on the layer geometry (hidden, heads, layers, intermediate, queries, cross frequency, llm_dim);
+// encoder width, rows, T and Nk may differ.
+namespace {
 
-    const int S = Nq + T;
-    const int Mq = rows * Nq, Mt = rows * T, Mtot = Mq + Mt;
-    const int kv_ld = h->n_cross * 2 * H;
+constexpr int MAX_CTX = 2;
+
+struct Ctx {
+    mra_qformer* h;
+    const mra_qformer_io* io;
+    Workspace ws;
+    int rows, T, Nk, S, Mq, Mt, Mtot, kv_ld;
+    bool save;
+    const float* self_mask;
+    const float* enc_mask;
+};
+
+int forward_multi(int n, mra_qformer_t* const* hs, const mra_qformer_io* const* ios, void* const* workspaces,
+                  const size_t* workspace_bytes, cudaStream_t s) {
+    MRA_REQUIRE(n >= 1 && n <= MAX_CTX, "forward takes 1..%d Q-Formers per call, got %d", MAX_CTX, n);
+    if (int e = device_check()) return e;
+    Ctx cx[MAX_CTX];
+    mra_qformer* h0 = hs[0];
+    const auto& c = h0->cfg;
+    const int Nq = c.num_query, H = c.hidden, I = c.inter;
+    for (int i = 0; i < n; ++i) {
+        mra_qformer* h = hs[i];
+        const mra_qformer_io* io = ios[i];
+        MRA_REQUIRE(h && io && workspaces[i], "mra_qformer_forward: NULL argument");
+        MRA_REQUIRE(h->has_weights, "mra_qformer_forward: weights not set");
+        const auto& ci = h->cfg;
+        MRA_REQUIRE(ci.hidden == c.hidden && ci.layers == c.layers && ci.heads == c.heads && ci.inter == c.inter &&
+                        ci.cross_freq == c.cross_freq && ci.num_query == c.num_query && ci.llm_dim == c.llm_dim &&
+                        ci.ln_eps == c.ln_eps,
+                    "Q-Formers run in lockstep must share the layer geometry");
+        const auto& W = h->w;
+        const int rows = io->rows, T = io->T, Nk = io->Nk;
+        MRA_REQUIRE(rows > 0 && Nk > 0 && T >= 0, "bad shape rows=%d T=%d Nk=%d", rows, T, Nk);
+        MRA_REQUIRE(T <= ci.max_pos, "T=%d exceeds max_position_embeddings=%d", T, ci.max_pos);
+        MRA_REQUIRE(io->enc && io->query_embeds, "enc / query_embeds must not be NULL");
+        MRA_REQUIRE(io->q_rows == 1 || io->q_rows == rows, "query_embeds rows must be 1 or %d, got %d", rows, io->q_rows);
+        MRA_REQUIRE(T == 0 || (io->input_ids && W.word_emb && W.pos_emb), "text tokens need input_ids and embedding tables");
+        MRA_REQUIRE(T == 0 || W.layer[0].w_ft1, "text tokens need the text FFN weights");
+        MRA_REQUIRE(!io->llm_out || (W.w_proj && W.b_proj && ci.llm_dim > 0), "llm_out requested but no projection weights");
+        MRA_REQUIRE((io->flags & MRA_FWD_SAVE_FOR_BACKWARD) == (ios[0]->flags & MRA_FWD_SAVE_FOR_BACKWARD) &&
+                        (io->llm_out != nullptr) == (ios[0]->llm_out != nullptr),
+                    "Q-Formers run in lockstep must agree on SAVE_FOR_BACKWARD and on llm_out");
+        Ctx& x = cx[i];
+        x.h = h; x.io = io;
+        x.save = (io->flags & MRA_FWD_SAVE_FOR_BACKWARD) != 0;
+        x.ws = carve(h, rows, T, Nk, io->flags, workspaces[i]);
+        MRA_REQUIRE(workspace_bytes[i] >= x.ws.total, "workspace too small: %zu < %zu bytes", workspace_bytes[i], x.ws.total);
+        MRA_REQUIRE((reinterpret_cast<uintptr_t>(workspaces[i]) & 255) == 0, "workspace must be 256-byte aligned");
+        x.rows = rows; x.T = T; x.Nk = Nk; x.S = Nq + T;
+        x.Mq = rows * Nq; x.Mt = rows * T; x.Mtot = x.Mq + x.Mt;
+        x.kv_ld = h->n_cross * 2 * H;
+        x.self_mask = x.enc_mask = nullptr;
+    }
+    const bool save = cx[0].save;
     int launches = 0;
-    // profiling spans: MRA_PROFILE_DOMINANT brackets only GEMM launches, MRA_PROFILE_ALL every launch
+    // profiling spans (recorded on the first handle): MRA_PROFILE_DOMINANT brackets only GEMM launches, _ALL every launch
     int cur_cat = -1;
     cudaEvent_t cur_ev = nullptr;
     auto span_begin = [&](int cat) {
         cur_cat = -1;
-        if (h->profile_mode == MRA_PROFILE_OFF) return;
-        if (h->profile_mode == MRA_PROFILE_DOMINANT && cat > MRA_CAT_GEMM) return;
+        if (h0->profile_mode == MRA_PROFILE_OFF) return;
+        if (h0->profile_mode == MRA_PROFILE_DOMINANT && cat > MRA_CAT_GEMM) return;
         cur_cat = cat;
-        cur_ev = h->get_event();
+        cur_ev = h0->get_event();
         cudaEventRecord(cur_ev, s);
     };
     auto span_end = [&]() {
         if (cur_cat < 0) return;
-        cudaEvent_t b = h->get_event();
+        cudaEvent_t b = h0->get_event();
         cudaEventRecord(b, s);
-        h->spans.push_back({cur_cat, cur_ev, b});
+        h0->spans.push_back({cur_cat, cur_ev, b});
         cur_cat = -1;
     };
-    int gemm_cat = MRA_CAT_GEMM;
-    auto gemm = [&](const void* A, int64_t lda, const void* Wt, int64_t ldw, const float* bias, const float* res,
-                    int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int gelu, int f32) -> int {
-        GemmArgs a{A, lda, Wt, ldw, bias, res, ldr, C, ldc, M, N, K, gelu, f32};
-        ++launches;
-        span_begin(gemm_cat);
-        int e = h->gemm_impl == MRA_GEMM_IMPL_SIMT_DEBUG ? launch_gemm_simt(a, s) : launch_gemm_tc(a, s);
+    // grouped GEMM launch over the problems queued with add()
+    GemmArgs ga[4];
+    int ng = 0;
+    auto add = [&](const void* A, int64_t lda, const void* Wt, int64_t ldw, const float* bias, const float* res, int64_t ldr,
+                   void* C, int64_t ldc, int M, int N, int K, int gelu, int f32) {
+        if (M > 0) ga[ng++] = GemmArgs{A, lda, Wt, ldw, bias, res, ldr, C, ldc, M, N, K, gelu, f32};
+    };
+    auto flush = [&](int cat) -> int {
+        if (ng == 0) return 0;
+        int e = 0;
+        span_begin(cat);
+        if (h0->gemm_impl == MRA_GEMM_IMPL_SIMT_DEBUG) {
+            for (int g = 0; g < ng && e == 0; ++g) { e = launch_gemm_simt(ga[g], s); ++launches; }
+        } else {
+            e = launch_gemm_tc_grouped(ga, ng, s);
+            ++launches;
+        }
         span_end();
+        ng = 0;
         return e;
     };
-    auto layernorm = [&](const float* pre, const float* g, const float* b, float* y32, void* y16, int M) -> int {
+    LnSegment ls[4];
+    int nl = 0;
+    auto add_ln = [&](const float* pre, const float* g, const float* b, float* y32, void* y16, int M) {
+        if (M > 0) ls[nl++] = LnSegment{pre, g, b, y32, y16, M};
+    };
+    auto flush_ln = [&]() -> int {
+        if (nl == 0) return 0;
         span_begin(MRA_CAT_LAYERNORM);
-        int e = launch_layernorm(pre, g, b, y32, y16, M, H, c.ln_eps, s);
+        int e = launch_layernorm_grouped(ls, nl, H, c.ln_eps, s);
         span_end();
         ++launches;
+        nl = 0;
         return e;
     };
 #define MRA_TRY(expr)            \
@@ -307,109 +362,171 @@ extern "C" int mra_qformer_forward(mra_qformer_t* h, const mra_qformer_io* io, v
         if (int _e = (expr)) return _e; \
     } while (0)
 
-    // ---- embeddings + masks
-    span_begin(MRA_CAT_OTHER);
-    MRA_TRY(launch_embed_layernorm(io->query_embeds, io->q_rows, io->input_ids, W.word_emb, W.pos_emb, W.ln_e_g, W.ln_e_b,
-                                   ws.x32, ws.layer[0].xb, ws.pre_e, rows, Nq, T, H, c.vocab, c.ln_eps, s));
-    span_end();
-    ++launches;
-    const float* self_mask = nullptr;
-    if (io->attn_mask) {
-        MRA_TRY(launch_build_enc_mask(io->attn_mask, ws.self_mask, rows, Nq + T, s));
+    // ---- embeddings + masks + cross-attention keys / values of ALL cross layers (one GEMM per context: the encoder
+    //      tokens are read once; the contexts differ in K = encoder width, so these are separate launches)
+    for (int i = 0; i < n; ++i) {
+        Ctx& x = cx[i];
+        const auto& W = x.h->w;
+        span_begin(MRA_CAT_OTHER);
+        MRA_TRY(launch_embed_layernorm(x.io->query_embeds, x.io->q_rows, x.io->input_ids, W.word_emb, W.pos_emb, W.ln_e_g,
+                                       W.ln_e_b, x.ws.x32, x.ws.layer[0].xb, x.ws.pre_e, x.rows, Nq, x.T, H, x.h->cfg.vocab,
+                                       c.ln_eps, s));
+        span_end();
         ++launches;
-        self_mask = ws.self_mask;
-    }
-    const float* enc_mask = nullptr;
-    if (io->enc_mask) {
-        MRA_TRY(launch_build_enc_mask(io->enc_mask, ws.enc_mask, rows, Nk, s));
-        ++launches;
-        enc_mask = ws.enc_mask;
-    }
-    // ---- cross-attention keys / values of ALL cross layers in one GEMM: the encoder tokens are read once
-    gemm_cat = MRA_CAT_GEMM_CROSS_KV;
-    MRA_TRY(gemm(io->enc, c.enc_width, W.w_ckv, c.enc_width, W.b_ckv, nullptr, 0, ws.kv, kv_ld, rows * Nk, kv_ld,
-                 c.enc_width, 0, 0));
-    gemm_cat = MRA_CAT_GEMM;
-
-    // FFN over the row range [r0, r0 + n): y = LN(x + W2 gelu(W1 x)), x = a32 / in16, output -> x32 / out16
-    auto ffn = [&](const LayerBufs& B, const __nv_bfloat16* in16, __nv_bfloat16* out16, size_t r0, int n, const void* w1,
-                   const float* b1, const void* w2, const float* b2, const float* g, const float* be) -> int {
-        const size_t o = r0 * H, oi = r0 * I;
-        if (save) {
-            MRA_TRY(gemm(in16 + o, H, w1, H, b1, nullptr, 0, B.z + oi, I, n, I, H, 0, 0));
-            span_begin(MRA_CAT_OTHER);
-            MRA_TRY(launch_gelu_fwd(B.z + oi, B.inter + oi, static_cast<int64_t>(n) * I, s));
-            span_end();
+        if (x.io->attn_mask) {
+            MRA_TRY(launch_build_enc_mask(x.io->attn_mask, x.ws.self_mask, x.rows, x.S, s));
             ++launches;
-        } else {
-            MRA_TRY(gemm(in16 + o, H, w1, H, b1, nullptr, 0, B.inter + oi, I, n, I, H, 1, 0));
+            x.self_mask = x.ws.self_mask;
         }
-        MRA_TRY(gemm(B.inter + oi, I, w2, I, b2, ws.a32 + o, H, B.pre_f + o, H, n, H, I, 0, 1));
-        return layernorm(B.pre_f + o, g, be, ws.x32 + o, out16 + o, n);
-    };
+        if (x.io->enc_mask) {
+            MRA_TRY(launch_build_enc_mask(x.io->enc_mask, x.ws.enc_mask, x.rows, x.Nk, s));
+            ++launches;
+            x.enc_mask = x.ws.enc_mask;
+        }
+        const int Wd = x.h->cfg.enc_width;
+        add(x.io->enc, Wd, W.w_ckv, Wd, W.b_ckv, nullptr, 0, x.ws.kv, x.kv_ld, x.rows * x.Nk, x.kv_ld, Wd, 0, 0);
+        MRA_TRY(flush(MRA_CAT_GEMM_CROSS_KV));
+    }
 
     for (int l = 0; l < c.layers; ++l) {
-        const auto& L = W.layer[l];
-        const LayerBufs& B = ws.layer[l];
-        __nv_bfloat16* xb_next = ws.layer[l + 1].xb;
         const bool last = l == c.layers - 1;
-        // self-attention over queries || text
-        MRA_TRY(gemm(B.xb, H, L.w_qkv, H, L.b_qkv, nullptr, 0, B.qkv, 3 * H, Mtot, 3 * H, H, 0, 0));
-        {
-            AttnArgs a{B.qkv, 3 * H, B.qkv + H, 3 * H, B.qkv + 2 * H, 3 * H, B.ctx, H, self_mask, rows, c.heads, S, S, Nq, 0};
+        const bool cross = h0->cross_slot[l] >= 0;
+        // ---- self-attention over queries || text
+        for (int i = 0; i < n; ++i) {
+            const auto& L = cx[i].h->w.layer[l];
+            const LayerBufs& B = cx[i].ws.layer[l];
+            add(B.xb, H, L.w_qkv, H, L.b_qkv, nullptr, 0, B.qkv, 3 * H, cx[i].Mtot, 3 * H, H, 0, 0);
+        }
+        MRA_TRY(flush(MRA_CAT_GEMM));
+        for (int i = 0; i < n; ++i) {
+            const LayerBufs& B = cx[i].ws.layer[l];
+            AttnArgs a{B.qkv, 3 * H, B.qkv + H, 3 * H, B.qkv + 2 * H, 3 * H, B.ctx, H, cx[i].self_mask, cx[i].rows, c.heads,
+                       cx[i].S, cx[i].S, Nq, 0};
             span_begin(MRA_CAT_ATTENTION);
             MRA_TRY(launch_attention(a, s));
             span_end();
             ++launches;
         }
-        MRA_TRY(gemm(B.ctx, H, L.w_ao, H, L.b_ao, ws.x32, H, B.pre_a, H, Mtot, H, H, 0, 1));
-        MRA_TRY(layernorm(B.pre_a, L.ln_a_g, L.ln_a_b, ws.a32, B.ab, Mtot));
-        // cross-attention of the query tokens onto this row's encoder tokens
-        const __nv_bfloat16* fq_in = B.ab;
-        if (h->cross_slot[l] >= 0) {
-            const __nv_bfloat16* kbase = ws.kv + static_cast<size_t>(h->cross_slot[l]) * 2 * H;
-            MRA_TRY(gemm(B.ab, H, L.w_cq, H, L.b_cq, nullptr, 0, B.cq, H, Mq, H, H, 0, 0));
-            AttnArgs a{B.cq, H, kbase, kv_ld, kbase + H, kv_ld, B.cctx, H, enc_mask, rows, c.heads, Nq, Nk, Nq, 1};
-            span_begin(MRA_CAT_ATTENTION);
-            MRA_TRY(launch_attention(a, s));
-            span_end();
-            ++launches;
-            MRA_TRY(gemm(B.cctx, H, L.w_co, H, L.b_co, ws.a32, H, B.pre_c, H, Mq, H, H, 0, 1));
-            MRA_TRY(layernorm(B.pre_c, L.ln_c_g, L.ln_c_b, ws.a32, B.ab2, Mq));
-            fq_in = B.ab2;
+        for (int i = 0; i < n; ++i) {
+            const auto& L = cx[i].h->w.layer[l];
+            const LayerBufs& B = cx[i].ws.layer[l];
+            add(B.ctx, H, L.w_ao, H, L.b_ao, cx[i].ws.x32, H, B.pre_a, H, cx[i].Mtot, H, H, 0, 1);
+            add_ln(B.pre_a, L.ln_a_g, L.ln_a_b, cx[i].ws.a32, B.ab, cx[i].Mtot);
         }
-        // FFN_query on the query rows
-        MRA_TRY(ffn(B, fq_in, xb_next, 0, Mq, L.w_fq1, L.b_fq1, L.w_fq2, L.b_fq2, L.ln_fq_g, L.ln_fq_b));
-        // FFN_text on the text rows
-        if (T > 0) {
-            const size_t o = static_cast<size_t>(Mq) * H;
-            if (last && (io->flags & MRA_FWD_SKIP_DEAD_TEXT_FFN)) {
-                // never read by llm_proj; keep last_hidden well-defined by passing the attention output through
-                if (io->last_hidden) {
-                    MRA_CHECK_CUDA(cudaMemcpyAsync(ws.x32 + o, ws.a32 + o, static_cast<size_t>(Mt) * H * 4,
-                                                   cudaMemcpyDeviceToDevice, s));
-                    ++launches;
-                }
-            } else {
+        MRA_TRY(flush(MRA_CAT_GEMM));
+        MRA_TRY(flush_ln());
+        // ---- cross-attention of the query tokens onto this row's encoder tokens
+        if (cross) {
+            for (int i = 0; i < n; ++i) {
+                const auto& L = cx[i].h->w.layer[l];
+                const LayerBufs& B = cx[i].ws.layer[l];
+                add(B.ab, H, L.w_cq, H, L.b_cq, nullptr, 0, B.cq, H, cx[i].Mq, H, H, 0, 0);
+            }
+            MRA_TRY(flush(MRA_CAT_GEMM));
+            for (int i = 0; i < n; ++i) {
+                const LayerBufs& B = cx[i].ws.layer[l];
+                const __nv_bfloat16* kbase = cx[i].ws.kv + static_cast<size_t>(cx[i].h->cross_slot[l]) * 2 * H;
+                AttnArgs a{B.cq, H, kbase, cx[i].kv_ld, kbase + H, cx[i].kv_ld, B.cctx, H, cx[i].enc_mask, cx[i].rows, c.heads,
+                           Nq, cx[i].Nk, Nq, 1};
+                span_begin(MRA_CAT_ATTENTION);
+                MRA_TRY(launch_attention(a, s));
+                span_end();
+                ++launches;
+            }
+            for (int i = 0; i < n; ++i) {
+                const auto& L = cx[i].h->w.layer[l];
+                const LayerBufs& B = cx[i].ws.layer[l];
+                add(B.cctx, H, L.w_co, H, L.b_co, cx[i].ws.a32, H, B.pre_c, H, cx[i].Mq, H, H, 0, 1);
+                add_ln(B.pre_c, L.ln_c_g, L.ln_c_b, cx[i].ws.a32, B.ab2, cx[i].Mq);
+            }
+            MRA_TRY(flush(MRA_CAT_GEMM));
+            MRA_TRY(flush_ln());
+        }
+        // ---- FFN_query (rows < Mq) and FFN_text (the rest) of every context: ONE grouped launch per Linear
+        bool text_on[MAX_CTX];
+        for (int i = 0; i < n; ++i) {
+            text_on[i] = cx[i].Mt > 0 && !(last && (cx[i].io->flags & MRA_FWD_SKIP_DEAD_TEXT_FFN));
+            if (text_on[i]) {
+                const auto& L = cx[i].h->w.layer[l];
                 MRA_REQUIRE(L.w_ft1 && L.b_ft1 && L.w_ft2 && L.b_ft2 && L.ln_ft_g && L.ln_ft_b, "layer %d: text FFN weights missing", l);
-                MRA_TRY(ffn(B, B.ab, xb_next, Mq, Mt, L.w_ft1, L.b_ft1, L.w_ft2, L.b_ft2, L.ln_ft_g, L.ln_ft_b));
+            }
+        }
+        for (int i = 0; i < n; ++i) {
+            const auto& L = cx[i].h->w.layer[l];
+            const LayerBufs& B = cx[i].ws.layer[l];
+            const __nv_bfloat16* fq_in = cross ? B.ab2 : B.ab;
+            __nv_bfloat16* h1 = save ? B.z : B.inter;
+            const size_t o = static_cast<size_t>(cx[i].Mq) * H, oi = static_cast<size_t>(cx[i].Mq) * I;
+            add(fq_in, H, L.w_fq1, H, L.b_fq1, nullptr, 0, h1, I, cx[i].Mq, I, H, save ? 0 : 1, 0);
+            if (text_on[i]) add(B.ab + o, H, L.w_ft1, H, L.b_ft1, nullptr, 0, h1 + oi, I, cx[i].Mt, I, H, save ? 0 : 1, 0);
+        }
+        MRA_TRY(flush(MRA_CAT_GEMM));
+        if (save) {
+            for (int i = 0; i < n; ++i) {
+                const LayerBufs& B = cx[i].ws.layer[l];
+                const int nrow = cx[i].Mq + (text_on[i] ? cx[i].Mt : 0);
+                span_begin(MRA_CAT_OTHER);
+                MRA_TRY(launch_gelu_fwd(B.z, B.inter, static_cast<int64_t>(nrow) * I, s));
+                span_end();
+                ++launches;
+            }
+        }
+        for (int i = 0; i < n; ++i) {
+            const auto& L = cx[i].h->w.layer[l];
+            const LayerBufs& B = cx[i].ws.layer[l];
+            __nv_bfloat16* xb_next = cx[i].ws.layer[l + 1].xb;
+            const size_t o = static_cast<size_t>(cx[i].Mq) * H, oi = static_cast<size_t>(cx[i].Mq) * I;
+            add(B.inter, I, L.w_fq2, I, L.b_fq2, cx[i].ws.a32, H, B.pre_f, H, cx[i].Mq, H, I, 0, 1);
+            add_ln(B.pre_f, L.ln_fq_g, L.ln_fq_b, cx[i].ws.x32, xb_next, cx[i].Mq);
+            if (text_on[i]) {
+                add(B.inter + oi, I, L.w_ft2, I, L.b_ft2, cx[i].ws.a32 + o, H, B.pre_f + o, H, cx[i].Mt, H, I, 0, 1);
+                add_ln(B.pre_f + o, L.ln_ft_g, L.ln_ft_b, cx[i].ws.x32 + o, xb_next + o, cx[i].Mt);
+            }
+        }
+        MRA_TRY(flush(MRA_CAT_GEMM));
+        MRA_TRY(flush_ln());
+        for (int i = 0; i < n; ++i) {
+            if (cx[i].Mt > 0 && !text_on[i] && cx[i].io->last_hidden) {
+                // dead last-layer text FFN: keep last_hidden well-defined by passing the attention output through
+                const size_t o = static_cast<size_t>(cx[i].Mq) * H;
+                MRA_CHECK_CUDA(cudaMemcpyAsync(cx[i].ws.x32 + o, cx[i].ws.a32 + o, static_cast<size_t>(cx[i].Mt) * H * 4,
+                                               cudaMemcpyDeviceToDevice, s));
+                ++launches;
             }
         }
     }
-    const __nv_bfloat16* xb_final = ws.layer[c.layers].xb;
     // ---- outputs
-    if (io->last_hidden) {
-        span_begin(MRA_CAT_OTHER);
-        MRA_TRY(launch_gather_last_hidden(ws.x32, io->last_hidden, rows, Nq, T, H, s));
-        span_end();
-        ++launches;
+    for (int i = 0; i < n; ++i) {
+        if (cx[i].io->last_hidden) {
+            span_begin(MRA_CAT_OTHER);
+            MRA_TRY(launch_gather_last_hidden(cx[i].ws.x32, cx[i].io->last_hidden, cx[i].rows, Nq, cx[i].T, H, s));
+            span_end();
+            ++launches;
+        }
+        if (cx[i].io->llm_out) {
+            const auto& W = cx[i].h->w;
+            add(cx[i].ws.layer[c.layers].xb, H, W.w_proj, H, W.b_proj, nullptr, 0, cx[i].io->llm_out, c.llm_dim, cx[i].Mq,
+                c.llm_dim, H, 0, 0);
+        }
     }
-    if (io->llm_out) {
-        MRA_TRY(gemm(xb_final, H, W.w_proj, H, W.b_proj, nullptr, 0, io->llm_out, c.llm_dim, Mq, c.llm_dim, H, 0, 0));
-    }
+    MRA_TRY(flush(MRA_CAT_GEMM));
 #undef MRA_TRY
-    h->last_launches = launches;
+    for (int i = 0; i < n; ++i) hs[i]->last_launches = i == 0 ? launches : 0;
     return 0;
+}
+
+}  // namespace
+
+extern "C" int mra_qformer_forward(mra_qformer_t* h, const mra_qformer_io* io, void* workspace, size_t workspace_bytes,
+                                   void* stream_) {
+    MRA_REQUIRE(h && io && workspace, "mra_qformer_forward: NULL argument");
+    return forward_multi(1, &h, &io, &workspace, &workspace_bytes, reinterpret_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int mra_qformer_forward_multi(int32_t n, mra_qformer_t* const* hs, const mra_qformer_io* const* ios,
+                                         void* const* workspaces, const size_t* workspace_bytes, void* stream_) {
+    MRA_REQUIRE(hs && ios && workspaces && workspace_bytes, "mra_qformer_forward_multi: NULL argument");
+    return forward_multi(n, hs, ios, workspaces, workspace_bytes, reinterpret_cast<cudaStream_t>(stream_));
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

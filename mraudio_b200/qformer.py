@@ -272,9 +272,12 @@ class BertModelB200(nn.Module):
         return W
 
     # ------------------------------------------------------------------------------------------------------- forward
-    def forward(self, input_ids=None, attention_mask=None, position_ids=None, query_embeds=None,
-                encoder_hidden_states=None, encoder_attention_mask=None, return_dict=True, llm_proj: nn.Linear = None,
-                need_last_hidden: bool = True, skip_dead_text_ffn: bool = False, **unused):
+    def prepare(self, input_ids=None, attention_mask=None, position_ids=None, query_embeds=None, encoder_hidden_states=None,
+                encoder_attention_mask=None, llm_proj: nn.Linear = None, need_last_hidden: bool = True,
+                skip_dead_text_ffn: bool = False):
+        """Validate the arguments of one ``Qformer.bert(...)`` call and stage everything the C-ABI needs (handle, packed
+        weights, io struct, workspace, output tensors) without launching.  ``launch_prepared`` enqueues one or two such
+        calls (two = both modalities in lockstep, grouped GEMM launches)."""
         if query_embeds is None or encoder_hidden_states is None:
             raise ValueError("BertModelB200 needs query_embeds and encoder_hidden_states (the Q-Former call of "
                              "models/xinstructblip.py:286-293)")
@@ -332,15 +335,48 @@ class BertModelB200(nn.Module):
         io = _lib.QFormerIO(enc=enc_b.data_ptr(), input_ids=_lib.ptr(ids), attn_mask=_lib.ptr(tmask), enc_mask=_lib.ptr(emask),
                             query_embeds=qe.data_ptr(), q_rows=q_rows, rows=rows, T=T, Nk=Nk, flags=flags,
                             last_hidden=_lib.ptr(last_hidden), llm_out=_lib.ptr(llm_out))
-        check(lib.mra_qformer_forward(h, C.byref(io), self._workspace.data_ptr(), self._workspace.numel(), current_stream()))
-        self.last_launches = lib.mra_qformer_last_launch_count(h)
-        # the tensors handed to the asynchronous launch must outlive it on this stream
-        for t in (enc_b, qe, ids, tmask, emask):
-            if t is not None:
-                t.record_stream(torch.cuda.current_stream())
         out = QFormerOutput(last_hidden_state=last_hidden,
                             llm_inputs=llm_out.view(rows, Nq, llm_dim) if llm_out is not None else None)
-        return out if return_dict else (last_hidden,)
+        return _Prepared(self, h, io, self._workspace, out, (enc_b, qe, ids, tmask, emask))
+
+    def forward(self, input_ids=None, attention_mask=None, position_ids=None, query_embeds=None,
+                encoder_hidden_states=None, encoder_attention_mask=None, return_dict=True, llm_proj: nn.Linear = None,
+                need_last_hidden: bool = True, skip_dead_text_ffn: bool = False, **unused):
+        prep = self.prepare(input_ids, attention_mask, position_ids, query_embeds, encoder_hidden_states,
+                            encoder_attention_mask, llm_proj, need_last_hidden, skip_dead_text_ffn)
+        launch_prepared([prep])
+        return prep.out if return_dict else (prep.out.last_hidden_state,)
+
+
+class _Prepared:
+    __slots__ = ("bert", "handle", "io", "workspace", "out", "keep")
+
+    def __init__(self, bert, handle, io, workspace, out, keep):
+        self.bert, self.handle, self.io, self.workspace, self.out, self.keep = bert, handle, io, workspace, out, keep
+
+
+def launch_prepared(preps) -> int:
+    """Enqueue 1 or 2 prepared Q-Former calls on the current stream (2 = lockstep with grouped GEMM launches, see
+    ``mra_qformer_forward_multi``).  Returns the number of kernels launched."""
+    n = len(preps)
+    if n == 1:
+        p = preps[0]
+        check(lib.mra_qformer_forward(p.handle, C.byref(p.io), p.workspace.data_ptr(), p.workspace.numel(), current_stream()))
+    else:
+        hs = (C.c_void_p * n)(*[p.handle for p in preps])
+        ios = (C.POINTER(_lib.QFormerIO) * n)(*[C.pointer(p.io) for p in preps])
+        wss = (C.c_void_p * n)(*[p.workspace.data_ptr() for p in preps])
+        wsb = (C.c_size_t * n)(*[p.workspace.numel() for p in preps])
+        check(lib.mra_qformer_forward_multi(n, hs, ios, wss, wsb, current_stream()))
+    launches = 0
+    stream = torch.cuda.current_stream()
+    for p in preps:
+        p.bert.last_launches = lib.mra_qformer_last_launch_count(p.handle)
+        launches += p.bert.last_launches
+        for t in p.keep:   # the tensors handed to the asynchronous launch must outlive it on this stream
+            if t is not None:
+                t.record_stream(stream)
+    return launches
 
 
 class BertLMHeadModel(nn.Module):

@@ -18,7 +18,6 @@ outputs ("cached features"), BERT ``input_ids`` / ``attention_mask`` of the prom
 """
 from __future__ import annotations
 
-import contextlib
 import os
 from typing import Dict, List, Optional, Sequence, Union
 
@@ -26,7 +25,7 @@ import torch
 from torch import nn
 
 from . import _lib, ops
-from .qformer import BertConfig, BertLMHeadModel, LLMProjB200
+from .qformer import BertConfig, BertLMHeadModel, LLMProjB200, launch_prepared
 
 Features = Union[torch.Tensor, Sequence[torch.Tensor]]
 
@@ -82,10 +81,8 @@ class XInstructBLIPQFormers(nn.Module):
             setattr(self, f"{modality}_llm_proj", proj)
         if freeze:
             self.freeze_qformers()
-        # Optional: run the modalities' Q-Formers on separate CUDA streams.  Off by default: the persistent GEMM assigns
-        # tiles statically to its 148 CTAs, so two such kernels time-slicing the SMs lengthen each other's critical path.
-        self.concurrent_modalities = False
-        self._side_streams = []
+        self.lockstep_modalities = True     # both Q-Formers in one lockstep call with grouped GEMM launches
+        self.last_hidden_states = {}
         self.last_launches = 0
 
     def freeze_qformers(self, frozen: bool = True):
@@ -187,52 +184,43 @@ class XInstructBLIPQFormers(nn.Module):
         input_ids / attention_mask: ``text_Qformer.input_ids`` / ``.attention_mask`` ``[bs, T]`` (:233-239).
         """
         inputs_llm, atts_llm = {}, {}
-        self.last_launches = 0
         todo = [m for m in self.modalities if m in feats]
-        dev = input_ids.device
-        # The modalities are independent until the LLM prompt is assembled: each runs on its own stream so that one
-        # Q-Former's kernels fill the SMs the other leaves idle in its wave tails; the caller's stream joins at the end.
-        concurrent = self.concurrent_modalities and len(todo) > 1 and dev.type == "cuda"
-        main = torch.cuda.current_stream(dev) if dev.type == "cuda" else None
-        if concurrent:
-            if len(self._side_streams) < len(todo):
-                self._side_streams = [torch.cuda.Stream(dev) for _ in todo]
-            fork = torch.cuda.Event()
-            fork.record(main)
-        for idx, modality in enumerate(todo):
-            stream = self._side_streams[idx] if concurrent else main
-            if concurrent:
-                stream.wait_event(fork)
-            with torch.cuda.stream(stream) if concurrent else contextlib.nullcontext():
-                enc = self.fold_frames(modality, feats[modality], apply_ln)
-                bs = input_ids.shape[0]
-                num = enc.shape[0] // bs
-                if match_reference_text_tiling:
-                    ids = input_ids.repeat(num, 1)                                    # :287 (frame-major tiling)
-                    tmask = attention_mask.repeat(num, 1)
-                else:
-                    ids = input_ids.repeat_interleave(num, 0)
-                    tmask = attention_mask.repeat_interleave(num, 0)
-                query_tokens = getattr(self, f"{modality}_query_tokens")
-                q_atts = torch.ones(enc.shape[0], self.num_query_token, dtype=tmask.dtype, device=tmask.device)   # :246
-                qformer = getattr(self, f"{modality}_Qformer")
-                proj = getattr(self, f"{modality}_llm_proj")
-                out = qformer.bert(ids, attention_mask=torch.cat([q_atts, tmask], 1), query_embeds=query_tokens,
-                                   encoder_hidden_states=enc, encoder_attention_mask=None, return_dict=True,
-                                   llm_proj=proj, need_last_hidden=need_last_hidden,
-                                   skip_dead_text_ffn=not need_last_hidden)
-                self.last_launches += qformer.bert.last_launches + (1 if apply_ln else 0)
-                y = out.llm_inputs                                                     # [bs*num, 32, D]
-                inputs_llm[modality] = y.reshape(bs, num, self.num_query_token, -1).view(bs, num * self.num_query_token, -1)
-                atts_llm[modality] = torch.ones(inputs_llm[modality].size()[:-1], dtype=torch.long, device=y.device)  # :306
-                if concurrent:
-                    for t in (enc, input_ids, attention_mask):
-                        t.record_stream(stream)
-                    join = torch.cuda.Event()
-                    join.record(stream)
-                    main.wait_event(join)
-                    inputs_llm[modality].record_stream(main)
-                    atts_llm[modality].record_stream(main)
+        preps, shapes = [], []
+        extra = 0
+        for modality in todo:
+            enc = self.fold_frames(modality, feats[modality], apply_ln)
+            extra += 1 if apply_ln else 0
+            bs = input_ids.shape[0]
+            num = enc.shape[0] // bs
+            if match_reference_text_tiling:
+                ids = input_ids.repeat(num, 1)                                    # :287 (frame-major tiling)
+                tmask = attention_mask.repeat(num, 1)
+            else:
+                ids = input_ids.repeat_interleave(num, 0)
+                tmask = attention_mask.repeat_interleave(num, 0)
+            query_tokens = getattr(self, f"{modality}_query_tokens")
+            q_atts = torch.ones(enc.shape[0], self.num_query_token, dtype=tmask.dtype, device=tmask.device)   # :246
+            qformer = getattr(self, f"{modality}_Qformer")
+            proj = getattr(self, f"{modality}_llm_proj")
+            preps.append(qformer.bert.prepare(ids, attention_mask=torch.cat([q_atts, tmask], 1), query_embeds=query_tokens,
+                                              encoder_hidden_states=enc, encoder_attention_mask=None, llm_proj=proj,
+                                              need_last_hidden=need_last_hidden, skip_dead_text_ffn=not need_last_hidden))
+            shapes.append((bs, num))
+        # Both Q-Formers share the layer geometry: run them in lockstep, every Linear as ONE grouped GEMM launch over
+        # (video queries, video text, audio queries, audio text) -- see mra_qformer_forward_multi.
+        launches = 0
+        if self.lockstep_modalities and len(preps) == 2:
+            launches = launch_prepared(preps)
+        else:
+            for p in preps:
+                launches += launch_prepared([p])
+        self.last_launches = launches + extra
+        for modality, p, (bs, num) in zip(todo, preps, shapes):
+            y = p.out.llm_inputs                                                   # [bs*num, 32, D]
+            inputs_llm[modality] = y.reshape(bs, num, self.num_query_token, -1).view(bs, num * self.num_query_token, -1)
+            atts_llm[modality] = torch.ones(inputs_llm[modality].size()[:-1], dtype=torch.long, device=y.device)  # :306
+            if need_last_hidden:
+                self.last_hidden_states[modality] = p.out.last_hidden_state
         return inputs_llm, atts_llm
 
     def host_pipeline(self, bs: int, frames: int, tokens: Dict[str, int], text_len: int, slots: int = 2) -> "HostPipeline":

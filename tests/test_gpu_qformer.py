@@ -141,3 +141,45 @@ def test_errors_are_loud():
         model.bert(query_embeds=w["query_tokens"], encoder_hidden_states=torch.zeros(1, 4, 768))  # CPU tensors
     with pytest.raises(ValueError):
         model.bert(query_embeds=w["query_tokens"].cuda(), encoder_hidden_states=torch.zeros(1, 4, 1408).cuda())
+
+
+def test_xinstructblip_encode_modalities_lockstep_matches_oracle_and_separate_calls():
+    """models/xinstructblip.py:280-305 through the host mirror: both modalities in one lockstep call (grouped GEMM
+    launches) == one call per modality == oracle, including the reference's frame-major text tiling for bs > 1."""
+    from mraudio_b200.xinstructblip import XInstructBLIPQFormers
+    torch.manual_seed(0)
+    widths = {"video": 1408, "audio": 768}
+    model = XInstructBLIPQFormers(modalities=("video", "audio"), encoder_num_features=widths, llm_hidden_size=512,
+                                  num_hidden_layers=3).cuda().eval()
+    g = torch.Generator().manual_seed(4)
+    bs, Fr, T = 3, 2, 9
+    feats = {"video": torch.randn(bs, Fr, 257, 1408, generator=g).to(torch.bfloat16),
+             "audio": torch.randn(bs, Fr, 40, 768, generator=g).to(torch.bfloat16)}
+    ids = torch.randint(1000, 30000, (bs, T), generator=g)
+    mask = torch.ones(bs, T, dtype=torch.long)
+    mask[1, 5:] = 0
+    dfe = {m: t.cuda() for m, t in feats.items()}
+    with torch.no_grad():
+        a, atts = model.encode_modalities(dfe, ids.cuda(), mask.cuda())
+        n_lock = model.last_launches
+        model.lockstep_modalities = False
+        b, _ = model.encode_modalities(dfe, ids.cuda(), mask.cuda())
+        n_sep = model.last_launches
+        # the reference's per-frame list form gives the same rows (frame fold + batch-major reorder, :280-285)
+        lists = {m: [t[:, f].contiguous() for f in range(Fr)] for m, t in dfe.items()}
+        c, _ = model.encode_modalities(lists, ids.cuda(), mask.cuda())
+    assert n_lock < n_sep
+    for m in ("video", "audio"):
+        assert a[m].shape == (bs, Fr * 32, 512) and atts[m].shape == (bs, Fr * 32)
+        assert torch.equal(a[m], b[m]) and torch.equal(a[m], c[m])
+        cfg = qo.QFormerOracleConfig(encoder_width=widths[m], num_hidden_layers=3)
+        w = {"bert." + k[len(f"{m}_Qformer.bert."):]: v.detach().cpu().float() for k, v in model.state_dict().items()
+             if k.startswith(f"{m}_Qformer.bert.")}
+        w["query_tokens"] = getattr(model, f"{m}_query_tokens").detach().cpu()
+        w["llm_proj.weight"] = getattr(model, f"{m}_llm_proj").weight.detach().cpu()
+        w["llm_proj.bias"] = getattr(model, f"{m}_llm_proj").bias.detach().cpu()
+        with torch.no_grad():
+            ref = qo.xinstructblip_encode(w, cfg, feats[m].float(), ids, mask)
+            other = qo.xinstructblip_encode(w, cfg, feats[m].float(), ids, mask, match_reference_text_tiling=False)
+        assert _rel(a[m], ref) < TOL_FP32_REF
+        assert _rel(a[m], other) > _rel(a[m], ref)      # the "fixed" tiling is NOT what the reference computes

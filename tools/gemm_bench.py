@@ -9,6 +9,7 @@ SHAPES = [  # name, M, N, K, gelu, f32+res
     ("kv_video", 65792, 9216, 1408, 0, 0), ("kv_audio", 65536, 9216, 768, 0, 0),
     ("qkv", 16384, 2304, 768, 0, 0), ("ao", 16384, 768, 768, 0, 1), ("cq", 8192, 768, 768, 0, 0),
     ("co", 8192, 768, 768, 0, 1), ("f1", 8192, 3072, 768, 1, 0), ("f2", 8192, 768, 3072, 0, 1),
+    ("f1_nogelu", 8192, 3072, 768, 0, 0), ("f2_nores", 8192, 768, 3072, 0, 0), ("ao_nores", 16384, 768, 768, 0, 0),
     ("f1x2", 16384, 3072, 768, 1, 0), ("f2x2", 16384, 768, 3072, 0, 1), ("proj", 8192, 4096, 768, 0, 0),
 ]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
