@@ -63,6 +63,8 @@ __global__ void __launch_bounds__(NWARPS * 32) attention_kernel(const Params p) 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     constexpr int NT = NWARPS * 32;
+    ptx::griddep_wait();
+    ptx::griddep_launch_dependents();
 
     // ---- stage Q (all Sq rows of this (row, head)); rows >= Sq are zero
     for (int idx = tid; idx < sq_pad * 8; idx += NT) {
@@ -303,6 +305,10 @@ attention_tma_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_cons
         ptx::prefetch_tensormap(&tmV0);
         for (int i = 0; i < 1 + TMA_STAGES; ++i) ptx::mbar_init(&bars[i], 1);
         ptx::fence_mbar_init();
+    }
+    ptx::griddep_wait();               // the producers of q / k / v have completed
+    ptx::griddep_launch_dependents();
+    if (tid == 0) {
         ptx::mbar_arrive_expect_tx(&bars[0], QBOXES * BOX_BYTES);
 #pragma unroll
         for (int b = 0; b < QBOXES; ++b) {
@@ -517,8 +523,8 @@ int launch_tma_variant(const AttnArgs& a, const TmaParams& p, const CUtensorMap*
         MRA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         attr_set = true;
     }
-    kern<<<static_cast<unsigned>(a.rows) * a.heads, NWARPS * 32, smem, s>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
-    MRA_CHECK_CUDA(cudaGetLastError());
+    MRA_CHECK_CUDA(launch_pdl(kern, dim3(static_cast<unsigned>(a.rows) * a.heads), dim3(NWARPS * 32), smem, s, maps[0], maps[1],
+                              maps[2], maps[3], maps[4], maps[5], p));
     return 0;
 }
 
@@ -594,10 +600,9 @@ int launch_attention(const AttnArgs& a, cudaStream_t s) {
         attr_set = true;
     }
     if (a.Sq <= 32)
-        attention_kernel<2><<<grid, 64, smem, s>>>(p);
+        MRA_CHECK_CUDA(launch_pdl(attention_kernel<2>, dim3(grid), dim3(64), smem, s, p));
     else
-        attention_kernel<4><<<grid, 128, smem, s>>>(p);
-    MRA_CHECK_CUDA(cudaGetLastError());
+        MRA_CHECK_CUDA(launch_pdl(attention_kernel<4>, dim3(grid), dim3(128), smem, s, p));
     return 0;
 }
 

@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string>
 
 #include "../../include/mraudio_b200.h"
@@ -28,6 +29,28 @@ void set_error(const char* fmt, ...);
             return 2;                   \
         }                               \
     } while (0)
+
+// Programmatic dependent launch: the kernel may be scheduled while its predecessor in the stream is still draining, runs
+// its prologue (barrier init, TMEM allocation, descriptor prefetch), and blocks in ptx::griddep_wait() until the
+// predecessor has completed and flushed.  EVERY kernel launched through this helper must call ptx::griddep_wait()
+// before touching global memory.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    // Measured on B200 (round 1): no gain for this launch chain (the gaps are kernel tails, not launch latency) and it
+    // slows the three-stream host pipeline, so it is opt-in (MRA_PDL=1) until the fused kernels shorten the tails.
+    static const bool enabled = getenv("MRA_PDL") != nullptr;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = enabled ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 int device_check();
 int sm_count();

@@ -118,6 +118,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 layernorm_grouped_kernel(const LnGroup grp, int n, float eps) {
     const int grow = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
+    ptx::griddep_wait();
+    ptx::griddep_launch_dependents();
     if (grow >= grp.start[grp.n]) return;
     int g = 0;
 #pragma unroll
@@ -199,6 +201,8 @@ embed_ln_kernel(const float* __restrict__ query_embeds, int q_rows, const int32_
     const int64_t orow = static_cast<int64_t>(blockIdx.x) * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     const int64_t nquery = static_cast<int64_t>(rows) * Nq;
+    ptx::griddep_wait();
+    ptx::griddep_launch_dependents();
     if (orow >= nquery + static_cast<int64_t>(rows) * T) return;
     float v[MAX_VEC][8];
     const int nvec = H >> 3;
@@ -282,8 +286,7 @@ int launch_layernorm_grouped(const LnSegment* segs, int nseg, int n, float eps, 
     for (int i = nseg; i <= 4; ++i) grp.start[i] = total;
     grp.n = nseg;
     const int blocks = (total + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
-    layernorm_grouped_kernel<<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(grp, n, eps);
-    MRA_CHECK_CUDA(cudaGetLastError());
+    MRA_CHECK_CUDA(launch_pdl(layernorm_grouped_kernel, dim3(blocks), dim3(WARPS_PER_BLOCK * 32), 0, s, grp, n, eps));
     return 0;
 }
 
@@ -323,11 +326,9 @@ int launch_embed_layernorm(const float* query_embeds, int q_rows, const int32_t*
     MRA_REQUIRE(T == 0 || (ids && word_emb && pos_emb), "text tokens given but ids / embedding tables are NULL");
     const int64_t total = static_cast<int64_t>(rows) * (Nq + T);
     const unsigned blocks = static_cast<unsigned>((total + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
-    embed_ln_kernel<<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(query_embeds, q_rows, ids,
-                                                           reinterpret_cast<const __nv_bfloat16*>(word_emb),
-                                                           reinterpret_cast<const __nv_bfloat16*>(pos_emb), g, b, y32,
-                                                           reinterpret_cast<__nv_bfloat16*>(y16), pre_out, rows, Nq, T, H, vocab, eps);
-    MRA_CHECK_CUDA(cudaGetLastError());
+    MRA_CHECK_CUDA(launch_pdl(embed_ln_kernel, dim3(blocks), dim3(WARPS_PER_BLOCK * 32), 0, s, query_embeds, q_rows, ids,
+                              reinterpret_cast<const __nv_bfloat16*>(word_emb), reinterpret_cast<const __nv_bfloat16*>(pos_emb), g,
+                              b, y32, reinterpret_cast<__nv_bfloat16*>(y16), pre_out, rows, Nq, T, H, vocab, eps));
     return 0;
 }
 

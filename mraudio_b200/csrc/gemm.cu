@@ -147,6 +147,9 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    // everything above overlapped the tail of the previous kernel in the stream (programmatic dependent launch)
+    ptx::griddep_wait();
+    ptx::griddep_launch_dependents();
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
@@ -481,8 +484,7 @@ int launch_tc_variant(const GemmArgs* ga, int n, cudaStream_t s) {
     p.tile_start[MAX_GROUPS] = total;
     for (int g = n; g <= MAX_GROUPS; ++g) p.tile_start[g] = total;
     const int grid = total < sm_count() ? total : sm_count();
-    kern<<<grid, NUM_THREADS, L::TOTAL, s>>>(maps, p);
-    MRA_CHECK_CUDA(cudaGetLastError());
+    MRA_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), L::TOTAL, s, maps, p));
     return 0;
 }
 
