@@ -179,6 +179,14 @@ int mra_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const 
                   int64_t ldr, void* C, int64_t ldc, int32_t M, int32_t N, int32_t K, int32_t gelu, int32_t out_fp32,
                   int32_t impl, void* stream);
 
+/* Fused  y = LayerNorm(A . W^T + bias + residual) * gamma + beta  for N == 768: Linear + residual add + post-LayerNorm of
+ * BertSelfOutput / BertOutput (HF port modeling_instructblip.py:549-553, 606-610) in one kernel; the pre-LayerNorm sums
+ * stay in TMEM.  A bf16 [M, K], W bf16 [768, K], residual fp32 [M, 768]; writes y32 (fp32) and y16 (bf16).
+ * A 2-CTA cluster owns each 128-row block (384 columns per CTA) and combines the row statistics through DSMEM. */
+int mra_gemm_ln_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const float* residual,
+                     int64_t ldr, const float* gamma, const float* beta, float* y32, int64_t ldy32, void* y16, int64_t ldy16,
+                     int32_t M, int32_t N, int32_t K, float eps, void* stream);
+
 /* Tuning aid: force the output-tile width of the tcgen05 GEMM (128, 192 or 256; 0 = automatic choice). */
 int mra_gemm_tile_override(int32_t bn);
 

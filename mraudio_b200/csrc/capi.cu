@@ -68,6 +68,15 @@ extern "C" int mra_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t 
     return launch_gemm_tc(a, s);
 }
 
+extern "C" int mra_gemm_ln_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const float* residual,
+                                int64_t ldr, const float* gamma, const float* beta, float* y32, int64_t ldy32, void* y16,
+                                int64_t ldy16, int32_t M, int32_t N, int32_t K, float eps, void* stream) {
+    MRA_REQUIRE(N == 768, "mra_gemm_ln_bf16: the fused GEMM + LayerNorm kernel is built for N = 768 (Q-Former hidden size), got %d", N);
+    if (int e = device_check()) return e;
+    GemmLnArgs a{A, lda, W, ldw, bias, residual, ldr, gamma, beta, y32, ldy32, y16, ldy16, M, K};
+    return launch_gemm_ln_grouped(&a, 1, eps, reinterpret_cast<cudaStream_t>(stream));
+}
+
 extern "C" int mra_gemm_tile_override(int32_t bn) {
     MRA_REQUIRE(bn == 0 || bn == 128 || bn == 192 || bn == 256, "tile width override must be 0 (auto), 128, 192 or 256");
     set_gemm_tile_override(bn);

@@ -1,5 +1,6 @@
 // Internal declarations shared by the translation units of libmraudio_b200.so.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -69,7 +70,23 @@ struct GemmArgs {
 int launch_gemm_tc(const GemmArgs& a, cudaStream_t s);
 int launch_gemm_tc_grouped(const GemmArgs* a, int n, cudaStream_t s);   // n <= 4 problems sharing N, K, epilogue kind
 int launch_gemm_simt(const GemmArgs& a, cudaStream_t s);
+// cached TMA descriptor of a row-major [rows, cols] matrix (2- or 4-byte elements), box {box_cols, box_rows}, 128B swizzle
+int get_tensor_map(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols, int elem_bytes,
+                   CUtensorMap* out);
 void set_gemm_tile_override(int bn);
+
+// fused  y = LayerNorm(A W^T + bias + residual) * gamma + beta,  N = 768  (gemm_ln.cu)
+struct GemmLnArgs {
+    const void* A; int64_t lda;        // bf16 [M, K]
+    const void* W; int64_t ldw;        // bf16 [768, K]
+    const float* bias;                 // fp32 [768] or NULL
+    const float* residual; int64_t ldr;   // fp32 [M, 768]
+    const float* gamma; const float* beta;
+    float* y32; int64_t ldy32;         // fp32 [M, 768]
+    void* y16; int64_t ldy16;          // bf16 [M, 768]
+    int M, K;
+};
+int launch_gemm_ln_grouped(const GemmLnArgs* a, int n, float eps, cudaStream_t s);
 
 struct AttnArgs {
     const void* q; int64_t ldq;

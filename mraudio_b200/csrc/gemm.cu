@@ -406,6 +406,8 @@ struct MapKeyHash {
 
 // Row-major [rows, cols] matrix of 2-byte (bf16) or 4-byte (fp32) elements with row stride ld (elements);
 // box = {box_cols, box_rows} with box_cols * elem_bytes == 128; 128B swizzle; out-of-bounds reads -> 0, writes clipped.
+}  // namespace
+
 int get_tensor_map(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols, int elem_bytes,
                    CUtensorMap* out) {
     static std::mutex mu;
@@ -442,6 +444,8 @@ int get_tensor_map(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int 
     *out = m;
     return 0;
 }
+
+namespace {
 
 template <int BN, int STAGES, bool GELU, bool OUT_F32, bool RES>
 int launch_tc_variant(const GemmArgs* ga, int n, cudaStream_t s) {

@@ -19,6 +19,7 @@ struct mra_qformer {
     int cross_slot[MRA_MAX_LAYERS];  // index of the layer's K/V block inside w_ckv, or -1
     int last_launches = 0;
     int gemm_impl = MRA_GEMM_IMPL_TCGEN05;
+    bool fuse_ln = true;   // Linear + residual + LayerNorm in one cluster kernel (MRA_NO_FUSED_LN=1 disables: A/B runs)
     // optional per-category device timing (CUDA events on the caller's stream), see mra_qformer_profile_*
     int profile_mode = MRA_PROFILE_OFF;
     struct Span { int cat; cudaEvent_t a, b; };
@@ -180,6 +181,7 @@ extern "C" int mra_qformer_create(const mra_qformer_config* cfg, mra_qformer_t**
     for (int l = 0; l < cfg->layers; ++l) h->cross_slot[l] = (l % cfg->cross_freq == 0) ? h->n_cross++ : -1;
     const char* impl = getenv("MRA_GEMM_IMPL");
     if (impl && std::string(impl) == "simt") h->gemm_impl = MRA_GEMM_IMPL_SIMT_DEBUG;
+    if (getenv("MRA_NO_FUSED_LN")) h->fuse_ln = false;
     *out = h;
     return 0;
 }
@@ -343,6 +345,23 @@ int forward_multi(int n, mra_qformer_t* const* hs, const mra_qformer_io* const* 
         ng = 0;
         return e;
     };
+    // Linear + residual + LayerNorm in one kernel (gemm_ln.cu) whenever the pre-LayerNorm sums need not be kept
+    const bool fuse_ln = !save && H == 768 && h0->gemm_impl == MRA_GEMM_IMPL_TCGEN05 && h0->fuse_ln;
+    GemmLnArgs gl[4];
+    int ngl = 0;
+    auto add_gl = [&](const void* A, int64_t lda, const void* Wt, int64_t ldw, const float* bias, const float* res, const float* g,
+                      const float* b, float* y32, void* y16, int M, int K) {
+        if (M > 0) gl[ngl++] = GemmLnArgs{A, lda, Wt, ldw, bias, res, H, g, b, y32, H, y16, H, M, K};
+    };
+    auto flush_gl = [&]() -> int {
+        if (ngl == 0) return 0;
+        span_begin(MRA_CAT_GEMM);
+        int e = launch_gemm_ln_grouped(gl, ngl, c.ln_eps, s);
+        span_end();
+        ++launches;
+        ngl = 0;
+        return e;
+    };
     LnSegment ls[4];
     int nl = 0;
     auto add_ln = [&](const float* pre, const float* g, const float* b, float* y32, void* y16, int M) {
@@ -410,9 +429,14 @@ int forward_multi(int n, mra_qformer_t* const* hs, const mra_qformer_io* const* 
         for (int i = 0; i < n; ++i) {
             const auto& L = cx[i].h->w.layer[l];
             const LayerBufs& B = cx[i].ws.layer[l];
-            add(B.ctx, H, L.w_ao, H, L.b_ao, cx[i].ws.x32, H, B.pre_a, H, cx[i].Mtot, H, H, 0, 1);
-            add_ln(B.pre_a, L.ln_a_g, L.ln_a_b, cx[i].ws.a32, B.ab, cx[i].Mtot);
+            if (fuse_ln) {
+                add_gl(B.ctx, H, L.w_ao, H, L.b_ao, cx[i].ws.x32, L.ln_a_g, L.ln_a_b, cx[i].ws.a32, B.ab, cx[i].Mtot, H);
+            } else {
+                add(B.ctx, H, L.w_ao, H, L.b_ao, cx[i].ws.x32, H, B.pre_a, H, cx[i].Mtot, H, H, 0, 1);
+                add_ln(B.pre_a, L.ln_a_g, L.ln_a_b, cx[i].ws.a32, B.ab, cx[i].Mtot);
+            }
         }
+        MRA_TRY(flush_gl());
         MRA_TRY(flush(MRA_CAT_GEMM));
         MRA_TRY(flush_ln());
         // ---- cross-attention of the query tokens onto this row's encoder tokens
@@ -436,9 +460,14 @@ int forward_multi(int n, mra_qformer_t* const* hs, const mra_qformer_io* const* 
             for (int i = 0; i < n; ++i) {
                 const auto& L = cx[i].h->w.layer[l];
                 const LayerBufs& B = cx[i].ws.layer[l];
-                add(B.cctx, H, L.w_co, H, L.b_co, cx[i].ws.a32, H, B.pre_c, H, cx[i].Mq, H, H, 0, 1);
-                add_ln(B.pre_c, L.ln_c_g, L.ln_c_b, cx[i].ws.a32, B.ab2, cx[i].Mq);
+                if (fuse_ln) {
+                    add_gl(B.cctx, H, L.w_co, H, L.b_co, cx[i].ws.a32, L.ln_c_g, L.ln_c_b, cx[i].ws.a32, B.ab2, cx[i].Mq, H);
+                } else {
+                    add(B.cctx, H, L.w_co, H, L.b_co, cx[i].ws.a32, H, B.pre_c, H, cx[i].Mq, H, H, 0, 1);
+                    add_ln(B.pre_c, L.ln_c_g, L.ln_c_b, cx[i].ws.a32, B.ab2, cx[i].Mq);
+                }
             }
+            MRA_TRY(flush_gl());
             MRA_TRY(flush(MRA_CAT_GEMM));
             MRA_TRY(flush_ln());
         }
@@ -476,13 +505,21 @@ int forward_multi(int n, mra_qformer_t* const* hs, const mra_qformer_io* const* 
             const LayerBufs& B = cx[i].ws.layer[l];
             __nv_bfloat16* xb_next = cx[i].ws.layer[l + 1].xb;
             const size_t o = static_cast<size_t>(cx[i].Mq) * H, oi = static_cast<size_t>(cx[i].Mq) * I;
-            add(B.inter, I, L.w_fq2, I, L.b_fq2, cx[i].ws.a32, H, B.pre_f, H, cx[i].Mq, H, I, 0, 1);
-            add_ln(B.pre_f, L.ln_fq_g, L.ln_fq_b, cx[i].ws.x32, xb_next, cx[i].Mq);
-            if (text_on[i]) {
-                add(B.inter + oi, I, L.w_ft2, I, L.b_ft2, cx[i].ws.a32 + o, H, B.pre_f + o, H, cx[i].Mt, H, I, 0, 1);
-                add_ln(B.pre_f + o, L.ln_ft_g, L.ln_ft_b, cx[i].ws.x32 + o, xb_next + o, cx[i].Mt);
+            if (fuse_ln) {
+                add_gl(B.inter, I, L.w_fq2, I, L.b_fq2, cx[i].ws.a32, L.ln_fq_g, L.ln_fq_b, cx[i].ws.x32, xb_next, cx[i].Mq, I);
+                if (text_on[i])
+                    add_gl(B.inter + oi, I, L.w_ft2, I, L.b_ft2, cx[i].ws.a32 + o, L.ln_ft_g, L.ln_ft_b, cx[i].ws.x32 + o,
+                           xb_next + o, cx[i].Mt, I);
+            } else {
+                add(B.inter, I, L.w_fq2, I, L.b_fq2, cx[i].ws.a32, H, B.pre_f, H, cx[i].Mq, H, I, 0, 1);
+                add_ln(B.pre_f, L.ln_fq_g, L.ln_fq_b, cx[i].ws.x32, xb_next, cx[i].Mq);
+                if (text_on[i]) {
+                    add(B.inter + oi, I, L.w_ft2, I, L.b_ft2, cx[i].ws.a32 + o, H, B.pre_f + o, H, cx[i].Mt, H, I, 0, 1);
+                    add_ln(B.pre_f + o, L.ln_ft_g, L.ln_ft_b, cx[i].ws.x32 + o, xb_next + o, cx[i].Mt);
+                }
             }
         }
+        MRA_TRY(flush_gl());
         MRA_TRY(flush(MRA_CAT_GEMM));
         MRA_TRY(flush_ln());
         for (int i = 0; i < n; ++i) {

@@ -42,6 +42,21 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     return out
 
 
+def linear_residual_layernorm(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], residual: torch.Tensor,
+                              gamma: torch.Tensor, beta: torch.Tensor, eps: float):
+    """(fp32, bf16) copies of LayerNorm(x @ weight.T + bias + residual) * gamma + beta; weight [768, K] bf16."""
+    _need_cuda(x, weight, bias, residual, gamma, beta)
+    assert x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and residual.dtype == torch.float32
+    M, K = x.shape
+    N = weight.shape[0]
+    assert residual.shape == (M, N) and x.stride(1) == 1 and weight.stride(1) == 1 and residual.stride(1) == 1
+    y32 = torch.empty(M, N, device=x.device, dtype=torch.float32)
+    y16 = torch.empty(M, N, device=x.device, dtype=torch.bfloat16)
+    check(lib.mra_gemm_ln_bf16(ptr(x), x.stride(0), ptr(weight), weight.stride(0), ptr(bias), ptr(residual), residual.stride(0),
+                               ptr(gamma), ptr(beta), ptr(y32), N, ptr(y16), N, M, N, K, eps, current_stream()))
+    return y32, y16
+
+
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, rows: int, heads: int, Sq: int, Sk: int,
               nq_split: int, kv_dense: bool, add_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
     """q [rows*Sq, >=heads*64] (split layout), k/v likewise or dense [rows*Sk, ...]; returns o [rows*Sq, heads*64]."""

@@ -87,6 +87,32 @@ def test_gemm_every_tile_width(bn, M, N, K):
         _lib.lib.mra_gemm_tile_override(0)
 
 
+@pytest.mark.parametrize("M,K", [(128, 768), (256, 768), (1000, 768), (8192, 768), (4096, 3072), (130, 64), (1, 768), (33000, 768)])
+def test_fused_linear_residual_layernorm(M, K):
+    """2-CTA-cluster GEMM + bias + residual + LayerNorm (N = 768) against fp32 PyTorch on the same bf16 operands."""
+    from mraudio_b200 import ops
+    g = torch.Generator().manual_seed(M + K)
+    N = 768
+    x = torch.randn(M, K, generator=g).to(_dev(), torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) * 0.03).to(_dev(), torch.bfloat16)
+    b = torch.randn(N, generator=g).to(_dev())
+    res = (torch.randn(M, N, generator=g) * 2 + 0.3).to(_dev())
+    gam = (1 + 0.2 * torch.randn(N, generator=g)).to(_dev())
+    bet = (0.3 * torch.randn(N, generator=g)).to(_dev())
+    pre = x.float() @ w.float().t() + b + res
+    ref = torch.nn.functional.layer_norm(pre, (N,), gam, bet, 1e-12)
+    y32, y16 = ops.linear_residual_layernorm(x, w, b, res, gam, bet, 1e-12)
+    torch.cuda.synchronize()
+    assert (y32 - ref).abs().max().item() < 2e-4 * max(1.0, ref.abs().max().item())
+    assert torch.equal(y16, y32.to(torch.bfloat16))
+    # no bias; deterministic
+    y32b, _ = ops.linear_residual_layernorm(x, w, None, res, gam, bet, 1e-12)
+    ref_b = torch.nn.functional.layer_norm(pre - b, (N,), gam, bet, 1e-12)
+    assert (y32b - ref_b).abs().max().item() < 2e-4 * max(1.0, ref_b.abs().max().item())
+    y32c, _ = ops.linear_residual_layernorm(x, w, b, res, gam, bet, 1e-12)
+    assert torch.equal(y32, y32c)
+
+
 def test_gemm_tcgen05_equals_simt_bitwise_ordering_free():
     """Same bf16 operands, fp32 accumulation: the two implementations agree to fp32 rounding noise."""
     from mraudio_b200 import ops

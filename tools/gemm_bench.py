@@ -42,3 +42,18 @@ for name, M, N, K, gelu, res in SHAPES:
         e0.record(); y = x @ w.t(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
     line += f" | cublas(no epi) {min(ts[1:])*1e3:7.1f}us"
     print(line, flush=True)
+
+print("--- fused Linear + residual + LayerNorm (2-CTA cluster), N = 768")
+for name, M, K in (("ao", 16384, 768), ("ao_x2", 32768, 768), ("co", 8192, 768), ("f2", 8192, 3072), ("f2_x4", 32768, 3072)):
+    x = torch.randn(M, K, device=dev).to(torch.bfloat16)
+    w = (torch.randn(768, K, device=dev) * 0.02).to(torch.bfloat16)
+    b = torch.randn(768, device=dev); r = torch.randn(M, 768, device=dev)
+    g = torch.ones(768, device=dev); be = torch.zeros(768, device=dev)
+    ts = []
+    for it in range(6):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); ops.linear_residual_layernorm(x, w, b, r, g, be, 1e-12); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    t = sorted(ts[1:])[2]
+    print(f"{name:6s} M={M:6d} K={K:5d} fused {t*1e3:7.1f}us {2*M*768*K/t/1e9:6.0f}TF")
