@@ -244,6 +244,21 @@ def run_b200(args):
             pipe.submit(host_feats, ids_h, mask_h)
         pipe.drain()
 
+    # PCIe probe: pinned host -> device and back, alone on the bus (explains e2e when the step is copy-bound)
+    def copy_gbs(src, dst):
+        best = 0.0
+        for _ in range(3):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            dst.copy_(src, non_blocking=True)
+            b.record()
+            torch.cuda.synchronize()
+            best = max(best, src.numel() * src.element_size() / (a.elapsed_time(b) * 1e-3) / 1e9)
+        return best
+    h2d_gbs = copy_gbs(host_feats["video"], feats["video"])
+    slot0 = pipe.slots[0]
+    d2h_gbs = copy_gbs(torch.empty_like(slot0.out_host["video"], device=dev), slot0.out_host["video"])
+
     e2e_steps(max(2, args.warmup))
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -297,6 +312,8 @@ def run_b200(args):
         "cpu_baseline": {"value": cpu_v, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": clips * world / (ms_e2e * 1e-3), "unit": "clips/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
+                "pcie_probe_gbs": {"h2d": h2d_gbs, "d2h": d2h_gbs},
+                "copy_bound_ms_per_step": max(pipe.h2d_bytes / (h2d_gbs * 1e9), pipe.d2h_bytes / (d2h_gbs * 1e9)) * 1e3,
                 "api": "XInstructBLIPQFormers.host_pipeline(...).submit(pinned host features) -> pinned host inputs_llm"},
         "gpu_launches": launches,
         "clocks": clocks,

@@ -190,6 +190,10 @@ int mra_gemm_ln_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, con
 /* Tuning aid: force the output-tile width of the tcgen05 GEMM (128, 192 or 256; 0 = automatic choice). */
 int mra_gemm_tile_override(int32_t bn);
 
+/* Tuning / test aid: 2 lets the GEMM pair CTAs into clusters that share the W slab by TMA multicast when every problem
+ * has >= 4 row blocks; 1 (default) never pairs. */
+int mra_gemm_cluster_override(int32_t cm);
+
 /* Fused multi-head attention core, head_dim 64: O = softmax(Q K^T / 8 + mask) V, per (row, head).
  *   q: bf16, row `qrow(r, i)` at q + qrow*ldq + head*64;  k, v likewise with ldk/ldv; o bf16 with ldo.
  *   Row addressing: "split" layout used by the forward: query tokens of all rows first, then text tokens:

@@ -83,6 +83,12 @@ extern "C" int mra_gemm_tile_override(int32_t bn) {
     return 0;
 }
 
+extern "C" int mra_gemm_cluster_override(int32_t cm) {
+    MRA_REQUIRE(cm == 1 || cm == 2, "cluster override must be 1 or 2");
+    set_gemm_cluster_override(cm);
+    return 0;
+}
+
 extern "C" int mra_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
                              int64_t ldo, const float* add_mask, int32_t rows, int32_t heads, int32_t Sq, int32_t Sk,
                              int32_t nq_split, int32_t kv_dense, void* stream) {

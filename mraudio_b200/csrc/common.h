@@ -74,6 +74,7 @@ int launch_gemm_simt(const GemmArgs& a, cudaStream_t s);
 int get_tensor_map(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols, int elem_bytes,
                    CUtensorMap* out);
 void set_gemm_tile_override(int bn);
+void set_gemm_cluster_override(int cm);   // 1 = never pair CTAs, 2 = pair along M when possible (default)
 
 // fused  y = LayerNorm(A W^T + bias + residual) * gamma + beta,  N = 768  (gemm_ln.cu)
 struct GemmLnArgs {

@@ -95,7 +95,10 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // byte offset of 16-byte unit `j` of row `r` inside a 32-row x 128-byte chunk buffer with the TMA 128-byte swizzle
 __device__ __forceinline__ uint32_t swz(int r, int j) { return static_cast<uint32_t>(r * 128 + ((j ^ (r & 7)) << 4)); }
 
-template <int BN, int STAGES, bool GELU, bool OUT_F32, bool RES>
+// CM = CTAs per cluster along M (1 or 2).  With CM = 2 the two CTAs of a cluster compute the tiles (2 mp, n) and
+// (2 mp + 1, n): they need the same W rows, so each loads HALF of the W slab and multicasts it to both (the kernels are
+// L2 -> SM bandwidth bound: 128 x 256 tiles need 96 B/clk/SM at full tensor rate; sharing W cuts that by a third).
+template <int BN, int STAGES, bool GELU, bool OUT_F32, bool RES, int CM>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ EpiParams p) {
     using L = SmemLayout<BN, STAGES, RES>;
@@ -118,7 +121,10 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int n_tiles = (p.N + BN - 1) / BN;
-    const int total_tiles = p.tile_start[p.groups];
+    const int total_tiles = p.tile_start[p.groups];   // work items: (group, m-block [pair], n-block)
+    const uint32_t crank = CM > 1 ? ptx::cluster_ctarank() : 0u;
+    const int first_item = CM > 1 ? static_cast<int>(blockIdx.x) / CM : static_cast<int>(blockIdx.x);
+    const int item_stride = CM > 1 ? static_cast<int>(gridDim.x) / CM : static_cast<int>(gridDim.x);
     const int k_blocks = (p.K + BK - 1) / BK;
 
     if (warp == 0 && lane == 0) {
@@ -130,7 +136,7 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
         }
         for (int i = 0; i < STAGES; ++i) {
             ptx::mbar_init(&full_bar[i], 1);
-            ptx::mbar_init(&empty_bar[i], 1);
+            ptx::mbar_init(&empty_bar[i], CM);          // every CTA of the cluster must have consumed the slab
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tfull_bar[i], 1);
@@ -146,6 +152,7 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
+    if (CM > 1) ptx::cluster_sync_all();   // the peer's barriers exist before anything is multicast to them
     const uint32_t tmem_base = *tmem_ptr_smem;
     // everything above overlapped the tail of the previous kernel in the stream (programmatic dependent launch)
     ptx::griddep_wait();
@@ -156,16 +163,24 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = first_item; tile < total_tiles; tile += item_stride) {
                 int g, m_blk, n_blk;
                 decode_tile(p, tile, n_tiles, g, m_blk, n_blk);
+                m_blk = m_blk * CM + static_cast<int>(crank);
                 const CUtensorMap* tmA = &maps.a[g];
                 const CUtensorMap* tmB = &maps.b[g];
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     ptx::mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
                     ptx::tma_load_2d(sA + stage * A_STAGE_BYTES, tmA, &full_bar[stage], kb * BK, m_blk * BM);
-                    ptx::tma_load_2d(sB + stage * L::B_STAGE_BYTES, tmB, &full_bar[stage], kb * BK, n_blk * BN);
+                    if (CM == 1) {
+                        ptx::tma_load_2d(sB + stage * L::B_STAGE_BYTES, tmB, &full_bar[stage], kb * BK, n_blk * BN);
+                    } else {
+                        // my half of the W slab, delivered to both CTAs of the pair (the box of tmB is BN / 2 rows)
+                        ptx::tma_load_2d_multicast(sB + stage * L::B_STAGE_BYTES + crank * (L::B_STAGE_BYTES / 2), tmB,
+                                                   &full_bar[stage], kb * BK, n_blk * BN + static_cast<int>(crank) * (BN / 2),
+                                                   static_cast<uint16_t>(0x3));
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -177,7 +192,7 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
             int stage = 0;
             uint32_t phase = 0;
             int iter = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+            for (int tile = first_item; tile < total_tiles; tile += item_stride, ++iter) {
                 const int acc = iter & 1;
                 const uint32_t acc_phase = (iter >> 1) & 1;
                 ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
@@ -193,7 +208,9 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
                         // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in the >>4 address field
                         ptx::umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
                     }
-                    ptx::umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+                    // smem slot reusable once these MMAs have read it (CM = 2: the peer multicasts into it too)
+                    if (CM == 1) ptx::umma_commit(&empty_bar[stage]);
+                    else ptx::umma_commit_multicast(&empty_bar[stage], static_cast<uint16_t>(0x3));
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 ptx::umma_commit(&tfull_bar[acc]);  // accumulator complete
@@ -213,9 +230,10 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
         uint32_t rphase = 0;
         constexpr int RSUB = CH / 32;   // 32-column residual sub-chunks per output chunk
         int iter = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+        for (int tile = first_item; tile < total_tiles; tile += item_stride, ++iter) {
             int g, m_blk, n_blk;
             decode_tile(p, tile, n_tiles, g, m_blk, n_blk);
+            m_blk = m_blk * CM + static_cast<int>(crank);
             const CUtensorMap* tmC = &maps.c[g];
             const CUtensorMap* tmR = &maps.r[g];
             const float* bias = p.bias[g];
@@ -318,6 +336,7 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
     }
     ptx::tc_fence_before();
     __syncthreads();
+    if (CM > 1) ptx::cluster_sync_all();   // no CTA exits while its peer may still multicast into it
     if (warp == 1) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, TMEM_COLS);
@@ -447,10 +466,10 @@ int get_tensor_map(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int 
 
 namespace {
 
-template <int BN, int STAGES, bool GELU, bool OUT_F32, bool RES>
+template <int BN, int STAGES, bool GELU, bool OUT_F32, bool RES, int CM>
 int launch_tc_variant(const GemmArgs* ga, int n, cudaStream_t s) {
     using L = SmemLayout<BN, STAGES, RES>;
-    auto kern = gemm_tc_kernel<BN, STAGES, GELU, OUT_F32, RES>;
+    auto kern = gemm_tc_kernel<BN, STAGES, GELU, OUT_F32, RES, CM>;
     static bool attr_set = false;
     if (!attr_set) {
         MRA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -467,7 +486,7 @@ int launch_tc_variant(const GemmArgs* ga, int n, cudaStream_t s) {
         const GemmArgs& a = ga[g < n ? g : 0];
         if (g < n) {
             if (int e = get_tensor_map(a.A, a.M, a.K, a.lda, BM, BK, 2, &maps.a[g])) return e;
-            if (int e = get_tensor_map(a.W, a.N, a.K, a.ldw, BN, BK, 2, &maps.b[g])) return e;
+            if (int e = get_tensor_map(a.W, a.N, a.K, a.ldw, BN / CM, BK, 2, &maps.b[g])) return e;
             if (int e = get_tensor_map(a.C, a.M, a.N, a.ldc, 32, OUT_F32 ? 32 : 64, OUT_F32 ? 4 : 2, &maps.c[g])) return e;
             if (RES) {
                 if (int e = get_tensor_map(a.residual, a.M, a.N, a.ldr, 32, 32, 4, &maps.r[g])) return e;
@@ -477,7 +496,7 @@ int launch_tc_variant(const GemmArgs* ga, int n, cudaStream_t s) {
             p.bias[g] = a.bias;
             p.M[g] = a.M;
             p.tile_start[g] = total;
-            total += ((a.M + BM - 1) / BM) * n_tiles;
+            total += (((a.M + BM - 1) / BM + CM - 1) / CM) * n_tiles;   // work items: m-block pairs when CM == 2
         } else {
             maps.a[g] = maps.a[0]; maps.b[g] = maps.b[0]; maps.c[g] = maps.c[0]; maps.r[g] = maps.r[0];
             p.bias[g] = nullptr;
@@ -487,23 +506,38 @@ int launch_tc_variant(const GemmArgs* ga, int n, cudaStream_t s) {
     }
     p.tile_start[MAX_GROUPS] = total;
     for (int g = n; g <= MAX_GROUPS; ++g) p.tile_start[g] = total;
-    const int grid = total < sm_count() ? total : sm_count();
-    MRA_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), L::TOTAL, s, maps, p));
+    if (CM == 1) {
+        const int grid = total < sm_count() ? total : sm_count();
+        MRA_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), L::TOTAL, s, maps, p));
+        return 0;
+    }
+    const int clusters = total < sm_count() / CM ? total : sm_count() / CM;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(clusters * CM);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = L::TOTAL;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CM; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    MRA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, p));
     return 0;
 }
 
-template <int BN, int ST_PLAIN, int ST_RES>
+template <int BN, int ST_PLAIN, int ST_RES, int CM>
 int dispatch_epi(const GemmArgs* a, int n, cudaStream_t s) {
     const int code = (a[0].gelu ? 4 : 0) | (a[0].out_fp32 ? 2 : 0) | (a[0].residual ? 1 : 0);
     switch (code) {
-        case 0: return launch_tc_variant<BN, ST_PLAIN, false, false, false>(a, n, s);
-        case 1: return launch_tc_variant<BN, ST_RES, false, false, true>(a, n, s);
-        case 2: return launch_tc_variant<BN, ST_PLAIN, false, true, false>(a, n, s);
-        case 3: return launch_tc_variant<BN, ST_RES, false, true, true>(a, n, s);
-        case 4: return launch_tc_variant<BN, ST_PLAIN, true, false, false>(a, n, s);
-        case 5: return launch_tc_variant<BN, ST_RES, true, false, true>(a, n, s);
-        case 6: return launch_tc_variant<BN, ST_PLAIN, true, true, false>(a, n, s);
-        default: return launch_tc_variant<BN, ST_RES, true, true, true>(a, n, s);
+        case 0: return launch_tc_variant<BN, ST_PLAIN, false, false, false, CM>(a, n, s);
+        case 1: return launch_tc_variant<BN, ST_RES, false, false, true, CM>(a, n, s);
+        case 2: return launch_tc_variant<BN, ST_PLAIN, false, true, false, CM>(a, n, s);
+        case 3: return launch_tc_variant<BN, ST_RES, false, true, true, CM>(a, n, s);
+        case 4: return launch_tc_variant<BN, ST_PLAIN, true, false, false, CM>(a, n, s);
+        case 5: return launch_tc_variant<BN, ST_RES, true, false, true, CM>(a, n, s);
+        case 6: return launch_tc_variant<BN, ST_PLAIN, true, true, false, CM>(a, n, s);
+        default: return launch_tc_variant<BN, ST_RES, true, true, true, CM>(a, n, s);
     }
 }
 
@@ -525,7 +559,9 @@ int check_args(const GemmArgs& a) {
 }  // namespace
 
 static int g_forced_bn = [] { const char* e = getenv("MRA_GEMM_BN"); return e ? atoi(e) : 0; }();
+static int g_cluster_m = [] { const char* e = getenv("MRA_GEMM_CLUSTER"); return e ? atoi(e) : 1; }();
 void set_gemm_tile_override(int bn) { g_forced_bn = bn; }
+void set_gemm_cluster_override(int cm) { g_cluster_m = cm; }
 
 int launch_gemm_tc_grouped(const GemmArgs* a, int n, cudaStream_t s) {
     MRA_REQUIRE(n >= 1 && n <= MAX_GROUPS, "grouped GEMM takes 1..%d problems, got %d", MAX_GROUPS, n);
@@ -552,9 +588,19 @@ int launch_gemm_tc_grouped(const GemmArgs* a, int n, cudaStream_t s) {
         const double cost = double((tiles + sms - 1) / sms) * bn * factor[i];
         if (cost < best) { best = cost; best_bn = bn; }
     }
-    if (best_bn == 256) return dispatch_epi<256, 4, 3>(a, n, s);
-    if (best_bn == 192) return dispatch_epi<192, 4, 4>(a, n, s);
-    return dispatch_epi<128, 6, 5>(a, n, s);
+    // 2-CTA clusters along M (W slab multicast) when every problem has enough row blocks to pair up.  Opt-in
+    // (MRA_GEMM_CLUSTER=2 / mra_gemm_cluster_override): measured on B200 it neither helps nor hurts (1425 vs 1450 TF/s on
+    // the cross-K/V GEMM), i.e. these GEMMs are not L2 -> SM bandwidth bound.
+    bool pair = g_cluster_m != 1;
+    for (int g = 0; g < n; ++g) pair = pair && a[g].M >= 4 * BM;
+    if (pair) {
+        if (best_bn == 256) return dispatch_epi<256, 4, 3, 2>(a, n, s);
+        if (best_bn == 192) return dispatch_epi<192, 4, 4, 2>(a, n, s);
+        return dispatch_epi<128, 6, 5, 2>(a, n, s);
+    }
+    if (best_bn == 256) return dispatch_epi<256, 4, 3, 1>(a, n, s);
+    if (best_bn == 192) return dispatch_epi<192, 4, 4, 1>(a, n, s);
+    return dispatch_epi<128, 6, 5, 1>(a, n, s);
 }
 
 int launch_gemm_tc(const GemmArgs& a, cudaStream_t s) { return launch_gemm_tc_grouped(&a, 1, s); }

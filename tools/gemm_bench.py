@@ -20,8 +20,9 @@ for name, M, N, K, gelu, res in SHAPES:
     r = torch.randn(M, N, device=dev) if res else None
     out = torch.empty(M, N, device=dev, dtype=torch.float32 if res else torch.bfloat16)
     line = f"{name:9s} M={M:6d} N={N:5d} K={K:5d}"
-    for bn in (128, 192, 256, 0):
-        _lib.lib.mra_gemm_tile_override(bn)
+    for bn in (-256, 128, 192, 256, 0):
+        _lib.lib.mra_gemm_cluster_override(1 if bn < 0 else 2)   # bn < 0: unpaired kernel at |bn| for comparison
+        _lib.lib.mra_gemm_tile_override(abs(bn))
         ts = []
         for it in range(6):
             flush.zero_()
@@ -32,8 +33,9 @@ for name, M, N, K, gelu, res in SHAPES:
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
         t = sorted(ts[1:])[len(ts[1:]) // 2]
-        line += f" | bn{bn:3d} {t*1e3:7.1f}us {2*M*N*K/t/1e9:6.0f}TF"
+        line += f" | {'solo' if bn < 0 else 'bn'}{abs(bn):3d} {t*1e3:7.1f}us {2*M*N*K/t/1e9:6.0f}TF"
     _lib.lib.mra_gemm_tile_override(0)
+    _lib.lib.mra_gemm_cluster_override(1)
     # cuBLAS (torch.matmul) for orientation only
     ts = []
     for it in range(4):
