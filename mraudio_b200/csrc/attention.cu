@@ -521,6 +521,8 @@ int launch_tma_variant(const AttnArgs& a, const TmaParams& p, const CUtensorMap*
     static bool attr_set = false;
     if (!attr_set) {
         MRA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        // same L1 / shared-memory split as the GEMM kernels around it: no SM reconfiguration between launches
+        MRA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
     MRA_CHECK_CUDA(launch_pdl(kern, dim3(static_cast<unsigned>(a.rows) * a.heads), dim3(NWARPS * 32), smem, s, maps[0], maps[1],
