@@ -267,11 +267,27 @@ __device__ __forceinline__ uint32_t tile_addr(uint32_t base, int row, int u) {
     return base + row * 128 + ((u ^ (row & 7)) << 4);
 }
 
+// up to two independent attention problems per launch (the video and the audio Q-Former of a lockstep forward)
+struct TmaMaps {
+    CUtensorMap m[12];   // per problem: Q0, Q1, K0, K1, V0, V1
+};
+struct TmaParams2 {
+    TmaParams p[2];
+    int split;           // first block of problem 1 (== grid size when there is one problem)
+};
+
 template <int NWARPS>
 __global__ void __launch_bounds__(NWARPS * 32)
-attention_tma_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ CUtensorMap tmQ1,
-                     const __grid_constant__ CUtensorMap tmK0, const __grid_constant__ CUtensorMap tmK1,
-                     const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmV1, const TmaParams p) {
+attention_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaParams2 pp) {
+    const int prob = static_cast<int>(blockIdx.x) >= pp.split ? 1 : 0;
+    const TmaParams& p = pp.p[prob];
+    const int bid = static_cast<int>(blockIdx.x) - (prob ? pp.split : 0);
+    const CUtensorMap* tmQ0 = &maps.m[prob * 6 + 0];
+    const CUtensorMap* tmQ1 = &maps.m[prob * 6 + 1];
+    const CUtensorMap* tmK0 = &maps.m[prob * 6 + 2];
+    const CUtensorMap* tmK1 = &maps.m[prob * 6 + 3];
+    const CUtensorMap* tmV0 = &maps.m[prob * 6 + 4];
+    const CUtensorMap* tmV1 = &maps.m[prob * 6 + 5];
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr int QBOXES = (NWARPS * 16 + 31) / 32;
@@ -280,8 +296,8 @@ attention_tma_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_cons
     float* sMask = reinterpret_cast<float*>(sKV + TMA_STAGES * STAGE_BYTES_ATT);   // [nchunks * 64]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sMask + p.nchunks * 64);          // q_full, full[TMA_STAGES]
 
-    const int head = blockIdx.x % p.heads;
-    const int r = blockIdx.x / p.heads;
+    const int head = bid % p.heads;
+    const int r = bid / p.heads;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     constexpr int NT = NWARPS * 32;
@@ -294,15 +310,15 @@ attention_tma_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_cons
             const int key0 = kc * 64 + h * 32;
             const bool seg1 = p.k_n1 > 0 && key0 >= p.k_n0;
             const int tok = seg1 ? key0 - p.k_n0 : key0;   // past the end -> zero fill
-            tma_load_3d(dst + h * BOX_BYTES, seg1 ? &tmK1 : &tmK0, &bars[1 + stage], head * HD, tok, r);
-            tma_load_3d(dst + (2 + h) * BOX_BYTES, seg1 ? &tmV1 : &tmV0, &bars[1 + stage], head * HD, tok, r);
+            tma_load_3d(dst + h * BOX_BYTES, seg1 ? tmK1 : tmK0, &bars[1 + stage], head * HD, tok, r);
+            tma_load_3d(dst + (2 + h) * BOX_BYTES, seg1 ? tmV1 : tmV0, &bars[1 + stage], head * HD, tok, r);
         }
     };
 
     if (tid == 0) {
-        ptx::prefetch_tensormap(&tmQ0);
-        ptx::prefetch_tensormap(&tmK0);
-        ptx::prefetch_tensormap(&tmV0);
+        ptx::prefetch_tensormap(tmQ0);
+        ptx::prefetch_tensormap(tmK0);
+        ptx::prefetch_tensormap(tmV0);
         for (int i = 0; i < 1 + TMA_STAGES; ++i) ptx::mbar_init(&bars[i], 1);
         ptx::fence_mbar_init();
     }
@@ -314,7 +330,7 @@ attention_tma_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_cons
         for (int b = 0; b < QBOXES; ++b) {
             const int q0 = b * 32;
             const bool seg1 = p.q_n1 > 0 && q0 >= p.q_n0;
-            tma_load_3d(sQ + b * BOX_BYTES, seg1 ? &tmQ1 : &tmQ0, &bars[0], head * HD, seg1 ? q0 - p.q_n0 : q0, r);
+            tma_load_3d(sQ + b * BOX_BYTES, seg1 ? tmQ1 : tmQ0, &bars[0], head * HD, seg1 ? q0 - p.q_n0 : q0, r);
         }
         for (int s = 0; s < TMA_STAGES && s < p.nchunks; ++s) load_kv_chunk(s, s);
     }
@@ -516,7 +532,7 @@ int get_map3(const void* ptr, int64_t ld, int width, int ntok, int rows, CUtenso
 }
 
 template <int NWARPS>
-int launch_tma_variant(const AttnArgs& a, const TmaParams& p, const CUtensorMap* maps, size_t smem, cudaStream_t s) {
+int launch_tma_variant(const TmaMaps& maps, const TmaParams2& pp, unsigned grid, size_t smem, cudaStream_t s) {
     auto kern = attention_tma_kernel<NWARPS>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -525,19 +541,18 @@ int launch_tma_variant(const AttnArgs& a, const TmaParams& p, const CUtensorMap*
         MRA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
-    MRA_CHECK_CUDA(launch_pdl(kern, dim3(static_cast<unsigned>(a.rows) * a.heads), dim3(NWARPS * 32), smem, s, maps[0], maps[1],
-                              maps[2], maps[3], maps[4], maps[5], p));
+    MRA_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(NWARPS * 32), smem, s, maps, pp));
     return 0;
 }
 
-// returns -1 when the shape is outside what the TMA kernel covers (the caller then uses the generic kernel)
-int try_launch_attention_tma(const AttnArgs& a, cudaStream_t s) {
+// fills problem slot `slot`; returns -1 when the shape is outside what the TMA kernel covers
+int prepare_tma_problem(const AttnArgs& a, int slot, TmaMaps& maps, TmaParams2& pp) {
     const bool split_q = a.nq_split < a.Sq;                  // queries in two segments
     const bool split_k = !a.kv_dense && a.nq_split < a.Sk;   // keys in two segments
     if (a.Sq > 256 || a.Sk > 4096) return -1;
     if ((split_q || split_k) && a.nq_split % 32 != 0) return -1;
     if (a.ldo % 2 != 0) return -1;
-    TmaParams p;
+    TmaParams& p = pp.p[slot];
     p.o = reinterpret_cast<__nv_bfloat16*>(a.o); p.ldo = a.ldo; p.add_mask = a.add_mask;
     p.rows = a.rows; p.heads = a.heads; p.Sq = a.Sq; p.Sk = a.Sk;
     p.q_n0 = split_q ? a.nq_split : a.Sq; p.q_n1 = split_q ? a.Sq - a.nq_split : 0;
@@ -547,29 +562,51 @@ int try_launch_attention_tma(const AttnArgs& a, cudaStream_t s) {
     const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(a.q);
     const __nv_bfloat16* k = reinterpret_cast<const __nv_bfloat16*>(a.k);
     const __nv_bfloat16* v = reinterpret_cast<const __nv_bfloat16*>(a.v);
-    CUtensorMap maps[6];
-    if (int e = get_map3(q, a.ldq, width, p.q_n0, a.rows, &maps[0])) return e;
-    maps[1] = maps[0];
+    CUtensorMap* m = &maps.m[slot * 6];
+    if (int e = get_map3(q, a.ldq, width, p.q_n0, a.rows, &m[0])) return e;
+    m[1] = m[0];
     if (p.q_n1 > 0)
-        if (int e = get_map3(q + static_cast<int64_t>(a.rows) * p.q_n0 * a.ldq, a.ldq, width, p.q_n1, a.rows, &maps[1])) return e;
-    if (int e = get_map3(k, a.ldk, width, p.k_n0, a.rows, &maps[2])) return e;
-    maps[3] = maps[2];
+        if (int e = get_map3(q + static_cast<int64_t>(a.rows) * p.q_n0 * a.ldq, a.ldq, width, p.q_n1, a.rows, &m[1])) return e;
+    if (int e = get_map3(k, a.ldk, width, p.k_n0, a.rows, &m[2])) return e;
+    m[3] = m[2];
     if (p.k_n1 > 0)
-        if (int e = get_map3(k + static_cast<int64_t>(a.rows) * p.k_n0 * a.ldk, a.ldk, width, p.k_n1, a.rows, &maps[3])) return e;
-    if (int e = get_map3(v, a.ldv, width, p.k_n0, a.rows, &maps[4])) return e;
-    maps[5] = maps[4];
+        if (int e = get_map3(k + static_cast<int64_t>(a.rows) * p.k_n0 * a.ldk, a.ldk, width, p.k_n1, a.rows, &m[3])) return e;
+    if (int e = get_map3(v, a.ldv, width, p.k_n0, a.rows, &m[4])) return e;
+    m[5] = m[4];
     if (p.k_n1 > 0)
-        if (int e = get_map3(v + static_cast<int64_t>(a.rows) * p.k_n0 * a.ldv, a.ldv, width, p.k_n1, a.rows, &maps[5])) return e;
-    const int nw = (a.Sq + 15) / 16;
-    auto smem_for = [&](int nwarps) {
-        const int qboxes = (nwarps * 16 + 31) / 32;
-        return static_cast<size_t>(qboxes) * BOX_BYTES + TMA_STAGES * STAGE_BYTES_ATT + static_cast<size_t>(p.nchunks) * 64 * 4 +
-               (1 + TMA_STAGES) * 8 + 1024;
-    };
-    if (nw <= 2) return launch_tma_variant<2>(a, p, maps, smem_for(2), s);
-    if (nw <= 4) return launch_tma_variant<4>(a, p, maps, smem_for(4), s);
-    if (nw <= 8) return launch_tma_variant<8>(a, p, maps, smem_for(8), s);
-    return launch_tma_variant<16>(a, p, maps, smem_for(16), s);
+        if (int e = get_map3(v + static_cast<int64_t>(a.rows) * p.k_n0 * a.ldv, a.ldv, width, p.k_n1, a.rows, &m[5])) return e;
+    return 0;
+}
+
+// one launch for `n` (1 or 2) problems with the same number of query warps; -1 = not covered by the TMA kernel
+int try_launch_attention_tma(const AttnArgs* a, int n, cudaStream_t s) {
+    TmaMaps maps;
+    TmaParams2 pp;
+    int nw = 0, nchunks = 0;
+    unsigned grid = 0;
+    for (int i = 0; i < n; ++i) {
+        const int e = prepare_tma_problem(a[i], i, maps, pp);
+        if (e != 0) return e;
+        const int w = (a[i].Sq + 15) / 16;
+        const int wc = w <= 2 ? 2 : (w <= 4 ? 4 : (w <= 8 ? 8 : 16));
+        if (i > 0 && wc != nw) return -1;
+        nw = wc;
+        nchunks = pp.p[i].nchunks > nchunks ? pp.p[i].nchunks : nchunks;
+        if (i == 0) pp.split = static_cast<int>(a[i].rows) * a[i].heads;
+        grid += static_cast<unsigned>(a[i].rows) * a[i].heads;
+    }
+    if (n == 1) {
+        pp.p[1] = pp.p[0];
+        for (int i = 0; i < 6; ++i) maps.m[6 + i] = maps.m[i];
+        pp.split = static_cast<int>(grid);
+    }
+    const int qboxes = (nw * 16 + 31) / 32;
+    const size_t smem = static_cast<size_t>(qboxes) * BOX_BYTES + TMA_STAGES * STAGE_BYTES_ATT + static_cast<size_t>(nchunks) * 64 * 4 +
+                        (1 + TMA_STAGES) * 8 + 1024;
+    if (nw == 2) return launch_tma_variant<2>(maps, pp, grid, smem, s);
+    if (nw == 4) return launch_tma_variant<4>(maps, pp, grid, smem, s);
+    if (nw == 8) return launch_tma_variant<8>(maps, pp, grid, smem, s);
+    return launch_tma_variant<16>(maps, pp, grid, smem, s);
 }
 
 }  // namespace
@@ -586,7 +623,7 @@ int launch_attention(const AttnArgs& a, cudaStream_t s) {
                 "attention operands must be 16-byte aligned");
     MRA_REQUIRE(static_cast<int64_t>(a.rows) * a.heads < (1ll << 31), "attention grid too large");
     if (!g_force_generic) {
-        const int e = try_launch_attention_tma(a, s);
+        const int e = try_launch_attention_tma(&a, 1, s);
         if (e >= 0) return e;
     }
     Params p{reinterpret_cast<const __nv_bfloat16*>(a.q), a.ldq, reinterpret_cast<const __nv_bfloat16*>(a.k), a.ldk,
@@ -605,6 +642,23 @@ int launch_attention(const AttnArgs& a, cudaStream_t s) {
         MRA_CHECK_CUDA(launch_pdl(attention_kernel<2>, dim3(grid), dim3(64), smem, s, p));
     else
         MRA_CHECK_CUDA(launch_pdl(attention_kernel<4>, dim3(grid), dim3(128), smem, s, p));
+    return 0;
+}
+
+// Two problems (both Q-Formers of a lockstep forward) in ONE launch when the TMA kernel covers both with the same warp
+// count; otherwise one launch each.  *launches receives the number of kernels enqueued.
+int launch_attention_pair(const AttnArgs* a, int n, cudaStream_t s, int* launches) {
+    if (n == 2 && !g_force_generic) {
+        const int e = try_launch_attention_tma(a, 2, s);
+        if (e >= 0) {
+            if (launches) *launches += 1;
+            return e;
+        }
+    }
+    for (int i = 0; i < n; ++i) {
+        if (int e = launch_attention(a[i], s)) return e;
+        if (launches) *launches += 1;
+    }
     return 0;
 }
 

@@ -98,6 +98,7 @@ struct AttnArgs {
     int rows, heads, Sq, Sk, nq_split, kv_dense;
 };
 int launch_attention(const AttnArgs& a, cudaStream_t s);
+int launch_attention_pair(const AttnArgs* a, int n, cudaStream_t s, int* launches);   // n <= 2, one launch when possible
 void set_attention_impl_override(int generic);
 
 int launch_layernorm(const float* x, const float* g, const float* b, float* y32, void* y16, int rows, int n, float eps,

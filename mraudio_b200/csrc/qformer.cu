@@ -417,14 +417,16 @@ int forward_multi(int n, mra_qformer_t* const* hs, const mra_qformer_io* const* 
             add(B.xb, H, L.w_qkv, H, L.b_qkv, nullptr, 0, B.qkv, 3 * H, cx[i].Mtot, 3 * H, H, 0, 0);
         }
         MRA_TRY(flush(MRA_CAT_GEMM));
-        for (int i = 0; i < n; ++i) {
-            const LayerBufs& B = cx[i].ws.layer[l];
-            AttnArgs a{B.qkv, 3 * H, B.qkv + H, 3 * H, B.qkv + 2 * H, 3 * H, B.ctx, H, cx[i].self_mask, cx[i].rows, c.heads,
-                       cx[i].S, cx[i].S, Nq, 0};
+        {
+            AttnArgs aa[MAX_CTX];
+            for (int i = 0; i < n; ++i) {
+                const LayerBufs& B = cx[i].ws.layer[l];
+                aa[i] = AttnArgs{B.qkv, 3 * H, B.qkv + H, 3 * H, B.qkv + 2 * H, 3 * H, B.ctx, H, cx[i].self_mask, cx[i].rows, c.heads,
+                                 cx[i].S, cx[i].S, Nq, 0};
+            }
             span_begin(MRA_CAT_ATTENTION);
-            MRA_TRY(launch_attention(a, s));
+            MRA_TRY(launch_attention_pair(aa, n, s, &launches));
             span_end();
-            ++launches;
         }
         for (int i = 0; i < n; ++i) {
             const auto& L = cx[i].h->w.layer[l];
@@ -447,15 +449,17 @@ int forward_multi(int n, mra_qformer_t* const* hs, const mra_qformer_io* const* 
                 add(B.ab, H, L.w_cq, H, L.b_cq, nullptr, 0, B.cq, H, cx[i].Mq, H, H, 0, 0);
             }
             MRA_TRY(flush(MRA_CAT_GEMM));
-            for (int i = 0; i < n; ++i) {
-                const LayerBufs& B = cx[i].ws.layer[l];
-                const __nv_bfloat16* kbase = cx[i].ws.kv + static_cast<size_t>(cx[i].h->cross_slot[l]) * 2 * H;
-                AttnArgs a{B.cq, H, kbase, cx[i].kv_ld, kbase + H, cx[i].kv_ld, B.cctx, H, cx[i].enc_mask, cx[i].rows, c.heads,
-                           Nq, cx[i].Nk, Nq, 1};
+            {
+                AttnArgs aa[MAX_CTX];
+                for (int i = 0; i < n; ++i) {
+                    const LayerBufs& B = cx[i].ws.layer[l];
+                    const __nv_bfloat16* kbase = cx[i].ws.kv + static_cast<size_t>(cx[i].h->cross_slot[l]) * 2 * H;
+                    aa[i] = AttnArgs{B.cq, H, kbase, cx[i].kv_ld, kbase + H, cx[i].kv_ld, B.cctx, H, cx[i].enc_mask, cx[i].rows,
+                                     c.heads, Nq, cx[i].Nk, Nq, 1};
+                }
                 span_begin(MRA_CAT_ATTENTION);
-                MRA_TRY(launch_attention(a, s));
+                MRA_TRY(launch_attention_pair(aa, n, s, &launches));
                 span_end();
-                ++launches;
             }
             for (int i = 0; i < n; ++i) {
                 const auto& L = cx[i].h->w.layer[l];

@@ -4,7 +4,7 @@ import torch
 from mraudio_b200 import ops
 dev = torch.device("cuda:0")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-for name, M, K in (("ao_x2", 32768, 768), ("f2_x4", 32768, 3072)):
+for name, M, K in (("f2_x4", 32768, 3072), ("ao_x2", 32768, 768)):
     x = torch.randn(M, K, device=dev).to(torch.bfloat16); w = (torch.randn(768, K, device=dev) * 0.02).to(torch.bfloat16)
     b = torch.randn(768, device=dev); r = torch.randn(M, 768, device=dev); g = torch.ones(768, device=dev); be = torch.zeros(768, device=dev)
     ts = []
