@@ -46,6 +46,19 @@ def flops_per_row(Nk, W, T, layers=LAYERS, cross_freq=2):
     return float(lin), float(core), float(kv)
 
 
+def load_ncu_traffic():
+    """dram bytes per launch of the captured launch types (one `ncu --set full` capture, profiles/r01d_ncu_full_summary.json)"""
+    p = os.path.join(ROOT, "profiles", "r01d_ncu_full_summary.json")
+    if not os.path.exists(p):
+        return None
+    rows = json.load(open(p))
+    names = {0: "cross_kv_video (gemm_tc_kernel)", 1: "cross_kv_audio (gemm_tc_kernel)", 2: "qkv_grouped (gemm_tc_kernel)"}
+    out = {}
+    for i, r in enumerate(rows[:3]):
+        out[names[i]] = {"dram_bytes_per_launch": r.get("dram_bytes"), "tensor_pipe_active_pct": float(r["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"])}
+    return out
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -308,7 +321,10 @@ def run_b200(args):
         "step_tflops_algorithmic": step_flops / 1e12,
         "frac_of_bf16_peak_whole_step": step_flops / (ms_dev * 1e-3) / 1e12 / peak,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src + ", sustained figure (kernel timed inside a long step)",
+                     "traffic": (load_ncu_traffic() or {}).get("cross_kv_video (gemm_tc_kernel)", {}).get("dram_bytes_per_launch"),
+                     "traffic_note": "dram read+write bytes of the largest launch (cross-K/V GEMM, video: 1.42 GB algorithmic) from "
+                                     "profiles/r01d_ncu_full_summary.json; other captured launch types in ncu_captures",
+                     "ncu_captures": load_ncu_traffic(), "peak_source": peak_src + ", sustained figure (kernel timed inside a long step)",
                      "kernel": "tcgen05 Linear kernels gemm_tc_kernel + gemm_ln_kernel (all launches of a step, flops-weighted)",
                      "launches_per_step": gemm_n, "ms_per_step_in_kernel": gemm_ms, "ms_per_step_instrumented": ms_instr,
                      "algorithmic_tflop_per_step": lin / 1e12,
