@@ -179,6 +179,12 @@ int mra_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const 
                   int64_t ldr, void* C, int64_t ldc, int32_t M, int32_t N, int32_t K, int32_t gelu, int32_t out_fp32,
                   int32_t impl, void* stream);
 
+/* Weight gradient of a Linear:  dW[n_out, k_in] (+)= dY[n, n_out]^T . X[n, k_in]  on the same tcgen05 kernel, reading dY and X
+ * as they lie in memory (row-major, the reduction index n is the row index) through MN-major shared-memory descriptors:
+ * no transposed copies.  dY, X bf16; dW fp32 (row stride ldw); accumulate != 0 adds to dW. */
+int mra_wgrad_bf16(const void* dY, int64_t ldy, const void* X, int64_t ldx, float* dW, int64_t ldw, int32_t n, int32_t n_out,
+                   int32_t k_in, int32_t accumulate, void* stream);
+
 /* Fused  y = LayerNorm(A . W^T + bias + residual) * gamma + beta  for N == 768: Linear + residual add + post-LayerNorm of
  * BertSelfOutput / BertOutput (HF port modeling_instructblip.py:549-553, 606-610) in one kernel; the pre-LayerNorm sums
  * stay in TMEM.  A bf16 [M, K], W bf16 [768, K], residual fp32 [M, 768]; writes y32 (fp32) and y16 (bf16).

@@ -89,6 +89,7 @@ def _load():
     lib.mra_qformer_profile_mode.argtypes = [vp, i32]
     lib.mra_qformer_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.mra_gemm_bf16.argtypes = [vp, i64, vp, i64, vp, vp, i64, vp, i64, i32, i32, i32, i32, i32, i32, vp]
+    lib.mra_wgrad_bf16.argtypes = [vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, vp]
     lib.mra_gemm_ln_bf16.argtypes = [vp, i64, vp, i64, vp, vp, i64, vp, vp, vp, i64, vp, i64, i32, i32, i32, f32, vp]
     lib.mra_gemm_tile_override.argtypes = [i32]
     lib.mra_gemm_cluster_override.argtypes = [i32]
@@ -109,7 +110,7 @@ EXPORTED_SYMBOLS = (
     "mra_qformer_destroy", "mra_qformer_workspace_bytes", "mra_qformer_forward", "mra_qformer_forward_multi", "mra_qformer_last_launch_count", "mra_qformer_backward_workspace_bytes", "mra_qformer_backward", "mra_adam_step",
     "mra_cast_bf16",
     "mra_qformer_profile_mode", "mra_qformer_profile_read",
-    "mra_gemm_bf16", "mra_gemm_ln_bf16", "mra_gemm_tile_override", "mra_gemm_cluster_override", "mra_attention", "mra_attention_impl_override", "mra_layernorm", "mra_modality_layernorm", "mra_add_frame_position", "mra_mr_score",
+    "mra_gemm_bf16", "mra_wgrad_bf16", "mra_gemm_ln_bf16", "mra_gemm_tile_override", "mra_gemm_cluster_override", "mra_attention", "mra_attention_impl_override", "mra_layernorm", "mra_modality_layernorm", "mra_add_frame_position", "mra_mr_score",
 )
 
 

@@ -47,6 +47,35 @@ transpose_kernel(const __nv_bfloat16* __restrict__ in, int64_t ld_in, __nv_bfloa
     }
 }
 
+// ------------------------------------------------------------------------------------------------ column sums
+// colsum[c] += sum_r in[r, c]   (bias gradient of a Linear whose output gradient is `in`); bf16 in, fp32 atomics out.
+// Block = 32 column pairs x 8 row lanes over a chunk of 512 rows.
+__global__ void __launch_bounds__(256)
+colsum_kernel(const __nv_bfloat16* __restrict__ in, int64_t ld, int R, int C, float* __restrict__ colsum) {
+    __shared__ float2 red[8][32];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int c = blockIdx.x * 64 + 2 * cx;
+    const int r0 = blockIdx.y * 512;
+    float2 acc = make_float2(0.f, 0.f);
+    if (c < C) {
+        const int r1 = min(R, r0 + 512);
+        for (int r = r0 + ry; r < r1; r += 8) {
+            const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(in + static_cast<int64_t>(r) * ld + c));
+            acc.x += v.x;
+            acc.y += v.y;
+        }
+    }
+    red[ry][cx] = acc;
+    __syncthreads();
+    if (ry == 0 && c < C) {
+        float2 s = red[0][cx];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) { s.x += red[i][cx].x; s.y += red[i][cx].y; }
+        atomicAdd(&colsum[c], s.x);
+        atomicAdd(&colsum[c + 1], s.y);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ LayerNorm backward
 constexpr int LNB_WARPS = 8;
 constexpr int LNB_MAXV = 8;   // columns per lane = 8 * LNB_MAXV  (n <= 2048)
@@ -368,6 +397,14 @@ int launch_transpose(const void* in, int64_t ld_in, void* out, int64_t ld_out, i
     dim3 grid((C + 31) / 32, static_cast<unsigned>((ld_out + 31) / 32));
     transpose_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(in), ld_in, reinterpret_cast<__nv_bfloat16*>(out),
                                           ld_out, R, C, colsum);
+    MRA_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_colsum(const void* in, int64_t ld, int R, int C, float* colsum, cudaStream_t s) {
+    MRA_REQUIRE(R > 0 && C > 0 && C % 2 == 0 && ld % 2 == 0, "colsum: bad shape R=%d C=%d", R, C);
+    dim3 grid((C + 63) / 64, (R + 511) / 512);
+    colsum_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(in), ld, R, C, colsum);
     MRA_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -68,6 +68,15 @@ extern "C" int mra_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t 
     return launch_gemm_tc(a, s);
 }
 
+extern "C" int mra_wgrad_bf16(const void* dY, int64_t ldy, const void* X, int64_t ldx, float* dW, int64_t ldw, int32_t n, int32_t n_out,
+                              int32_t k_in, int32_t accumulate, void* stream) {
+    MRA_REQUIRE(dY && X && dW, "mra_wgrad_bf16: NULL operand");
+    if (int e = device_check()) return e;
+    GemmArgs a{dY, ldy, X, ldx, nullptr, accumulate ? dW : nullptr, ldw, dW, ldw, n_out, k_in, n, 0, 1};
+    a.tn = 1;
+    return launch_gemm_tc(a, reinterpret_cast<cudaStream_t>(stream));
+}
+
 extern "C" int mra_gemm_ln_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const float* residual,
                                 int64_t ldr, const float* gamma, const float* beta, float* y32, int64_t ldy32, void* y16,
                                 int64_t ldy16, int32_t M, int32_t N, int32_t K, float eps, void* stream) {

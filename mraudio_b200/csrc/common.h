@@ -66,6 +66,9 @@ struct GemmArgs {
     int M, N, K;
     int gelu;
     int out_fp32;
+    // tn != 0: A is [K, M] and W is [K, N] (the reduction index is the row index of both, row strides lda / ldw):
+    // C[M, N] = A^T W  -- the weight-gradient form dW = dY^T X; needs out_fp32, no GELU
+    int tn = 0;
 };
 int launch_gemm_tc(const GemmArgs& a, cudaStream_t s);
 int launch_gemm_tc_grouped(const GemmArgs* a, int n, cudaStream_t s);   // n <= 4 problems sharing N, K, epilogue kind
@@ -136,6 +139,7 @@ struct AttnBwdArgs {
 };
 int launch_attention_bwd(const AttnBwdArgs& a, cudaStream_t s);
 int launch_transpose(const void* in, int64_t ld_in, void* out, int64_t ld_out, int R, int C, float* colsum, cudaStream_t s);
+int launch_colsum(const void* in, int64_t ld, int R, int C, float* colsum, cudaStream_t s);
 int launch_ln_bwd(const float* dy, const float* pre, const float* gamma, float* dx32, void* dx16, float* dgamma, float* dbeta,
                   int rows, int n, float eps, cudaStream_t s);
 int launch_gelu_fwd(const void* z, void* out, int64_t n, cudaStream_t s);

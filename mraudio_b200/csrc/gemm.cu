@@ -98,7 +98,10 @@ __device__ __forceinline__ uint32_t swz(int r, int j) { return static_cast<uint3
 // CM = CTAs per cluster along M (1 or 2).  With CM = 2 the two CTAs of a cluster compute the tiles (2 mp, n) and
 // (2 mp + 1, n): they need the same W rows, so each loads HALF of the W slab and multicasts it to both (the kernels are
 // L2 -> SM bandwidth bound: 128 x 256 tiles need 96 B/clk/SM at full tensor rate; sharing W cuts that by a third).
-template <int BN, int STAGES, bool GELU, bool OUT_F32, bool RES, int CM>
+// TN = both operands are given with the REDUCTION index as their row index (A: [K, M], W: [K, N], row-major): the
+// weight-gradient GEMM dW[out, in] = dY[n, out]^T . X[n, in] reads dY and X as they lie in memory, through MN-major
+// shared-memory descriptors -- no transposed copies.
+template <int BN, int STAGES, bool GELU, bool OUT_F32, bool RES, int CM, bool TN = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ EpiParams p) {
     using L = SmemLayout<BN, STAGES, RES>;
@@ -172,6 +175,17 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     ptx::mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+                    if (TN) {
+                        // boxes of {64 MN elements, 64 reduction rows}: one per 64 output rows (A) / columns (W)
+#pragma unroll
+                        for (int i = 0; i < BM / 64; ++i)
+                            ptx::tma_load_2d(sA + stage * A_STAGE_BYTES + i * 8192, tmA, &full_bar[stage], m_blk * BM + i * 64, kb * BK);
+#pragma unroll
+                        for (int j = 0; j < BN / 64; ++j)
+                            ptx::tma_load_2d(sB + stage * L::B_STAGE_BYTES + j * 8192, tmB, &full_bar[stage], n_blk * BN + j * 64, kb * BK);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     ptx::tma_load_2d(sA + stage * A_STAGE_BYTES, tmA, &full_bar[stage], kb * BK, m_blk * BM);
                     if (CM == 1) {
                         ptx::tma_load_2d(sB + stage * L::B_STAGE_BYTES, tmB, &full_bar[stage], kb * BK, n_blk * BN);
@@ -188,7 +202,7 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (single thread)
         if (lane == 0) {
-            constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(BM, BN);
+            constexpr uint32_t idesc = TN ? ptx::make_idesc_bf16_f32_mn(BM, BN) : ptx::make_idesc_bf16_f32(BM, BN);
             int stage = 0;
             uint32_t phase = 0;
             int iter = 0;
@@ -201,12 +215,22 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     ptx::mbar_wait(&full_bar[stage], phase);
                     ptx::tc_fence_after();
-                    const uint64_t a_desc = ptx::make_sw128_kmajor_desc(ptx::smem_u32(sA + stage * A_STAGE_BYTES));
-                    const uint64_t b_desc = ptx::make_sw128_kmajor_desc(ptx::smem_u32(sB + stage * L::B_STAGE_BYTES));
+                    if (TN) {
+                        const uint64_t a_desc = ptx::make_sw128_mnmajor_desc(ptx::smem_u32(sA + stage * A_STAGE_BYTES), 8192);
+                        const uint64_t b_desc = ptx::make_sw128_mnmajor_desc(ptx::smem_u32(sB + stage * L::B_STAGE_BYTES), 8192);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in the >>4 address field
-                        ptx::umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                        for (int k = 0; k < BK / 16; ++k) {
+                            // advance 16 reduction rows of 128 B: +2048 B = +128 in the >>4 address field
+                            ptx::umma_bf16_ss(d_tmem, a_desc + 128 * k, b_desc + 128 * k, idesc, (kb | k) != 0);
+                        }
+                    } else {
+                        const uint64_t a_desc = ptx::make_sw128_kmajor_desc(ptx::smem_u32(sA + stage * A_STAGE_BYTES));
+                        const uint64_t b_desc = ptx::make_sw128_kmajor_desc(ptx::smem_u32(sB + stage * L::B_STAGE_BYTES));
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) {
+                            // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in the >>4 address field
+                            ptx::umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                        }
                     }
                     // smem slot reusable once these MMAs have read it (CM = 2: the peer multicasts into it too)
                     if (CM == 1) ptx::umma_commit(&empty_bar[stage]);
@@ -466,10 +490,10 @@ int get_tensor_map(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int 
 
 namespace {
 
-template <int BN, int STAGES, bool GELU, bool OUT_F32, bool RES, int CM>
+template <int BN, int STAGES, bool GELU, bool OUT_F32, bool RES, int CM, bool TN = false>
 int launch_tc_variant(const GemmArgs* ga, int n, cudaStream_t s) {
     using L = SmemLayout<BN, STAGES, RES>;
-    auto kern = gemm_tc_kernel<BN, STAGES, GELU, OUT_F32, RES, CM>;
+    auto kern = gemm_tc_kernel<BN, STAGES, GELU, OUT_F32, RES, CM, TN>;
     static bool attr_set = false;
     if (!attr_set) {
         MRA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -485,8 +509,13 @@ int launch_tc_variant(const GemmArgs* ga, int n, cudaStream_t s) {
     for (int g = 0; g < MAX_GROUPS; ++g) {
         const GemmArgs& a = ga[g < n ? g : 0];
         if (g < n) {
-            if (int e = get_tensor_map(a.A, a.M, a.K, a.lda, BM, BK, 2, &maps.a[g])) return e;
-            if (int e = get_tensor_map(a.W, a.N, a.K, a.ldw, BN / CM, BK, 2, &maps.b[g])) return e;
+            if (TN) {
+                if (int e = get_tensor_map(a.A, a.K, a.M, a.lda, BK, 64, 2, &maps.a[g])) return e;
+                if (int e = get_tensor_map(a.W, a.K, a.N, a.ldw, BK, 64, 2, &maps.b[g])) return e;
+            } else {
+                if (int e = get_tensor_map(a.A, a.M, a.K, a.lda, BM, BK, 2, &maps.a[g])) return e;
+                if (int e = get_tensor_map(a.W, a.N, a.K, a.ldw, BN / CM, BK, 2, &maps.b[g])) return e;
+            }
             if (int e = get_tensor_map(a.C, a.M, a.N, a.ldc, 32, OUT_F32 ? 32 : 64, OUT_F32 ? 4 : 2, &maps.c[g])) return e;
             if (RES) {
                 if (int e = get_tensor_map(a.residual, a.M, a.N, a.ldr, 32, 32, 4, &maps.r[g])) return e;
@@ -544,7 +573,8 @@ int dispatch_epi(const GemmArgs* a, int n, cudaStream_t s) {
 int check_args(const GemmArgs& a) {
     MRA_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "GEMM with empty dimension M=%d N=%d K=%d", a.M, a.N, a.K);
     MRA_REQUIRE(a.N % 8 == 0, "GEMM N must be a multiple of 8, got %d", a.N);
-    MRA_REQUIRE(a.K % 8 == 0, "GEMM K must be a multiple of 8, got %d", a.K);
+    MRA_REQUIRE(a.tn || a.K % 8 == 0, "GEMM K must be a multiple of 8, got %d", a.K);
+    MRA_REQUIRE(!a.tn || a.M % 8 == 0, "transposed-operand GEMM: M must be a multiple of 8, got %d", a.M);
     MRA_REQUIRE((a.ldc * (a.out_fp32 ? 4 : 2)) % 16 == 0, "GEMM output row stride must be a multiple of 16 bytes, got ldc=%lld",
                 (long long)a.ldc);
     MRA_REQUIRE((reinterpret_cast<uintptr_t>(a.C) & 15) == 0, "GEMM output pointer must be 16-byte aligned");
@@ -568,7 +598,7 @@ int launch_gemm_tc_grouped(const GemmArgs* a, int n, cudaStream_t s) {
     for (int g = 0; g < n; ++g) {
         if (int e = check_args(a[g])) return e;
         MRA_REQUIRE(a[g].N == a[0].N && a[g].K == a[0].K && a[g].gelu == a[0].gelu && a[g].out_fp32 == a[0].out_fp32 &&
-                        (a[g].residual != nullptr) == (a[0].residual != nullptr),
+                        (a[g].residual != nullptr) == (a[0].residual != nullptr) && (a[g].tn != 0) == (a[0].tn != 0),
                     "grouped GEMM problems must share N, K and the epilogue kind");
     }
     // Tile-width choice by a wave-quantisation estimate: cost = waves x (tile width) x (a factor for how well that
@@ -587,6 +617,17 @@ int launch_gemm_tc_grouped(const GemmArgs* a, int n, cudaStream_t s) {
         const long tiles = m_tiles * ((a[0].N + bn - 1) / bn);
         const double cost = double((tiles + sms - 1) / sms) * bn * factor[i];
         if (cost < best) { best = cost; best_bn = bn; }
+    }
+    if (a[0].tn) {
+        for (int g = 0; g < n; ++g)
+            MRA_REQUIRE(a[g].tn && a[g].out_fp32 && !a[g].gelu, "transposed-operand GEMM (tn) needs fp32 output and no GELU");
+        const bool res = a[0].residual != nullptr;
+        if (best_bn == 256) return res ? launch_tc_variant<256, 3, false, true, true, 1, true>(a, n, s)
+                                       : launch_tc_variant<256, 4, false, true, false, 1, true>(a, n, s);
+        if (best_bn == 192) return res ? launch_tc_variant<192, 4, false, true, true, 1, true>(a, n, s)
+                                       : launch_tc_variant<192, 4, false, true, false, 1, true>(a, n, s);
+        return res ? launch_tc_variant<128, 5, false, true, true, 1, true>(a, n, s)
+                   : launch_tc_variant<128, 6, false, true, false, 1, true>(a, n, s);
     }
     // 2-CTA clusters along M (W slab multicast) when every problem has enough row blocks to pair up.  Opt-in
     // (MRA_GEMM_CLUSTER=2 / mra_gemm_cluster_override): measured on B200 it neither helps nor hurts (1425 vs 1450 TF/s on

@@ -168,6 +168,19 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
     d |= static_cast<uint64_t>(2) << 61;
     return d;
 }
+// Same for an MN-major operand (the reduction index selects the 128-byte row, 64 MN-contiguous elements per row):
+// what TMA boxes {64 elements, rows = K slab} from a row-major [K][MN] matrix produce, one box per 64 MN elements.
+// Canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units: LBO = distance between 64-element MN blocks
+// (one box), SBO = distance between 8-row K groups (1024 B).
+__device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= static_cast<uint64_t>((1024u >> 4) & 0x3FFF) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
 // Instruction descriptor, kind::f16, A=B=bf16 (K-major), D=f32, dense.
 __host__ __device__ constexpr uint32_t make_idesc_bf16_f32(uint32_t M, uint32_t N) {
     return (1u << 4)            // c_format = F32
@@ -177,6 +190,10 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16_f32(uint32_t M, uint32_t 
            | (0u << 16)         // b_major = K
            | ((N >> 3) << 17)   // n_dim
            | ((M >> 4) << 24);  // m_dim
+}
+// Same with both operands MN-major (a_major = b_major = 1): D[M,N] = sum_k A[k][m] * B[k][n]  (weight gradients).
+__host__ __device__ constexpr uint32_t make_idesc_bf16_f32_mn(uint32_t M, uint32_t N) {
+    return make_idesc_bf16_f32(M, N) | (1u << 15) | (1u << 16);
 }
 
 // ---------------------------------------------------------------- misc

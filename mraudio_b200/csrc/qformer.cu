@@ -593,7 +593,7 @@ extern "C" int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, 
     const int S = Nq + T;
     const int Mq = rows * Nq, Mt = rows * T, Mtot = Mq + Mt;
     const int kv_ld = h->n_cross * 2 * H;
-    const int NK = rows * Nk, NKp = pad8(NK);
+    const int NK = rows * Nk;
     const bool skip_dead = (io->flags & MRA_FWD_SKIP_DEAD_TEXT_FFN) != 0;
     int launches = 0;
 #define MRA_TRY(expr)            \
@@ -606,16 +606,14 @@ extern "C" int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, 
         GemmArgs a{A, lda, Wt, ldw, nullptr, res, ldr, C, ldc, M, N, K, 0, f32};
         return h->gemm_impl == MRA_GEMM_IMPL_SIMT_DEBUG ? launch_gemm_simt(a, s) : launch_gemm_tc(a, s);
     };
-    // dW[N_out, K_in] += dY^T X  (+ db += colsum dY):  dY bf16 [n, N_out] (ld ldy), X bf16 [n, K_in] (ld ldx)
+    // dW[N_out, K_in] += dY^T X  (+ db += colsum dY):  dY bf16 [n, N_out] (ld ldy), X bf16 [n, K_in] (ld ldx).
+    // The GEMM reads dY and X as they lie (MN-major descriptors, gemm.cu "TN"): no transposed copies.
     auto wgrad = [&](const __nv_bfloat16* dY, int64_t ldy, const __nv_bfloat16* X, int64_t ldx, int n, int N_out, int K_in,
-                     float* gW, int64_t ldg, float* gB, const __nv_bfloat16* XT /* pre-transposed X or nullptr */) -> int {
-        const int np = pad8(n);
-        MRA_TRY(launch_transpose(dY, ldy, bw.t1, np, n, N_out, gB, s));
-        if (XT == nullptr) {
-            MRA_TRY(launch_transpose(X, ldx, bw.t2, np, n, K_in, nullptr, s));
-            XT = bw.t2;
-        }
-        MRA_TRY(gemm(bw.t1, np, XT, np, gW, ldg, gW, ldg, N_out, K_in, np, 1));
+                     float* gW, int64_t ldg, float* gB) -> int {
+        if (gB != nullptr) MRA_TRY(launch_colsum(dY, ldy, n, N_out, gB, s));
+        GemmArgs a{dY, ldy, X, ldx, nullptr, gW, ldg, gW, ldg, N_out, K_in, n, 0, 1};
+        a.tn = 1;
+        MRA_TRY(launch_gemm_tc(a, s));   // (the SIMT debug kernel has no transposed-operand form)
         return 0;
     };
     auto ln_bwd = [&](const float* dy, const float* pre, const float* gamma, float* dgam, float* dbet, size_t r0, int n) -> int {
@@ -628,24 +626,22 @@ extern "C" int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, 
                        const float* gamma, float* g_w1, float* g_b1, float* g_w2, float* g_b2, float* g_gam, float* g_bet) -> int {
         const size_t o = r0 * H, oi = r0 * I;
         if (int e = ln_bwd(bw.g_x, B.pre_f, gamma, g_gam, g_bet, r0, n)) return e;
-        if (int e = wgrad(bw.g_pre16 + o, H, B.inter + oi, I, n, H, I, g_w2, I, g_b2, nullptr)) return e;
+        if (int e = wgrad(bw.g_pre16 + o, H, B.inter + oi, I, n, H, I, g_w2, I, g_b2)) return e;
         MRA_TRY(gemm(bw.g_pre16 + o, H, w2T, H, nullptr, 0, bw.g_big16, I, n, I, H, 0));          // d_inter
         MRA_TRY(launch_gelu_bwd(B.z + oi, bw.g_big16, bw.g_big2, static_cast<int64_t>(n) * I, s)); // dz
-        if (int e = wgrad(bw.g_big2, I, in16 + o, H, n, I, H, g_w1, H, g_b1, nullptr)) return e;
+        if (int e = wgrad(bw.g_big2, I, in16 + o, H, n, I, H, g_w1, H, g_b1)) return e;
         MRA_TRY(gemm(bw.g_big2, I, w1T, I, bw.g_pre32 + o, H, bw.g_a + o, H, n, H, I, 1));          // + residual path
         return 0;
     };
 
     // ---- llm_proj
     const __nv_bfloat16* dl = reinterpret_cast<const __nv_bfloat16*>(d_llm);
-    if (int e = wgrad(dl, D, ws.layer[c.layers].xb, H, Mq, D, H, g->w_proj, H, g->b_proj, nullptr)) return e;
+    if (int e = wgrad(dl, D, ws.layer[c.layers].xb, H, Mq, D, H, g->w_proj, H, g->b_proj)) return e;
     MRA_TRY(gemm(dl, D, wT->w_proj, D, nullptr, 0, bw.g_x, H, Mq, H, D, 1));
     if (Mt > 0) {
         MRA_CHECK_CUDA(cudaMemsetAsync(bw.g_x + static_cast<size_t>(Mq) * H, 0, static_cast<size_t>(Mt) * H * 4, s));
         ++launches;
     }
-    // enc^T once for the wgrad of all cross K/V projections
-    MRA_TRY(launch_transpose(io->enc, c.enc_width, bw.encT, NKp, NK, c.enc_width, nullptr, s));
 
     for (int l = c.layers - 1; l >= 0; --l) {
         const auto& L = W.layer[l];
@@ -673,20 +669,20 @@ extern "C" int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, 
             const int slot = h->cross_slot[l];
             const __nv_bfloat16* kbase = ws.kv + static_cast<size_t>(slot) * 2 * H;
             if (int e = ln_bwd(bw.g_a, B.pre_c, L.ln_c_g, G.ln_c_g, G.ln_c_b, 0, Mq)) return e;
-            if (int e = wgrad(bw.g_pre16, H, B.cctx, H, Mq, H, H, G.w_co, H, G.b_co, nullptr)) return e;
+            if (int e = wgrad(bw.g_pre16, H, B.cctx, H, Mq, H, H, G.w_co, H, G.b_co)) return e;
             MRA_TRY(gemm(bw.g_pre16, H, LT.w_co, H, nullptr, 0, bw.g_ctx16, H, Mq, H, H, 0));      // d_cctx
             AttnBwdArgs a{B.cq, H, kbase, kv_ld, kbase + H, kv_ld, bw.g_ctx16, H, bw.g_cq16, H, bw.g_kv16, 2 * H,
                           bw.g_kv16 + H, 2 * H, io->enc_mask ? ws.enc_mask : nullptr, rows, c.heads, Nq, Nk, Nq, 1};
             MRA_TRY(launch_attention_bwd(a, s));
-            if (int e = wgrad(bw.g_cq16, H, B.ab, H, Mq, H, H, G.w_cq, H, G.b_cq, nullptr)) return e;
+            if (int e = wgrad(bw.g_cq16, H, B.ab, H, Mq, H, H, G.w_cq, H, G.b_cq)) return e;
             MRA_TRY(gemm(bw.g_cq16, H, LT.w_cq, H, bw.g_pre32, H, bw.g_a, H, Mq, H, H, 1));         // -> grad of LN_a out (query rows)
-            if (int e = wgrad(bw.g_kv16, 2 * H, nullptr, 0, NK, 2 * H, c.enc_width,
+            if (int e = wgrad(bw.g_kv16, 2 * H, reinterpret_cast<const __nv_bfloat16*>(io->enc), c.enc_width, NK, 2 * H, c.enc_width,
                               g->w_ckv + static_cast<size_t>(slot) * 2 * H * c.enc_width, c.enc_width,
-                              g->b_ckv + static_cast<size_t>(slot) * 2 * H, bw.encT)) return e;
+                              g->b_ckv + static_cast<size_t>(slot) * 2 * H)) return e;
         }
         // ---- self-attention block (all rows)
         if (int e = ln_bwd(bw.g_a, B.pre_a, L.ln_a_g, G.ln_a_g, G.ln_a_b, 0, Mtot)) return e;
-        if (int e = wgrad(bw.g_pre16, H, B.ctx, H, Mtot, H, H, G.w_ao, H, G.b_ao, nullptr)) return e;
+        if (int e = wgrad(bw.g_pre16, H, B.ctx, H, Mtot, H, H, G.w_ao, H, G.b_ao)) return e;
         MRA_TRY(gemm(bw.g_pre16, H, LT.w_ao, H, nullptr, 0, bw.g_ctx16, H, Mtot, H, H, 0));         // d_ctx
         {
             AttnBwdArgs a{B.qkv, 3 * H, B.qkv + H, 3 * H, B.qkv + 2 * H, 3 * H, bw.g_ctx16, H, bw.g_big16, 3 * H,
@@ -694,7 +690,7 @@ extern "C" int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, 
                           rows, c.heads, S, S, Nq, 0};
             MRA_TRY(launch_attention_bwd(a, s));
         }
-        if (int e = wgrad(bw.g_big16, 3 * H, B.xb, H, Mtot, 3 * H, H, G.w_qkv, H, G.b_qkv, nullptr)) return e;
+        if (int e = wgrad(bw.g_big16, 3 * H, B.xb, H, Mtot, 3 * H, H, G.w_qkv, H, G.b_qkv)) return e;
         MRA_TRY(gemm(bw.g_big16, 3 * H, LT.w_qkv, 3 * H, bw.g_pre32, H, bw.g_x, H, Mtot, H, 3 * H, 1));  // grad of the layer input
     }
     // ---- embeddings

@@ -42,6 +42,21 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     return out
 
 
+def wgrad(dy: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    """dW[n_out, k_in] (+)= dy[n, n_out]^T @ x[n, k_in]; dy, x bf16 row-major; dW fp32."""
+    _need_cuda(dy, x, out)
+    assert dy.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and dy.shape[0] == x.shape[0]
+    assert dy.stride(1) == 1 and x.stride(1) == 1
+    n, n_out = dy.shape
+    k_in = x.shape[1]
+    if out is None:
+        assert not accumulate
+        out = torch.empty(n_out, k_in, device=dy.device, dtype=torch.float32)
+    check(lib.mra_wgrad_bf16(ptr(dy), dy.stride(0), ptr(x), x.stride(0), ptr(out), out.stride(0), n, n_out, k_in,
+                             int(accumulate), current_stream()))
+    return out
+
+
 def linear_residual_layernorm(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], residual: torch.Tensor,
                               gamma: torch.Tensor, beta: torch.Tensor, eps: float):
     """(fp32, bf16) copies of LayerNorm(x @ weight.T + bias + residual) * gamma + beta; weight [768, K] bf16."""

@@ -136,6 +136,31 @@ def test_gemm_cluster_multicast_variant(cm, M, N, K):
         _lib.lib.mra_gemm_tile_override(0)
 
 
+@pytest.mark.parametrize("n,n_out,k_in", [(64, 128, 64), (4096, 768, 768), (2048, 3072, 768), (2048, 768, 3072), (1000, 2304, 768),
+                                          (16448, 1536, 1408), (77, 72, 200), (130, 4096, 768)])
+def test_wgrad_mn_major_operands(n, n_out, k_in):
+    """dW = dY^T X straight from the row-major dY / X (MN-major UMMA descriptors), incl. in-place accumulation."""
+    from mraudio_b200 import ops, _lib
+    g = torch.Generator().manual_seed(n + n_out)
+    dy = torch.randn(n, n_out, generator=g).to(_dev(), torch.bfloat16)
+    x = torch.randn(n, k_in, generator=g).to(_dev(), torch.bfloat16)
+    ref = dy.float().t() @ x.float()
+    try:
+        for bn in (0, 128, 192, 256):
+            _lib.check(_lib.lib.mra_gemm_tile_override(bn))
+            dw = ops.wgrad(dy, x)
+            assert _rel(dw, ref) < 1e-4, bn
+            acc = torch.full_like(dw, 0.5)
+            ops.wgrad(dy, x, out=acc, accumulate=True)
+            assert _rel(acc, ref + 0.5) < 1e-4, bn
+    finally:
+        _lib.lib.mra_gemm_tile_override(0)
+    # strided views (a column block of a wider matrix, as the backward passes them)
+    big = torch.randn(n, n_out + 64, generator=g).to(_dev(), torch.bfloat16)
+    dw = ops.wgrad(big[:, 64:], x)
+    assert _rel(dw, big[:, 64:].float().t() @ x.float()) < 1e-4
+
+
 def test_gemm_tcgen05_equals_simt_bitwise_ordering_free():
     """Same bf16 operands, fp32 accumulation: the two implementations agree to fp32 rounding noise."""
     from mraudio_b200 import ops
