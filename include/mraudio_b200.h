@@ -101,6 +101,13 @@ typedef struct mra_qformer_io {
     /* outputs (either may be NULL) */
     float* last_hidden;         /* fp32 [rows, Nq+T, H]  == Qformer.bert(...).last_hidden_state */
     void* llm_out;              /* bf16 [rows*Nq, D]     == llm_proj(last_hidden_state[:, :Nq]) viewed [bs, F*Nq, D] */
+    /* Optional scatter of llm_out into the interleaved LLM prompt (models/xinstructblip.py:359-366: per frame
+     * cue || 32 video tokens || cue || 32 audio tokens || timestamp): with llm_frames = F > 0, row (b*F + f)*Nq + q is
+     * written to llm_out + b*llm_video_stride + f*llm_frame_stride + q*llm_ld (bf16 elements; llm_ld 0 = llm_dim), i.e.
+     * llm_out points at the slot of (video 0, frame 0) inside inputs_embeds [bs, L, D].  Needs Nq == 32.  All 0 = dense. */
+    int32_t llm_frames;
+    int32_t reserved0;
+    int64_t llm_ld, llm_frame_stride, llm_video_stride;
 } mra_qformer_io;
 
 /* Replaces `{modality}_Qformer.bert(input_ids, attention_mask=, query_embeds=, encoder_hidden_states=,
@@ -165,6 +172,24 @@ int mra_cast_bf16(const float* in, void* out, int64_t n, void* stream);
 #define MRA_NUM_CATS 5
 int mra_qformer_profile_mode(mra_qformer_t* h, int32_t mode);
 int mra_qformer_profile_read(mra_qformer_t* h, double* ms_by_cat, int64_t* launches_by_cat);
+
+/* ---- LLM prompt assembly (models/xinstructblip.py:342-385, 544-594) -----------------------------------------------
+ * inputs_embeds [bs, L, D] bf16 is the concatenation, per video, of F frame blocks (optional enumeration tokens, cue,
+ * 32 video tokens, cue, 32 audio tokens, timestamp tokens) followed by the duration and the prompt embeddings.  The
+ * Q-Former tokens are written in place by llm_proj (mra_qformer_io::llm_frames); this call copies every OTHER piece
+ * (embeddings of LLM tokens, produced by the caller's frozen LLM embedding table) to its slot in one launch.
+ * Segment s: rows [0, rows) of src (bf16, row length D) go to dst rows [dst_row + f*dst_frame_rows, ...) of every video b,
+ * for f in [0, frames); the source row block is src + b*src_video_stride + f*src_frame_stride (elements; 0 = the same
+ * piece for every video / frame, as for the cues). */
+typedef struct mra_prompt_segment {
+    const void* src;
+    int64_t src_video_stride, src_frame_stride;
+    int32_t rows, frames;
+    int32_t dst_row, dst_frame_rows;
+} mra_prompt_segment;
+#define MRA_MAX_PROMPT_SEGMENTS 16
+int mra_prompt_assemble(void* inputs_embeds, int32_t bs, int32_t L, int32_t D, const mra_prompt_segment* segs, int32_t n_segs,
+                        void* stream);
 
 /* ---- building-block ops (each is also what the forward above launches; exposed for parity tests and backward) */
 

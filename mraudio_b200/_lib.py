@@ -56,7 +56,12 @@ class QFormerGrads(C.Structure):
 class QFormerIO(C.Structure):
     _fields_ = [("enc", C.c_void_p), ("input_ids", C.c_void_p), ("attn_mask", C.c_void_p), ("enc_mask", C.c_void_p),
                 ("query_embeds", C.c_void_p), ("q_rows", C.c_int32), ("rows", C.c_int32), ("T", C.c_int32),
-                ("Nk", C.c_int32), ("flags", C.c_uint32), ("last_hidden", C.c_void_p), ("llm_out", C.c_void_p)]
+                ("Nk", C.c_int32), ("flags", C.c_uint32), ("last_hidden", C.c_void_p), ("llm_out", C.c_void_p),
+                ("llm_frames", C.c_int32), ("reserved0", C.c_int32), ("llm_ld", C.c_int64), ("llm_frame_stride", C.c_int64),
+                ("llm_video_stride", C.c_int64)]
+
+
+MAX_PROMPT_SEGMENTS = 16
 
 
 def _load():
@@ -98,6 +103,7 @@ def _load():
     lib.mra_layernorm.argtypes = [vp, vp, vp, vp, vp, i32, i32, f32, vp]
     lib.mra_modality_layernorm.argtypes = [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp]
     lib.mra_add_frame_position.argtypes = [vp, i32, vp, vp, i32, i32, i32, i32, vp]
+    lib.mra_prompt_assemble.argtypes = [vp, i32, i32, i32, vp, i32, vp]
     lib.mra_mr_score.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]
     return lib
 
@@ -110,7 +116,7 @@ EXPORTED_SYMBOLS = (
     "mra_qformer_destroy", "mra_qformer_workspace_bytes", "mra_qformer_forward", "mra_qformer_forward_multi", "mra_qformer_last_launch_count", "mra_qformer_backward_workspace_bytes", "mra_qformer_backward", "mra_adam_step",
     "mra_cast_bf16",
     "mra_qformer_profile_mode", "mra_qformer_profile_read",
-    "mra_gemm_bf16", "mra_wgrad_bf16", "mra_gemm_ln_bf16", "mra_gemm_tile_override", "mra_gemm_cluster_override", "mra_attention", "mra_attention_impl_override", "mra_layernorm", "mra_modality_layernorm", "mra_add_frame_position", "mra_mr_score",
+    "mra_gemm_bf16", "mra_wgrad_bf16", "mra_gemm_ln_bf16", "mra_gemm_tile_override", "mra_gemm_cluster_override", "mra_attention", "mra_attention_impl_override", "mra_layernorm", "mra_modality_layernorm", "mra_add_frame_position", "mra_prompt_assemble", "mra_mr_score",
 )
 
 

@@ -135,6 +135,13 @@ extern "C" int mra_add_frame_position(const void* x, int32_t in_dtype, const flo
     return launch_add_frame_pos(x, in_dtype, pos, out, bs, frames, n, W, reinterpret_cast<cudaStream_t>(stream));
 }
 
+extern "C" int mra_prompt_assemble(void* inputs_embeds, int32_t bs, int32_t L, int32_t D, const mra_prompt_segment* segs,
+                                   int32_t n_segs, void* stream) {
+    MRA_REQUIRE(inputs_embeds && (segs || n_segs == 0), "mra_prompt_assemble: NULL argument");
+    if (int e = device_check()) return e;
+    return launch_prompt_assemble(inputs_embeds, bs, L, D, segs, n_segs, reinterpret_cast<cudaStream_t>(stream));
+}
+
 extern "C" int mra_mr_score(const double* pred, const int32_t* n_pred, const double* gt, const int32_t* n_gt,
                             const double* thds, int32_t Q, int32_t Pmax, int32_t Gmax, double* out_ap, double* out_iou,
                             uint8_t* out_invalid, void* stream) {

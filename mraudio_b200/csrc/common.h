@@ -69,6 +69,11 @@ struct GemmArgs {
     // tn != 0: A is [K, M] and W is [K, N] (the reduction index is the row index of both, row strides lda / ldw):
     // C[M, N] = A^T W  -- the weight-gradient form dW = dY^T X; needs out_fp32, no GELU
     int tn = 0;
+    // c_frames > 0: C is not one [M, N] matrix but a scatter target: output row r = (b * c_frames + f) * 32 + q goes to
+    // C + b * c_batch_stride + f * c_frame_stride + q * ldc (elements) -- llm_proj writing each frame's 32 query tokens
+    // into their slot of the interleaved LLM prompt (models/xinstructblip.py:359-366).  bf16 output, M % 32 == 0.
+    int c_frames = 0;
+    int64_t c_frame_stride = 0, c_batch_stride = 0;
 };
 int launch_gemm_tc(const GemmArgs& a, cudaStream_t s);
 int launch_gemm_tc_grouped(const GemmArgs* a, int n, cudaStream_t s);   // n <= 4 problems sharing N, K, epilogue kind
@@ -76,6 +81,9 @@ int launch_gemm_simt(const GemmArgs& a, cudaStream_t s);
 // cached TMA descriptor of a row-major [rows, cols] matrix (2- or 4-byte elements), box {box_cols, box_rows}, 128B swizzle
 int get_tensor_map(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols, int elem_bytes,
                    CUtensorMap* out);
+// bf16 [batch][frames][32][cols] with element strides (batch_stride, frame_stride, ld, 1); box {64 cols, 32 rows, 1, 1}
+int get_tensor_map_scatter(const void* ptr, int64_t batch, int64_t frames, int64_t cols, int64_t ld, int64_t frame_stride,
+                           int64_t batch_stride, CUtensorMap* out);
 void set_gemm_tile_override(int bn);
 void set_gemm_cluster_override(int cm);   // 1 = never pair CTAs, 2 = pair along M when possible (default)
 
@@ -123,6 +131,7 @@ int launch_embed_layernorm(const float* query_embeds, int q_rows, const int32_t*
 // additive masks (LAVIS get_extended_attention_mask): out[r, j] = (1 - mask[r, j]) * -10000
 int launch_build_enc_mask(const int32_t* enc_mask, float* out, int rows, int Nk, cudaStream_t s);
 // split layout [queries ; text] fp32 -> interleaved [rows, Nq+T, H] fp32
+int launch_prompt_assemble(void* out, int bs, int L, int D, const mra_prompt_segment* segs, int n, cudaStream_t s);
 int launch_gather_last_hidden(const float* split, float* out, int rows, int Nq, int T, int H, cudaStream_t s);
 
 // ---- backward / optimizer (backward.cu)

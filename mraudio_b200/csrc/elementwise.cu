@@ -339,6 +339,54 @@ int launch_build_enc_mask(const int32_t* enc_mask, float* out, int rows, int Nk,
     return 0;
 }
 
+// LLM prompt assembly: one block per (segment row, frame, video) copies D bf16 (16-byte accesses) into inputs_embeds.
+struct PromptSegs {
+    mra_prompt_segment seg[MRA_MAX_PROMPT_SEGMENTS];
+    int row_start[MRA_MAX_PROMPT_SEGMENTS + 1];   // prefix sums of rows * frames
+    int n;
+};
+namespace {
+__global__ void __launch_bounds__(256) prompt_assemble_kernel(__nv_bfloat16* __restrict__ out, int L, int D, const PromptSegs ps) {
+    const int item = blockIdx.x, b = blockIdx.y;
+    int s = 0;
+    for (int i = 1; i < ps.n; ++i)
+        if (item >= ps.row_start[i]) s = i;
+    const mra_prompt_segment& sg = ps.seg[s];
+    const int t = item - ps.row_start[s];
+    const int f = t / sg.rows, r = t - f * sg.rows;
+    const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(sg.src) + b * sg.src_video_stride + f * sg.src_frame_stride +
+                               static_cast<int64_t>(r) * D;
+    __nv_bfloat16* dst = out + (static_cast<int64_t>(b) * L + sg.dst_row + static_cast<int64_t>(f) * sg.dst_frame_rows + r) * D;
+    for (int c = threadIdx.x * 8; c < D; c += blockDim.x * 8)
+        *reinterpret_cast<uint4*>(dst + c) = __ldg(reinterpret_cast<const uint4*>(src + c));
+}
+}  // namespace
+
+int launch_prompt_assemble(void* out, int bs, int L, int D, const mra_prompt_segment* segs, int n, cudaStream_t s) {
+    MRA_REQUIRE(out && bs > 0 && L > 0 && D > 0 && D % 8 == 0, "prompt assembly: bad shape bs=%d L=%d D=%d", bs, L, D);
+    MRA_REQUIRE(n >= 0 && n <= MRA_MAX_PROMPT_SEGMENTS, "prompt assembly takes at most %d segments, got %d", MRA_MAX_PROMPT_SEGMENTS, n);
+    MRA_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "inputs_embeds must be 16-byte aligned");
+    PromptSegs ps;
+    ps.n = n;
+    int total = 0;
+    for (int i = 0; i < n; ++i) {
+        const mra_prompt_segment& g = segs[i];
+        MRA_REQUIRE(g.src && g.rows > 0 && g.frames > 0, "prompt segment %d: empty", i);
+        MRA_REQUIRE((reinterpret_cast<uintptr_t>(g.src) & 15) == 0 && g.src_video_stride % 8 == 0 && g.src_frame_stride % 8 == 0,
+                    "prompt segment %d: source must be 16-byte aligned", i);
+        MRA_REQUIRE(g.dst_row >= 0 && g.dst_row + static_cast<int64_t>(g.frames - 1) * g.dst_frame_rows + g.rows <= L,
+                    "prompt segment %d exceeds the sequence (L=%d)", i, L);
+        ps.seg[i] = g;
+        ps.row_start[i] = total;
+        total += g.rows * g.frames;
+    }
+    for (int i = n; i <= MRA_MAX_PROMPT_SEGMENTS; ++i) ps.row_start[i] = total;
+    if (total == 0) return 0;
+    prompt_assemble_kernel<<<dim3(total, bs), 256, 0, s>>>(reinterpret_cast<__nv_bfloat16*>(out), L, D, ps);
+    MRA_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int launch_gather_last_hidden(const float* split, float* out, int rows, int Nq, int T, int H, cudaStream_t s) {
     MRA_REQUIRE(H % 4 == 0, "hidden size must be a multiple of 4");
     const int64_t n = static_cast<int64_t>(rows) * (Nq + T) * (H / 4);

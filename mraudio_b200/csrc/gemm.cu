@@ -43,6 +43,7 @@ struct GroupMaps {
 struct EpiParams {
     const float* bias[MAX_GROUPS];
     int M[MAX_GROUPS];
+    int c_frames[MAX_GROUPS];         // > 0: the C map of this group is the 4-D scatter map (GemmArgs::c_frames)
     int tile_start[MAX_GROUPS + 1];   // first tile index of each group (tiles of a group: m-block major, n fastest)
     int groups;
     int N, K;
@@ -360,7 +361,18 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
                 ptx::fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA (async proxy)
                 __syncwarp();
                 if (lane == 0) {
-                    if (col0 < p.N && row0 < Mg) ptx::tma_store_2d(tmC, odst, col0, row0);  // edges clipped by TMA
+                    if (col0 < p.N && row0 < Mg) {
+                        bool scattered = false;
+                        if constexpr (!OUT_F32) {
+                            const int cf = p.c_frames[g];
+                            if (cf > 0) {   // 32-row slab = the 32 query tokens of one (video, frame): coordinates (col, q, f, b)
+                                const int rf = row0 >> 5;
+                                ptx::tma_store_4d(tmC, odst, col0, 0, rf % cf, rf / cf);
+                                scattered = true;
+                            }
+                        }
+                        if (!scattered) ptx::tma_store_2d(tmC, odst, col0, row0);  // edges clipped by TMA
+                    }
                     ptx::tma_store_commit();
                 }
             }
@@ -502,6 +514,27 @@ int get_tensor_map(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int 
     return 0;
 }
 
+int get_tensor_map_scatter(const void* ptr, int64_t batch, int64_t frames, int64_t cols, int64_t ld, int64_t frame_stride,
+                           int64_t batch_stride, CUtensorMap* out) {
+    EncodeTiledFn enc = get_encode_fn();
+    MRA_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+    MRA_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ld % 8 == 0 && frame_stride % 8 == 0 && batch_stride % 8 == 0,
+                "scatter output: pointer and strides must be multiples of 16 bytes");
+    MRA_REQUIRE(batch > 0 && frames > 0 && ld >= cols && frame_stride >= 32 * ld && (batch == 1 || batch_stride >= frames * frame_stride),
+                "scatter output: overlapping slots (ld=%lld frame_stride=%lld batch_stride=%lld)", (long long)ld,
+                (long long)frame_stride, (long long)batch_stride);
+    cuuint64_t gdim[4] = {static_cast<cuuint64_t>(cols), 32, static_cast<cuuint64_t>(frames), static_cast<cuuint64_t>(batch)};
+    cuuint64_t gstride[3] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(frame_stride) * 2,
+                             static_cast<cuuint64_t>(batch > 1 ? batch_stride : frames * frame_stride) * 2};
+    cuuint32_t box[4] = {64, 32, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MRA_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (4-D scatter) failed with CUresult %d", (int)r);
+    return 0;
+}
+
 namespace {
 
 template <int BN, int STAGES, bool GELU, bool OUT_F32, bool RES, int CM, bool TN = false>
@@ -530,7 +563,13 @@ int launch_tc_variant(const GemmArgs* ga, int n, cudaStream_t s) {
                 if (int e = get_tensor_map(a.A, a.M, a.K, a.lda, BM, BK, 2, &maps.a[g])) return e;
                 if (int e = get_tensor_map(a.W, a.N, a.K, a.ldw, BN / CM, BK, 2, &maps.b[g])) return e;
             }
-            if (int e = get_tensor_map(a.C, a.M, a.N, a.ldc, 32, OUT_F32 ? 32 : 64, OUT_F32 ? 4 : 2, &maps.c[g])) return e;
+            p.c_frames[g] = a.c_frames;
+            if (a.c_frames > 0) {
+                MRA_REQUIRE(!OUT_F32 && a.M % 32 == 0 && (a.M / 32) % a.c_frames == 0,
+                            "scatter output needs bf16 C and M = videos * frames * 32 (M=%d frames=%d)", a.M, a.c_frames);
+                if (int e = get_tensor_map_scatter(a.C, a.M / 32 / a.c_frames, a.c_frames, a.N, a.ldc, a.c_frame_stride,
+                                                   a.c_batch_stride, &maps.c[g])) return e;
+            } else if (int e = get_tensor_map(a.C, a.M, a.N, a.ldc, 32, OUT_F32 ? 32 : 64, OUT_F32 ? 4 : 2, &maps.c[g])) return e;
             if (RES) {
                 if (int e = get_tensor_map(a.residual, a.M, a.N, a.ldr, 32, 32, 4, &maps.r[g])) return e;
             } else {
@@ -544,6 +583,7 @@ int launch_tc_variant(const GemmArgs* ga, int n, cudaStream_t s) {
             maps.a[g] = maps.a[0]; maps.b[g] = maps.b[0]; maps.c[g] = maps.c[0]; maps.r[g] = maps.r[0];
             p.bias[g] = nullptr;
             p.M[g] = 0;
+            p.c_frames[g] = 0;
             p.tile_start[g] = total;
         }
     }

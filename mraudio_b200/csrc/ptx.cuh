@@ -80,6 +80,13 @@ __device__ __forceinline__ void tma_store_2d(const void* desc, const void* smem_
                  "r"(smem_u32(smem_src)), "r"(crd0), "r"(crd1)
                  : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const void* desc, const void* smem_src, int32_t crd0, int32_t crd1, int32_t crd2,
+                                             int32_t crd3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(desc)),
+                 "r"(smem_u32(smem_src)), "r"(crd0), "r"(crd1), "r"(crd2), "r"(crd3)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() {

@@ -546,8 +546,17 @@ int forward_multi(int n, mra_qformer_t* const* hs, const mra_qformer_io* const* 
         }
         if (cx[i].io->llm_out) {
             const auto& W = cx[i].h->w;
-            add(cx[i].ws.layer[c.layers].xb, H, W.w_proj, H, W.b_proj, nullptr, 0, cx[i].io->llm_out, c.llm_dim, cx[i].Mq,
-                c.llm_dim, H, 0, 0);
+            const mra_qformer_io* io = cx[i].io;
+            add(cx[i].ws.layer[c.layers].xb, H, W.w_proj, H, W.b_proj, nullptr, 0, io->llm_out,
+                io->llm_frames > 0 && io->llm_ld > 0 ? io->llm_ld : c.llm_dim, cx[i].Mq, c.llm_dim, H, 0, 0);
+            if (io->llm_frames > 0) {   // scatter into the interleaved LLM prompt (4-D TMA store map)
+                MRA_REQUIRE(Nq == 32 && cx[i].rows % io->llm_frames == 0 && h0->gemm_impl != MRA_GEMM_IMPL_SIMT_DEBUG,
+                            "llm_frames=%d needs 32 queries and rows (%d) = videos * frames", io->llm_frames, cx[i].rows);
+                GemmArgs& a = ga[ng - 1];
+                a.c_frames = io->llm_frames;
+                a.c_frame_stride = io->llm_frame_stride;
+                a.c_batch_stride = io->llm_video_stride;
+            }
         }
     }
     MRA_TRY(flush(MRA_CAT_GEMM));

@@ -274,8 +274,11 @@ class BertModelB200(nn.Module):
     # ------------------------------------------------------------------------------------------------------- forward
     def prepare(self, input_ids=None, attention_mask=None, position_ids=None, query_embeds=None, encoder_hidden_states=None,
                 encoder_attention_mask=None, llm_proj: nn.Linear = None, need_last_hidden: bool = True,
-                skip_dead_text_ffn: bool = False):
-        """Validate the arguments of one ``Qformer.bert(...)`` call and stage everything the C-ABI needs (handle, packed
+                skip_dead_text_ffn: bool = False, llm_scatter=None):
+        """``llm_scatter = (view [bs, F, Nq, D] into inputs_embeds)``: llm_proj writes each frame's tokens into that strided
+        view (4-D TMA store, see ``mraudio_b200/prompt.py``) instead of a dense ``[rows*Nq, D]`` tensor.
+
+        Validate the arguments of one ``Qformer.bert(...)`` call and stage everything the C-ABI needs (handle, packed
         weights, io struct, workspace, output tensors) without launching.  ``launch_prepared`` enqueues one or two such
         calls (two = both modalities in lockstep, grouped GEMM launches)."""
         if query_embeds is None or encoder_hidden_states is None:
@@ -331,12 +334,21 @@ class BertModelB200(nn.Module):
         if self._workspace is None or self._workspace.numel() < need or self._workspace.device != dev:
             self._workspace = torch.empty(need, device=dev, dtype=torch.uint8)
         last_hidden = torch.empty(rows, Nq + T, cfg.hidden_size, device=dev, dtype=torch.float32) if need_last_hidden else None
-        llm_out = torch.empty(rows * Nq, llm_dim, device=dev, dtype=torch.bfloat16) if llm_proj is not None else None
+        scatter = {}
+        if llm_scatter is not None:
+            v = llm_scatter
+            if llm_proj is None or v.dtype != torch.bfloat16 or v.dim() != 4 or v.shape[2:] != (Nq, llm_dim) or \
+                    v.shape[0] * v.shape[1] != rows or v.stride(3) != 1:
+                raise ValueError(f"llm_scatter must be a bf16 [bs, F, {Nq}, {llm_dim}] view with bs*F == {rows}")
+            llm_out, llm_view = v, v
+            scatter = dict(llm_frames=v.shape[1], llm_ld=v.stride(2), llm_frame_stride=v.stride(1), llm_video_stride=v.stride(0))
+        else:
+            llm_out = torch.empty(rows * Nq, llm_dim, device=dev, dtype=torch.bfloat16) if llm_proj is not None else None
+            llm_view = llm_out.view(rows, Nq, llm_dim) if llm_out is not None else None
         io = _lib.QFormerIO(enc=enc_b.data_ptr(), input_ids=_lib.ptr(ids), attn_mask=_lib.ptr(tmask), enc_mask=_lib.ptr(emask),
                             query_embeds=qe.data_ptr(), q_rows=q_rows, rows=rows, T=T, Nk=Nk, flags=flags,
-                            last_hidden=_lib.ptr(last_hidden), llm_out=_lib.ptr(llm_out))
-        out = QFormerOutput(last_hidden_state=last_hidden,
-                            llm_inputs=llm_out.view(rows, Nq, llm_dim) if llm_out is not None else None)
+                            last_hidden=_lib.ptr(last_hidden), llm_out=_lib.ptr(llm_out), **scatter)
+        out = QFormerOutput(last_hidden_state=last_hidden, llm_inputs=llm_view)
         return _Prepared(self, h, io, self._workspace, out, (enc_b, qe, ids, tmask, emask))
 
     def forward(self, input_ids=None, attention_mask=None, position_ids=None, query_embeds=None,

@@ -13,8 +13,11 @@ Reference surface kept (file:line under /root/reference/models/xinstructblip.py)
   query-token expand, mask build, frame fold + batch-major reorder, ``Qformer.bert``, slice, ``llm_proj``, reshape to
   ``[bs, F*32, D]``, ``atts_llm`` -- including the reference's frame-major text tiling for bs > 1 (:287-289).
 
-Everything out of scope (ViT / BEATs encoders, tokenizers, the LLM, prompt assembly) is taken as input: the encoders'
-outputs ("cached features"), BERT ``input_ids`` / ``attention_mask`` of the prompt.
+* ``encode_modalities(..., prompt=PromptPieces)`` continues through the LLM-prompt assembly of :342-386 / :544-594
+  (``mraudio_b200/prompt.py``) and returns ``(inputs_embeds, attention_mask)``.
+
+Everything out of scope (ViT / BEATs encoders, tokenizers, the LLM and its embedding table) is taken as input: the
+encoders' outputs ("cached features"), BERT ``input_ids`` / ``attention_mask`` of the prompt, embeddings of LLM tokens.
 """
 from __future__ import annotations
 
@@ -25,6 +28,7 @@ import torch
 from torch import nn
 
 from . import _lib, ops
+from . import prompt as prompt_mod
 from .qformer import BertConfig, BertLMHeadModel, LLMProjB200, launch_prepared
 
 Features = Union[torch.Tensor, Sequence[torch.Tensor]]
@@ -178,13 +182,28 @@ class XInstructBLIPQFormers(nn.Module):
 
     def encode_modalities(self, feats: Dict[str, Features], input_ids: torch.Tensor, attention_mask: torch.Tensor,
                           apply_ln: bool = False, match_reference_text_tiling: bool = True,
-                          need_last_hidden: bool = False):
+                          need_last_hidden: bool = False, prompt: Optional["prompt_mod.PromptPieces"] = None,
+                          scatter_epilogue: bool = True):
         """Returns ``(inputs_llm, atts_llm)`` dicts exactly as :296-306 builds them.
 
         input_ids / attention_mask: ``text_Qformer.input_ids`` / ``.attention_mask`` ``[bs, T]`` (:233-239).
+
+        With ``prompt`` (the LLM-token pieces of :320-386) the call continues through the prompt assembly and returns
+        ``(inputs_embeds [bs, L, D], attention_mask [bs, L])`` -- what :388-392 hands to ``llm_model.generate``: the
+        llm_proj epilogue writes the query tokens straight into their slots (``scatter_epilogue``; off = dense outputs +
+        copy, kept for the parity test) and one more launch copies the text pieces.
         """
         inputs_llm, atts_llm = {}, {}
         todo = [m for m in self.modalities if m in feats]
+        lay = embeds = None
+        if prompt is not None:
+            bs0 = input_ids.shape[0]
+            f0 = feats[todo[0]]
+            frames = len(f0) if isinstance(f0, (list, tuple)) else f0.shape[1]
+            prompt = prompt_mod.normalise_pieces(prompt, input_ids.device)
+            lay = prompt_mod.PromptLayout.build(prompt, bs0, frames, self.num_query_token, todo)
+            embeds = torch.empty(bs0, lay.L, lay.D, device=input_ids.device, dtype=torch.bfloat16)
+            scatter_epilogue = scatter_epilogue and lay.uniform and self.num_query_token == 32
         preps, shapes = [], []
         extra = 0
         for modality in todo:
@@ -204,7 +223,9 @@ class XInstructBLIPQFormers(nn.Module):
             proj = getattr(self, f"{modality}_llm_proj")
             preps.append(qformer.bert.prepare(ids, attention_mask=torch.cat([q_atts, tmask], 1), query_embeds=query_tokens,
                                               encoder_hidden_states=enc, encoder_attention_mask=None, llm_proj=proj,
-                                              need_last_hidden=need_last_hidden, skip_dead_text_ffn=not need_last_hidden))
+                                              need_last_hidden=need_last_hidden, skip_dead_text_ffn=not need_last_hidden,
+                                              llm_scatter=prompt_mod.query_slot_view(embeds, lay, modality)
+                                              if lay is not None and scatter_epilogue else None))
             shapes.append((bs, num))
         # Both Q-Formers share the layer geometry: run them in lockstep, every Linear as ONE grouped GEMM launch over
         # (video queries, video text, audio queries, audio text) -- see mra_qformer_forward_multi.
@@ -215,6 +236,12 @@ class XInstructBLIPQFormers(nn.Module):
             for p in preps:
                 launches += launch_prepared([p])
         self.last_launches = launches + extra
+        if lay is not None:
+            dense = None if scatter_epilogue else {m: p.out.llm_inputs.view(lay.bs, lay.frames, self.num_query_token, lay.D)
+                                                   for m, p in zip(todo, preps)}
+            self.last_launches += prompt_mod.copy_pieces(embeds, prompt, lay, dense)
+            self.last_prompt_layout = lay
+            return embeds, prompt_mod.attention_mask(prompt, lay, embeds.device)
         for modality, p, (bs, num) in zip(todo, preps, shapes):
             y = p.out.llm_inputs                                                   # [bs*num, 32, D]
             inputs_llm[modality] = y.reshape(bs, num, self.num_query_token, -1).view(bs, num * self.num_query_token, -1)
