@@ -328,6 +328,257 @@ attn_bwd_kernel(const AttnBwdParams p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------ attention backward (tensor cores)
+// Same contract as attn_bwd_kernel, every product on mma.sync.m16n8k16 (bf16 in, fp32 accumulate): the tiles of one
+// (row, head) -- 32..160 queries x 64..272 keys x 64 dims -- are far below a tcgen05 128-row atom, as in the forward.
+// One CTA (8 warps) per (row, head); Q, dO, K, V staged once in shared memory (144-byte rows: conflict-free fragment loads
+// and ldmatrix), then
+//   phase 0  row statistics of S = Q K^T / 8 + mask (online max / sum in the log2 domain, split over key slices when
+//            there are fewer 16-query tiles than warps); delta_i = dO_i . O_i from the saved forward output
+//   phase 1  per (16 queries x 32 keys) item: S and dP = dO V^T tiles -> P = exp2(S - m) / l and dS = P o (dP - delta)
+//            written to shared memory as bf16 [query][key]
+//   phase 2  dQ = dS K / 8 (A fragments straight from dS, K^T fragments by ldmatrix.trans), dK = dS^T Q / 8 and
+//            dV = P^T dO (A fragments by ldmatrix.trans of the [query][key] tiles): one (16 x 64) output tile per item.
+struct AttnBwdTcParams {
+    AttnBwdParams b;
+    const __nv_bfloat16* o; int64_t ldof;   // forward output (context) of the same attention
+};
+constexpr int ABT_LD = 72;
+constexpr int ABT_WARPS = 8;
+constexpr float ABT_LOG2E = 1.4426950408889634f;
+
+__device__ __forceinline__ void abt_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void abt_ldsm_t(uint32_t (&r)[4], const void* smem_row_ptr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(ptx::smem_u32(smem_row_ptr)));
+}
+// A fragments (16 x 64, reduction index contiguous) of rows [r0, r0 + 16) of a staged [rows][ABT_LD] tile
+__device__ __forceinline__ void abt_load_a(uint32_t (&f)[4][4], const __nv_bfloat16* tile, int r0, int g, int t) {
+    const __nv_bfloat16* b = tile + (r0 + g) * ABT_LD + 2 * t;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        f[ks][0] = *reinterpret_cast<const uint32_t*>(b + ks * 16);
+        f[ks][1] = *reinterpret_cast<const uint32_t*>(b + 8 * ABT_LD + ks * 16);
+        f[ks][2] = *reinterpret_cast<const uint32_t*>(b + ks * 16 + 8);
+        f[ks][3] = *reinterpret_cast<const uint32_t*>(b + 8 * ABT_LD + ks * 16 + 8);
+    }
+}
+// merge two (max, sum) pairs of an online softmax (log2 domain); -inf max = nothing seen yet
+__device__ __forceinline__ void abt_merge(float& m, float& l, float m2, float l2) {
+    const float mn = fmaxf(m, m2);
+    if (mn == -INFINITY) return;
+    l = l * exp2f(m - mn) + l2 * exp2f(m2 - mn);
+    m = mn;
+}
+
+__global__ void __launch_bounds__(ABT_WARPS * 32)
+attn_bwd_tc_kernel(const AttnBwdTcParams pp) {
+    const AttnBwdParams& p = pp.b;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int Sqp = (p.Sq + 15) & ~15, Skp = (p.Sk + 15) & ~15, ldp = Skp + 8;
+    __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_raw);     // [Sqp][72]
+    __nv_bfloat16* sDO = sQ + Sqp * ABT_LD;                             // [Sqp][72]
+    __nv_bfloat16* sK = sDO + Sqp * ABT_LD;                             // [Skp][72]
+    __nv_bfloat16* sV = sK + Skp * ABT_LD;                              // [Skp][72]
+    __nv_bfloat16* sP = sV + Skp * ABT_LD;                              // [Sqp][ldp]
+    __nv_bfloat16* sDS = sP + Sqp * ldp;                                // [Sqp][ldp]
+    float* sMask = reinterpret_cast<float*>(sDS + Sqp * ldp);           // [Skp]   additive mask * log2e, -inf on padding keys
+    float* sDelta = sMask + Skp;                                        // [Sqp]
+    float* sMx = sDelta + Sqp;                                          // [Sqp]   row max (log2 domain)
+    float* sIl = sMx + Sqp;                                             // [Sqp]   1 / row sum
+    float* sPM = sIl + Sqp;                                             // [ABT_WARPS][Sqp] partial max
+    float* sPL = sPM + ABT_WARPS * Sqp;                                 // [ABT_WARPS][Sqp] partial sum
+    const int head = blockIdx.x % p.heads, r = blockIdx.x / p.heads;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    constexpr int NT = ABT_WARPS * 32;
+    const bool q_dense = p.nq_split >= p.Sq;
+
+    // ---- stage Q, dO (+ delta = dO . O), K, V; rows past the end are zero
+    for (int idx = tid; idx < Sqp * 8; idx += NT) {
+        const int i = idx >> 3, c = idx & 7;
+        uint4 qv = make_uint4(0, 0, 0, 0), dv = qv, ov = qv;
+        if (i < p.Sq) {
+            const int64_t gi = tok_index(r, i, p.rows, p.nq_split, p.Sq, q_dense);
+            qv = *reinterpret_cast<const uint4*>(p.q + gi * p.ldq + head * 64 + c * 8);
+            dv = *reinterpret_cast<const uint4*>(p.d_o + gi * p.ldo + head * 64 + c * 8);
+            ov = *reinterpret_cast<const uint4*>(pp.o + gi * pp.ldof + head * 64 + c * 8);
+        }
+        *reinterpret_cast<uint4*>(sQ + i * ABT_LD + c * 8) = qv;
+        *reinterpret_cast<uint4*>(sDO + i * ABT_LD + c * 8) = dv;
+        const uint32_t dd[4] = {dv.x, dv.y, dv.z, dv.w}, oo[4] = {ov.x, ov.y, ov.z, ov.w};
+        float d = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) d = fmaf(ptx::bf16lo(dd[k]), ptx::bf16lo(oo[k]), fmaf(ptx::bf16hi(dd[k]), ptx::bf16hi(oo[k]), d));
+        d += __shfl_xor_sync(0xffffffffu, d, 1);
+        d += __shfl_xor_sync(0xffffffffu, d, 2);
+        d += __shfl_xor_sync(0xffffffffu, d, 4);
+        if (c == 0) sDelta[i] = d;
+    }
+    for (int idx = tid; idx < Skp * 8; idx += NT) {
+        const int j = idx >> 3, c = idx & 7;
+        uint4 kv = make_uint4(0, 0, 0, 0), vv = kv;
+        if (j < p.Sk) {
+            const int64_t gj = tok_index(r, j, p.rows, p.nq_split, p.Sk, p.kv_dense != 0);
+            kv = *reinterpret_cast<const uint4*>(p.k + gj * p.ldk + head * 64 + c * 8);
+            vv = *reinterpret_cast<const uint4*>(p.v + gj * p.ldv + head * 64 + c * 8);
+        }
+        *reinterpret_cast<uint4*>(sK + j * ABT_LD + c * 8) = kv;
+        *reinterpret_cast<uint4*>(sV + j * ABT_LD + c * 8) = vv;
+    }
+    for (int j = tid; j < Skp; j += NT)
+        sMask[j] = j < p.Sk ? (p.add_mask ? p.add_mask[static_cast<int64_t>(r) * p.Sk + j] * ABT_LOG2E : 0.f) : -INFINITY;
+    __syncthreads();
+
+    const int nQT = Sqp >> 4, nK8 = Skp >> 3, nKT = Skp >> 4;
+    const float scale2 = 0.125f * ABT_LOG2E;
+    // ---- phase 0: row max / sum
+    const int nsplit = nQT >= ABT_WARPS ? 1 : ABT_WARPS / nQT;
+    for (int item = warp; item < nQT * nsplit; item += ABT_WARPS) {
+        const int qt = item / nsplit, sp = item - qt * nsplit;
+        uint32_t qf[4][4];
+        abt_load_a(qf, sQ, qt * 16, g, t);
+        float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+        for (int nt = sp; nt < nK8; nt += nsplit) {
+            float s[4] = {0.f, 0.f, 0.f, 0.f};
+            const __nv_bfloat16* kb = sK + (nt * 8 + g) * ABT_LD + 2 * t;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+                abt_mma(s, qf[ks], *reinterpret_cast<const uint32_t*>(kb + ks * 16), *reinterpret_cast<const uint32_t*>(kb + ks * 16 + 8));
+            const float k0 = sMask[nt * 8 + 2 * t], k1 = sMask[nt * 8 + 2 * t + 1];
+            const float v[4] = {fmaf(s[0], scale2, k0), fmaf(s[1], scale2, k1), fmaf(s[2], scale2, k0), fmaf(s[3], scale2, k1)};
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float mn = fmaxf(m[h], fmaxf(v[2 * h], v[2 * h + 1]));
+                if (mn != -INFINITY) {
+                    l[h] = l[h] * exp2f(m[h] - mn) + exp2f(v[2 * h] - mn) + exp2f(v[2 * h + 1] - mn);
+                    m[h] = mn;
+                }
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int o = 1; o <= 2; o <<= 1) {
+                const float m2 = __shfl_xor_sync(0xffffffffu, m[h], o), l2 = __shfl_xor_sync(0xffffffffu, l[h], o);
+                abt_merge(m[h], l[h], m2, l2);
+            }
+            if (t == 0) {
+                sPM[sp * Sqp + qt * 16 + g + 8 * h] = m[h];
+                sPL[sp * Sqp + qt * 16 + g + 8 * h] = l[h];
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < Sqp; i += NT) {
+        float m = -INFINITY, l = 0.f;
+        for (int sp = 0; sp < nsplit; ++sp) abt_merge(m, l, sPM[sp * Sqp + i], sPL[sp * Sqp + i]);
+        sMx[i] = m == -INFINITY ? 0.f : m;
+        sIl[i] = l > 0.f ? 1.f / l : 0.f;
+    }
+    __syncthreads();
+    // ---- phase 1: P and dS tiles (16 queries x 32 keys per item) -> shared memory, bf16
+    const int nCH = (nK8 + 3) >> 2;
+    for (int item = warp; item < nQT * nCH; item += ABT_WARPS) {
+        const int qt = item / nCH, ch = item - qt * nCH;
+        uint32_t qf[4][4], df[4][4];
+        abt_load_a(qf, sQ, qt * 16, g, t);
+        abt_load_a(df, sDO, qt * 16, g, t);
+        const int i0 = qt * 16 + g, i1 = i0 + 8;
+        const float m0 = sMx[i0], m1 = sMx[i1], il0 = sIl[i0], il1 = sIl[i1], d0 = sDelta[i0], d1 = sDelta[i1];
+        const int nt_end = min(ch * 4 + 4, nK8);
+        for (int nt = ch * 4; nt < nt_end; ++nt) {
+            float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
+            const __nv_bfloat16* kb = sK + (nt * 8 + g) * ABT_LD + 2 * t;
+            const __nv_bfloat16* vb = sV + (nt * 8 + g) * ABT_LD + 2 * t;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                abt_mma(s, qf[ks], *reinterpret_cast<const uint32_t*>(kb + ks * 16), *reinterpret_cast<const uint32_t*>(kb + ks * 16 + 8));
+                abt_mma(dp, df[ks], *reinterpret_cast<const uint32_t*>(vb + ks * 16), *reinterpret_cast<const uint32_t*>(vb + ks * 16 + 8));
+            }
+            const float k0 = sMask[nt * 8 + 2 * t], k1 = sMask[nt * 8 + 2 * t + 1];
+            const float p0 = exp2f(fmaf(s[0], scale2, k0) - m0) * il0, p1 = exp2f(fmaf(s[1], scale2, k1) - m0) * il0;
+            const float p2 = exp2f(fmaf(s[2], scale2, k0) - m1) * il1, p3 = exp2f(fmaf(s[3], scale2, k1) - m1) * il1;
+            const int c = nt * 8 + 2 * t;
+            *reinterpret_cast<uint32_t*>(sP + i0 * ldp + c) = ptx::pack_bf16x2(p0, p1);
+            *reinterpret_cast<uint32_t*>(sP + i1 * ldp + c) = ptx::pack_bf16x2(p2, p3);
+            *reinterpret_cast<uint32_t*>(sDS + i0 * ldp + c) = ptx::pack_bf16x2(p0 * (dp[0] - d0), p1 * (dp[1] - d0));
+            *reinterpret_cast<uint32_t*>(sDS + i1 * ldp + c) = ptx::pack_bf16x2(p2 * (dp[2] - d1), p3 * (dp[3] - d1));
+        }
+    }
+    __syncthreads();
+    // ---- phase 2: one 16 x 64 output tile per item: dQ tiles, then dK tiles, then dV tiles
+    const int lrow = ((lane >> 3) & 1) * 8 + (lane & 7), lcol = (lane >> 4) * 8;     // ldmatrix.trans of a [reduction][dim] tile (B)
+    const int arow = ((lane >> 4) & 1) * 8 + (lane & 7), acol = ((lane >> 3) & 1) * 8;   // ... of a [query][key] tile (A^T)
+    for (int item = warp; item < nQT + 2 * nKT; item += ABT_WARPS) {
+        float acc[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+        if (item < nQT) {
+            const int i0 = item * 16 + g, i1 = i0 + 8;
+            for (int kt = 0; kt < nKT; ++kt) {
+                uint32_t a[4];
+                const __nv_bfloat16* ab = sDS + i0 * ldp + kt * 16 + 2 * t;
+                a[0] = *reinterpret_cast<const uint32_t*>(ab);
+                a[1] = *reinterpret_cast<const uint32_t*>(ab + 8 * ldp);
+                a[2] = *reinterpret_cast<const uint32_t*>(ab + 8);
+                a[3] = *reinterpret_cast<const uint32_t*>(ab + 8 * ldp + 8);
+#pragma unroll
+                for (int dp = 0; dp < 4; ++dp) {
+                    uint32_t bf[4];
+                    abt_ldsm_t(bf, sK + (kt * 16 + lrow) * ABT_LD + dp * 16 + lcol);
+                    abt_mma(acc[2 * dp], a, bf[0], bf[1]);
+                    abt_mma(acc[2 * dp + 1], a, bf[2], bf[3]);
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int i = h ? i1 : i0;
+                if (i < p.Sq) {
+                    __nv_bfloat16* dst = p.dq + tok_index(r, i, p.rows, p.nq_split, p.Sq, q_dense) * p.lddq + head * 64 + 2 * t;
+#pragma unroll
+                    for (int nt = 0; nt < 8; ++nt)
+                        *reinterpret_cast<uint32_t*>(dst + nt * 8) = ptx::pack_bf16x2(acc[nt][2 * h] * 0.125f, acc[nt][2 * h + 1] * 0.125f);
+                }
+            }
+        } else {
+            const bool is_dk = item < nQT + nKT;
+            const int kt = item - nQT - (is_dk ? 0 : nKT);
+            const __nv_bfloat16* lhs = is_dk ? sDS : sP;     // [query][key], read transposed
+            const __nv_bfloat16* rhs = is_dk ? sQ : sDO;     // [query][dim]
+            for (int qt = 0; qt < nQT; ++qt) {
+                uint32_t a[4];
+                abt_ldsm_t(a, lhs + (qt * 16 + arow) * ldp + kt * 16 + acol);
+#pragma unroll
+                for (int dp = 0; dp < 4; ++dp) {
+                    uint32_t bf[4];
+                    abt_ldsm_t(bf, rhs + (qt * 16 + lrow) * ABT_LD + dp * 16 + lcol);
+                    abt_mma(acc[2 * dp], a, bf[0], bf[1]);
+                    abt_mma(acc[2 * dp + 1], a, bf[2], bf[3]);
+                }
+            }
+            const float sc = is_dk ? 0.125f : 1.0f;
+            __nv_bfloat16* out = is_dk ? p.dk : p.dv;
+            const int64_t ld = is_dk ? p.lddk : p.lddv;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = kt * 16 + g + 8 * h;
+                if (j < p.Sk) {
+                    __nv_bfloat16* dst = out + tok_index(r, j, p.rows, p.nq_split, p.Sk, p.kv_dense != 0) * ld + head * 64 + 2 * t;
+#pragma unroll
+                    for (int nt = 0; nt < 8; ++nt)
+                        *reinterpret_cast<uint32_t*>(dst + nt * 8) = ptx::pack_bf16x2(acc[nt][2 * h] * sc, acc[nt][2 * h + 1] * sc);
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ embedding backward
 // d_emb: fp32 [rows*Nq + rows*T, H] (split layout).  query rows -> d_query[q_rows, Nq, H]; text rows -> scatter-add into
 // the word / position embedding gradients.
@@ -439,8 +690,32 @@ int launch_gelu_bwd(const void* z, const void* dy, void* dz, int64_t n, cudaStre
     return 0;
 }
 
+static size_t attn_bwd_tc_smem(int Sq, int Sk) {
+    const size_t Sqp = (Sq + 15) & ~15, Skp = (Sk + 15) & ~15, ldp = Skp + 8;
+    return (2 * Sqp + 2 * Skp) * ABT_LD * 2 + 2 * Sqp * ldp * 2 + (Skp + 3 * Sqp + 2 * ABT_WARPS * Sqp) * 4;
+}
+
 int launch_attention_bwd(const AttnBwdArgs& a, cudaStream_t s) {
     MRA_REQUIRE(a.rows > 0 && a.heads > 0 && a.Sq > 0 && a.Sk > 0, "attention backward with empty dimension");
+    // tensor-core kernel when the forward output is available and the tiles fit in shared memory; MRA_ATTN_BWD_SIMT=1
+    // forces the fp32 CUDA-core kernel (tests compare the two)
+    static const bool force_simt = getenv("MRA_ATTN_BWD_SIMT") != nullptr;
+    const size_t tc_smem = attn_bwd_tc_smem(a.Sq, a.Sk);
+    if (a.o != nullptr && !force_simt && tc_smem <= 220 * 1024) {
+        static bool tc_attr_set = false;
+        if (!tc_attr_set) {
+            MRA_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+            tc_attr_set = true;
+        }
+        AttnBwdTcParams pp{{reinterpret_cast<const __nv_bfloat16*>(a.q), a.ldq, reinterpret_cast<const __nv_bfloat16*>(a.k), a.ldk,
+                            reinterpret_cast<const __nv_bfloat16*>(a.v), a.ldv, reinterpret_cast<const __nv_bfloat16*>(a.d_o), a.ldo,
+                            reinterpret_cast<__nv_bfloat16*>(a.dq), a.lddq, reinterpret_cast<__nv_bfloat16*>(a.dk), a.lddk,
+                            reinterpret_cast<__nv_bfloat16*>(a.dv), a.lddv, a.add_mask, a.rows, a.heads, a.Sq, a.Sk, a.nq_split, a.kv_dense},
+                           reinterpret_cast<const __nv_bfloat16*>(a.o), a.ldof};
+        attn_bwd_tc_kernel<<<static_cast<unsigned>(a.rows) * a.heads, ABT_WARPS * 32, tc_smem, s>>>(pp);
+        MRA_CHECK_CUDA(cudaGetLastError());
+        return 0;
+    }
     const size_t smem = static_cast<size_t>(2 * a.Sq + 2 * a.Sk) * AB_LD * 2 + 16 + static_cast<size_t>(a.Sq) * a.Sk * 8;
     MRA_REQUIRE(smem <= 220 * 1024, "attention backward: Sq=%d x Sk=%d needs %zu bytes of shared memory (max 220 KiB)", a.Sq, a.Sk, smem);
     static bool attr_set = false;

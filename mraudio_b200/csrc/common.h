@@ -145,6 +145,7 @@ struct AttnBwdArgs {
     void* dv; int64_t lddv;
     const float* add_mask;
     int rows, heads, Sq, Sk, nq_split, kv_dense;
+    const void* o = nullptr; int64_t ldof = 0;   // forward output of the same attention (enables the tensor-core kernel)
 };
 int launch_attention_bwd(const AttnBwdArgs& a, cudaStream_t s);
 int launch_transpose(const void* in, int64_t ld_in, void* out, int64_t ld_out, int R, int C, float* colsum, cudaStream_t s);

@@ -682,6 +682,7 @@ extern "C" int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, 
             MRA_TRY(gemm(bw.g_pre16, H, LT.w_co, H, nullptr, 0, bw.g_ctx16, H, Mq, H, H, 0));      // d_cctx
             AttnBwdArgs a{B.cq, H, kbase, kv_ld, kbase + H, kv_ld, bw.g_ctx16, H, bw.g_cq16, H, bw.g_kv16, 2 * H,
                           bw.g_kv16 + H, 2 * H, io->enc_mask ? ws.enc_mask : nullptr, rows, c.heads, Nq, Nk, Nq, 1};
+            a.o = B.cctx; a.ldof = H;
             MRA_TRY(launch_attention_bwd(a, s));
             if (int e = wgrad(bw.g_cq16, H, B.ab, H, Mq, H, H, G.w_cq, H, G.b_cq)) return e;
             MRA_TRY(gemm(bw.g_cq16, H, LT.w_cq, H, bw.g_pre32, H, bw.g_a, H, Mq, H, H, 1));         // -> grad of LN_a out (query rows)
@@ -697,6 +698,7 @@ extern "C" int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, 
             AttnBwdArgs a{B.qkv, 3 * H, B.qkv + H, 3 * H, B.qkv + 2 * H, 3 * H, bw.g_ctx16, H, bw.g_big16, 3 * H,
                           bw.g_big16 + H, 3 * H, bw.g_big16 + 2 * H, 3 * H, io->attn_mask ? ws.self_mask : nullptr,
                           rows, c.heads, S, S, Nq, 0};
+            a.o = B.ctx; a.ldof = H;
             MRA_TRY(launch_attention_bwd(a, s));
         }
         if (int e = wgrad(bw.g_big16, 3 * H, B.xb, H, Mtot, 3 * H, H, G.w_qkv, H, G.b_qkv)) return e;
