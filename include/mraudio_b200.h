@@ -131,7 +131,8 @@ int mra_qformer_last_launch_count(const mra_qformer_t* h);
  *   1. mra_qformer_forward(io with MRA_FWD_SAVE_FOR_BACKWARD) keeps per-layer activations in `workspace`;
  *   2. mra_qformer_backward(same io, same workspace, d_llm = dL/d(llm_out) bf16 [rows*Nq, D]) ACCUMULATES fp32
  *      gradients into `g` (same packed layout as mra_qformer_weights: stacked q,k,v / stacked cross k,v);
- *      `wT` holds the bf16 weights transposed ([in, out] row-major; w_ckv / embeddings unused) for the dgrad GEMMs;
+ *      `wT` is ignored and may be NULL (earlier versions took transposed weight copies for the dgrad GEMMs; they now
+ *      read the forward's weights in place through MN-major descriptors, see mra_dgrad_bf16);
  *   3. mra_adam_step: torch.optim.Adam semantics on flat fp32 buffers (utils/trainer.py:65), grads pre-multiplied by
  *      grad_scale (1 / (accum_grad_iters * world_size) after a sum all-reduce);  mra_cast_bf16 refreshes bf16 copies. */
 typedef struct mra_qformer_layer_grads {
@@ -155,6 +156,12 @@ int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, const void*
                          size_t bwd_bytes, void* stream);
 int mra_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                   float beta2, float eps, float weight_decay, int32_t step, float grad_scale, void* stream);
+/* The same Adam update fused with what always follows it in the fine-tuning loop (utils/trainer.py:137-140): the bf16
+ * operand copy of the updated parameters (params_bf16, may be NULL) and optimizer.zero_grad() (zero_grads != 0).
+ * n must be a multiple of 4, buffers 16-byte aligned. */
+int mra_adam_step_fused(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* params_bf16, int64_t n, float lr,
+                        float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
+                        int32_t zero_grads, void* stream);
 int mra_cast_bf16(const float* in, void* out, int64_t n, void* stream);
 
 /* Device-side timing of the launches of mra_qformer_forward with CUDA events recorded on the caller's stream.
@@ -209,6 +216,12 @@ int mra_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const 
  * no transposed copies.  dY, X bf16; dW fp32 (row stride ldw); accumulate != 0 adds to dW. */
 int mra_wgrad_bf16(const void* dY, int64_t ldy, const void* X, int64_t ldx, float* dW, int64_t ldw, int32_t n, int32_t n_out,
                    int32_t k_in, int32_t accumulate, void* stream);
+
+/* Data gradient of a Linear:  dX[n, k_in] = dY[n, n_out] . W[n_out, k_in] (+ residual)  on the same kernel, reading the
+ * forward's weight matrix W as it lies (MN-major descriptor for the second operand): no transposed weight copies.
+ * dY, W bf16; dX bf16 or fp32 (out_fp32); residual fp32 [n, k_in] or NULL (only with fp32 output; may alias dX). */
+int mra_dgrad_bf16(const void* dY, int64_t ldy, const void* W, int64_t ldw, const float* residual, int64_t ldr, void* dX,
+                   int64_t ldx, int32_t n, int32_t n_out, int32_t k_in, int32_t out_fp32, void* stream);
 
 /* Fused  y = LayerNorm(A . W^T + bias + residual) * gamma + beta  for N == 768: Linear + residual add + post-LayerNorm of
  * BertSelfOutput / BertOutput (HF port modeling_instructblip.py:549-553, 606-610) in one kernel; the pre-LayerNorm sums

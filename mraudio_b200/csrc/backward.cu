@@ -747,6 +747,50 @@ int launch_embed_bwd(const float* d_emb, const int32_t* ids, float* d_query, int
     return 0;
 }
 
+// Same update with the two passes that always follow it folded in: the bf16 operand copy of the new parameters (what the
+// GEMMs read) and the reset of the gradient accumulator -- 7 instead of 10 fp32 streams over the 186 M parameters.
+__global__ void __launch_bounds__(256)
+adam_fused_kernel(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
+                  uint2* __restrict__ p16, int64_t n4, float lr, float beta1, float beta2, float eps, float weight_decay, float bc1,
+                  float bc2_sqrt, float grad_scale, int zero_grad) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 g4 = g[i], m4 = m[i], v4 = v[i];
+    float4 p4 = p[i];
+    const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+    float pp[4] = {p4.x, p4.y, p4.z, p4.w}, mo[4], vo[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float gi = gg[k] * grad_scale;
+        if (weight_decay != 0.f) gi = fmaf(weight_decay, pp[k], gi);
+        mo[k] = fmaf(beta1, mm[k], (1.f - beta1) * gi);
+        vo[k] = fmaf(beta2, vv[k], (1.f - beta2) * gi * gi);
+        const float denom = sqrtf(vo[k]) / bc2_sqrt + eps;
+        pp[k] = pp[k] - (lr / bc1) * (mo[k] / denom);
+    }
+    m[i] = make_float4(mo[0], mo[1], mo[2], mo[3]);
+    v[i] = make_float4(vo[0], vo[1], vo[2], vo[3]);
+    p[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
+    if (p16) p16[i] = make_uint2(ptx::pack_bf16x2(pp[0], pp[1]), ptx::pack_bf16x2(pp[2], pp[3]));
+    if (zero_grad) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+int launch_adam_fused(float* p, float* g, float* m, float* v, void* p16, int64_t n, float lr, float beta1, float beta2, float eps,
+                      float weight_decay, int step, float grad_scale, int zero_grad, cudaStream_t s) {
+    MRA_REQUIRE(n > 0 && n % 4 == 0 && step >= 1, "fused adam: n must be a positive multiple of 4");
+    MRA_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                  reinterpret_cast<uintptr_t>(v)) & 15) == 0 && (reinterpret_cast<uintptr_t>(p16) & 7) == 0,
+                "fused adam: buffers must be 16-byte aligned");
+    const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
+    const float bc2 = sqrtf(1.f - powf(beta2, static_cast<float>(step)));
+    const int64_t n4 = n / 4;
+    adam_fused_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, s>>>(
+        reinterpret_cast<float4*>(p), reinterpret_cast<float4*>(g), reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v),
+        reinterpret_cast<uint2*>(p16), n4, lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale, zero_grad);
+    MRA_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                 float weight_decay, int step, float grad_scale, cudaStream_t s) {
     MRA_REQUIRE(n > 0 && step >= 1, "adam: bad arguments");

@@ -77,6 +77,15 @@ extern "C" int mra_wgrad_bf16(const void* dY, int64_t ldy, const void* X, int64_
     return launch_gemm_tc(a, reinterpret_cast<cudaStream_t>(stream));
 }
 
+extern "C" int mra_dgrad_bf16(const void* dY, int64_t ldy, const void* W, int64_t ldw, const float* residual, int64_t ldr, void* dX,
+                              int64_t ldx, int32_t n, int32_t n_out, int32_t k_in, int32_t out_fp32, void* stream) {
+    MRA_REQUIRE(dY && W && dX, "mra_dgrad_bf16: NULL operand");
+    if (int e = device_check()) return e;
+    GemmArgs a{dY, ldy, W, ldw, nullptr, residual, ldr, dX, ldx, n, k_in, n_out, 0, out_fp32};
+    a.tn = 2;
+    return launch_gemm_tc(a, reinterpret_cast<cudaStream_t>(stream));
+}
+
 extern "C" int mra_gemm_ln_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const float* residual,
                                 int64_t ldr, const float* gamma, const float* beta, float* y32, int64_t ldy32, void* y16,
                                 int64_t ldy16, int32_t M, int32_t N, int32_t K, float eps, void* stream) {

@@ -113,10 +113,13 @@ __device__ __forceinline__ uint32_t swz(int r, int j) { return static_cast<uint3
 // CM = CTAs per cluster along M (1 or 2).  With CM = 2 the two CTAs of a cluster compute the tiles (2 mp, n) and
 // (2 mp + 1, n): they need the same W rows, so each loads HALF of the W slab and multicasts it to both (the kernels are
 // L2 -> SM bandwidth bound: 128 x 256 tiles need 96 B/clk/SM at full tensor rate; sharing W cuts that by a third).
-// TN = both operands are given with the REDUCTION index as their row index (A: [K, M], W: [K, N], row-major): the
-// weight-gradient GEMM dW[out, in] = dY[n, out]^T . X[n, in] reads dY and X as they lie in memory, through MN-major
-// shared-memory descriptors -- no transposed copies.
-template <int BN, int STAGES, bool GELU, bool OUT_F32, bool RES, int CM, bool TN = false>
+// TN (operand form): 0 = A [M, K] and W [N, K], reduction index contiguous (the Linear forward);
+//   1 = both operands given with the REDUCTION index as their row index (A: [K, M], W: [K, N], row-major): the
+//       weight-gradient GEMM dW[out, in] = dY[n, out]^T . X[n, in] reads dY and X as they lie in memory;
+//   2 = A [M, K] as in the forward, W [K, N] with the reduction index as its row index: the data-gradient GEMM
+//       dX[n, in] = dY[n, out] . W[out, in] reads the forward's weight matrix as it lies.
+// Operands whose reduction index is the row index go through MN-major shared-memory descriptors -- no transposed copies.
+template <int BN, int STAGES, bool GELU, bool OUT_F32, bool RES, int CM, int TN = 0>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ EpiParams p) {
     using L = SmemLayout<BN, STAGES, RES>;
@@ -190,11 +193,15 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     ptx::mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-                    if (TN) {
+                    if (TN != 0) {
                         // boxes of {64 MN elements, 64 reduction rows}: one per 64 output rows (A) / columns (W)
+                        if (TN == 1) {
 #pragma unroll
-                        for (int i = 0; i < BM / 64; ++i)
-                            ptx::tma_load_2d(sA + stage * A_STAGE_BYTES + i * 8192, tmA, &full_bar[stage], m_blk * BM + i * 64, kb * BK);
+                            for (int i = 0; i < BM / 64; ++i)
+                                ptx::tma_load_2d(sA + stage * A_STAGE_BYTES + i * 8192, tmA, &full_bar[stage], m_blk * BM + i * 64, kb * BK);
+                        } else {
+                            ptx::tma_load_2d(sA + stage * A_STAGE_BYTES, tmA, &full_bar[stage], kb * BK, m_blk * BM);
+                        }
 #pragma unroll
                         for (int j = 0; j < BN / 64; ++j)
                             ptx::tma_load_2d(sB + stage * L::B_STAGE_BYTES + j * 8192, tmB, &full_bar[stage], n_blk * BN + j * 64, kb * BK);
@@ -217,7 +224,9 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (single thread)
         if (lane == 0) {
-            constexpr uint32_t idesc = TN ? ptx::make_idesc_bf16_f32_mn(BM, BN) : ptx::make_idesc_bf16_f32(BM, BN);
+            constexpr uint32_t idesc = TN == 1 ? ptx::make_idesc_bf16_f32_mn(BM, BN)
+                                       : TN == 2 ? (ptx::make_idesc_bf16_f32(BM, BN) | (1u << 16))   // b_major = MN only
+                                                 : ptx::make_idesc_bf16_f32(BM, BN);
             int stage = 0;
             uint32_t phase = 0;
             int iter = 0;
@@ -230,13 +239,15 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     ptx::mbar_wait(&full_bar[stage], phase);
                     ptx::tc_fence_after();
-                    if (TN) {
-                        const uint64_t a_desc = ptx::make_sw128_mnmajor_desc(ptx::smem_u32(sA + stage * A_STAGE_BYTES), 8192);
+                    if (TN != 0) {
+                        const uint64_t a_desc = TN == 1 ? ptx::make_sw128_mnmajor_desc(ptx::smem_u32(sA + stage * A_STAGE_BYTES), 8192)
+                                                        : ptx::make_sw128_kmajor_desc(ptx::smem_u32(sA + stage * A_STAGE_BYTES));
                         const uint64_t b_desc = ptx::make_sw128_mnmajor_desc(ptx::smem_u32(sB + stage * L::B_STAGE_BYTES), 8192);
+                        constexpr int A_STEP = TN == 1 ? 128 : 2;
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
-                            // advance 16 reduction rows of 128 B: +2048 B = +128 in the >>4 address field
-                            ptx::umma_bf16_ss(d_tmem, a_desc + 128 * k, b_desc + 128 * k, idesc, (kb | k) != 0);
+                            // MN-major: advance 16 reduction rows of 128 B: +2048 B = +128 in the >>4 address field
+                            ptx::umma_bf16_ss(d_tmem, a_desc + A_STEP * k, b_desc + 128 * k, idesc, (kb | k) != 0);
                         }
                     } else {
                         const uint64_t a_desc = ptx::make_sw128_kmajor_desc(ptx::smem_u32(sA + stage * A_STAGE_BYTES));
@@ -537,7 +548,7 @@ int get_tensor_map_scatter(const void* ptr, int64_t batch, int64_t frames, int64
 
 namespace {
 
-template <int BN, int STAGES, bool GELU, bool OUT_F32, bool RES, int CM, bool TN = false>
+template <int BN, int STAGES, bool GELU, bool OUT_F32, bool RES, int CM, int TN = 0>
 int launch_tc_variant(const GemmArgs* ga, int n, cudaStream_t s) {
     using L = SmemLayout<BN, STAGES, RES>;
     auto kern = gemm_tc_kernel<BN, STAGES, GELU, OUT_F32, RES, CM, TN>;
@@ -556,8 +567,10 @@ int launch_tc_variant(const GemmArgs* ga, int n, cudaStream_t s) {
     for (int g = 0; g < MAX_GROUPS; ++g) {
         const GemmArgs& a = ga[g < n ? g : 0];
         if (g < n) {
-            if (TN) {
-                if (int e = get_tensor_map(a.A, a.K, a.M, a.lda, BK, 64, 2, &maps.a[g])) return e;
+            if (TN != 0) {
+                if (TN == 1) {
+                    if (int e = get_tensor_map(a.A, a.K, a.M, a.lda, BK, 64, 2, &maps.a[g])) return e;
+                } else if (int e = get_tensor_map(a.A, a.M, a.K, a.lda, BM, BK, 2, &maps.a[g])) return e;
                 if (int e = get_tensor_map(a.W, a.K, a.N, a.ldw, BK, 64, 2, &maps.b[g])) return e;
             } else {
                 if (int e = get_tensor_map(a.A, a.M, a.K, a.lda, BM, BK, 2, &maps.a[g])) return e;
@@ -627,8 +640,9 @@ int dispatch_epi(const GemmArgs* a, int n, cudaStream_t s) {
 int check_args(const GemmArgs& a) {
     MRA_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "GEMM with empty dimension M=%d N=%d K=%d", a.M, a.N, a.K);
     MRA_REQUIRE(a.N % 8 == 0, "GEMM N must be a multiple of 8, got %d", a.N);
-    MRA_REQUIRE(a.tn || a.K % 8 == 0, "GEMM K must be a multiple of 8, got %d", a.K);
-    MRA_REQUIRE(!a.tn || a.M % 8 == 0, "transposed-operand GEMM: M must be a multiple of 8, got %d", a.M);
+    MRA_REQUIRE(a.tn >= 0 && a.tn <= 2, "GEMM operand form must be 0, 1 or 2, got %d", a.tn);
+    MRA_REQUIRE(a.tn == 1 || a.K % 8 == 0, "GEMM K must be a multiple of 8, got %d", a.K);
+    MRA_REQUIRE(a.tn != 1 || a.M % 8 == 0, "transposed-operand GEMM: M must be a multiple of 8, got %d", a.M);
     MRA_REQUIRE((a.ldc * (a.out_fp32 ? 4 : 2)) % 16 == 0, "GEMM output row stride must be a multiple of 16 bytes, got ldc=%lld",
                 (long long)a.ldc);
     MRA_REQUIRE((reinterpret_cast<uintptr_t>(a.C) & 15) == 0, "GEMM output pointer must be 16-byte aligned");
@@ -652,7 +666,7 @@ int launch_gemm_tc_grouped(const GemmArgs* a, int n, cudaStream_t s) {
     for (int g = 0; g < n; ++g) {
         if (int e = check_args(a[g])) return e;
         MRA_REQUIRE(a[g].N == a[0].N && a[g].K == a[0].K && a[g].gelu == a[0].gelu && a[g].out_fp32 == a[0].out_fp32 &&
-                        (a[g].residual != nullptr) == (a[0].residual != nullptr) && (a[g].tn != 0) == (a[0].tn != 0),
+                        (a[g].residual != nullptr) == (a[0].residual != nullptr) && a[g].tn == a[0].tn,
                     "grouped GEMM problems must share N, K and the epilogue kind");
     }
     // Tile-width choice by a wave-quantisation estimate: cost = waves x (tile width) x (a factor for how well that
@@ -672,16 +686,31 @@ int launch_gemm_tc_grouped(const GemmArgs* a, int n, cudaStream_t s) {
         const double cost = double((tiles + sms - 1) / sms) * bn * factor[i];
         if (cost < best) { best = cost; best_bn = bn; }
     }
-    if (a[0].tn) {
+    if (a[0].tn == 1) {
         for (int g = 0; g < n; ++g)
-            MRA_REQUIRE(a[g].tn && a[g].out_fp32 && !a[g].gelu, "transposed-operand GEMM (tn) needs fp32 output and no GELU");
+            MRA_REQUIRE(a[g].out_fp32 && !a[g].gelu, "transposed-operand GEMM (tn = 1) needs fp32 output and no GELU");
         const bool res = a[0].residual != nullptr;
-        if (best_bn == 256) return res ? launch_tc_variant<256, 3, false, true, true, 1, true>(a, n, s)
-                                       : launch_tc_variant<256, 4, false, true, false, 1, true>(a, n, s);
-        if (best_bn == 192) return res ? launch_tc_variant<192, 4, false, true, true, 1, true>(a, n, s)
-                                       : launch_tc_variant<192, 4, false, true, false, 1, true>(a, n, s);
-        return res ? launch_tc_variant<128, 5, false, true, true, 1, true>(a, n, s)
-                   : launch_tc_variant<128, 6, false, true, false, 1, true>(a, n, s);
+        if (best_bn == 256) return res ? launch_tc_variant<256, 3, false, true, true, 1, 1>(a, n, s)
+                                       : launch_tc_variant<256, 4, false, true, false, 1, 1>(a, n, s);
+        if (best_bn == 192) return res ? launch_tc_variant<192, 4, false, true, true, 1, 1>(a, n, s)
+                                       : launch_tc_variant<192, 4, false, true, false, 1, 1>(a, n, s);
+        return res ? launch_tc_variant<128, 5, false, true, true, 1, 1>(a, n, s)
+                   : launch_tc_variant<128, 6, false, true, false, 1, 1>(a, n, s);
+    }
+    if (a[0].tn == 2) {
+        const bool res = a[0].residual != nullptr, f32 = a[0].out_fp32 != 0;
+        MRA_REQUIRE(!a[0].gelu && (f32 || !res), "data-gradient GEMM (tn = 2): no GELU, residual only with fp32 output");
+        if (best_bn == 256)
+            return !f32 ? launch_tc_variant<256, 4, false, false, false, 1, 2>(a, n, s)
+                        : res ? launch_tc_variant<256, 3, false, true, true, 1, 2>(a, n, s)
+                              : launch_tc_variant<256, 4, false, true, false, 1, 2>(a, n, s);
+        if (best_bn == 192)
+            return !f32 ? launch_tc_variant<192, 4, false, false, false, 1, 2>(a, n, s)
+                        : res ? launch_tc_variant<192, 4, false, true, true, 1, 2>(a, n, s)
+                              : launch_tc_variant<192, 4, false, true, false, 1, 2>(a, n, s);
+        return !f32 ? launch_tc_variant<128, 6, false, false, false, 1, 2>(a, n, s)
+                    : res ? launch_tc_variant<128, 5, false, true, true, 1, 2>(a, n, s)
+                          : launch_tc_variant<128, 6, false, true, false, 1, 2>(a, n, s);
     }
     // 2-CTA clusters along M (W slab multicast) when every problem has enough row blocks to pair up.  Opt-in
     // (MRA_GEMM_CLUSTER=2 / mra_gemm_cluster_override): measured on B200 it neither helps nor hurts (1425 vs 1450 TF/s on

@@ -585,7 +585,7 @@ extern "C" int mra_qformer_forward_multi(int32_t n, mra_qformer_t* const* hs, co
 extern "C" int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, const void* d_llm,
                                     const mra_qformer_weights* wT, const mra_qformer_grads* g, void* workspace,
                                     size_t workspace_bytes, void* bwd_workspace, size_t bwd_bytes, void* stream_) {
-    MRA_REQUIRE(h && io && d_llm && wT && g && workspace && bwd_workspace, "mra_qformer_backward: NULL argument");
+    MRA_REQUIRE(h && io && d_llm && g && workspace && bwd_workspace, "mra_qformer_backward: NULL argument");
     MRA_REQUIRE(h->has_weights, "mra_qformer_backward: weights not set");
     MRA_REQUIRE(io->flags & MRA_FWD_SAVE_FOR_BACKWARD, "mra_qformer_backward: the forward must run with MRA_FWD_SAVE_FOR_BACKWARD");
     if (int e = device_check()) return e;
@@ -593,7 +593,8 @@ extern "C" int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, 
     const auto& W = h->w;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
     const int rows = io->rows, T = io->T, Nk = io->Nk, Nq = c.num_query, H = c.hidden, I = c.inter, D = c.llm_dim;
-    MRA_REQUIRE(D > 0 && wT->w_proj && g->w_proj && g->b_proj, "mra_qformer_backward needs the projection (llm_dim > 0)");
+    (void)wT;   // transposed weight copies are no longer needed (see mraudio_b200.h)
+    MRA_REQUIRE(D > 0 && W.w_proj && g->w_proj && g->b_proj, "mra_qformer_backward needs the projection (llm_dim > 0)");
     Workspace ws = carve(h, rows, T, Nk, io->flags, workspace);
     MRA_REQUIRE(workspace_bytes >= ws.total, "workspace too small: %zu < %zu bytes", workspace_bytes, ws.total);
     BwdWorkspace bw = carve_bwd(h, rows, T, Nk, bwd_workspace);
@@ -610,10 +611,13 @@ extern "C" int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, 
         if (int _e = (expr)) return _e; \
         ++launches;              \
     } while (0)
-    auto gemm = [&](const void* A, int64_t lda, const void* Wt, int64_t ldw, const float* res, int64_t ldr, void* C, int64_t ldc,
+    // data gradient dX[M, N] = dY[M, K] . W[K, N] (+ res): W is the forward's [out = K, in = N] weight, read in place
+    // (gemm.cu operand form 2); the ldw argument of the call sites (stride of the former transposed copies) is unused
+    auto gemm = [&](const void* A, int64_t lda, const void* Wfwd, int64_t, const float* res, int64_t ldr, void* C, int64_t ldc,
                     int M, int N, int K, int f32) -> int {
-        GemmArgs a{A, lda, Wt, ldw, nullptr, res, ldr, C, ldc, M, N, K, 0, f32};
-        return h->gemm_impl == MRA_GEMM_IMPL_SIMT_DEBUG ? launch_gemm_simt(a, s) : launch_gemm_tc(a, s);
+        GemmArgs a{A, lda, Wfwd, N, nullptr, res, ldr, C, ldc, M, N, K, 0, f32};
+        a.tn = 2;
+        return launch_gemm_tc(a, s);
     };
     // dW[N_out, K_in] += dY^T X  (+ db += colsum dY):  dY bf16 [n, N_out] (ld ldy), X bf16 [n, K_in] (ld ldx).
     // The GEMM reads dY and X as they lie (MN-major descriptors, gemm.cu "TN"): no transposed copies.
@@ -646,7 +650,7 @@ extern "C" int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, 
     // ---- llm_proj
     const __nv_bfloat16* dl = reinterpret_cast<const __nv_bfloat16*>(d_llm);
     if (int e = wgrad(dl, D, ws.layer[c.layers].xb, H, Mq, D, H, g->w_proj, H, g->b_proj)) return e;
-    MRA_TRY(gemm(dl, D, wT->w_proj, D, nullptr, 0, bw.g_x, H, Mq, H, D, 1));
+    MRA_TRY(gemm(dl, D, W.w_proj, D, nullptr, 0, bw.g_x, H, Mq, H, D, 1));
     if (Mt > 0) {
         MRA_CHECK_CUDA(cudaMemsetAsync(bw.g_x + static_cast<size_t>(Mq) * H, 0, static_cast<size_t>(Mt) * H * 4, s));
         ++launches;
@@ -654,7 +658,7 @@ extern "C" int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, 
 
     for (int l = c.layers - 1; l >= 0; --l) {
         const auto& L = W.layer[l];
-        const auto& LT = wT->layer[l];
+        const auto& LT = W.layer[l];   // forward weights, read in place by the data-gradient GEMMs
         const auto& G = g->layer[l];
         const LayerBufs& B = ws.layer[l];
         const bool last = l == c.layers - 1;
@@ -668,7 +672,7 @@ extern "C" int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, 
                 MRA_CHECK_CUDA(cudaMemcpyAsync(bw.g_a + o, bw.g_x + o, static_cast<size_t>(Mt) * H * 4, cudaMemcpyDeviceToDevice, s));
                 ++launches;
             } else {
-                MRA_REQUIRE(LT.w_ft1 && LT.w_ft2 && G.w_ft1 && G.w_ft2, "layer %d: text FFN transposed weights / grads missing", l);
+                MRA_REQUIRE(LT.w_ft1 && LT.w_ft2 && G.w_ft1 && G.w_ft2, "layer %d: text FFN weights / grads missing", l);
                 if (int e = ffn_bwd(B, B.ab, Mq, Mt, LT.w_ft1, LT.w_ft2, L.ln_ft_g, G.w_ft1, G.b_ft1, G.w_ft2, G.b_ft2,
                                     G.ln_ft_g, G.ln_ft_b)) return e;
             }
@@ -720,6 +724,15 @@ extern "C" int mra_adam_step(float* params, const float* grads, float* exp_avg, 
     if (int e = device_check()) return e;
     return launch_adam(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale,
                        reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mra_adam_step_fused(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* params_bf16, int64_t n,
+                                   float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
+                                   float grad_scale, int32_t zero_grads, void* stream) {
+    MRA_REQUIRE(params && grads && exp_avg && exp_avg_sq, "mra_adam_step_fused: NULL argument");
+    if (int e = device_check()) return e;
+    return launch_adam_fused(params, grads, exp_avg, exp_avg_sq, params_bf16, n, lr, beta1, beta2, eps, weight_decay, step,
+                             grad_scale, zero_grads, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int mra_cast_bf16(const float* in, void* out, int64_t n, void* stream) {

@@ -57,6 +57,20 @@ def wgrad(dy: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None,
     return out
 
 
+def dgrad(dy: torch.Tensor, weight: torch.Tensor, residual: Optional[torch.Tensor] = None, out_fp32: bool = False) -> torch.Tensor:
+    """dX[n, k_in] = dy[n, n_out] @ weight[n_out, k_in] (+ residual): the Linear's weight is read as it lies."""
+    _need_cuda(dy, weight, residual)
+    assert dy.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and dy.shape[1] == weight.shape[0]
+    assert dy.stride(1) == 1 and weight.stride(1) == 1
+    n, n_out = dy.shape
+    k_in = weight.shape[1]
+    out = torch.empty(n, k_in, device=dy.device, dtype=torch.float32 if out_fp32 else torch.bfloat16)
+    check(lib.mra_dgrad_bf16(ptr(dy), dy.stride(0), ptr(weight), weight.stride(0), ptr(residual),
+                             residual.stride(0) if residual is not None else 0, ptr(out), out.stride(0), n, n_out, k_in,
+                             int(out_fp32), current_stream()))
+    return out
+
+
 def linear_residual_layernorm(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], residual: torch.Tensor,
                               gamma: torch.Tensor, beta: torch.Tensor, eps: float):
     """(fp32, bf16) copies of LayerNorm(x @ weight.T + bias + residual) * gamma + beta; weight [768, K] bf16."""

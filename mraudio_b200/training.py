@@ -112,10 +112,7 @@ class TrainableQFormer:
             self._bind(L.intermediate.dense.weight, p + "w_ft1"); self._bind(L.intermediate.dense.bias, p + "b_ft1")
             self._bind(L.output.dense.weight, p + "w_ft2"); self._bind(L.output.dense.bias, p + "b_ft2")
             self._bind(L.output.LayerNorm.weight, p + "ln_ft_g"); self._bind(L.output.LayerNorm.bias, p + "ln_ft_b")
-        # ---- transposed bf16 copies for the dgrad GEMMs: name -> tensor [in, out]
-        self._t_names = ["w_proj"] + [f"L{l}.{n}" for l, c in enumerate(self.cross)
-                                      for n in (["w_qkv", "w_ao"] + (["w_cq", "w_co"] if c else []) + ["w_fq1", "w_fq2", "w_ft1", "w_ft2"])]
-        self.wT = {n: torch.empty(self.seg[n][1][1], self.seg[n][1][0], device=dev, dtype=torch.bfloat16) for n in self._t_names}
+        # (the dgrad GEMMs read the bf16 weights in place through MN-major descriptors: no transposed copies are kept)
         self._handle = bert._handle(D)
         self._structs = None
         self._ws = self._bws = None
@@ -144,21 +141,18 @@ class TrainableQFormer:
         return buf.data_ptr() + self.seg[name][0] * esize
 
     def refresh_operands(self):
-        """bf16 operand copy of the master weights (one cast kernel) + transposed copies for dgrad."""
+        """bf16 operand copy of the master weights (one cast kernel; ``adam_step`` refreshes it in the same pass)."""
         check(lib.mra_cast_bf16(self.flat.data_ptr(), self.flat16.data_ptr(), self.numel, current_stream()))
-        for n, t in self.wT.items():
-            t.copy_(self._view(self.flat16, n).t())
         if self._structs is None:
             self._structs = self._build_structs()
             check(lib.mra_qformer_set_weights(self._handle, C.byref(self._structs[0])))
 
     def _build_structs(self):
-        W, WT, G = _lib.QFormerWeights(), _lib.QFormerWeights(), _lib.QFormerGrads()
+        W, G = _lib.QFormerWeights(), _lib.QFormerGrads()
         for f in ("word_emb", "pos_emb", "w_ckv", "w_proj"):
             setattr(W, f, self._ptr(self.flat16, f, 2))
         for f in ("ln_e_g", "ln_e_b", "b_ckv", "b_proj"):
             setattr(W, f, self._ptr(self.flat, f, 4))
-        WT.w_proj = self.wT["w_proj"].data_ptr()
         for f in ("word_emb", "pos_emb", "ln_e_g", "ln_e_b", "w_ckv", "b_ckv", "w_proj", "b_proj", "query_tokens"):
             setattr(G, f, self._ptr(self.grad, f, 4))
         for l, c in enumerate(self.cross):
@@ -167,9 +161,7 @@ class TrainableQFormer:
                 is_mat = len(shp) == 2
                 setattr(W.layer[l], n, self._ptr(self.flat16, key, 2) if is_mat else self._ptr(self.flat, key, 4))
                 setattr(G.layer[l], n, self._ptr(self.grad, key, 4))
-                if key in self.wT:
-                    setattr(WT.layer[l], n, self.wT[key].data_ptr())
-        return W, WT, G
+        return W, G
 
     # ------------------------------------------------------------------------------------------------ forward / backward
     def forward(self, enc: torch.Tensor, input_ids: Optional[torch.Tensor], attention_mask: Optional[torch.Tensor]) -> torch.Tensor:
@@ -209,8 +201,8 @@ class TrainableQFormer:
         need = lib.mra_qformer_backward_workspace_bytes(self._handle, rows, T, Nk)
         if self._bws is None or self._bws.numel() < need:
             self._bws = torch.empty(need, device=d.device, dtype=torch.uint8)
-        W, WT, G = self._structs
-        check(lib.mra_qformer_backward(self._handle, C.byref(io), d.data_ptr(), C.byref(WT), C.byref(G), self._ws.data_ptr(),
+        W, G = self._structs
+        check(lib.mra_qformer_backward(self._handle, C.byref(io), d.data_ptr(), None, C.byref(G), self._ws.data_ptr(),
                                        self._ws.numel(), self._bws.data_ptr(), self._bws.numel(), current_stream()))
         self.last_backward_launches = lib.mra_qformer_last_launch_count(self._handle)
         self._saved = None
@@ -219,12 +211,14 @@ class TrainableQFormer:
     def zero_grad(self):
         self.grad.zero_()
 
-    def adam_step(self, lr: float, grad_scale: float = 1.0, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0):
+    def adam_step(self, lr: float, grad_scale: float = 1.0, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
+                  zero_grad: bool = False):
+        """``optimizer.step()`` (+ ``optimizer.zero_grad()`` with ``zero_grad``) and the refresh of the bf16 operand copy
+        in ONE pass over the flat buffers."""
         self.step_count += 1
-        check(lib.mra_adam_step(self.flat.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
-                                self.numel, lr, betas[0], betas[1], eps, weight_decay, self.step_count, grad_scale,
-                                current_stream()))
-        self.refresh_operands()
+        check(lib.mra_adam_step_fused(self.flat.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
+                                      self.exp_avg_sq.data_ptr(), self.flat16.data_ptr(), self.numel, lr, betas[0], betas[1], eps,
+                                      weight_decay, self.step_count, grad_scale, int(zero_grad), current_stream()))
 
 
 class _QFormerTrainFn(torch.autograd.Function):
@@ -308,8 +302,7 @@ class QFormerTrainer:
                 for st in self.states.values():       # DDP's gradient averaging: one flat all-reduce per modality
                     dist.all_reduce(st.grad, op=dist.ReduceOp.SUM, group=self.group)
             for st in self.states.values():
-                st.adam_step(self.lr, grad_scale=1.0 / world)
-                st.zero_grad()
+                st.adam_step(self.lr, grad_scale=1.0 / world, zero_grad=True)
         return loss.detach()
 
     def state_dict_trainable(self):

@@ -161,6 +161,26 @@ def test_wgrad_mn_major_operands(n, n_out, k_in):
     assert _rel(dw, big[:, 64:].float().t() @ x.float()) < 1e-4
 
 
+@pytest.mark.parametrize("n,n_out,k_in", [(64, 64, 64), (4096, 768, 768), (2048, 3072, 768), (2048, 768, 3072), (1000, 2304, 768),
+                                          (130, 4096, 768), (77, 72, 200)])
+def test_dgrad_reads_forward_weight_in_place(n, n_out, k_in):
+    """dX = dY W straight from the forward's [n_out, k_in] weight (MN-major descriptor for the second operand)."""
+    from mraudio_b200 import ops, _lib
+    g = torch.Generator().manual_seed(n + k_in)
+    dy = torch.randn(n, n_out, generator=g).to(_dev(), torch.bfloat16)
+    w = (torch.randn(n_out, k_in, generator=g) * 0.05).to(_dev(), torch.bfloat16)
+    res = torch.randn(n, k_in, generator=g).to(_dev())
+    ref = dy.float() @ w.float()
+    try:
+        for bn in (0, 128, 192, 256):
+            _lib.check(_lib.lib.mra_gemm_tile_override(bn))
+            assert _rel(ops.dgrad(dy, w), ref) < 6e-3, bn
+            assert _rel(ops.dgrad(dy, w, out_fp32=True), ref) < 1e-4, bn
+            assert _rel(ops.dgrad(dy, w, residual=res, out_fp32=True), ref + res) < 1e-4, bn
+    finally:
+        _lib.lib.mra_gemm_tile_override(0)
+
+
 def test_gemm_tcgen05_equals_simt_bitwise_ordering_free():
     """Same bf16 operands, fp32 accumulation: the two implementations agree to fp32 rounding noise."""
     from mraudio_b200 import ops

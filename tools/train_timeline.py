@@ -30,7 +30,7 @@ def step(timed=False):
     e0 = ev(); y = st.forward(enc, ids, atts); e1 = ev()
     loss = (y.float() * G).sum(); e2 = ev()
     loss.backward(); e3 = ev()
-    st.adam_step(1e-4); e4 = ev(); st.zero_grad(); e5 = ev()
+    st.adam_step(1e-4, zero_grad=True); e4 = ev(); e5 = ev()
     if timed:
         torch.cuda.synchronize()
         print(f"fwd {e0.elapsed_time(e1):.2f} | loss {e1.elapsed_time(e2):.2f} | bwd {e2.elapsed_time(e3):.2f} | adam+refresh "
