@@ -78,22 +78,29 @@ colsum_kernel(const __nv_bfloat16* __restrict__ in, int64_t ld, int R, int C, fl
 
 // ------------------------------------------------------------------------------------------------ LayerNorm backward
 constexpr int LNB_WARPS = 8;
-constexpr int LNB_MAXV = 8;   // columns per lane = 8 * LNB_MAXV  (n <= 2048)
+constexpr int LNB_MAXV_WIDE = 8;   // columns per lane = 8 * MAXV  (n <= 2048)
+constexpr int LNB_MAXV_H = 3;      // n <= 768 (the Q-Former hidden size)
 
 // dx = rstd * (dyg - mean(dyg) - xhat * mean(dyg * xhat)),  dyg = dy * gamma, statistics recomputed from `pre`.
 // dgamma += sum_rows dy * xhat, dbeta += sum_rows dy.   One warp per row, grid-stride over rows.
+// DBIAS (narrow rows only, register budget): dbias += sum_rows dx -- the bias gradient of the Linear that produced `pre`
+// (its output gradient IS dx), saving a separate column-sum pass over dx.
+template <int LNB_MAXV, bool DBIAS>
 __global__ void __launch_bounds__(LNB_WARPS * 32)
 ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ pre, const float* __restrict__ gamma,
               float* __restrict__ dx32, __nv_bfloat16* __restrict__ dx16, float* __restrict__ dgamma,
-              float* __restrict__ dbeta, int rows, int n, float eps) {
+              float* __restrict__ dbeta, float* __restrict__ dbias, int rows, int n, float eps) {
     __shared__ float red[LNB_WARPS][256];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nvec = n >> 3;
-    float ag[LNB_MAXV][8], ab[LNB_MAXV][8];
+    float ag[LNB_MAXV][8], ab[LNB_MAXV][8], ax[DBIAS ? LNB_MAXV : 1][8];
 #pragma unroll
     for (int i = 0; i < LNB_MAXV; ++i)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) ag[i][e] = ab[i][e] = 0.f;
+        for (int e = 0; e < 8; ++e) {
+            ag[i][e] = ab[i][e] = 0.f;
+            if (DBIAS) ax[i][e] = 0.f;
+        }
 
     for (int row = blockIdx.x * LNB_WARPS + warp; row < rows; row += gridDim.x * LNB_WARPS) {
         const float* pr = pre + static_cast<int64_t>(row) * n;
@@ -147,7 +154,10 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ pre, const
             if (vi < nvec) {
                 float o[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = rstd * (d[i][e] - c1 - x[i][e] * c2);
+                for (int e = 0; e < 8; ++e) {
+                    o[e] = rstd * (d[i][e] - c1 - x[i][e] * c2);
+                    if (DBIAS) ax[i][e] += o[e];
+                }
                 if (dx32) {
                     float* p = dx32 + static_cast<int64_t>(row) * n + vi * 8;
                     *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
@@ -168,16 +178,17 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ pre, const
     for (int i = 0; i < LNB_MAXV; ++i) {
         if (i * 256 < n) {
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
+            for (int half = 0; half < (DBIAS ? 3 : 2); ++half) {
+                if (half == 2 && dbias == nullptr) break;
                 __syncthreads();
 #pragma unroll
-                for (int e = 0; e < 8; ++e) red[warp][lane * 8 + e] = half == 0 ? ag[i][e] : ab[i][e];
+                for (int e = 0; e < 8; ++e) red[warp][lane * 8 + e] = half == 0 ? ag[i][e] : (half == 1 ? ab[i][e] : ax[DBIAS ? i : 0][e]);
                 __syncthreads();
                 float v = 0.f;
 #pragma unroll
                 for (int w = 0; w < LNB_WARPS; ++w) v += red[w][threadIdx.x];
                 const int col = i * 256 + threadIdx.x;
-                if (col < n) atomicAdd((half == 0 ? dgamma : dbeta) + col, v);
+                if (col < n) atomicAdd((half == 0 ? dgamma : (half == 1 ? dbeta : dbias)) + col, v);
             }
         }
     }
@@ -342,6 +353,7 @@ attn_bwd_kernel(const AttnBwdParams p) {
 struct AttnBwdTcParams {
     AttnBwdParams b;
     const __nv_bfloat16* o; int64_t ldof;   // forward output (context) of the same attention
+    float* db_q; float* db_k; float* db_v;  // optional fused bias gradients of the q / k / v projections: [heads * 64] column sums
 };
 constexpr int ABT_LD = 72;
 constexpr int ABT_WARPS = 8;
@@ -377,6 +389,23 @@ __device__ __forceinline__ void abt_merge(float& m, float& l, float m2, float l2
     m = mn;
 }
 
+// column sums of a warp's 16 x 64 accumulator tile (rows beyond the valid range are exactly zero) -> shared memory
+__device__ __forceinline__ void abt_colsum(const float (&acc)[8][4], float scale, float* scol, int lane) {
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        float c0 = acc[nt][0] + acc[nt][2], c1 = acc[nt][1] + acc[nt][3];
+#pragma unroll
+        for (int o = 4; o <= 16; o <<= 1) {
+            c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+            c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+        }
+        if (lane < 4) {
+            atomicAdd(scol + nt * 8 + 2 * lane, c0 * scale);
+            atomicAdd(scol + nt * 8 + 2 * lane + 1, c1 * scale);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(ABT_WARPS * 32)
 attn_bwd_tc_kernel(const AttnBwdTcParams pp) {
     const AttnBwdParams& p = pp.b;
@@ -394,11 +423,14 @@ attn_bwd_tc_kernel(const AttnBwdTcParams pp) {
     float* sIl = sMx + Sqp;                                             // [Sqp]   1 / row sum
     float* sPM = sIl + Sqp;                                             // [ABT_WARPS][Sqp] partial max
     float* sPL = sPM + ABT_WARPS * Sqp;                                 // [ABT_WARPS][Sqp] partial sum
+    float* sCol = sPL + ABT_WARPS * Sqp;                                // [3][64] column sums of dQ / dK / dV (bias gradients)
     const int head = blockIdx.x % p.heads, r = blockIdx.x / p.heads;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     constexpr int NT = ABT_WARPS * 32;
     const bool q_dense = p.nq_split >= p.Sq;
 
+    if (tid < 192) sCol[tid] = 0.f;
+    __syncthreads();
     // ---- stage Q, dO (+ delta = dO . O), K, V; rows past the end are zero
     for (int idx = tid; idx < Sqp * 8; idx += NT) {
         const int i = idx >> 3, c = idx & 7;
@@ -419,6 +451,21 @@ attn_bwd_tc_kernel(const AttnBwdTcParams pp) {
         d += __shfl_xor_sync(0xffffffffu, d, 2);
         d += __shfl_xor_sync(0xffffffffu, d, 4);
         if (c == 0) sDelta[i] = d;
+        if (pp.db_v) {
+            // bias gradient of the value projection: sum_j dV_j = sum_q (sum_j P_qj) dO_q = sum_q dO_q (softmax rows sum to 1)
+            float e8[8];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { e8[2 * k] = ptx::bf16lo(dd[k]); e8[2 * k + 1] = ptx::bf16hi(dd[k]); }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                e8[k] += __shfl_xor_sync(0xffffffffu, e8[k], 8);
+                e8[k] += __shfl_xor_sync(0xffffffffu, e8[k], 16);
+            }
+            if (lane < 8) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) atomicAdd(sCol + 128 + c * 8 + k, e8[k]);
+            }
+        }
     }
     for (int idx = tid; idx < Skp * 8; idx += NT) {
         const int j = idx >> 3, c = idx & 7;
@@ -536,6 +583,7 @@ attn_bwd_tc_kernel(const AttnBwdTcParams pp) {
                     abt_mma(acc[2 * dp + 1], a, bf[2], bf[3]);
                 }
             }
+            if (pp.db_q) abt_colsum(acc, 0.125f, sCol, lane);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int i = h ? i1 : i0;
@@ -575,6 +623,15 @@ attn_bwd_tc_kernel(const AttnBwdTcParams pp) {
                         *reinterpret_cast<uint32_t*>(dst + nt * 8) = ptx::pack_bf16x2(acc[nt][2 * h] * sc, acc[nt][2 * h + 1] * sc);
                 }
             }
+        }
+    }
+    // ---- bias gradients: this (row, head)'s column sums -> global (one atomic per column and CTA)
+    if (pp.db_q || pp.db_k || pp.db_v) {
+        __syncthreads();
+        // (the key-projection bias gradient is exactly zero: sum_j dS_qj = 0 for a softmax; db_k is left untouched)
+        if (tid < 192 && (tid < 64 || tid >= 128)) {
+            float* dst = tid < 64 ? pp.db_q : pp.db_v;
+            if (dst) atomicAdd(dst + head * 64 + (tid & 63), sCol[tid]);
         }
     }
 }
@@ -661,13 +718,66 @@ int launch_colsum(const void* in, int64_t ld, int R, int C, float* colsum, cudaS
 }
 
 int launch_ln_bwd(const float* dy, const float* pre, const float* gamma, float* dx32, void* dx16, float* dgamma, float* dbeta,
-                  int rows, int n, float eps, cudaStream_t s) {
-    MRA_REQUIRE(rows > 0 && n % 8 == 0 && n <= 32 * LNB_MAXV * 8, "layernorm backward width %d unsupported", n);
+                  float* dbias, int rows, int n, float eps, cudaStream_t s) {
+    MRA_REQUIRE(rows > 0 && n % 8 == 0 && n <= 32 * LNB_MAXV_WIDE * 8, "layernorm backward width %d unsupported", n);
+    MRA_REQUIRE(dbias == nullptr || (n <= 32 * LNB_MAXV_H * 8 && dgamma != nullptr),
+                "layernorm backward: the fused bias gradient needs width <= %d and dgamma", 32 * LNB_MAXV_H * 8);
     int blocks = (rows + LNB_WARPS - 1) / LNB_WARPS;
     const int cap = sm_count() * 4;
     if (blocks > cap) blocks = cap;
-    ln_bwd_kernel<<<blocks, LNB_WARPS * 32, 0, s>>>(dy, pre, gamma, dx32, reinterpret_cast<__nv_bfloat16*>(dx16), dgamma, dbeta,
-                                                    rows, n, eps);
+    __nv_bfloat16* d16 = reinterpret_cast<__nv_bfloat16*>(dx16);
+    if (n <= 32 * LNB_MAXV_H * 8)
+        ln_bwd_kernel<LNB_MAXV_H, true><<<blocks, LNB_WARPS * 32, 0, s>>>(dy, pre, gamma, dx32, d16, dgamma, dbeta, dbias, rows, n, eps);
+    else
+        ln_bwd_kernel<LNB_MAXV_WIDE, false><<<blocks, LNB_WARPS * 32, 0, s>>>(dy, pre, gamma, dx32, d16, dgamma, dbeta, nullptr, rows, n, eps);
+    MRA_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// dz = dy * gelu'(z) over [rows, cols] with the bias gradient of the producing Linear fused: colsum[c] += sum_r dz[r, c].
+// Block = 128 threads x 8 columns over a chunk of GB_ROWS rows.
+constexpr int GB_ROWS = 64;
+__global__ void __launch_bounds__(256)
+gelu_bwd_colsum_kernel(const __nv_bfloat16* __restrict__ z, const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ out,
+                       float* __restrict__ colsum, int rows, int cols) {
+    __shared__ float red[8][32][9];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int c = (blockIdx.x * 32 + cx) * 8;
+    const int r0 = blockIdx.y * GB_ROWS, r1 = min(rows, r0 + GB_ROWS);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (c < cols) {
+#pragma unroll 4
+        for (int r = r0 + ry; r < r1; r += 8) {
+            const int64_t off = static_cast<int64_t>(r) * cols + c;
+            const uint4 zv = *reinterpret_cast<const uint4*>(z + off), dv = *reinterpret_cast<const uint4*>(dy + off);
+            const uint32_t zz[4] = {zv.x, zv.y, zv.z, zv.w}, dd[4] = {dv.x, dv.y, dv.z, dv.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                o[k] = ptx::pack_bf16x2(ptx::bf16lo(dd[k]) * gelu_grad(ptx::bf16lo(zz[k])), ptx::bf16hi(dd[k]) * gelu_grad(ptx::bf16hi(zz[k])));
+                acc[2 * k] += ptx::bf16lo(o[k]);      // the rounded values, i.e. exactly the column sums of what the wgrad GEMM reads
+                acc[2 * k + 1] += ptx::bf16hi(o[k]);
+            }
+            *reinterpret_cast<uint4*>(out + off) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[ry][cx][e] = acc[e];
+    __syncthreads();
+    // 256 threads reduce the 8 row lanes of the block's 256 columns
+    const int col = threadIdx.x, vcx = col >> 3, ve = col & 7;
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v += red[i][vcx][ve];
+    const int gc = blockIdx.x * 256 + col;
+    if (gc < cols) atomicAdd(colsum + gc, v);
+}
+
+int launch_gelu_bwd_colsum(const void* z, const void* dy, void* dz, float* colsum, int rows, int cols, cudaStream_t s) {
+    MRA_REQUIRE(rows > 0 && cols > 0 && cols % 8 == 0 && colsum, "gelu backward: bad shape rows=%d cols=%d", rows, cols);
+    dim3 grid((cols + 255) / 256, (rows + GB_ROWS - 1) / GB_ROWS);
+    gelu_bwd_colsum_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(z), reinterpret_cast<const __nv_bfloat16*>(dy),
+                                                reinterpret_cast<__nv_bfloat16*>(dz), colsum, rows, cols);
     MRA_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -692,7 +802,7 @@ int launch_gelu_bwd(const void* z, const void* dy, void* dz, int64_t n, cudaStre
 
 static size_t attn_bwd_tc_smem(int Sq, int Sk) {
     const size_t Sqp = (Sq + 15) & ~15, Skp = (Sk + 15) & ~15, ldp = Skp + 8;
-    return (2 * Sqp + 2 * Skp) * ABT_LD * 2 + 2 * Sqp * ldp * 2 + (Skp + 3 * Sqp + 2 * ABT_WARPS * Sqp) * 4;
+    return (2 * Sqp + 2 * Skp) * ABT_LD * 2 + 2 * Sqp * ldp * 2 + (Skp + 3 * Sqp + 2 * ABT_WARPS * Sqp + 192) * 4;
 }
 
 int launch_attention_bwd(const AttnBwdArgs& a, cudaStream_t s) {
@@ -711,7 +821,7 @@ int launch_attention_bwd(const AttnBwdArgs& a, cudaStream_t s) {
                             reinterpret_cast<const __nv_bfloat16*>(a.v), a.ldv, reinterpret_cast<const __nv_bfloat16*>(a.d_o), a.ldo,
                             reinterpret_cast<__nv_bfloat16*>(a.dq), a.lddq, reinterpret_cast<__nv_bfloat16*>(a.dk), a.lddk,
                             reinterpret_cast<__nv_bfloat16*>(a.dv), a.lddv, a.add_mask, a.rows, a.heads, a.Sq, a.Sk, a.nq_split, a.kv_dense},
-                           reinterpret_cast<const __nv_bfloat16*>(a.o), a.ldof};
+                           reinterpret_cast<const __nv_bfloat16*>(a.o), a.ldof, a.db_q, a.db_k, a.db_v};
         attn_bwd_tc_kernel<<<static_cast<unsigned>(a.rows) * a.heads, ABT_WARPS * 32, tc_smem, s>>>(pp);
         MRA_CHECK_CUDA(cudaGetLastError());
         return 0;
@@ -729,6 +839,11 @@ int launch_attention_bwd(const AttnBwdArgs& a, cudaStream_t s) {
                     reinterpret_cast<__nv_bfloat16*>(a.dv), a.lddv, a.add_mask, a.rows, a.heads, a.Sq, a.Sk, a.nq_split, a.kv_dense};
     attn_bwd_kernel<<<static_cast<unsigned>(a.rows) * a.heads, 256, smem, s>>>(p);
     MRA_CHECK_CUDA(cudaGetLastError());
+    // bias gradients by separate column-sum passes on this path
+    const int HC = a.heads * 64;
+    if (a.db_q) { if (int e = launch_colsum(a.dq, a.lddq, static_cast<int>(a.n_q_tokens), HC, a.db_q, s)) return e; }
+    if (a.db_k) { if (int e = launch_colsum(a.dk, a.lddk, static_cast<int>(a.n_k_tokens), HC, a.db_k, s)) return e; }
+    if (a.db_v) { if (int e = launch_colsum(a.dv, a.lddv, static_cast<int>(a.n_k_tokens), HC, a.db_v, s)) return e; }
     return 0;
 }
 

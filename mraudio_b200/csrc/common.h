@@ -146,12 +146,17 @@ struct AttnBwdArgs {
     const float* add_mask;
     int rows, heads, Sq, Sk, nq_split, kv_dense;
     const void* o = nullptr; int64_t ldof = 0;   // forward output of the same attention (enables the tensor-core kernel)
+    // optional bias gradients of the q / k / v projections (fp32 [heads * 64], accumulated): column sums of dq / dk / dv over
+    // all tokens; the tensor-core kernel produces them in the same pass
+    float* db_q = nullptr; float* db_k = nullptr; float* db_v = nullptr;
+    int64_t n_q_tokens = 0, n_k_tokens = 0;      // total token rows of dq and of dk / dv (for the fallback column-sum pass)
 };
 int launch_attention_bwd(const AttnBwdArgs& a, cudaStream_t s);
 int launch_transpose(const void* in, int64_t ld_in, void* out, int64_t ld_out, int R, int C, float* colsum, cudaStream_t s);
 int launch_colsum(const void* in, int64_t ld, int R, int C, float* colsum, cudaStream_t s);
 int launch_ln_bwd(const float* dy, const float* pre, const float* gamma, float* dx32, void* dx16, float* dgamma, float* dbeta,
-                  int rows, int n, float eps, cudaStream_t s);
+                  float* dbias, int rows, int n, float eps, cudaStream_t s);
+int launch_gelu_bwd_colsum(const void* z, const void* dy, void* dz, float* colsum, int rows, int cols, cudaStream_t s);
 int launch_gelu_fwd(const void* z, void* out, int64_t n, cudaStream_t s);
 int launch_gelu_bwd(const void* z, const void* dy, void* dz, int64_t n, cudaStream_t s);
 int launch_embed_bwd(const float* d_emb, const int32_t* ids, float* d_query, int q_rows, float* d_word, float* d_pos, int rows,

@@ -629,20 +629,23 @@ extern "C" int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, 
         MRA_TRY(launch_gemm_tc(a, s));   // (the SIMT debug kernel has no transposed-operand form)
         return 0;
     };
-    auto ln_bwd = [&](const float* dy, const float* pre, const float* gamma, float* dgam, float* dbet, size_t r0, int n) -> int {
+    // LayerNorm backward of a post-LN block; dbias = bias gradient of the Linear feeding the LayerNorm (fused column sums)
+    auto ln_bwd = [&](const float* dy, const float* pre, const float* gamma, float* dgam, float* dbet, float* dbias, size_t r0,
+                      int n) -> int {
         const size_t o = r0 * H;
-        MRA_TRY(launch_ln_bwd(dy + o, pre + o, gamma, bw.g_pre32 + o, bw.g_pre16 + o, dgam, dbet, n, H, c.ln_eps, s));
+        MRA_TRY(launch_ln_bwd(dy + o, pre + o, gamma, bw.g_pre32 + o, bw.g_pre16 + o, dgam, dbet, dbias, n, H, c.ln_eps, s));
         return 0;
     };
     // FFN backward over rows [r0, r0+n): g_out = bw.g_x rows -> g_in accumulated into bw.g_a rows
     auto ffn_bwd = [&](const LayerBufs& B, const __nv_bfloat16* in16, size_t r0, int n, const void* w1T, const void* w2T,
                        const float* gamma, float* g_w1, float* g_b1, float* g_w2, float* g_b2, float* g_gam, float* g_bet) -> int {
         const size_t o = r0 * H, oi = r0 * I;
-        if (int e = ln_bwd(bw.g_x, B.pre_f, gamma, g_gam, g_bet, r0, n)) return e;
-        if (int e = wgrad(bw.g_pre16 + o, H, B.inter + oi, I, n, H, I, g_w2, I, g_b2)) return e;
+        if (int e = ln_bwd(bw.g_x, B.pre_f, gamma, g_gam, g_bet, g_b2, r0, n)) return e;
+        if (int e = wgrad(bw.g_pre16 + o, H, B.inter + oi, I, n, H, I, g_w2, I, nullptr)) return e;
         MRA_TRY(gemm(bw.g_pre16 + o, H, w2T, H, nullptr, 0, bw.g_big16, I, n, I, H, 0));          // d_inter
-        MRA_TRY(launch_gelu_bwd(B.z + oi, bw.g_big16, bw.g_big2, static_cast<int64_t>(n) * I, s)); // dz
-        if (int e = wgrad(bw.g_big2, I, in16 + o, H, n, I, H, g_w1, H, g_b1)) return e;
+        if (g_b1 != nullptr) MRA_TRY(launch_gelu_bwd_colsum(B.z + oi, bw.g_big16, bw.g_big2, g_b1, n, I, s));   // dz (+ db1)
+        else MRA_TRY(launch_gelu_bwd(B.z + oi, bw.g_big16, bw.g_big2, static_cast<int64_t>(n) * I, s));
+        if (int e = wgrad(bw.g_big2, I, in16 + o, H, n, I, H, g_w1, H, nullptr)) return e;
         MRA_TRY(gemm(bw.g_big2, I, w1T, I, bw.g_pre32 + o, H, bw.g_a + o, H, n, H, I, 1));          // + residual path
         return 0;
     };
@@ -681,35 +684,40 @@ extern "C" int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, 
         if (cross) {
             const int slot = h->cross_slot[l];
             const __nv_bfloat16* kbase = ws.kv + static_cast<size_t>(slot) * 2 * H;
-            if (int e = ln_bwd(bw.g_a, B.pre_c, L.ln_c_g, G.ln_c_g, G.ln_c_b, 0, Mq)) return e;
-            if (int e = wgrad(bw.g_pre16, H, B.cctx, H, Mq, H, H, G.w_co, H, G.b_co)) return e;
+            if (int e = ln_bwd(bw.g_a, B.pre_c, L.ln_c_g, G.ln_c_g, G.ln_c_b, G.b_co, 0, Mq)) return e;
+            if (int e = wgrad(bw.g_pre16, H, B.cctx, H, Mq, H, H, G.w_co, H, nullptr)) return e;
             MRA_TRY(gemm(bw.g_pre16, H, LT.w_co, H, nullptr, 0, bw.g_ctx16, H, Mq, H, H, 0));      // d_cctx
             AttnBwdArgs a{B.cq, H, kbase, kv_ld, kbase + H, kv_ld, bw.g_ctx16, H, bw.g_cq16, H, bw.g_kv16, 2 * H,
                           bw.g_kv16 + H, 2 * H, io->enc_mask ? ws.enc_mask : nullptr, rows, c.heads, Nq, Nk, Nq, 1};
             a.o = B.cctx; a.ldof = H;
+            a.db_q = G.b_cq;
+            a.db_k = g->b_ckv + static_cast<size_t>(slot) * 2 * H;
+            a.db_v = a.db_k + H;
+            a.n_q_tokens = Mq; a.n_k_tokens = NK;
             MRA_TRY(launch_attention_bwd(a, s));
-            if (int e = wgrad(bw.g_cq16, H, B.ab, H, Mq, H, H, G.w_cq, H, G.b_cq)) return e;
+            if (int e = wgrad(bw.g_cq16, H, B.ab, H, Mq, H, H, G.w_cq, H, nullptr)) return e;
             MRA_TRY(gemm(bw.g_cq16, H, LT.w_cq, H, bw.g_pre32, H, bw.g_a, H, Mq, H, H, 1));         // -> grad of LN_a out (query rows)
             if (int e = wgrad(bw.g_kv16, 2 * H, reinterpret_cast<const __nv_bfloat16*>(io->enc), c.enc_width, NK, 2 * H, c.enc_width,
-                              g->w_ckv + static_cast<size_t>(slot) * 2 * H * c.enc_width, c.enc_width,
-                              g->b_ckv + static_cast<size_t>(slot) * 2 * H)) return e;
+                              g->w_ckv + static_cast<size_t>(slot) * 2 * H * c.enc_width, c.enc_width, nullptr)) return e;
         }
         // ---- self-attention block (all rows)
-        if (int e = ln_bwd(bw.g_a, B.pre_a, L.ln_a_g, G.ln_a_g, G.ln_a_b, 0, Mtot)) return e;
-        if (int e = wgrad(bw.g_pre16, H, B.ctx, H, Mtot, H, H, G.w_ao, H, G.b_ao)) return e;
+        if (int e = ln_bwd(bw.g_a, B.pre_a, L.ln_a_g, G.ln_a_g, G.ln_a_b, G.b_ao, 0, Mtot)) return e;
+        if (int e = wgrad(bw.g_pre16, H, B.ctx, H, Mtot, H, H, G.w_ao, H, nullptr)) return e;
         MRA_TRY(gemm(bw.g_pre16, H, LT.w_ao, H, nullptr, 0, bw.g_ctx16, H, Mtot, H, H, 0));         // d_ctx
         {
             AttnBwdArgs a{B.qkv, 3 * H, B.qkv + H, 3 * H, B.qkv + 2 * H, 3 * H, bw.g_ctx16, H, bw.g_big16, 3 * H,
                           bw.g_big16 + H, 3 * H, bw.g_big16 + 2 * H, 3 * H, io->attn_mask ? ws.self_mask : nullptr,
                           rows, c.heads, S, S, Nq, 0};
             a.o = B.ctx; a.ldof = H;
+            a.db_q = G.b_qkv; a.db_k = G.b_qkv + H; a.db_v = G.b_qkv + 2 * H;
+            a.n_q_tokens = a.n_k_tokens = Mtot;
             MRA_TRY(launch_attention_bwd(a, s));
         }
-        if (int e = wgrad(bw.g_big16, 3 * H, B.xb, H, Mtot, 3 * H, H, G.w_qkv, H, G.b_qkv)) return e;
+        if (int e = wgrad(bw.g_big16, 3 * H, B.xb, H, Mtot, 3 * H, H, G.w_qkv, H, nullptr)) return e;
         MRA_TRY(gemm(bw.g_big16, 3 * H, LT.w_qkv, 3 * H, bw.g_pre32, H, bw.g_x, H, Mtot, H, 3 * H, 1));  // grad of the layer input
     }
     // ---- embeddings
-    if (int e = ln_bwd(bw.g_x, ws.pre_e, W.ln_e_g, g->ln_e_g, g->ln_e_b, 0, Mtot)) return e;
+    if (int e = ln_bwd(bw.g_x, ws.pre_e, W.ln_e_g, g->ln_e_g, g->ln_e_b, nullptr, 0, Mtot)) return e;
     MRA_TRY(launch_embed_bwd(bw.g_pre32, io->input_ids, g->query_tokens, io->q_rows, g->word_emb, g->pos_emb, rows, Nq, T, H,
                              c.vocab, s));
 #undef MRA_TRY
