@@ -154,6 +154,12 @@ size_t mra_qformer_backward_workspace_bytes(const mra_qformer_t* h, int32_t rows
 int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, const void* d_llm, const mra_qformer_weights* wT,
                          const mra_qformer_grads* g, void* workspace, size_t workspace_bytes, void* bwd_workspace,
                          size_t bwd_bytes, void* stream);
+/* Overlap of the data-parallel gradient all-reduce (DistributedDataParallel, utils/trainer.py:69) with the backward:
+ * events[l] (cudaEvent_t, owned by the caller; NULL entries allowed) is recorded on the backward's stream as soon as the
+ * gradients of layer l -- and therefore of all layers above it -- are final, so the caller can start the all-reduce of
+ * that bucket on another stream while the lower layers are still running.  (The stacked cross-attention K/V gradients,
+ * the embeddings and the query tokens are final only when mra_qformer_backward has finished.)  n = 0 clears. */
+int mra_qformer_backward_layer_events(mra_qformer_t* h, void* const* events, int32_t n);
 int mra_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                   float beta2, float eps, float weight_decay, int32_t step, float grad_scale, void* stream);
 /* The same Adam update fused with what always follows it in the fine-tuning loop (utils/trainer.py:137-140): the bf16

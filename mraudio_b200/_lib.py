@@ -89,6 +89,7 @@ def _load():
     lib.mra_qformer_backward_workspace_bytes.restype = C.c_size_t
     lib.mra_qformer_backward.argtypes = [vp, C.POINTER(QFormerIO), vp, C.POINTER(QFormerWeights), C.POINTER(QFormerGrads), vp,
                                          C.c_size_t, vp, C.c_size_t, vp]
+    lib.mra_qformer_backward_layer_events.argtypes = [vp, C.POINTER(vp), i32]
     lib.mra_adam_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, vp]
     lib.mra_adam_step_fused.argtypes = [vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, i32, vp]
     lib.mra_cast_bf16.argtypes = [vp, vp, i64, vp]
@@ -115,7 +116,7 @@ lib = _load()
 # every symbol include/mraudio_b200.h declares (checked by tests/test_capi_symbols.py)
 EXPORTED_SYMBOLS = (
     "mra_last_error", "mra_version", "mra_device_check", "mra_qformer_create", "mra_qformer_set_weights",
-    "mra_qformer_destroy", "mra_qformer_workspace_bytes", "mra_qformer_forward", "mra_qformer_forward_multi", "mra_qformer_last_launch_count", "mra_qformer_backward_workspace_bytes", "mra_qformer_backward", "mra_adam_step", "mra_adam_step_fused",
+    "mra_qformer_destroy", "mra_qformer_workspace_bytes", "mra_qformer_forward", "mra_qformer_forward_multi", "mra_qformer_last_launch_count", "mra_qformer_backward_workspace_bytes", "mra_qformer_backward", "mra_qformer_backward_layer_events", "mra_adam_step", "mra_adam_step_fused",
     "mra_cast_bf16",
     "mra_qformer_profile_mode", "mra_qformer_profile_read",
     "mra_gemm_bf16", "mra_wgrad_bf16", "mra_dgrad_bf16", "mra_gemm_ln_bf16", "mra_gemm_tile_override", "mra_gemm_cluster_override", "mra_attention", "mra_attention_impl_override", "mra_layernorm", "mra_modality_layernorm", "mra_add_frame_position", "mra_prompt_assemble", "mra_mr_score",

@@ -19,6 +19,7 @@ struct mra_qformer {
     int cross_slot[MRA_MAX_LAYERS];  // index of the layer's K/V block inside w_ckv, or -1
     int last_launches = 0;
     int gemm_impl = MRA_GEMM_IMPL_TCGEN05;
+    cudaEvent_t layer_done[MRA_MAX_LAYERS] = {};   // optional: recorded by the backward when a layer's gradients are final
     bool fuse_ln = true;   // Linear + residual + LayerNorm in one cluster kernel (MRA_NO_FUSED_LN=1 disables: A/B runs)
     // optional per-category device timing (CUDA events on the caller's stream), see mra_qformer_profile_*
     int profile_mode = MRA_PROFILE_OFF;
@@ -715,6 +716,8 @@ extern "C" int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, 
         }
         if (int e = wgrad(bw.g_big16, 3 * H, B.xb, H, Mtot, 3 * H, H, G.w_qkv, H, nullptr)) return e;
         MRA_TRY(gemm(bw.g_big16, 3 * H, LT.w_qkv, 3 * H, bw.g_pre32, H, bw.g_x, H, Mtot, H, 3 * H, 1));  // grad of the layer input
+        // the gradients of layers >= l (except the stacked cross K/V weights) are final: a bucketed all-reduce may start
+        if (h->layer_done[l]) MRA_CHECK_CUDA(cudaEventRecord(h->layer_done[l], s));
     }
     // ---- embeddings
     if (int e = ln_bwd(bw.g_x, ws.pre_e, W.ln_e_g, g->ln_e_g, g->ln_e_b, nullptr, 0, Mtot)) return e;
@@ -722,6 +725,12 @@ extern "C" int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, 
                              c.vocab, s));
 #undef MRA_TRY
     h->last_launches = launches;
+    return 0;
+}
+
+extern "C" int mra_qformer_backward_layer_events(mra_qformer_t* h, void* const* events, int32_t n) {
+    MRA_REQUIRE(h != nullptr && n >= 0 && n <= MRA_MAX_LAYERS && (events != nullptr || n == 0), "mra_qformer_backward_layer_events: bad arguments");
+    for (int l = 0; l < MRA_MAX_LAYERS; ++l) h->layer_done[l] = l < n ? reinterpret_cast<cudaEvent_t>(events[l]) : nullptr;
     return 0;
 }
 

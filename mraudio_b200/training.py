@@ -114,6 +114,26 @@ class TrainableQFormer:
             self._bind(L.output.LayerNorm.weight, p + "ln_ft_g"); self._bind(L.output.LayerNorm.bias, p + "ln_ft_b")
         # (the dgrad GEMMs read the bf16 weights in place through MN-major descriptors: no transposed copies are kept)
         self._handle = bert._handle(D)
+        # ---- gradient buckets for the overlapped all-reduce: [start of layer b, end of the previous bucket), top layers first;
+        #      the last bucket also holds the front of the buffer (embeddings, stacked cross K/V, projection, query tokens)
+        nl = len(layers)
+        cuts = sorted({nl * 2 // 3, nl // 3} - {0}, reverse=True)           # 12 layers -> buckets from layer 8 and layer 4
+        self.buckets: List[Tuple[Optional[int], int, int]] = []            # (layer whose "done" event gates it | None, lo, hi)
+        hi = self.numel
+        for b in cuts:
+            lo = self.seg[f"L{b}.w_qkv"][0]
+            self.buckets.append((b, lo, hi))
+            hi = lo
+        self.buckets.append((None, 0, hi))
+        self.layer_events = [torch.cuda.Event() for _ in range(nl)]
+        for e in self.layer_events:
+            e.record()                                                     # creates the underlying cudaEvent_t
+        ev = (C.c_void_p * nl)(*[e.cuda_event for e in self.layer_events])
+        check(lib.mra_qformer_backward_layer_events(self._handle, ev, nl))
+        self.comm_stream = torch.cuda.Stream(dev)
+        self.reduce_group = None
+        self.reduce_after_backward = False     # set by the trainer on optimizer-step iterations when world > 1
+        self.reduce_done: Optional[torch.cuda.Event] = None
         self._structs = None
         self._ws = self._bws = None
         self._saved = None
@@ -206,6 +226,30 @@ class TrainableQFormer:
                                        self._ws.numel(), self._bws.data_ptr(), self._bws.numel(), current_stream()))
         self.last_backward_launches = lib.mra_qformer_last_launch_count(self._handle)
         self._saved = None
+        if self.reduce_after_backward:
+            self.launch_grad_allreduce()
+
+    def launch_grad_allreduce(self):
+        """DDP's gradient all-reduce (utils/trainer.py:69), bucketed and overlapped: the bucket of the top layers starts on
+        ``comm_stream`` as soon as the backward has recorded that layer's event, while the lower layers (and the other
+        modality's backward) are still running on the compute stream.  Sum semantics; ``adam_step(grad_scale=1/world)``
+        turns it into DDP's mean.  ``wait_grad_allreduce`` makes the current stream wait for it."""
+        import torch.distributed as dist
+        main = torch.cuda.current_stream()
+        tail = torch.cuda.Event()
+        tail.record(main)                      # end of this backward: gates the last bucket
+        with torch.cuda.stream(self.comm_stream):
+            for layer, lo, hi in self.buckets:
+                self.comm_stream.wait_event(self.layer_events[layer] if layer is not None else tail)
+                dist.all_reduce(self.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.reduce_group)
+            self.reduce_done = torch.cuda.Event()
+            self.reduce_done.record(self.comm_stream)
+        self.reduce_after_backward = False
+
+    def wait_grad_allreduce(self):
+        if self.reduce_done is not None:
+            torch.cuda.current_stream().wait_event(self.reduce_done)
+            self.reduce_done = None
 
     # ------------------------------------------------------------------------------------------------ optimizer
     def zero_grad(self):
@@ -252,7 +296,7 @@ class QFormerTrainer:
     (out of scope); the default is the surrogate ``sum(inputs_llm * G)`` used by the parity tests and the benchmark."""
 
     def __init__(self, model, max_epoch: int = 1, accum_grad_iters: int = 2, init_lr: float = 3e-4, warmup_steps: int = 1000,
-                 loss_fn=None, group=None):
+                 loss_fn=None, group=None, overlap_allreduce: bool = True):
         self.model = model
         model.freeze_qformers(False)
         self.states = {m: TrainableQFormer(getattr(model, f"{m}_Qformer"), getattr(model, f"{m}_query_tokens"),
@@ -260,6 +304,7 @@ class QFormerTrainer:
         self.accum_grad_iters, self.max_epoch, self.init_lr, self.warmup_steps = accum_grad_iters, max_epoch, init_lr, warmup_steps
         self.loss_fn = loss_fn
         self.group = group
+        self.overlap_allreduce = overlap_allreduce
         self.iter = 0
         self.lr = init_lr
 
@@ -294,13 +339,22 @@ class QFormerTrainer:
             loss = self.loss_fn(inputs_llm, atts_llm, samples)
         else:
             loss = sum((inputs_llm[m].float() * surrogate[m]).sum() for m in inputs_llm)
+        world = self._world()
+        stepping = (self.iter + 1) % self.accum_grad_iters == 0                                                    # :137
+        if stepping and world > 1:
+            # DDP's gradient averaging, only on optimizer-step iterations (the reference all-reduces on every backward):
+            # each modality's backward node launches its bucketed all-reduce on a side stream as its layers finish
+            for st in self.states.values():
+                st.reduce_group, st.reduce_after_backward = self.group, self.overlap_allreduce
         (loss / self.accum_grad_iters).backward()                                                                  # :131-133
         self.iter += 1
-        if self.iter % self.accum_grad_iters == 0:                                                                  # :137
-            world = self._world()
+        if stepping:
             if world > 1:
-                for st in self.states.values():       # DDP's gradient averaging: one flat all-reduce per modality
-                    dist.all_reduce(st.grad, op=dist.ReduceOp.SUM, group=self.group)
+                for st in self.states.values():
+                    if self.overlap_allreduce:
+                        st.wait_grad_allreduce()
+                    else:                              # one flat all-reduce per modality after the backward (A/B baseline)
+                        dist.all_reduce(st.grad, op=dist.ReduceOp.SUM, group=self.group)
             for st in self.states.values():
                 st.adam_step(self.lr, grad_scale=1.0 / world, zero_grad=True)
         return loss.detach()

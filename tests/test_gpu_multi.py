@@ -50,6 +50,16 @@ def _worker(rank, world, port, q):
         gathered = [torch.empty_like(flat) for _ in range(world)]
         dist.all_gather(gathered, flat)
         same = all(torch.equal(gathered[0], t) for t in gathered)      # replicas stay bit-identical after the step
+        # the same step with the flat after-backward all-reduce (no overlap) gives the same parameters
+        torch.manual_seed(0)
+        model2 = XInstructBLIPQFormers(modalities=("video", "audio"), encoder_num_features={"video": 128, "audio": 64},
+                                       llm_hidden_size=128, num_hidden_layers=2).cuda()
+        tr2 = QFormerTrainer(model2, accum_grad_iters=1, warmup_steps=0, init_lr=1e-3, overlap_allreduce=False)
+        tr2.train_step({m: t[lo:hi].cuda() for m, t in feats.items()}, ids[lo:hi].cuda(), mask[lo:hi].cuda(),
+                       surrogate={m: t[lo:hi].cuda() for m, t in sur.items()})
+        torch.cuda.synchronize()
+        flat2 = torch.cat([s.flat for s in tr2.states.values()])
+        same = same and torch.allclose(flat, flat2, rtol=0, atol=2e-5) and not torch.equal(flat2, torch.zeros_like(flat2))
         # ---- scorer: NCCL gather of scored moments == single-process result
         sub, gt = mo.synth_submission(333, seed=9)
         lo, hi = shard_range(len(sub), rank, world)
