@@ -359,10 +359,58 @@ class QFormerTrainer:
                 st.adam_step(self.lr, grad_scale=1.0 / world, zero_grad=True)
         return loss.detach()
 
+    def eval_epoch(self, generations, group=None):
+        """``Trainer.eval_epoch`` (utils/trainer.py:156-182) from the point where the LLM has produced its strings:
+        ``generations`` is this rank's iterable of ``(qid, query, vid, target_text, output_text)``; targets and outputs go
+        through ``moment_str_to_list(post_process(.))`` (:168-169), the records are scored on this rank's GPU, and -- unlike
+        the reference, which evaluates only the local shard on every rank -- gathered to rank 0 (one fixed-width gather,
+        ``mr_eval.score_records_distributed``) so that rank 0 returns the metrics of the WHOLE validation set
+        (``eval_submission(results, results)``, :181); other ranks return None."""
+        import torch.distributed as dist
+        from . import mr_eval
+        from .parsing import parse_output
+        group = group if group is not None else self.group
+        results = []
+        for qid, query, vid, target, output in generations:
+            results.append({"qid": qid, "query": query, "vid": vid, "relevant_windows": parse_output(target),
+                            "pred_relevant_windows": parse_output(output)})
+        distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        if not distributed:
+            return mr_eval.eval_submission(results, results, verbose=False) if results else None
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        # global submission order = (rank, local index); qids are made unique per rank for the rank-0 bookkeeping
+        counts = [None] * world
+        dist.all_gather_object(counts, len(results), group=group)
+        base = sum(counts[:rank])
+        mine = [dict(d, _order=base + i) for i, d in enumerate(results)]
+        rec = mr_eval.score_records_distributed(mine, mine, group=group)
+        if rank != 0:
+            return None
+        total = sum(counts)
+        stub = [{"qid": i, "pred_relevant_windows": [[0, 0]], "relevant_windows": [[0, 0]]} for i in range(total)]
+        return mr_eval.eval_submission(stub, stub, verbose=False, _records=rec)
+
     def state_dict_trainable(self):
         """``_save_checkpoint`` payload (utils/trainer.py:184-199): only parameters that require grad."""
         grad = {k: v.requires_grad for k, v in self.model.named_parameters()}
         return {k: v for k, v in self.model.state_dict().items() if grad.get(k, False)}
+
+    def load_checkpoint(self, path: str) -> int:
+        """``Trainer._load_checkpoint`` (utils/trainer.py:236-260): parameters (``strict=False``: only the trainable ones
+        were saved), Adam moments and step counts; returns the epoch to resume from (``checkpoint["epoch"] + 1``)."""
+        ckpt = torch.load(path, map_location=next(self.model.parameters()).device)
+        with torch.no_grad():
+            sd = self.model.state_dict()
+            for k, v in ckpt["model"].items():
+                if k in sd:
+                    sd[k].copy_(v)          # in place: the parameters are views of the flat master buffers
+        for m, st in self.states.items():
+            o = ckpt["optimizer"][m]
+            st.exp_avg.copy_(o["exp_avg"])
+            st.exp_avg_sq.copy_(o["exp_avg_sq"])
+            st.step_count = int(o["step"])
+            st.refresh_operands()
+        return int(ckpt["epoch"]) + 1
 
     def save_checkpoint(self, path: str, cur_epoch: int):
         os.makedirs(os.path.dirname(path) or ".", exist_ok=True)

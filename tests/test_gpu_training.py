@@ -137,3 +137,44 @@ def test_trainer_step_reduces_surrogate_loss():
     sd = tr.state_dict_trainable()
     assert "video_query_tokens" in sd and any(k.startswith("audio_Qformer.bert.encoder.layer.0") for k in sd)
     assert not any(k.endswith("_ln.weight") for k in sd)   # modality LNs stay frozen (models/xinstructblip.py:198-199)
+
+
+def test_checkpoint_resume_and_eval_epoch(tmp_path):
+    """Trainer shell: save -> load restores parameters, Adam moments and step count, so the next step
+    continues identically (up to the rounding order of the atomics); eval_epoch parses generations with the reference's parser and scores them (utils/trainer.py:156-260)."""
+    from mraudio_b200.training import QFormerTrainer
+    from mraudio_b200.xinstructblip import XInstructBLIPQFormers
+    from mraudio_b200 import mr_eval
+
+    def make():
+        torch.manual_seed(0)
+        model = XInstructBLIPQFormers(modalities=("video", "audio"), encoder_num_features={"video": 128, "audio": 64},
+                                      llm_hidden_size=128, num_hidden_layers=2).cuda()
+        return QFormerTrainer(model, accum_grad_iters=1, warmup_steps=0, init_lr=1e-3)
+    g = torch.Generator().manual_seed(3)
+    feats = {"video": torch.randn(2, 2, 17, 128, generator=g).to(torch.bfloat16).cuda(),
+             "audio": torch.randn(2, 2, 16, 64, generator=g).to(torch.bfloat16).cuda()}
+    ids = torch.randint(1000, 30000, (2, 8), generator=g).cuda()
+    mask = torch.ones(2, 8, dtype=torch.long).cuda()
+    sur = {m: torch.randn(2, 2 * 32, 128, generator=g).cuda() for m in feats}
+    a = make()
+    for _ in range(2):
+        a.train_step(feats, ids, mask, surrogate=sur)
+    path = str(tmp_path / "ckpt" / "checkpoint_1.pth")
+    a.save_checkpoint(path, cur_epoch=1)
+    b = make()
+    assert b.load_checkpoint(path) == 2
+    for m in a.states:
+        assert torch.equal(a.states[m].flat, b.states[m].flat) and b.states[m].step_count == 2
+    la = a.train_step(feats, ids, mask, surrogate=sur)
+    lb = b.train_step(feats, ids, mask, surrogate=sur)
+    torch.cuda.synchronize()
+    assert torch.equal(la, lb)
+    for m in a.states:   # (fp32 atomics in the gradient reductions make two runs differ in the last bits)
+        assert torch.allclose(a.states[m].flat, b.states[m].flat, rtol=0, atol=1e-5)
+    gens = [(1, "q", "v", "[[10, 20]]", "[[10 20]]</s>"), (2, "q", "v", "[[0, 8], [30, 40]]", "[[30, 38]]"), (3, "q", "v", "[[4, 6]]", "nonsense")]
+    res = a.eval_epoch(gens)
+    sub = [{"qid": q, "pred_relevant_windows": p, "relevant_windows": t} for q, p, t in
+           [(1, [[10, 20]], [[10, 20]]), (2, [[30, 38]], [[0, 8], [30, 40]]), (3, [[-1, -1]], [[4, 6]])]]
+    assert res["brief"] == mr_eval.eval_submission(sub, sub, verbose=False)["brief"]
+    assert res["brief"]["MR-full-invalid_pred_num"] == 1
