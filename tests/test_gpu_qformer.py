@@ -183,3 +183,66 @@ def test_xinstructblip_encode_modalities_lockstep_matches_oracle_and_separate_ca
             other = qo.xinstructblip_encode(w, cfg, feats[m].float(), ids, mask, match_reference_text_tiling=False)
         assert _rel(a[m], ref) < TOL_FP32_REF
         assert _rel(a[m], other) > _rel(a[m], ref)      # the "fixed" tiling is NOT what the reference computes
+
+
+def _oracle_weights(model, m):
+    w = {"bert." + k[len(f"{m}_Qformer.bert."):]: v.detach().cpu().float() for k, v in model.state_dict().items()
+         if k.startswith(f"{m}_Qformer.bert.")}
+    w["query_tokens"] = getattr(model, f"{m}_query_tokens").detach().cpu()
+    w["llm_proj.weight"] = getattr(model, f"{m}_llm_proj").weight.detach().cpu()
+    w["llm_proj.bias"] = getattr(model, f"{m}_llm_proj").bias.detach().cpu()
+    return w
+
+
+@pytest.mark.parametrize("bs,Fr,T", [(32, 8, 32), (4, 75, 32)], ids=["config2_32x8", "config5_shape_4x75"])
+def test_full_size_configs_row_independence_and_sampled_oracle_parity(bs, Fr, T):
+    """BASELINE.json's full sizes (config 2: 32 videos x 8 frames; config 5's 75-clip videos), 12 layers, both modalities in
+    lockstep.  The oracle cannot run 256 rows x 12 layers in seconds, so parity is shown through (a) a size-independent
+    property -- every (video, frame) row is independent of the rest of the batch: the rows of two videos computed inside
+    the full batch equal the same two videos computed alone -- and (b) the fp32 oracle on exactly those two videos."""
+    from mraudio_b200.xinstructblip import XInstructBLIPQFormers
+    torch.manual_seed(0)
+    model = XInstructBLIPQFormers(modalities=("video", "audio")).cuda().eval()
+    g = torch.Generator().manual_seed(bs + Fr)
+    feats = {"video": torch.randn(bs, Fr, 257, 1408, generator=g).to(torch.bfloat16),
+             "audio": torch.randn(bs, Fr, 256, 768, generator=g).to(torch.bfloat16)}
+    ids = torch.randint(1000, 30000, (bs, T), generator=g)
+    mask = torch.ones(bs, T, dtype=torch.long)
+    mask[1, T - 5:] = 0
+    pick = [1, bs - 1]
+    # frame-major text tiling (:287-289) pairs row b*F+f with text (b*F+f) % bs: a sub-batch sees other texts, so the
+    # independence check uses the batch-major pairing (each video with its own prompt)
+    with torch.no_grad():
+        full, _ = model.encode_modalities({m: t.cuda() for m, t in feats.items()}, ids.cuda(), mask.cuda(),
+                                          match_reference_text_tiling=False)
+        sub, _ = model.encode_modalities({m: t[pick].cuda() for m, t in feats.items()}, ids[pick].cuda(), mask[pick].cuda(),
+                                         match_reference_text_tiling=False)
+    for m in ("video", "audio"):
+        assert full[m].shape == (bs, Fr * 32, 4096) and torch.isfinite(full[m].float()).all()
+        assert torch.equal(full[m][pick], sub[m]), f"{m}: rows depend on the rest of the batch"
+    nf = min(Fr, 4)     # oracle on the first frames of the two videos (fp32 CPU, 12 layers)
+    for m in ("video", "audio"):
+        cfg = qo.QFormerOracleConfig(encoder_width=feats[m].shape[-1])
+        with torch.no_grad():
+            ref = qo.xinstructblip_encode(_oracle_weights(model, m), cfg, feats[m][pick][:, :nf].float(), ids[pick], mask[pick],
+                                          match_reference_text_tiling=False)
+        got = full[m][pick].view(2, Fr, 32, 4096)[:, :nf].reshape(2, nf * 32, 4096)
+        assert _rel(got, ref) < TOL_FP32_REF, (m, _rel(got, ref))
+
+
+def test_maximum_text_length_and_single_row():
+    """Edge sizes: T = 128 prompt tokens (the reference's max_txt_len) with ragged padding, and a single (video, frame) row."""
+    from mraudio_b200.xinstructblip import XInstructBLIPQFormers
+    torch.manual_seed(1)
+    model = XInstructBLIPQFormers(modalities=("video",), num_hidden_layers=2, llm_hidden_size=256).cuda().eval()
+    g = torch.Generator().manual_seed(9)
+    for bs, Fr, T in ((2, 2, 128), (1, 1, 5)):
+        feats = {"video": torch.randn(bs, Fr, 257, 1408, generator=g).to(torch.bfloat16)}
+        ids = torch.randint(1000, 30000, (bs, T), generator=g)
+        mask = torch.ones(bs, T, dtype=torch.long)
+        mask[0, T // 3:] = 0
+        with torch.no_grad():
+            out, _ = model.encode_modalities({"video": feats["video"].cuda()}, ids.cuda(), mask.cuda())
+            cfg = qo.QFormerOracleConfig(encoder_width=1408, num_hidden_layers=2)
+            ref = qo.xinstructblip_encode(_oracle_weights(model, "video"), cfg, feats["video"].float(), ids, mask)
+        assert _rel(out["video"], ref) < TOL_FP32_REF
