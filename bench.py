@@ -108,8 +108,14 @@ def cpu_reference_run(steps, warmup, videos_per_step, frames, T, threads=None):
     dependency of the reference -- timed on this box's host cores.  Returns (clips_per_s, ms_per_step, cores, sample)."""
     import torch
     from oracle import qformer_oracle as qo
-    if threads:
-        torch.set_num_threads(threads)
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which would otherwise time the
+    # reference on ONE core)
+    if not threads:
+        try:
+            threads = len(os.sched_getaffinity(0))
+        except AttributeError:
+            threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
     cores = torch.get_num_threads()
     g = torch.Generator().manual_seed(1234)
     state = {}
@@ -179,6 +185,9 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a B200 (no CPU fallback on the product path)"
     torch.cuda.set_device(local)
+    # pin this rank to the CPUs next to its GPU BEFORE any pinned host buffer is allocated (first-touch places the pages
+    # on that NUMA node): with 8 ranks pulling 286 MB per step each, un-bound ranks pile their buffers onto one socket
+    numa = _lib.bind_to_gpu_cpus(local) if not args.no_numa_bind else None
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -334,6 +343,7 @@ def run_b200(args):
                 "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
                 "pcie_probe_gbs": {"h2d": h2d_gbs, "d2h": d2h_gbs},
                 "copy_bound_ms_per_step": max(pipe.h2d_bytes / (h2d_gbs * 1e9), pipe.d2h_bytes / (d2h_gbs * 1e9)) * 1e3,
+                "host_cpu_binding": numa,
                 "api": "XInstructBLIPQFormers.host_pipeline(...).submit(pinned host features) -> pinned host inputs_llm"},
         "gpu_launches": launches,
         "clocks": clocks,
@@ -356,6 +366,7 @@ def main():
     ap.add_argument("--frames", type=int, default=8)
     ap.add_argument("--text-len", type=int, default=32)
     ap.add_argument("--device-only", action="store_true", help="run warm-up + timed device steps and exit (for ncu)")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not bind the rank to the CPUs next to its GPU (A/B)")
     ap.add_argument("--ref-videos", type=int, default=1, help="videos per step of the CPU reference arm (bounded sample)")
     args = ap.parse_args()
     if args.impl == "reference":

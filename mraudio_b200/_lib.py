@@ -136,3 +136,31 @@ def ptr(t) -> int:
 def current_stream() -> int:
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+def bind_to_gpu_cpus(device_index: int):
+    """Bind the calling process to the CPUs NVML reports as local to GPU ``device_index`` (same NUMA node / PCIe root), so
+    that pinned host staging buffers allocated afterwards are first-touched on that node.  Host-side plumbing for the
+    end-to-end path (``HostPipeline``) on multi-socket boxes with one process per GPU; returns a short description or
+    None when NVML / affinity control is unavailable (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[device_index]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else device_index
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {w * 64 + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        try:
+            node = pynvml.nvmlDeviceGetNumaNodeId(h)
+        except Exception:
+            node = None
+        return {"gpu": idx, "cpus": len(cpus), "numa_node": node}
+    except Exception:
+        return None
