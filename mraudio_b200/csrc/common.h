@@ -74,6 +74,8 @@ struct GemmArgs {
     // into their slot of the interleaved LLM prompt (models/xinstructblip.py:359-366).  bf16 output, M % 32 == 0.
     int c_frames = 0;
     int64_t c_frame_stride = 0, c_batch_stride = 0;
+    // (set by the launcher) split of the K range into separate work items + TMA reduce-add epilogue, see gemm.cu
+    int ksplit = 1, reduce_add = 0;
 };
 int launch_gemm_tc(const GemmArgs& a, cudaStream_t s);
 int launch_gemm_tc_grouped(const GemmArgs* a, int n, cudaStream_t s);   // n <= 4 problems sharing N, K, epilogue kind

@@ -47,6 +47,10 @@ struct EpiParams {
     int tile_start[MAX_GROUPS + 1];   // first tile index of each group (tiles of a group: m-block major, n fastest)
     int groups;
     int N, K;
+    // ksplit > 1: the K range of every tile is cut into ksplit slices that are separate work items (fills the grid when
+    // M x N gives few tiles and K is long: the weight gradients, K = number of tokens); needs reduce_add.
+    // reduce_add: the epilogue adds its tile into C with TMA reduce-add stores (fp32) instead of storing it.
+    int ksplit, kb_per_split, reduce_add;
 };
 
 __device__ __forceinline__ void decode_tile(const EpiParams& p, int tile, int n_tiles, int& g, int& m_blk, int& n_blk) {
@@ -142,7 +146,8 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int n_tiles = (p.N + BN - 1) / BN;
-    const int total_tiles = p.tile_start[p.groups];   // work items: (group, m-block [pair], n-block)
+    const int total_tiles = p.tile_start[p.groups];   // work items: (K slice, group, m-block [pair], n-block)
+    const int total_items = total_tiles * p.ksplit;
     const uint32_t crank = CM > 1 ? ptx::cluster_ctarank() : 0u;
     const int first_item = CM > 1 ? static_cast<int>(blockIdx.x) / CM : static_cast<int>(blockIdx.x);
     const int item_stride = CM > 1 ? static_cast<int>(gridDim.x) / CM : static_cast<int>(gridDim.x);
@@ -184,13 +189,15 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = first_item; tile < total_tiles; tile += item_stride) {
+            for (int item = first_item; item < total_items; item += item_stride) {
+                const int ks = item / total_tiles, tile = item - ks * total_tiles;
                 int g, m_blk, n_blk;
                 decode_tile(p, tile, n_tiles, g, m_blk, n_blk);
                 m_blk = m_blk * CM + static_cast<int>(crank);
                 const CUtensorMap* tmA = &maps.a[g];
                 const CUtensorMap* tmB = &maps.b[g];
-                for (int kb = 0; kb < k_blocks; ++kb) {
+                const int kb0 = ks * p.kb_per_split, kb1 = min(k_blocks, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     ptx::mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
                     if (TN != 0) {
@@ -230,13 +237,14 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
             int stage = 0;
             uint32_t phase = 0;
             int iter = 0;
-            for (int tile = first_item; tile < total_tiles; tile += item_stride, ++iter) {
+            for (int item = first_item; item < total_items; item += item_stride, ++iter) {
                 const int acc = iter & 1;
                 const uint32_t acc_phase = (iter >> 1) & 1;
                 ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
-                for (int kb = 0; kb < k_blocks; ++kb) {
+                const int kb0 = (item / total_tiles) * p.kb_per_split, kb1 = min(k_blocks, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     ptx::mbar_wait(&full_bar[stage], phase);
                     ptx::tc_fence_after();
                     if (TN != 0) {
@@ -247,7 +255,7 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
                             // MN-major: advance 16 reduction rows of 128 B: +2048 B = +128 in the >>4 address field
-                            ptx::umma_bf16_ss(d_tmem, a_desc + A_STEP * k, b_desc + 128 * k, idesc, (kb | k) != 0);
+                            ptx::umma_bf16_ss(d_tmem, a_desc + A_STEP * k, b_desc + 128 * k, idesc, kb > kb0 || k != 0);
                         }
                     } else {
                         const uint64_t a_desc = ptx::make_sw128_kmajor_desc(ptx::smem_u32(sA + stage * A_STAGE_BYTES));
@@ -255,7 +263,7 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
                             // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in the >>4 address field
-                            ptx::umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                            ptx::umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, kb > kb0 || k != 0);
                         }
                     }
                     // smem slot reusable once these MMAs have read it (CM = 2: the peer multicasts into it too)
@@ -280,7 +288,8 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
         uint32_t rphase = 0;
         constexpr int RSUB = CH / 32;   // 32-column residual sub-chunks per output chunk
         int iter = 0;
-        for (int tile = first_item; tile < total_tiles; tile += item_stride, ++iter) {
+        for (int item = first_item; item < total_items; item += item_stride, ++iter) {
+            const int tile = item % total_tiles;
             int g, m_blk, n_blk;
             decode_tile(p, tile, n_tiles, g, m_blk, n_blk);
             m_blk = m_blk * CM + static_cast<int>(crank);
@@ -382,7 +391,10 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
                                 scattered = true;
                             }
                         }
-                        if (!scattered) ptx::tma_store_2d(tmC, odst, col0, row0);  // edges clipped by TMA
+                        if (!scattered) {
+                            if (OUT_F32 && p.reduce_add) ptx::tma_reduce_add_2d(tmC, odst, col0, row0);
+                            else ptx::tma_store_2d(tmC, odst, col0, row0);  // edges clipped by TMA
+                        }
                     }
                     ptx::tma_store_commit();
                 }
@@ -562,6 +574,16 @@ int launch_tc_variant(const GemmArgs* ga, int n, cudaStream_t s) {
     p.groups = n;
     p.N = ga[0].N;
     p.K = ga[0].K;
+    p.reduce_add = ga[0].reduce_add;
+    {
+        const int k_blocks = (p.K + BK - 1) / BK;
+        int ks = ga[0].ksplit < 1 ? 1 : ga[0].ksplit;
+        if (ks > k_blocks) ks = k_blocks;
+        p.kb_per_split = (k_blocks + ks - 1) / ks;
+        p.ksplit = (k_blocks + p.kb_per_split - 1) / p.kb_per_split;   // no empty slice
+        MRA_REQUIRE(p.ksplit == 1 || (p.reduce_add && OUT_F32 && !RES && !GELU),
+                    "split-K needs the fp32 reduce-add epilogue (no residual, no GELU)");
+    }
     const int n_tiles = (p.N + BN - 1) / BN;
     int total = 0;
     for (int g = 0; g < MAX_GROUPS; ++g) {
@@ -603,7 +625,8 @@ int launch_tc_variant(const GemmArgs* ga, int n, cudaStream_t s) {
     p.tile_start[MAX_GROUPS] = total;
     for (int g = n; g <= MAX_GROUPS; ++g) p.tile_start[g] = total;
     if (CM == 1) {
-        const int grid = total < sm_count() ? total : sm_count();
+        const long items = static_cast<long>(total) * p.ksplit;
+        const int grid = items < sm_count() ? static_cast<int>(items) : sm_count();
         MRA_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), L::TOTAL, s, maps, p));
         return 0;
     }
@@ -689,7 +712,28 @@ int launch_gemm_tc_grouped(const GemmArgs* a, int n, cudaStream_t s) {
     if (a[0].tn == 1) {
         for (int g = 0; g < n; ++g)
             MRA_REQUIRE(a[g].out_fp32 && !a[g].gelu, "transposed-operand GEMM (tn = 1) needs fp32 output and no GELU");
-        const bool res = a[0].residual != nullptr;
+        bool res = a[0].residual != nullptr;
+        // "dW += dY^T X" (residual == C): accumulate with TMA reduce-add stores instead of reading C back, and cut the
+        // token dimension into slices so that the few (out x in) tiles of a weight matrix fill the 148 SMs
+        bool in_place = res;
+        for (int g = 0; g < n; ++g) in_place = in_place && a[g].residual == a[g].C && a[g].ldr == a[g].ldc && a[g].bias == nullptr;
+        static const bool no_split = getenv("MRA_NO_SPLITK") != nullptr;
+        GemmArgs split[MAX_GROUPS];
+        if (in_place && !no_split) {
+            const long tiles = m_tiles * ((a[0].N + best_bn - 1) / best_bn);
+            const int k_blocks = (a[0].K + BK - 1) / BK;
+            int ks = static_cast<int>(sms / (tiles > 0 ? tiles : 1));
+            if (ks > k_blocks / 4) ks = k_blocks / 4;     // at least 4 K slabs per slice
+            if (ks < 1) ks = 1;
+            for (int g = 0; g < n; ++g) {
+                split[g] = a[g];
+                split[g].residual = nullptr;
+                split[g].ksplit = ks;
+                split[g].reduce_add = 1;
+            }
+            a = split;
+            res = false;
+        }
         if (best_bn == 256) return res ? launch_tc_variant<256, 3, false, true, true, 1, 1>(a, n, s)
                                        : launch_tc_variant<256, 4, false, true, false, 1, 1>(a, n, s);
         if (best_bn == 192) return res ? launch_tc_variant<192, 4, false, true, true, 1, 1>(a, n, s)

@@ -80,6 +80,13 @@ __device__ __forceinline__ void tma_store_2d(const void* desc, const void* smem_
                  "r"(smem_u32(smem_src)), "r"(crd0), "r"(crd1)
                  : "memory");
 }
+// element-wise atomic add of a shared-memory box into global memory (fp32 tensor map): split-K partial sums / "C += ..."
+__device__ __forceinline__ void tma_reduce_add_2d(const void* desc, const void* smem_src, int32_t crd0, int32_t crd1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(desc)),
+                 "r"(smem_u32(smem_src)), "r"(crd0), "r"(crd1)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_store_4d(const void* desc, const void* smem_src, int32_t crd0, int32_t crd1, int32_t crd2,
                                              int32_t crd3) {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
