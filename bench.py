@@ -319,7 +319,7 @@ def run_b200(args):
     # CPU baseline: rank 0 at N = 1 only (bounded sample of the same workload)
     cpu = None
     if world == 1:
-        cpu_v, cpu_ms, cores, sample = cpu_reference_run(2, 1, 1, F, T)
+        cpu_v, cpu_ms, cores, sample = cpu_reference_run(6, 1, 4, F, T)   # ~5-10 s of CPU work on a 16-core host
         cpu = {"value": cpu_v, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample}
     line = {
         "metric": "qformer_video_audio_clips_per_sec", "value": clips * world / (ms_dev * 1e-3), "unit": "clips/s",
