@@ -284,6 +284,7 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
         uint8_t* my = smem + L::EPI_OFFSET + ew * L::EPI_BUFS_PER_WARP * CHUNK_BYTES;   // [out]([residual] when RES)
         uint8_t* odst = my;
         uint8_t* rsrc = my + CHUNK_BYTES;
+        const uint32_t odst_s = ptx::smem_u32(odst), rsrc_s = ptx::smem_u32(rsrc);
         uint64_t* rbar = res_bar + ew;
         uint32_t rphase = 0;
         constexpr int RSUB = CH / 32;   // 32-column residual sub-chunks per output chunk
@@ -342,7 +343,7 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
                         rphase ^= 1;
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const float4 x = *reinterpret_cast<const float4*>(rsrc + swz(lane, j));
+                            const float4 x = ptx::ld_shared_v4f(rsrc_s + swz(lane, j));
                             v[4 * j] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
                         }
                         __syncwarp();   // every lane has read the residual buffer: refill it with the next sub-chunk
@@ -358,17 +359,13 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
                     if (OUT_F32) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
-                            *reinterpret_cast<float4*>(odst + swz(lane, j)) =
-                                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            ptx::st_shared_v4f(odst_s + swz(lane, j), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                     } else {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            uint4 o;
-                            o.x = ptx::pack_bf16x2(v[8 * j], v[8 * j + 1]);
-                            o.y = ptx::pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-                            o.z = ptx::pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-                            o.w = ptx::pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-                            *reinterpret_cast<uint4*>(odst + swz(lane, half * 4 + j)) = o;
+                            ptx::st_shared_v4(odst_s + swz(lane, half * 4 + j), ptx::pack_bf16x2(v[8 * j], v[8 * j + 1]),
+                                              ptx::pack_bf16x2(v[8 * j + 2], v[8 * j + 3]), ptx::pack_bf16x2(v[8 * j + 4], v[8 * j + 5]),
+                                              ptx::pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
                         }
                     }
                 }

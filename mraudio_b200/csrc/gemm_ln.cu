@@ -209,6 +209,7 @@ gemm_ln_kernel(const __grid_constant__ LnMaps maps, const __grid_constant__ LnPa
         const int member = ew >> 2;           // column segment of this CTA: [128 member, 128 member + 128)
         const int seg = static_cast<int>(rank) * 2 + member;   // 0..5: position of the segment inside the 768 columns
         uint8_t* my = smem + EPI_OFFSET + ew * EPI_PER_WARP;
+        const uint32_t my_s = ptx::smem_u32(my);
         uint64_t* rbar = res_bar + 2 * ew;
         uint32_t rphase = 0;
         const int row_in_tile = quad * 32 + lane;
@@ -277,10 +278,10 @@ gemm_ln_kernel(const __grid_constant__ LnMaps maps, const __grid_constant__ LnPa
                     ptx::mbar_wait(&rbar[b], (rphase >> b) & 1u);
                     rphase ^= 1u << b;
                 }
-                const uint8_t* rs = my + b * CHUNK;
+                const uint32_t rs = my_s + b * CHUNK;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float4 x = *reinterpret_cast<const float4*>(rs + swz(lane, j));
+                    const float4 x = ptx::ld_shared_v4f(rs + swz(lane, j));
                     const float4 bv = *reinterpret_cast<const float4*>(bias + c * 32 + 4 * j);
                     const float v0 = __uint_as_float(r[4 * j]) + bv.x + x.x;
                     const float v1 = __uint_as_float(r[4 * j + 1]) + bv.y + x.y;
@@ -335,6 +336,7 @@ gemm_ln_kernel(const __grid_constant__ LnMaps maps, const __grid_constant__ LnPa
             const float nm = -mean * rstd;
             uint8_t* o16 = my;
             uint8_t* o32 = my + CHUNK;
+            const uint32_t o16_s = my_s, o32_s = my_s + CHUNK;
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
                 if (lane == 0) ptx::tma_store_wait_read<0>();   // the stores that last read the staging buffers are done
@@ -347,10 +349,10 @@ gemm_ln_kernel(const __grid_constant__ LnMaps maps, const __grid_constant__ LnPa
                     const float y1 = fmaf(fmaf(v[c][4 * j + 1], rstd, nm), gv.y, bv.y);
                     const float y2 = fmaf(fmaf(v[c][4 * j + 2], rstd, nm), gv.z, bv.z);
                     const float y3 = fmaf(fmaf(v[c][4 * j + 3], rstd, nm), gv.w, bv.w);
-                    *reinterpret_cast<float4*>(o32 + swz(lane, j)) = make_float4(y0, y1, y2, y3);
+                    ptx::st_shared_v4f(o32_s + swz(lane, j), y0, y1, y2, y3);
                     // 8 bytes of bf16 at column 4 j of this chunk: 16-byte unit (c & 1) * 4 + j / 2, half j & 1
-                    *reinterpret_cast<uint2*>(o16 + swz(lane, (c & 1) * 4 + (j >> 1)) + (j & 1) * 8) =
-                        make_uint2(ptx::pack_bf16x2(y0, y1), ptx::pack_bf16x2(y2, y3));
+                    ptx::st_shared_v2(o16_s + swz(lane, (c & 1) * 4 + (j >> 1)) + (j & 1) * 8, ptx::pack_bf16x2(y0, y1),
+                                      ptx::pack_bf16x2(y2, y3));
                 }
                 ptx::fence_proxy_async();
                 __syncwarp();
