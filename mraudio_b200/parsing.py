@@ -29,6 +29,11 @@ _TRAILING_COMMAS = re.compile(r",+$")
 _DIGIT_SPACE_DIGIT = re.compile(r"(\d) (\d)")
 _COMMA_RUN = re.compile(r",+")
 _UINT = re.compile(r"\d+")
+# canonical output of post_process for a well-formed generation: "[[s, e], [s, e], ...]" with plain non-negative decimal
+# integers (no leading zeros: ast.literal_eval rejects "007").  For these the literal_eval round trip below is just
+# "take the integers in pairs"; everything else goes through ast.literal_eval as in the reference.
+_INT = r"(?:0|[1-9]\d*)"
+_CANONICAL = re.compile(r"\[\[" + _INT + ", " + _INT + r"\](?:, \[" + _INT + ", " + _INT + r"\])*\]")
 
 
 def _repair_window(w: str) -> str:
@@ -72,6 +77,9 @@ def moment_str_to_list(m: str) -> list:
     """utils/utils.py:364-415."""
     if m == "[[-1, -1]]" or _NESTED.match(m) is None:
         return [[-1, -1]]
+    if _CANONICAL.fullmatch(m) is not None:      # fast path (about 5x faster than literal_eval), same result
+        nums = [int(x) for x in _UINT.findall(m)]
+        return [[nums[k], nums[k + 1]] for k in range(0, len(nums), 2)]
     try:
         parsed = ast.literal_eval(m)
     except Exception:   # the reference uses a bare except; KeyboardInterrupt / SystemExit cannot come out of literal_eval
