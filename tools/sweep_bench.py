@@ -81,6 +81,7 @@ t0 = time.perf_counter()
 records = [{"qid": base + i, "_order": base + i, "pred_relevant_windows": parse_output(synth_text(rng, 5)),
             "relevant_windows": parse_output(synth_text(rng, 3).replace("junk", "[[0, 2]]"))} for i in range(n_local)]
 t_parse = time.perf_counter() - t0
+mr_eval.score_records_distributed(records[:64], records[:64])     # warm-up: NCCL gather channels, pinned staging, module load
 barrier()
 t0 = time.perf_counter()
 rec = mr_eval.score_records_distributed(records, records)
