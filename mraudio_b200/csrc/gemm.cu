@@ -51,7 +51,10 @@ struct EpiParams {
     // M x N gives few tiles and K is long: the weight gradients, K = number of tokens); needs reduce_add.
     // reduce_add: the epilogue adds its tile into C with TMA reduce-add stores (fp32) instead of storing it.
     int ksplit, kb_per_split, reduce_add;
+    int dbg;   // MRA_GEMM_DEBUG=8: cycles per tile spent waiting for the accumulator vs in the epilogue (one warp of CTA 0)
 };
+
+__device__ unsigned long long g_gemm_timing[8];
 
 __device__ __forceinline__ void decode_tile(const EpiParams& p, int tile, int n_tiles, int& g, int& m_blk, int& n_blk) {
     g = 0;
@@ -307,7 +310,11 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
                 ptx::mbar_arrive_expect_tx(rbar, CHUNK_BYTES);
                 ptx::tma_load_2d(rsrc, tmR, rbar, col_base + member * CH, row0);
             }
+            const bool prof = (p.dbg & 8) && blockIdx.x == 0 && ew == 0 && lane == 0;
+            long long pt0 = 0, pt1 = 0;
+            if (prof) pt0 = clock64();
             ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+            if (prof) pt1 = clock64();
             ptx::tc_fence_after();
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * ACC_STRIDE;
 #pragma unroll 1
@@ -395,6 +402,10 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
                     }
                     ptx::tma_store_commit();
                 }
+            }
+            if (prof) {
+                const long long pt2 = clock64();
+                g_gemm_timing[0] += pt1 - pt0; g_gemm_timing[1] += pt2 - pt1; g_gemm_timing[2] += 1;
             }
             if (member >= NCH) {   // (only when a tile has a single chunk) nothing to read: release immediately
                 ptx::tc_fence_before();
@@ -572,6 +583,8 @@ int launch_tc_variant(const GemmArgs* ga, int n, cudaStream_t s) {
     p.N = ga[0].N;
     p.K = ga[0].K;
     p.reduce_add = ga[0].reduce_add;
+    static const int dbg_env = [] { const char* e = getenv("MRA_GEMM_DEBUG"); return e ? atoi(e) : 0; }();
+    p.dbg = dbg_env;
     {
         const int k_blocks = (p.K + BK - 1) / BK;
         int ks = ga[0].ksplit < 1 ? 1 : ga[0].ksplit;
@@ -625,6 +638,16 @@ int launch_tc_variant(const GemmArgs* ga, int n, cudaStream_t s) {
         const long items = static_cast<long>(total) * p.ksplit;
         const int grid = items < sm_count() ? static_cast<int>(items) : sm_count();
         MRA_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), L::TOTAL, s, maps, p));
+        if (p.dbg & 8) {
+            unsigned long long t[8];
+            cudaStreamSynchronize(s);
+            cudaMemcpyFromSymbol(t, g_gemm_timing, sizeof(t));
+            const double nt = t[2] ? double(t[2]) : 1.0;
+            fprintf(stderr, "[gemm timing BN=%d M=%d N=%d K=%d: %llu tiles on CTA 0] wait-accumulator %.0f | epilogue %.0f cycles per tile\n",
+                    BN, ga[0].M, p.N, p.K, t[2], t[0] / nt, t[1] / nt);
+            unsigned long long z[8] = {0};
+            cudaMemcpyToSymbol(g_gemm_timing, z, sizeof(z));
+        }
         return 0;
     }
     const int clusters = total < sm_count() / CM ? total : sm_count() / CM;
