@@ -326,8 +326,13 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
 #pragma unroll
                 for (int half = 0; half < RSUB; ++half) {
                     uint32_t r[32];
-                    ptx::tmem_ld_32x32b_x32(t_row + c * CH + half * 32, r);
-                    ptx::tmem_ld_wait();
+                    if (p.dbg & 16) {   // experiment: no TMEM reads (results are garbage) -- isolates the drain's cost
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) r[j] = 0;
+                    } else {
+                        ptx::tmem_ld_32x32b_x32(t_row + c * CH + half * 32, r);
+                        ptx::tmem_ld_wait();
+                    }
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);

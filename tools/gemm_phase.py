@@ -1,6 +1,6 @@
 """Per-tile cycles of the plain GEMM's epilogue warps: blocked on the accumulator vs working (MRA_GEMM_DEBUG=8)."""
 import os, sys
-os.environ["MRA_GEMM_DEBUG"] = "8"
+os.environ.setdefault("MRA_GEMM_DEBUG", "8")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from mraudio_b200 import ops
