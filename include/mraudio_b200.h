@@ -240,8 +240,9 @@ int mra_gemm_ln_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, con
 /* Tuning aid: force the output-tile width of the tcgen05 GEMM (128, 192 or 256; 0 = automatic choice). */
 int mra_gemm_tile_override(int32_t bn);
 
-/* Tuning / test aid: 2 lets the GEMM pair CTAs into clusters that share the W slab by TMA multicast when every problem
- * has >= 4 row blocks; 1 (default) never pairs. */
+/* Tuning / test aid, applied when every problem has >= 4 row blocks: 3 (default) pairs CTAs into 2-CTA clusters that run
+ * one tcgen05.mma.cta_group::2 per K step (M = 256, half of the W slab per CTA); 2 pairs them sharing the W slab by TMA
+ * multicast; 1 never pairs. */
 int mra_gemm_cluster_override(int32_t cm);
 
 /* Fused multi-head attention core, head_dim 64: O = softmax(Q K^T / 8 + mask) V, per (row, head).

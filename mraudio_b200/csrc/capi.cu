@@ -102,7 +102,7 @@ extern "C" int mra_gemm_tile_override(int32_t bn) {
 }
 
 extern "C" int mra_gemm_cluster_override(int32_t cm) {
-    MRA_REQUIRE(cm == 1 || cm == 2, "cluster override must be 1 or 2");
+    MRA_REQUIRE(cm >= 1 && cm <= 3, "cluster override must be 1 (single CTA), 2 (pair, W multicast) or 3 (pair, 2-CTA MMA)");
     set_gemm_cluster_override(cm);
     return 0;
 }

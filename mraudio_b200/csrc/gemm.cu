@@ -66,9 +66,9 @@ __device__ __forceinline__ void decode_tile(const EpiParams& p, int tile, int n_
     n_blk = t - m_blk * n_tiles;
 }
 
-template <int BN, int STAGES, bool RES>
+template <int BN, int STAGES, bool RES, bool U2 = false>
 struct SmemLayout {
-    static constexpr int B_STAGE_BYTES = BN * BK * 2;
+    static constexpr int B_STAGE_BYTES = (U2 ? BN / 2 : BN) * BK * 2;   // U2: each CTA of the pair keeps half of the W slab
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;
     static constexpr int EPI_BUFS_PER_WARP = RES ? 2 : 1;   // 1 output chunk (+ 1 residual chunk) of 4 KiB
@@ -126,10 +126,18 @@ __device__ __forceinline__ uint32_t swz(int r, int j) { return static_cast<uint3
 //   2 = A [M, K] as in the forward, W [K, N] with the reduction index as its row index: the data-gradient GEMM
 //       dX[n, in] = dY[n, out] . W[out, in] reads the forward's weight matrix as it lies.
 // Operands whose reduction index is the row index go through MN-major shared-memory descriptors -- no transposed copies.
-template <int BN, int STAGES, bool GELU, bool OUT_F32, bool RES, int CM, int TN = 0>
+// U2 (with CM = 2): the pair of CTAs runs ONE tcgen05.mma.cta_group::2 with M = 256 per K step: each CTA holds its 128
+// rows of A, HALF of the W slab (the tensor core reads the other half from the peer's shared memory) and its own
+// 128 x BN accumulator.  A CTA then receives 32 KiB instead of 48 KiB per K slab for the same MMA work -- the plain
+// kernel is bound by what an SM can take in (measured: the MMA thread waits for slabs arriving every ~620 cycles
+// instead of 512, tools/gemm_phase.py) -- and the ring gets 6 stages instead of 4.  The leader (rank 0) issues the
+// MMAs; both CTAs' TMA loads count their bytes on the leader's "full" barrier; tcgen05.commit multicasts the "slab
+// free" and "accumulator ready" arrivals to both CTAs; the peer's epilogue warps release the accumulator remotely.
+template <int BN, int STAGES, bool GELU, bool OUT_F32, bool RES, int CM, int TN = 0, bool U2 = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ EpiParams p) {
-    using L = SmemLayout<BN, STAGES, RES>;
+    static_assert(!U2 || (CM == 2 && TN == 0), "the 2-CTA MMA form needs a pair of CTAs and K-major operands");
+    using L = SmemLayout<BN, STAGES, RES, U2>;
     constexpr uint32_t TMEM_COLS = BN <= 128 ? 256 : 512;  // two accumulator stages, power of two
     constexpr int ACC_STRIDE = BN <= 128 ? 128 : 256;
     constexpr int CH = OUT_F32 ? 32 : 64;                  // columns per epilogue chunk (128 bytes of output per row)
@@ -165,18 +173,23 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
         }
         for (int i = 0; i < STAGES; ++i) {
             ptx::mbar_init(&full_bar[i], 1);
-            ptx::mbar_init(&empty_bar[i], CM);          // every CTA of the cluster must have consumed the slab
+            ptx::mbar_init(&empty_bar[i], U2 ? 1 : CM);   // every CTA of the cluster must have consumed the slab
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tfull_bar[i], 1);
-            ptx::mbar_init(&tempty_bar[i], EPI_WARPS);  // one arrival per epilogue warp
+            ptx::mbar_init(&tempty_bar[i], U2 ? 2 * EPI_WARPS : EPI_WARPS);  // one arrival per epilogue warp (of both CTAs)
         }
         for (int i = 0; i < EPI_WARPS; ++i) ptx::mbar_init(&res_bar[i], 1);
         ptx::fence_mbar_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc(tmem_ptr_smem, TMEM_COLS);
-        ptx::tmem_relinquish();
+        if (U2) {
+            ptx::tmem_alloc_pair(tmem_ptr_smem, TMEM_COLS);
+            ptx::tmem_relinquish_pair();
+        } else {
+            ptx::tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+            ptx::tmem_relinquish();
+        }
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -202,6 +215,16 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
                 const int kb0 = ks * p.kb_per_split, kb1 = min(k_blocks, kb0 + p.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (U2) {
+                        // both CTAs' boxes complete on the LEADER's barrier, which expects the bytes of the pair
+                        const uint32_t lead_bar = ptx::mapa_u32(ptx::smem_u32(&full_bar[stage]), 0);
+                        if (crank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
+                        ptx::tma_load_2d_pair(sA + stage * A_STAGE_BYTES, tmA, lead_bar, kb * BK, m_blk * BM);
+                        ptx::tma_load_2d_pair(sB + stage * L::B_STAGE_BYTES, tmB, lead_bar, kb * BK,
+                                              n_blk * BN + static_cast<int>(crank) * (BN / 2));
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     ptx::mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
                     if (TN != 0) {
                         // boxes of {64 MN elements, 64 reduction rows}: one per 64 output rows (A) / columns (W)
@@ -233,8 +256,9 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (single thread)
-        if (lane == 0) {
-            constexpr uint32_t idesc = TN == 1 ? ptx::make_idesc_bf16_f32_mn(BM, BN)
+        if (lane == 0 && (!U2 || crank == 0)) {
+            constexpr uint32_t idesc = U2      ? ptx::make_idesc_bf16_f32(2 * BM, BN)
+                                       : TN == 1 ? ptx::make_idesc_bf16_f32_mn(BM, BN)
                                        : TN == 2 ? (ptx::make_idesc_bf16_f32(BM, BN) | (1u << 16))   // b_major = MN only
                                                  : ptx::make_idesc_bf16_f32(BM, BN);
             int stage = 0;
@@ -243,12 +267,17 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
             for (int item = first_item; item < total_items; item += item_stride, ++iter) {
                 const int acc = iter & 1;
                 const uint32_t acc_phase = (iter >> 1) & 1;
+                const bool mprof = (p.dbg & 8) && blockIdx.x == 0;
+                long long mt0 = 0, mt1 = 0, mt2 = 0;
+                if (mprof) mt0 = clock64();
                 ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
                 ptx::tc_fence_after();
+                if (mprof) mt1 = clock64();
                 const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
                 const int kb0 = (item / total_tiles) * p.kb_per_split, kb1 = min(k_blocks, kb0 + p.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     ptx::mbar_wait(&full_bar[stage], phase);
+                    if (mprof && kb == kb0) mt2 = clock64();
                     ptx::tc_fence_after();
                     if (TN != 0) {
                         const uint64_t a_desc = TN == 1 ? ptx::make_sw128_mnmajor_desc(ptx::smem_u32(sA + stage * A_STAGE_BYTES), 8192)
@@ -266,15 +295,23 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
                             // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in the >>4 address field
-                            ptx::umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, kb > kb0 || k != 0);
+                            if (U2) ptx::umma_bf16_ss_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, kb > kb0 || k != 0);
+                            else ptx::umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, kb > kb0 || k != 0);
                         }
                     }
                     // smem slot reusable once these MMAs have read it (CM = 2: the peer multicasts into it too)
-                    if (CM == 1) ptx::umma_commit(&empty_bar[stage]);
+                    if (U2) ptx::umma_commit_pair(&empty_bar[stage], static_cast<uint16_t>(0x3));
+                    else if (CM == 1) ptx::umma_commit(&empty_bar[stage]);
                     else ptx::umma_commit_multicast(&empty_bar[stage], static_cast<uint16_t>(0x3));
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                ptx::umma_commit(&tfull_bar[acc]);  // accumulator complete
+                // accumulator complete (U2: in both CTAs of the pair)
+                if (U2) ptx::umma_commit_pair(&tfull_bar[acc], static_cast<uint16_t>(0x3));
+                else ptx::umma_commit(&tfull_bar[acc]);
+                if (mprof) {
+                    const long long mt3 = clock64();
+                    g_gemm_timing[3] += mt1 - mt0; g_gemm_timing[4] += mt2 - mt1; g_gemm_timing[5] += mt3 - mt2;
+                }
             }
         }
     } else {
@@ -385,7 +422,10 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
                     // this warp's tcgen05.ld of the tile are done: hand the accumulator back to the MMA warp
                     ptx::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+                    if (lane == 0) {
+                        if (U2) ptx::mbar_arrive_cluster(ptx::mapa_u32(ptx::smem_u32(&tempty_bar[acc]), 0));   // the leader's barrier
+                        else ptx::mbar_arrive(&tempty_bar[acc]);
+                    }
                 }
                 ptx::fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA (async proxy)
                 __syncwarp();
@@ -415,7 +455,10 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
             if (member >= NCH) {   // (only when a tile has a single chunk) nothing to read: release immediately
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+                if (lane == 0) {
+                        if (U2) ptx::mbar_arrive_cluster(ptx::mapa_u32(ptx::smem_u32(&tempty_bar[acc]), 0));   // the leader's barrier
+                        else ptx::mbar_arrive(&tempty_bar[acc]);
+                    }
             }
         }
         if (lane == 0) ptx::tma_store_wait<0>();
@@ -425,7 +468,8 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
     if (CM > 1) ptx::cluster_sync_all();   // no CTA exits while its peer may still multicast into it
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+        if (U2) ptx::tmem_dealloc_pair(tmem_base, TMEM_COLS);
+        else ptx::tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
@@ -573,10 +617,10 @@ int get_tensor_map_scatter(const void* ptr, int64_t batch, int64_t frames, int64
 
 namespace {
 
-template <int BN, int STAGES, bool GELU, bool OUT_F32, bool RES, int CM, int TN = 0>
+template <int BN, int STAGES, bool GELU, bool OUT_F32, bool RES, int CM, int TN = 0, bool U2 = false>
 int launch_tc_variant(const GemmArgs* ga, int n, cudaStream_t s) {
-    using L = SmemLayout<BN, STAGES, RES>;
-    auto kern = gemm_tc_kernel<BN, STAGES, GELU, OUT_F32, RES, CM, TN>;
+    using L = SmemLayout<BN, STAGES, RES, U2>;
+    auto kern = gemm_tc_kernel<BN, STAGES, GELU, OUT_F32, RES, CM, TN, U2>;
     static bool attr_set = false;
     if (!attr_set) {
         MRA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -643,13 +687,14 @@ int launch_tc_variant(const GemmArgs* ga, int n, cudaStream_t s) {
         const long items = static_cast<long>(total) * p.ksplit;
         const int grid = items < sm_count() ? static_cast<int>(items) : sm_count();
         MRA_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), L::TOTAL, s, maps, p));
-        if (p.dbg & 8) {
+        if (p.dbg & 8) {   // (single-CTA path; the paired paths print below)
             unsigned long long t[8];
             cudaStreamSynchronize(s);
             cudaMemcpyFromSymbol(t, g_gemm_timing, sizeof(t));
             const double nt = t[2] ? double(t[2]) : 1.0;
-            fprintf(stderr, "[gemm timing BN=%d M=%d N=%d K=%d: %llu tiles on CTA 0] wait-accumulator %.0f | epilogue %.0f cycles per tile\n",
-                    BN, ga[0].M, p.N, p.K, t[2], t[0] / nt, t[1] / nt);
+            fprintf(stderr, "[gemm timing BN=%d M=%d N=%d K=%d: %llu tiles on CTA 0] epilogue warp: wait-accumulator %.0f | work %.0f ; "
+                            "MMA thread: wait-tmem-free %.0f | wait-first-slab %.0f | issue-loop %.0f cycles per tile\n",
+                    BN, ga[0].M, p.N, p.K, t[2], t[0] / nt, t[1] / nt, t[3] / nt, t[4] / nt, t[5] / nt);
             unsigned long long z[8] = {0};
             cudaMemcpyToSymbol(g_gemm_timing, z, sizeof(z));
         }
@@ -667,21 +712,32 @@ int launch_tc_variant(const GemmArgs* ga, int n, cudaStream_t s) {
     cfg.attrs = at;
     cfg.numAttrs = 1;
     MRA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, p));
+    if (p.dbg & 8) {
+        unsigned long long t[8];
+        cudaStreamSynchronize(s);
+        cudaMemcpyFromSymbol(t, g_gemm_timing, sizeof(t));
+        const double nt = t[2] ? double(t[2]) : 1.0;
+        fprintf(stderr, "[gemm timing BN=%d CM=%d U2=%d M=%d N=%d K=%d: %llu tiles on CTA 0] epilogue warp: wait-accumulator %.0f | work %.0f ; "
+                        "MMA thread: wait-tmem-free %.0f | wait-first-slab %.0f | issue-loop %.0f cycles per tile\n",
+                BN, CM, int(U2), ga[0].M, p.N, p.K, t[2], t[0] / nt, t[1] / nt, t[3] / nt, t[4] / nt, t[5] / nt);
+        unsigned long long z[8] = {0};
+        cudaMemcpyToSymbol(g_gemm_timing, z, sizeof(z));
+    }
     return 0;
 }
 
-template <int BN, int ST_PLAIN, int ST_RES, int CM>
+template <int BN, int ST_PLAIN, int ST_RES, int CM, bool U2 = false>
 int dispatch_epi(const GemmArgs* a, int n, cudaStream_t s) {
     const int code = (a[0].gelu ? 4 : 0) | (a[0].out_fp32 ? 2 : 0) | (a[0].residual ? 1 : 0);
     switch (code) {
-        case 0: return launch_tc_variant<BN, ST_PLAIN, false, false, false, CM>(a, n, s);
-        case 1: return launch_tc_variant<BN, ST_RES, false, false, true, CM>(a, n, s);
-        case 2: return launch_tc_variant<BN, ST_PLAIN, false, true, false, CM>(a, n, s);
-        case 3: return launch_tc_variant<BN, ST_RES, false, true, true, CM>(a, n, s);
-        case 4: return launch_tc_variant<BN, ST_PLAIN, true, false, false, CM>(a, n, s);
-        case 5: return launch_tc_variant<BN, ST_RES, true, false, true, CM>(a, n, s);
-        case 6: return launch_tc_variant<BN, ST_PLAIN, true, true, false, CM>(a, n, s);
-        default: return launch_tc_variant<BN, ST_RES, true, true, true, CM>(a, n, s);
+        case 0: return launch_tc_variant<BN, ST_PLAIN, false, false, false, CM, 0, U2>(a, n, s);
+        case 1: return launch_tc_variant<BN, ST_RES, false, false, true, CM, 0, U2>(a, n, s);
+        case 2: return launch_tc_variant<BN, ST_PLAIN, false, true, false, CM, 0, U2>(a, n, s);
+        case 3: return launch_tc_variant<BN, ST_RES, false, true, true, CM, 0, U2>(a, n, s);
+        case 4: return launch_tc_variant<BN, ST_PLAIN, true, false, false, CM, 0, U2>(a, n, s);
+        case 5: return launch_tc_variant<BN, ST_RES, true, false, true, CM, 0, U2>(a, n, s);
+        case 6: return launch_tc_variant<BN, ST_PLAIN, true, true, false, CM, 0, U2>(a, n, s);
+        default: return launch_tc_variant<BN, ST_RES, true, true, true, CM, 0, U2>(a, n, s);
     }
 }
 
@@ -705,7 +761,8 @@ int check_args(const GemmArgs& a) {
 }  // namespace
 
 static int g_forced_bn = [] { const char* e = getenv("MRA_GEMM_BN"); return e ? atoi(e) : 0; }();
-static int g_cluster_m = [] { const char* e = getenv("MRA_GEMM_CLUSTER"); return e ? atoi(e) : 1; }();
+// 3 (default) = pairs of CTAs running tcgen05.mma.cta_group::2; 2 = pairs sharing the W slab by multicast; 1 = single CTAs
+static int g_cluster_m = [] { const char* e = getenv("MRA_GEMM_CLUSTER"); return e ? atoi(e) : 3; }();
 void set_gemm_tile_override(int bn) { g_forced_bn = bn; }
 void set_gemm_cluster_override(int cm) { g_cluster_m = cm; }
 
@@ -781,11 +838,17 @@ int launch_gemm_tc_grouped(const GemmArgs* a, int n, cudaStream_t s) {
                     : res ? launch_tc_variant<128, 5, false, true, true, 1, 2>(a, n, s)
                           : launch_tc_variant<128, 6, false, true, false, 1, 2>(a, n, s);
     }
-    // 2-CTA clusters along M (W slab multicast) when every problem has enough row blocks to pair up.  Opt-in
-    // (MRA_GEMM_CLUSTER=2 / mra_gemm_cluster_override): measured on B200 it neither helps nor hurts (1425 vs 1450 TF/s on
-    // the cross-K/V GEMM), i.e. these GEMMs are not L2 -> SM bandwidth bound.
+    // Pairs of CTAs along M when every problem has enough row blocks.  Measured on B200: sharing the W slab by multicast
+    // (mode 2) neither helps nor hurts -- each SM still takes in 48 KiB per K slab -- while the 2-CTA MMA (mode 3), where
+    // a CTA takes in 32 KiB, lifts the cross-K/V GEMM from 1412 to 1542 TF/s and the FFN-down shape from 868 to 1063.
     bool pair = g_cluster_m != 1;
     for (int g = 0; g < n; ++g) pair = pair && a[g].M >= 4 * BM;
+    if (pair && g_cluster_m == 3) {
+        // 2-CTA MMA (cta_group::2): half of the W slab per CTA, 6-stage ring
+        if (best_bn == 256) return dispatch_epi<256, 6, 5, 2, true>(a, n, s);
+        if (best_bn == 192) return dispatch_epi<192, 6, 5, 2, true>(a, n, s);
+        return dispatch_epi<128, 6, 6, 2, true>(a, n, s);
+    }
     if (pair) {
         if (best_bn == 256) return dispatch_epi<256, 4, 3, 2>(a, n, s);
         if (best_bn == 192) return dispatch_epi<192, 4, 4, 2>(a, n, s);

@@ -113,11 +113,11 @@ def test_fused_linear_residual_layernorm(M, K):
     assert torch.equal(y32, y32c)
 
 
-@pytest.mark.parametrize("cm", [1, 2])
+@pytest.mark.parametrize("cm", [1, 2, 3])
 @pytest.mark.parametrize("M,N,K", [(512, 768, 768), (771, 2304, 768), (1280, 3072, 768), (8192, 768, 3072), (640, 9216, 1408)])
 def test_gemm_cluster_multicast_variant(cm, M, N, K):
-    """2-CTA clusters along M sharing the W slab by TMA multicast (cm = 2) == unpaired kernel (cm = 1) == fp32 reference,
-    including an odd number of row blocks (the last pair has one empty tile)."""
+    """Pairs of CTAs along M: cm = 2 shares the W slab by TMA multicast, cm = 3 runs one tcgen05.mma.cta_group::2 (M = 256, half
+    of the W slab per CTA); both == unpaired kernel (cm = 1) == fp32 reference, including an odd number of row blocks."""
     from mraudio_b200 import ops, _lib
     g = torch.Generator().manual_seed(cm * 1000 + M)
     x = torch.randn(M, K, generator=g).to(_dev(), torch.bfloat16)
@@ -132,7 +132,7 @@ def test_gemm_cluster_multicast_variant(cm, M, N, K):
             assert _rel(ops.linear(x, w, b, residual=res, out_fp32=True), ref + res) < 1e-4, bn
             assert _rel(ops.linear(x, w, b, gelu=True), torch.nn.functional.gelu(ref)) < 6e-3, bn
     finally:
-        _lib.lib.mra_gemm_cluster_override(1)
+        _lib.lib.mra_gemm_cluster_override(3)
         _lib.lib.mra_gemm_tile_override(0)
 
 

@@ -21,7 +21,7 @@ for name, M, N, K, gelu, res in SHAPES:
     out = torch.empty(M, N, device=dev, dtype=torch.float32 if res else torch.bfloat16)
     line = f"{name:9s} M={M:6d} N={N:5d} K={K:5d}"
     for bn in (-256, 128, 192, 256, 0):
-        _lib.lib.mra_gemm_cluster_override(1 if bn < 0 else 2)   # bn < 0: unpaired kernel at |bn| for comparison
+        _lib.lib.mra_gemm_cluster_override(1 if bn < 0 else int(os.environ.get('GB_CLUSTER', '3')))   # bn < 0: unpaired kernel at |bn| for comparison
         _lib.lib.mra_gemm_tile_override(abs(bn))
         ts = []
         for it in range(6):
@@ -35,7 +35,7 @@ for name, M, N, K, gelu, res in SHAPES:
         t = sorted(ts[1:])[len(ts[1:]) // 2]
         line += f" | {'solo' if bn < 0 else 'bn'}{abs(bn):3d} {t*1e3:7.1f}us {2*M*N*K/t/1e9:6.0f}TF"
     _lib.lib.mra_gemm_tile_override(0)
-    _lib.lib.mra_gemm_cluster_override(1)
+    _lib.lib.mra_gemm_cluster_override(3)
     # cuBLAS (torch.matmul) for orientation only
     ts = []
     for it in range(4):
