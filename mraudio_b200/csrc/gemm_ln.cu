@@ -26,27 +26,38 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int NTOT = 768;                   // LayerNorm width handled by a cluster
-constexpr int CLUSTER = 3;
 constexpr int NCTA = 256;                   // columns per CTA (= one MMA)
 constexpr int NSEG = 128;                   // columns per epilogue thread
 constexpr int NSEGS = NTOT / NSEG;          // 6 partial-statistics sources per row
-constexpr int STAGES = 3;
+constexpr int NSLICES = NTOT / NCTA;        // 3 column slices of 256
 constexpr int A_BYTES = BM * BK * 2;        // 16 KiB
-constexpr int B_BYTES = NCTA * BK * 2;      // 32 KiB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int EPI_WARPS = 8;
 constexpr int NUM_THREADS = 128 + 32 * EPI_WARPS;   // warpgroup 0: producer, MMA, 2 idle warps; warpgroups 1-2: epilogue
 constexpr int CHUNK = 32 * 128;             // 32 rows x 128 bytes
 constexpr int EPI_PER_WARP = 2 * CHUNK;     // pass A: two residual chunks; pass B: fp32 out chunk + bf16 out chunk
-constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;
-constexpr int STATS_OFFSET = EPI_OFFSET + EPI_WARPS * EPI_PER_WARP;
 constexpr int STATS_BYTES = 2 * NSEGS * BM * 8;   // [slot][segment][row] float2
-constexpr int VEC_OFFSET = STATS_OFFSET + STATS_BYTES;
 constexpr int VEC_BYTES = 3 * NCTA * 4;     // bias | gamma | beta of this CTA's 256 columns (current group)
-constexpr int BAR_OFFSET = VEC_OFFSET + VEC_BYTES;
-constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * EPI_WARPS + 2;   // full, empty, tfull[2], tempty[2], res[8][2], stats[2]
-constexpr int SMEM_TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;
-static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget exceeded");
+
+// U2 = false: a cluster of 3 CTAs (one per 256-column slice) owns a 128-row block; every CTA runs its own M = 128 MMAs.
+// U2 = true : a cluster of 6 CTAs = 3 column slices x a PAIR of CTAs (ranks 2n, 2n+1) owns a 256-row block; each pair runs
+//             one tcgen05.mma.cta_group::2 (M = 256) per K step with half of the W slab per CTA, i.e. 32 KiB instead of
+//             48 KiB taken in per K slab and a 4-stage ring -- the single-CTA form is bound by SM ingress (gemm.cu).
+template <bool U2>
+struct LnCfg {
+    static constexpr int CLUSTER = U2 ? 6 : 3;
+    static constexpr int ROWS = U2 ? 2 * BM : BM;                       // rows of a cluster's block
+    static constexpr int STAGES = U2 ? 4 : 3;
+    static constexpr int B_ROWS = U2 ? NCTA / 2 : NCTA;                 // W rows held per CTA and stage
+    static constexpr int B_BYTES = B_ROWS * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int STATS_OFFSET = EPI_OFFSET + EPI_WARPS * EPI_PER_WARP;
+    static constexpr int VEC_OFFSET = STATS_OFFSET + STATS_BYTES;
+    static constexpr int BAR_OFFSET = VEC_OFFSET + VEC_BYTES;
+    static constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * EPI_WARPS + 2;   // full, empty, tfull[2], tempty[2], res[8][2], stats[2]
+    static constexpr int SMEM_TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;
+    static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget exceeded");
+};
 constexpr int MAX_GROUPS = 4;
 
 struct LnMaps {
@@ -98,15 +109,18 @@ __device__ __forceinline__ void decode_blk(const LnParams& p, int blk, int& g, i
     m_blk = blk - p.blk_start[g];
 }
 
-__global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+template <bool U2>
+__global__ void __cluster_dims__(LnCfg<U2>::CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_ln_kernel(const __grid_constant__ LnMaps maps, const __grid_constant__ LnParams p) {
+    using C = LnCfg<U2>;
+    constexpr int CLUSTER = C::CLUSTER, STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES;
     extern __shared__ uint8_t smem_raw[];
     // every CTA of the cluster computes the same offset (same kernel, same dynamic smem base): the distributed-shared-
     // memory addressing below relies on identical layouts
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    float2* stats = reinterpret_cast<float2*>(smem + STATS_OFFSET);   // [2][NSEGS][BM]
-    float* vecs = reinterpret_cast<float*>(smem + VEC_OFFSET);        // [bias|gamma|beta][256]
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + BAR_OFFSET);
+    float2* stats = reinterpret_cast<float2*>(smem + C::STATS_OFFSET);   // [2][NSEGS][BM]
+    float* vecs = reinterpret_cast<float*>(smem + C::VEC_OFFSET);        // [bias|gamma|beta][256]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::BAR_OFFSET);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
@@ -117,6 +131,9 @@ gemm_ln_kernel(const __grid_constant__ LnMaps maps, const __grid_constant__ LnPa
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
+    const uint32_t nidx = U2 ? rank >> 1 : rank;     // which 256-column slice
+    const uint32_t mhalf = U2 ? rank & 1u : 0u;      // which 128-row half of the cluster's block (pair member)
+    const uint32_t lead = U2 ? rank & ~1u : rank;    // rank of the pair's MMA issuer
     const int cluster_id = blockIdx.x / CLUSTER;
     const int num_clusters = gridDim.x / CLUSTER;
     const int total_blks = p.blk_start[p.groups];
@@ -137,15 +154,20 @@ gemm_ln_kernel(const __grid_constant__ LnMaps maps, const __grid_constant__ LnPa
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tfull_bar[i], 1);
-            ptx::mbar_init(&tempty_bar[i], EPI_WARPS);
+            ptx::mbar_init(&tempty_bar[i], U2 ? 2 * EPI_WARPS : EPI_WARPS);   // (U2: the epilogue warps of both pair members)
             ptx::mbar_init(&stats_bar[i], EPI_WARPS);   // + the peers' st.async bytes
         }
         for (int i = 0; i < 2 * EPI_WARPS; ++i) ptx::mbar_init(&res_bar[i], 1);
         ptx::fence_mbar_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc(tmem_ptr_smem, TMEM_COLS);
-        ptx::tmem_relinquish();
+        if (U2) {
+            ptx::tmem_alloc_pair(tmem_ptr_smem, TMEM_COLS);
+            ptx::tmem_relinquish_pair();
+        } else {
+            ptx::tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+            ptx::tmem_relinquish();
+        }
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -167,17 +189,28 @@ gemm_ln_kernel(const __grid_constant__ LnMaps maps, const __grid_constant__ LnPa
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* st = smem + stage * STAGE_BYTES;
-                    ptx::mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-                    ptx::tma_load_2d(st, tmA, &full_bar[stage], kb * BK, m_blk * BM);
-                    ptx::tma_load_2d(st + A_BYTES, tmB, &full_bar[stage], kb * BK, static_cast<int>(rank) * NCTA);
+                    const int a_row = m_blk * C::ROWS + static_cast<int>(mhalf) * BM;
+                    if (U2) {
+                        // both pair members' boxes complete on the leader's barrier, which expects the bytes of the pair
+                        const uint32_t lead_bar = mapa(ptx::smem_u32(&full_bar[stage]), lead);
+                        if (mhalf == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+                        ptx::tma_load_2d_pair(st, tmA, lead_bar, kb * BK, a_row);
+                        ptx::tma_load_2d_pair(st + A_BYTES, tmB, lead_bar, kb * BK,
+                                              static_cast<int>(nidx) * NCTA + static_cast<int>(mhalf) * C::B_ROWS);
+                    } else {
+                        ptx::mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+                        ptx::tma_load_2d(st, tmA, &full_bar[stage], kb * BK, a_row);
+                        ptx::tma_load_2d(st + A_BYTES, tmB, &full_bar[stage], kb * BK, static_cast<int>(nidx) * NCTA);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (single thread)
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(BM, NCTA);
+        if (lane == 0 && mhalf == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(U2 ? 2 * BM : BM, NCTA);
+            const uint16_t pair_mask = static_cast<uint16_t>(0x3u << lead);
             int stage = 0;
             uint32_t phase = 0;
             int iter = 0;
@@ -193,12 +226,16 @@ gemm_ln_kernel(const __grid_constant__ LnMaps maps, const __grid_constant__ LnPa
                     const uint64_t a_desc = ptx::make_sw128_kmajor_desc(st);
                     const uint64_t b_desc = ptx::make_sw128_kmajor_desc(st + A_BYTES);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)
-                        ptx::umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-                    ptx::umma_commit(&empty_bar[stage]);
+                    for (int k = 0; k < BK / 16; ++k) {
+                        if (U2) ptx::umma_bf16_ss_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                        else ptx::umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    if (U2) ptx::umma_commit_pair(&empty_bar[stage], pair_mask);
+                    else ptx::umma_commit(&empty_bar[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                ptx::umma_commit(&tfull_bar[acc]);
+                if (U2) ptx::umma_commit_pair(&tfull_bar[acc], pair_mask);
+                else ptx::umma_commit(&tfull_bar[acc]);
             }
         }
     } else if (warp >= 4) {
@@ -207,8 +244,8 @@ gemm_ln_kernel(const __grid_constant__ LnMaps maps, const __grid_constant__ LnPa
         const int quad = warp & 3;            // TMEM lanes / tile rows [32 quad, 32 quad + 32)
         const int ew = warp - 4;
         const int member = ew >> 2;           // column segment of this CTA: [128 member, 128 member + 128)
-        const int seg = static_cast<int>(rank) * 2 + member;   // 0..5: position of the segment inside the 768 columns
-        uint8_t* my = smem + EPI_OFFSET + ew * EPI_PER_WARP;
+        const int seg = static_cast<int>(nidx) * 2 + member;   // 0..5: position of the segment inside the 768 columns
+        uint8_t* my = smem + C::EPI_OFFSET + ew * EPI_PER_WARP;
         const uint32_t my_s = ptx::smem_u32(my);
         uint64_t* rbar = res_bar + 2 * ew;
         uint32_t rphase = 0;
@@ -225,7 +262,7 @@ gemm_ln_kernel(const __grid_constant__ LnMaps maps, const __grid_constant__ LnPa
             const CUtensorMap* tmC16 = &maps.c16[g];
             const int Mg = p.M[g];
             const int acc = iter & 1;
-            const int row0 = m_blk * BM + quad * 32;
+            const int row0 = m_blk * C::ROWS + static_cast<int>(mhalf) * BM + quad * 32;
             const int col0 = seg * NSEG;
             const int slot = iter & 1;
             const bool no_res = p.dbg & 1, no_xchg = p.dbg & 2, no_store = p.dbg & 4;
@@ -246,7 +283,7 @@ gemm_ln_kernel(const __grid_constant__ LnMaps maps, const __grid_constant__ LnPa
                 for (int i = threadIdx.x - 128; i < 3 * NCTA; i += EPI_WARPS * 32) {
                     const int k = i / NCTA, cidx = i - k * NCTA;
                     const float* src = k == 0 ? p.bias[g] : (k == 1 ? p.gamma[g] : p.beta[g]);
-                    vecs[i] = src != nullptr ? __ldg(src + rank * NCTA + cidx) : 0.f;
+                    vecs[i] = src != nullptr ? __ldg(src + nidx * NCTA + cidx) : 0.f;
                 }
                 epi_bar_sync();
                 cur_g = g;
@@ -272,7 +309,10 @@ gemm_ln_kernel(const __grid_constant__ LnMaps maps, const __grid_constant__ LnPa
                     // last TMEM read of this block by this warp: the MMA warp may reuse the accumulator stage
                     ptx::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+                    if (lane == 0) {
+                        if (U2) ptx::mbar_arrive_cluster(mapa(ptx::smem_u32(&tempty_bar[acc]), lead));   // the pair leader's barrier
+                        else ptx::mbar_arrive(&tempty_bar[acc]);
+                    }
                 }
                 if (!no_res) {
                     ptx::mbar_wait(&rbar[b], (rphase >> b) & 1u);
@@ -305,14 +345,16 @@ gemm_ln_kernel(const __grid_constant__ LnMaps maps, const __grid_constant__ LnPa
                 const uint64_t packed = (static_cast<uint64_t>(__float_as_uint(sumsq)) << 32) | __float_as_uint(sum);
                 if (!no_xchg) {
 #pragma unroll
-                    for (uint32_t d = 1; d < CLUSTER; ++d) {
-                        const uint32_t peer = (rank + d) % CLUSTER;
+                    for (uint32_t d = 1; d < NSLICES; ++d) {
+                        // the CTAs holding the other column slices of the SAME rows
+                        const uint32_t pn = (nidx + d) % NSLICES;
+                        const uint32_t peer = U2 ? 2 * pn + mhalf : pn;
                         st_async_b64(mapa(stats_local + off, peer), packed, mapa(ptx::smem_u32(&stats_bar[slot]), peer));
                     }
                 }
                 __syncwarp();
                 if (lane == 0) {
-                    if (ew == 0 && !no_xchg) ptx::mbar_arrive_expect_tx(&stats_bar[slot], (CLUSTER - 1) * EPI_WARPS * 32 * 8);
+                    if (ew == 0 && !no_xchg) ptx::mbar_arrive_expect_tx(&stats_bar[slot], (NSLICES - 1) * EPI_WARPS * 32 * 8);
                     else ptx::mbar_arrive(&stats_bar[slot]);
                 }
                 ptx::mbar_wait(&stats_bar[slot], (iter >> 1) & 1);
@@ -381,17 +423,18 @@ gemm_ln_kernel(const __grid_constant__ LnMaps maps, const __grid_constant__ LnPa
     cluster_sync_all();   // no CTA exits while a peer may still write into its shared memory
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+        if (U2) ptx::tmem_dealloc_pair(tmem_base, TMEM_COLS);
+        else ptx::tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
-}  // namespace
-
-int launch_gemm_ln_grouped(const GemmLnArgs* ga, int n, float eps, cudaStream_t s) {
-    MRA_REQUIRE(n >= 1 && n <= MAX_GROUPS, "fused GEMM+LayerNorm takes 1..%d problems, got %d", MAX_GROUPS, n);
+template <bool U2>
+static int launch_gemm_ln_variant(const GemmLnArgs* ga, int n, float eps, cudaStream_t s) {
+    using C = LnCfg<U2>;
+    auto kern = gemm_ln_kernel<U2>;
     static bool attr_set = false;
     if (!attr_set) {
-        MRA_CHECK_CUDA(cudaFuncSetAttribute(gemm_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+        MRA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_TOTAL));
         attr_set = true;
     }
     LnMaps maps;
@@ -408,14 +451,14 @@ int launch_gemm_ln_grouped(const GemmLnArgs* ga, int n, float eps, cudaStream_t 
             MRA_REQUIRE(a.M > 0 && a.K > 0 && a.K % 8 == 0 && a.K == ga[0].K, "fused GEMM+LayerNorm: bad / mismatching K");
             MRA_REQUIRE(a.A && a.W && a.residual && a.gamma && a.beta && a.y32 && a.y16, "fused GEMM+LayerNorm: NULL operand");
             if (int e = get_tensor_map(a.A, a.M, a.K, a.lda, BM, BK, 2, &maps.a[g])) return e;
-            if (int e = get_tensor_map(a.W, NTOT, a.K, a.ldw, NCTA, BK, 2, &maps.b[g])) return e;
+            if (int e = get_tensor_map(a.W, NTOT, a.K, a.ldw, C::B_ROWS, BK, 2, &maps.b[g])) return e;
             if (int e = get_tensor_map(a.residual, a.M, NTOT, a.ldr, 32, 32, 4, &maps.r[g])) return e;
             if (int e = get_tensor_map(a.y32, a.M, NTOT, a.ldy32, 32, 32, 4, &maps.c32[g])) return e;
             if (int e = get_tensor_map(a.y16, a.M, NTOT, a.ldy16, 32, 64, 2, &maps.c16[g])) return e;
             p.bias[g] = a.bias; p.gamma[g] = a.gamma; p.beta[g] = a.beta;
             p.M[g] = a.M;
             p.blk_start[g] = total;
-            total += (a.M + BM - 1) / BM;
+            total += (a.M + C::ROWS - 1) / C::ROWS;
         } else {
             maps.a[g] = maps.a[0]; maps.b[g] = maps.b[0]; maps.r[g] = maps.r[0]; maps.c32[g] = maps.c32[0]; maps.c16[g] = maps.c16[0];
             p.bias[g] = p.gamma[g] = p.beta[g] = nullptr;
@@ -424,38 +467,47 @@ int launch_gemm_ln_grouped(const GemmLnArgs* ga, int n, float eps, cudaStream_t 
         }
     }
     for (int g = n; g <= MAX_GROUPS; ++g) p.blk_start[g] = total;
-    // persistent grid = as many clusters as can be co-resident (3-CTA clusters do not tile every GPC completely)
+    // persistent grid = as many clusters as can be co-resident (3- / 6-CTA clusters do not tile every GPC completely)
     static int max_clusters = 0;
     if (max_clusters == 0) {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(CLUSTER * (sm_count() / CLUSTER));
+        cfg.gridDim = dim3(C::CLUSTER * (sm_count() / C::CLUSTER));
         cfg.blockDim = dim3(NUM_THREADS);
-        cfg.dynamicSmemBytes = SMEM_TOTAL;
+        cfg.dynamicSmemBytes = C::SMEM_TOTAL;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        at[0].val.clusterDim.x = C::CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at;
         cfg.numAttrs = 1;
-        int n = 0;
-        if (cudaOccupancyMaxActiveClusters(&n, gemm_ln_kernel, &cfg) != cudaSuccess || n <= 0) n = sm_count() / CLUSTER;
-        max_clusters = n;
-        if (getenv("MRA_LN_DEBUG")) fprintf(stderr, "[gemm_ln] max co-resident %d-CTA clusters: %d\n", CLUSTER, n);
+        int nc = 0;
+        if (cudaOccupancyMaxActiveClusters(&nc, kern, &cfg) != cudaSuccess || nc <= 0) nc = sm_count() / C::CLUSTER;
+        max_clusters = nc;
+        if (getenv("MRA_LN_DEBUG")) fprintf(stderr, "[gemm_ln] max co-resident %d-CTA clusters: %d\n", C::CLUSTER, nc);
     }
     int clusters = max_clusters;
     if (clusters > total) clusters = total;
-    gemm_ln_kernel<<<CLUSTER * clusters, NUM_THREADS, SMEM_TOTAL, s>>>(maps, p);
+    kern<<<C::CLUSTER * clusters, NUM_THREADS, C::SMEM_TOTAL, s>>>(maps, p);
     MRA_CHECK_CUDA(cudaGetLastError());
     if (dbg & 8) {
         unsigned long long t[16];
         cudaStreamSynchronize(s);
         cudaMemcpyFromSymbol(t, g_ln_timing, sizeof(t));
-        const double n = t[5] ? double(t[5]) : 1.0;
-        fprintf(stderr, "[gemm_ln timing, cycles/tile over %llu tiles] wait-mainloop %.0f | pass1 %.0f | exchange %.0f | pass2 %.0f | drain %.0f\n",
-                t[5], t[0] / n, t[1] / n, t[2] / n, t[3] / n, t[4] / n);
+        const double nt = t[5] ? double(t[5]) : 1.0;
+        fprintf(stderr, "[gemm_ln U2=%d timing, cycles/tile over %llu tiles] wait-mainloop %.0f | pass1 %.0f | exchange %.0f | pass2 %.0f | drain %.0f\n",
+                int(U2), t[5], t[0] / nt, t[1] / nt, t[2] / nt, t[3] / nt, t[4] / nt);
         unsigned long long z[16] = {0};
         cudaMemcpyToSymbol(g_ln_timing, z, sizeof(z));
     }
     return 0;
+}
+
+}  // namespace
+
+int launch_gemm_ln_grouped(const GemmLnArgs* ga, int n, float eps, cudaStream_t s) {
+    MRA_REQUIRE(n >= 1 && n <= MAX_GROUPS, "fused GEMM+LayerNorm takes 1..%d problems, got %d", MAX_GROUPS, n);
+    // 1 (default) = 6-CTA clusters with 2-CTA MMAs, 0 = 3-CTA clusters with single-CTA MMAs (A/B runs, tests)
+    static const bool u2 = [] { const char* e = getenv("MRA_LN_U2"); return e == nullptr || atoi(e) != 0; }();
+    return u2 ? launch_gemm_ln_variant<true>(ga, n, eps, s) : launch_gemm_ln_variant<false>(ga, n, eps, s);
 }
 
 }  // namespace mra
