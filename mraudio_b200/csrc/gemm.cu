@@ -350,12 +350,29 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
             const bool prof = (p.dbg & 8) && blockIdx.x == 0 && ew == 0 && lane == 0;
             long long pt0 = 0, pt1 = 0;
             if (prof) pt0 = clock64();
+            // Bias of this warp's chunks, fetched BEFORE the wait for the accumulator (the loads used to sit on the critical
+            // path of every chunk: ~1 k cycles per tile, tools/gemm_phase.py): lane l keeps columns l * BPL .. of each chunk
+            // and the values are handed out by shuffles below.
+            constexpr int MAXC = (NCH + 1) / 2;     // chunks of a tile per warp
+            constexpr int BPL = CH / 32;            // bias values per lane and chunk
+            float bq[MAXC][BPL];
+#pragma unroll
+            for (int ci = 0; ci < MAXC; ++ci) {
+                const int c = member + 2 * ci;
+#pragma unroll
+                for (int e = 0; e < BPL; ++e) {
+                    const int col = col_base + c * CH + lane * BPL + e;
+                    bq[ci][e] = (bias != nullptr && c < NCH && col < p.N) ? __ldg(bias + col) : 0.f;
+                }
+            }
             ptx::mbar_wait(&tfull_bar[acc], acc_phase);
             if (prof) pt1 = clock64();
             ptx::tc_fence_after();
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * ACC_STRIDE;
-#pragma unroll 1
-            for (int c = member; c < NCH; c += 2) {
+#pragma unroll
+            for (int ci = 0; ci < MAXC; ++ci) {
+                const int c = member + 2 * ci;
+                if (c >= NCH) break;
                 const int col0 = col_base + c * CH;
                 // the TMA store that last read this warp's staging buffer must have finished reading shared memory
                 if (lane == 0) ptx::tma_store_wait_read<0>();
@@ -373,14 +390,11 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    const int cc = col0 + half * 32;
                     if (bias != nullptr) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            if (cc + j < p.N) {
-                                const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + cc + j));
-                                v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
-                            }
+                        for (int j = 0; j < 32; ++j) {
+                            const int idx = half * 32 + j;      // column inside the chunk -> (lane, slot) that holds its bias
+                            v[j] += __shfl_sync(0xffffffffu, bq[ci][idx % BPL], idx / BPL);
                         }
                     }
                     if (GELU) {

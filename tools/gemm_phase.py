@@ -10,5 +10,5 @@ for name, M, N, K, gelu in [("ffn_up", 32768, 3072, 768, True), ("qkv", 32768, 2
     x = torch.randn(M, K, device=dev).bfloat16(); w = (torch.randn(N, K, device=dev) * 0.03).bfloat16(); b = torch.randn(N, device=dev)
     for _ in range(3):
         sys.stderr.write(name + " "); sys.stderr.flush()
-        ops.linear(x, w, b, gelu=gelu)
+        ops.linear(x, w, None if os.environ.get("GP_NOBIAS") else b, gelu=gelu)
     torch.cuda.synchronize()
