@@ -47,15 +47,19 @@ def flops_per_row(Nk, W, T, layers=LAYERS, cross_freq=2):
 
 
 def load_ncu_traffic():
-    """dram bytes per launch of the captured launch types (one `ncu --set full` capture, profiles/r01d_ncu_full_summary.json)"""
-    p = os.path.join(ROOT, "profiles", "r01d_ncu_full_summary.json")
+    """dram bytes per launch and tensor-pipe activity of the captured launch types (ONE `ncu --set full` capture of a
+    config-2 step, profiles/r01g_ncu_full_summary.json, written by tools/ncu_summary.py)"""
+    p = os.path.join(ROOT, "profiles", "r01g_ncu_full_summary.json")
     if not os.path.exists(p):
         return None
     rows = json.load(open(p))
-    names = {0: "cross_kv_video (gemm_tc_kernel)", 1: "cross_kv_audio (gemm_tc_kernel)", 2: "qkv_grouped (gemm_tc_kernel)"}
+    names = ["cross_kv_video (gemm_tc_kernel, 2-CTA MMA)", "cross_kv_audio (gemm_tc_kernel, 2-CTA MMA)", "qkv_grouped (gemm_tc_kernel)",
+             "attn_out+LN (gemm_ln_kernel)", "cross_q (gemm_tc_kernel)", "cross_out+LN (gemm_ln_kernel)", "ffn_up GELU (gemm_tc_kernel)",
+             "ffn_down+LN (gemm_ln_kernel)"]
     out = {}
-    for i, r in enumerate(rows[:3]):
-        out[names[i]] = {"dram_bytes_per_launch": r.get("dram_bytes"), "tensor_pipe_active_pct": float(r["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"])}
+    for name, r in zip(names, rows):
+        out[name] = {"dram_bytes_per_launch": r.get("dram_bytes"),
+                     "tensor_pipe_active_pct": float(r["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"])}
     return out
 
 
@@ -330,9 +334,9 @@ def run_b200(args):
         "step_tflops_algorithmic": step_flops / 1e12,
         "frac_of_bf16_peak_whole_step": step_flops / (ms_dev * 1e-3) / 1e12 / peak,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": (load_ncu_traffic() or {}).get("cross_kv_video (gemm_tc_kernel)", {}).get("dram_bytes_per_launch"),
+                     "traffic": (load_ncu_traffic() or {}).get("cross_kv_video (gemm_tc_kernel, 2-CTA MMA)", {}).get("dram_bytes_per_launch"),
                      "traffic_note": "dram read+write bytes of the largest launch (cross-K/V GEMM, video: 1.42 GB algorithmic) from "
-                                     "profiles/r01d_ncu_full_summary.json; other captured launch types in ncu_captures",
+                                     "profiles/r01g_ncu_full_summary.json; other captured launch types in ncu_captures",
                      "ncu_captures": load_ncu_traffic(), "peak_source": peak_src + ", sustained figure (kernel timed inside a long step)",
                      "kernel": "tcgen05 Linear kernels gemm_tc_kernel + gemm_ln_kernel (all launches of a step, flops-weighted)",
                      "launches_per_step": gemm_n, "ms_per_step_in_kernel": gemm_ms, "ms_per_step_instrumented": ms_instr,
