@@ -378,18 +378,23 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
                 if (lane == 0) ptx::tma_store_wait_read<0>();
                 __syncwarp();
 #pragma unroll
+                // all TMEM reads of the chunk are issued before the single wait (one exposed TMEM latency per chunk, not per half)
+                uint32_t racc[RSUB][32];
+#pragma unroll
                 for (int half = 0; half < RSUB; ++half) {
-                    uint32_t r[32];
                     if (p.dbg & 16) {   // experiment: no TMEM reads (results are garbage) -- isolates the drain's cost
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) r[j] = 0;
+                        for (int j = 0; j < 32; ++j) racc[half][j] = 0;
                     } else {
-                        ptx::tmem_ld_32x32b_x32(t_row + c * CH + half * 32, r);
-                        ptx::tmem_ld_wait();
+                        ptx::tmem_ld_32x32b_x32(t_row + c * CH + half * 32, racc[half]);
                     }
+                }
+                if (!(p.dbg & 16)) ptx::tmem_ld_wait();
+#pragma unroll
+                for (int half = 0; half < RSUB; ++half) {
                     float v[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(racc[half][j]);
                     if (bias != nullptr) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
