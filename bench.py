@@ -262,7 +262,7 @@ def run_b200(args):
     ms_instr = timed(device_step, args.steps)
     prof_ms, prof_n = read_profile()
     # ---- e2e: host buffers through the public host API
-    pipe = model.host_pipeline(B, F, {m: v[0] for m, v in MODAL.items()}, T, slots=2)
+    pipe = model.host_pipeline(B, F, {m: v[0] for m, v in MODAL.items()}, T, slots=int(os.environ.get("MRA_BENCH_SLOTS", "2")))
     set_profile(_lib.PROFILE_OFF)
 
     def e2e_steps(n):
