@@ -136,6 +136,37 @@ def test_gemm_cluster_multicast_variant(cm, M, N, K):
         _lib.lib.mra_gemm_tile_override(0)
 
 
+@pytest.mark.parametrize("M,N,K", [(771, 2304, 768), (1281, 768, 3072), (640, 776, 768)])
+def test_paired_kernels_write_nothing_outside_their_output(M, N, K):
+    """Guard rows around the outputs of the 2-CTA-MMA GEMM and of the fused GEMM+LayerNorm (6-CTA clusters) with an odd
+    number of 128-row blocks and a ragged last tile: the TMA stores must clip at M / N exactly."""
+    from mraudio_b200 import ops, _lib
+    g = torch.Generator().manual_seed(M + N)
+    x = torch.randn(M, K, generator=g).to(_dev(), torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) * 0.05).to(_dev(), torch.bfloat16)
+    b = torch.randn(N, generator=g).to(_dev())
+    pad = 64
+    buf = torch.full((M + 2 * pad, N), 7.0, device=_dev(), dtype=torch.bfloat16)
+    out = buf[pad:pad + M]
+    _lib.check(_lib.lib.mra_gemm_bf16(_lib.ptr(x), K, _lib.ptr(w), K, _lib.ptr(b), None, 0, _lib.ptr(out), N, M, N, K, 0, 0, 0,
+                                      _lib.current_stream()))
+    torch.cuda.synchronize()
+    assert (buf[:pad] == 7.0).all() and (buf[pad + M:] == 7.0).all()
+    assert _rel(out, x.float() @ w.float().t() + b) < 6e-3
+    if N == 768:
+        res = torch.randn(M, N, generator=g).to(_dev())
+        gam, bet = torch.ones(N, device=_dev()), torch.zeros(N, device=_dev())
+        b32 = torch.full((M + 2 * pad, N), 7.0, device=_dev(), dtype=torch.float32)
+        b16 = torch.full((M + 2 * pad, N), 7.0, device=_dev(), dtype=torch.bfloat16)
+        _lib.check(_lib.lib.mra_gemm_ln_bf16(_lib.ptr(x), K, _lib.ptr(w), K, _lib.ptr(b), _lib.ptr(res), N, _lib.ptr(gam), _lib.ptr(bet),
+                                             _lib.ptr(b32[pad:]), N, _lib.ptr(b16[pad:]), N, M, N, K, 1e-12, _lib.current_stream()))
+        torch.cuda.synchronize()
+        for t in (b32, b16):
+            assert (t[:pad] == 7.0).all() and (t[pad + M:] == 7.0).all()
+        ref = torch.nn.functional.layer_norm(x.float() @ w.float().t() + b + res, (N,), gam, bet, 1e-12)
+        assert _rel(b32[pad:pad + M], ref) < 2e-3
+
+
 @pytest.mark.parametrize("n,n_out,k_in", [(64, 128, 64), (4096, 768, 768), (2048, 3072, 768), (2048, 768, 3072), (1000, 2304, 768),
                                           (16448, 1536, 1408), (77, 72, 200), (130, 4096, 768)])
 def test_wgrad_mn_major_operands(n, n_out, k_in):
