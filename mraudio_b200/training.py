@@ -296,7 +296,7 @@ class QFormerTrainer:
     (out of scope); the default is the surrogate ``sum(inputs_llm * G)`` used by the parity tests and the benchmark."""
 
     def __init__(self, model, max_epoch: int = 1, accum_grad_iters: int = 2, init_lr: float = 3e-4, warmup_steps: int = 1000,
-                 loss_fn=None, group=None, overlap_allreduce: bool = True):
+                 loss_fn=None, group=None, overlap_allreduce: bool = True, parallel_modalities: bool = True):
         self.model = model
         model.freeze_qformers(False)
         self.states = {m: TrainableQFormer(getattr(model, f"{m}_Qformer"), getattr(model, f"{m}_query_tokens"),
@@ -305,6 +305,12 @@ class QFormerTrainer:
         self.loss_fn = loss_fn
         self.group = group
         self.overlap_allreduce = overlap_allreduce
+        # At fine-tuning batch sizes (64 rows per modality) most launches fill a fraction of the 148 SMs, so the video and
+        # the audio Q-Former run on two streams: autograd replays each modality's backward on the stream of its forward.
+        # (For the large-batch inference forward the opposite holds -- DESIGN.md section 4 -- and one stream is used.)
+        self.parallel_modalities = parallel_modalities
+        dev = next(model.parameters()).device
+        self.mod_streams = {m: torch.cuda.Stream(dev) for m in model.modalities}
         self.iter = 0
         self.lr = init_lr
 
@@ -316,6 +322,7 @@ class QFormerTrainer:
         """Training-mode ``encode_modalities`` (models/xinstructblip.py:456-477) -> (inputs_llm, atts_llm)."""
         model = self.model
         inputs_llm, atts_llm = {}, {}
+        joins = []
         for m in model.modalities:
             if m not in feats:
                 continue
@@ -325,9 +332,21 @@ class QFormerTrainer:
             ids = input_ids.repeat(num, 1)                      # reference tiling (:463)
             tmask = attention_mask.repeat(num, 1)
             q_atts = torch.ones(enc.shape[0], model.num_query_token, dtype=tmask.dtype, device=tmask.device)
-            y = self.states[m].forward(enc, ids, torch.cat([q_atts, tmask], 1))
+            full_mask = torch.cat([q_atts, tmask], 1)
+            if self.parallel_modalities and len(model.modalities) > 1:
+                main, side = torch.cuda.current_stream(), self.mod_streams[m]
+                side.wait_stream(main)                      # inputs prepared on the main stream
+                with torch.cuda.stream(side):
+                    y = self.states[m].forward(enc, ids, full_mask)
+                for t in (enc, ids, full_mask):
+                    t.record_stream(side)
+                joins.append(side)
+            else:
+                y = self.states[m].forward(enc, ids, full_mask)
             inputs_llm[m] = y.reshape(bs, num, model.num_query_token, -1).view(bs, num * model.num_query_token, -1)
             atts_llm[m] = torch.ones(inputs_llm[m].size()[:-1], dtype=torch.long, device=y.device)
+        for side in joins:                                  # the loss is computed on the main stream
+            torch.cuda.current_stream().wait_stream(side)
         return inputs_llm, atts_llm
 
     def train_step(self, feats, input_ids, attention_mask, samples=None, cur_epoch: int = 0, surrogate: Optional[Dict[str, torch.Tensor]] = None):
@@ -347,6 +366,11 @@ class QFormerTrainer:
             for st in self.states.values():
                 st.reduce_group, st.reduce_after_backward = self.group, self.overlap_allreduce
         (loss / self.accum_grad_iters).backward()                                                                  # :131-133
+        if self.parallel_modalities and len(self.mod_streams) > 1:
+            # the CUDA backward of each modality ran on its own stream and accumulated into the flat gradient buffers behind
+            # autograd's back (no AccumulateGrad node): join explicitly before anything on this stream touches them
+            for side in self.mod_streams.values():
+                torch.cuda.current_stream().wait_stream(side)
         self.iter += 1
         if stepping:
             if world > 1:
