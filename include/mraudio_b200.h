@@ -12,8 +12,9 @@
  *     the library owns only its handle (TMA descriptors, launch configuration).
  *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises, the legacy default
  *     stream is never used implicitly.  A handle is not thread-safe: one per rank/stream.
- *   - activations / weights are bf16 (row-major, K contiguous); biases, LayerNorm parameters, the residual stream and
- *     accumulators are fp32; ids and masks int32.
+ *   - activations / weights are bf16 (row-major, K contiguous); biases, LayerNorm parameters and accumulators are fp32;
+ *     the residual stream is fp32 (training) or a bf16 hi + lo pair (inference, see mra_gemm_ln_split_bf16); ids and
+ *     masks int32.
  *   - there is NO CPU fallback: on a machine without an sm_100 device every compute entry returns an error.
  */
 #ifndef MRAUDIO_B200_H
@@ -131,8 +132,8 @@ int mra_qformer_last_launch_count(const mra_qformer_t* h);
  *   1. mra_qformer_forward(io with MRA_FWD_SAVE_FOR_BACKWARD) keeps per-layer activations in `workspace`;
  *   2. mra_qformer_backward(same io, same workspace, d_llm = dL/d(llm_out) bf16 [rows*Nq, D]) ACCUMULATES fp32
  *      gradients into `g` (same packed layout as mra_qformer_weights: stacked q,k,v / stacked cross k,v);
- *      `wT` is ignored and may be NULL (earlier versions took transposed weight copies for the dgrad GEMMs; they now
- *      read the forward's weights in place through MN-major descriptors, see mra_dgrad_bf16);
+ *      `reserved` must be NULL (the dgrad GEMMs read the forward's weights in place through MN-major descriptors, see
+ *      mra_dgrad_bf16: no transposed weight copies exist);
  *   3. mra_adam_step: torch.optim.Adam semantics on flat fp32 buffers (utils/trainer.py:65), grads pre-multiplied by
  *      grad_scale (1 / (accum_grad_iters * world_size) after a sum all-reduce);  mra_cast_bf16 refreshes bf16 copies. */
 typedef struct mra_qformer_layer_grads {
@@ -151,7 +152,7 @@ typedef struct mra_qformer_grads {
 } mra_qformer_grads;
 
 size_t mra_qformer_backward_workspace_bytes(const mra_qformer_t* h, int32_t rows, int32_t T, int32_t Nk);
-int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, const void* d_llm, const mra_qformer_weights* wT,
+int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, const void* d_llm, const void* reserved,
                          const mra_qformer_grads* g, void* workspace, size_t workspace_bytes, void* bwd_workspace,
                          size_t bwd_bytes, void* stream);
 /* Overlap of the data-parallel gradient all-reduce (DistributedDataParallel, utils/trainer.py:69) with the backward:
@@ -231,11 +232,19 @@ int mra_dgrad_bf16(const void* dY, int64_t ldy, const void* W, int64_t ldw, cons
 
 /* Fused  y = LayerNorm(A . W^T + bias + residual) * gamma + beta  for N == 768: Linear + residual add + post-LayerNorm of
  * BertSelfOutput / BertOutput (HF port modeling_instructblip.py:549-553, 606-610) in one kernel; the pre-LayerNorm sums
- * stay in TMEM.  A bf16 [M, K], W bf16 [768, K], residual fp32 [M, 768]; writes y32 (fp32) and y16 (bf16).
- * A 2-CTA cluster owns each 128-row block (384 columns per CTA) and combines the row statistics through DSMEM. */
+ * never leave TMEM / registers.  A bf16 [M, K], W bf16 [768, K], residual fp32 [M, 768]; writes y32 (fp32) and y16 (bf16).
+ * A 6-CTA thread-block cluster (3 column slices of 256 x a CTA pair running tcgen05.mma.cta_group::2, M = 256) owns each
+ * 256-row block and combines the per-row statistics through distributed shared memory (csrc/gemm_ln.cu). */
 int mra_gemm_ln_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const float* residual,
                      int64_t ldr, const float* gamma, const float* beta, float* y32, int64_t ldy32, void* y16, int64_t ldy16,
                      int32_t M, int32_t N, int32_t K, float eps, void* stream);
+
+/* Same with the residual stream as a PAIR of bf16 tensors (value = hi + lo, hi = bf16(value), lo = bf16(value - hi): 16
+ * mantissa bits): res_hi / res_lo in (row stride ldr), y_hi / y_lo out (row stride ldy); y_hi is what the next Linear reads
+ * as its A operand.  4 + 4 instead of 4 + 6 bytes per post-LayerNorm element; this is the form mra_qformer_forward uses. */
+int mra_gemm_ln_split_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const void* res_hi,
+                           const void* res_lo, int64_t ldr, const float* gamma, const float* beta, void* y_hi, void* y_lo,
+                           int64_t ldy, int32_t M, int32_t N, int32_t K, float eps, void* stream);
 
 /* Tuning aid: force the output-tile width of the tcgen05 GEMM (128, 192 or 256; 0 = automatic choice). */
 int mra_gemm_tile_override(int32_t bn);

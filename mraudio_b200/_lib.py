@@ -1,7 +1,7 @@
 """ctypes binding of libmraudio_b200.so (C-ABI declared in include/mraudio_b200.h).
 
-There is no CPU fallback: importing this module without the built library raises, and every compute entry point
-returns an error on a machine without an sm_100 GPU (``MraError``).
+There is no CPU fallback: the first call into the library without the built ``.so`` raises ImportError, and every compute
+entry point returns an error on a machine without an sm_100 GPU (``MraError``).
 """
 from __future__ import annotations
 
@@ -9,7 +9,10 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmraudio_b200.so")
+# MRA_LIB=<name> loads libmraudio_b200_<name>.so: the instrumented build (make -C mraudio_b200/csrc INSTRUMENT=1 -> "instr")
+# or an A/B variant (make VARIANT=<name> EXTRA=-D...).  Tuning tools only; the product loads libmraudio_b200.so.
+_VARIANT = os.environ.get("MRA_LIB", "")
+LIB_PATH = os.path.join(_HERE, f"libmraudio_b200_{_VARIANT}.so" if _VARIANT else "libmraudio_b200.so")
 
 MRA_MAX_LAYERS = 16
 MRA_NUM_IOU_THDS = 10
@@ -87,7 +90,7 @@ def _load():
     lib.mra_qformer_last_launch_count.argtypes = [vp]
     lib.mra_qformer_backward_workspace_bytes.argtypes = [vp, i32, i32, i32]
     lib.mra_qformer_backward_workspace_bytes.restype = C.c_size_t
-    lib.mra_qformer_backward.argtypes = [vp, C.POINTER(QFormerIO), vp, C.POINTER(QFormerWeights), C.POINTER(QFormerGrads), vp,
+    lib.mra_qformer_backward.argtypes = [vp, C.POINTER(QFormerIO), vp, vp, C.POINTER(QFormerGrads), vp,
                                          C.c_size_t, vp, C.c_size_t, vp]
     lib.mra_qformer_backward_layer_events.argtypes = [vp, C.POINTER(vp), i32]
     lib.mra_adam_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, vp]
@@ -99,6 +102,7 @@ def _load():
     lib.mra_wgrad_bf16.argtypes = [vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, vp]
     lib.mra_dgrad_bf16.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, vp]
     lib.mra_gemm_ln_bf16.argtypes = [vp, i64, vp, i64, vp, vp, i64, vp, vp, vp, i64, vp, i64, i32, i32, i32, f32, vp]
+    lib.mra_gemm_ln_split_bf16.argtypes = [vp, i64, vp, i64, vp, vp, vp, i64, vp, vp, vp, vp, i64, i32, i32, i32, f32, vp]
     lib.mra_gemm_tile_override.argtypes = [i32]
     lib.mra_gemm_cluster_override.argtypes = [i32]
     lib.mra_attention.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, vp, i32, i32, i32, i32, i32, i32, vp]
@@ -111,7 +115,22 @@ def _load():
     return lib
 
 
-lib = _load()
+class _LazyLib:
+    """Loads libmraudio_b200.so on first use, so that the host-only modules (parsing, prompt layout, record packing) import
+    on a checkout where the library has not been built yet; any compute call without it raises the ImportError of
+    ``_load`` -- there is still no CPU fallback."""
+    _real = None
+
+    def _get(self):
+        if _LazyLib._real is None:
+            _LazyLib._real = _load()
+        return _LazyLib._real
+
+    def __getattr__(self, name):
+        return getattr(self._get(), name)
+
+
+lib = _LazyLib()
 
 # every symbol include/mraudio_b200.h declares (checked by tests/test_capi_symbols.py)
 EXPORTED_SYMBOLS = (
@@ -119,7 +138,7 @@ EXPORTED_SYMBOLS = (
     "mra_qformer_destroy", "mra_qformer_workspace_bytes", "mra_qformer_forward", "mra_qformer_forward_multi", "mra_qformer_last_launch_count", "mra_qformer_backward_workspace_bytes", "mra_qformer_backward", "mra_qformer_backward_layer_events", "mra_adam_step", "mra_adam_step_fused",
     "mra_cast_bf16",
     "mra_qformer_profile_mode", "mra_qformer_profile_read",
-    "mra_gemm_bf16", "mra_wgrad_bf16", "mra_dgrad_bf16", "mra_gemm_ln_bf16", "mra_gemm_tile_override", "mra_gemm_cluster_override", "mra_attention", "mra_attention_impl_override", "mra_layernorm", "mra_modality_layernorm", "mra_add_frame_position", "mra_prompt_assemble", "mra_mr_score",
+    "mra_gemm_bf16", "mra_wgrad_bf16", "mra_dgrad_bf16", "mra_gemm_ln_bf16", "mra_gemm_ln_split_bf16", "mra_gemm_tile_override", "mra_gemm_cluster_override", "mra_attention", "mra_attention_impl_override", "mra_layernorm", "mra_modality_layernorm", "mra_add_frame_position", "mra_prompt_assemble", "mra_mr_score",
 )
 
 

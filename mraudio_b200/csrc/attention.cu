@@ -534,13 +534,8 @@ int get_map3(const void* ptr, int64_t ld, int width, int ntok, int rows, CUtenso
 template <int NWARPS>
 int launch_tma_variant(const TmaMaps& maps, const TmaParams2& pp, unsigned grid, size_t smem, cudaStream_t s) {
     auto kern = attention_tma_kernel<NWARPS>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        MRA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        // same L1 / shared-memory split as the GEMM kernels around it: no SM reconfiguration between launches
-        MRA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        attr_set = true;
-    }
+    // same L1 / shared-memory split as the GEMM kernels around it: no SM reconfiguration between launches
+    if (int e = ensure_smem_attr(reinterpret_cast<const void*>(kern), 160 * 1024, true)) return e;
     MRA_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(NWARPS * 32), smem, s, maps, pp));
     return 0;
 }
@@ -632,12 +627,8 @@ int launch_attention(const AttnArgs& a, cudaStream_t s) {
     const int sq_pad = (a.Sq + 15) & ~15;
     const size_t smem = static_cast<size_t>(sq_pad + 2 * KC) * LDS_ROW * 2 + KC * sizeof(float);
     const unsigned grid = static_cast<unsigned>(a.rows) * a.heads;
-    static bool attr_set = false;
-    if (!attr_set) {
-        MRA_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        MRA_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        attr_set = true;
-    }
+    if (int e = ensure_smem_attr(reinterpret_cast<const void*>(attention_kernel<2>), 96 * 1024)) return e;
+    if (int e = ensure_smem_attr(reinterpret_cast<const void*>(attention_kernel<4>), 96 * 1024)) return e;
     if (a.Sq <= 32)
         MRA_CHECK_CUDA(launch_pdl(attention_kernel<2>, dim3(grid), dim3(64), smem, s, p));
     else

@@ -812,11 +812,7 @@ int launch_attention_bwd(const AttnBwdArgs& a, cudaStream_t s) {
     static const bool force_simt = getenv("MRA_ATTN_BWD_SIMT") != nullptr;
     const size_t tc_smem = attn_bwd_tc_smem(a.Sq, a.Sk);
     if (a.o != nullptr && !force_simt && tc_smem <= 220 * 1024) {
-        static bool tc_attr_set = false;
-        if (!tc_attr_set) {
-            MRA_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-            tc_attr_set = true;
-        }
+        if (int e = ensure_smem_attr(reinterpret_cast<const void*>(attn_bwd_tc_kernel), 220 * 1024)) return e;
         AttnBwdTcParams pp{{reinterpret_cast<const __nv_bfloat16*>(a.q), a.ldq, reinterpret_cast<const __nv_bfloat16*>(a.k), a.ldk,
                             reinterpret_cast<const __nv_bfloat16*>(a.v), a.ldv, reinterpret_cast<const __nv_bfloat16*>(a.d_o), a.ldo,
                             reinterpret_cast<__nv_bfloat16*>(a.dq), a.lddq, reinterpret_cast<__nv_bfloat16*>(a.dk), a.lddk,
@@ -828,11 +824,7 @@ int launch_attention_bwd(const AttnBwdArgs& a, cudaStream_t s) {
     }
     const size_t smem = static_cast<size_t>(2 * a.Sq + 2 * a.Sk) * AB_LD * 2 + 16 + static_cast<size_t>(a.Sq) * a.Sk * 8;
     MRA_REQUIRE(smem <= 220 * 1024, "attention backward: Sq=%d x Sk=%d needs %zu bytes of shared memory (max 220 KiB)", a.Sq, a.Sk, smem);
-    static bool attr_set = false;
-    if (!attr_set) {
-        MRA_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        attr_set = true;
-    }
+    if (int e = ensure_smem_attr(reinterpret_cast<const void*>(attn_bwd_kernel), 220 * 1024)) return e;
     AttnBwdParams p{reinterpret_cast<const __nv_bfloat16*>(a.q), a.ldq, reinterpret_cast<const __nv_bfloat16*>(a.k), a.ldk,
                     reinterpret_cast<const __nv_bfloat16*>(a.v), a.ldv, reinterpret_cast<const __nv_bfloat16*>(a.d_o), a.ldo,
                     reinterpret_cast<__nv_bfloat16*>(a.dq), a.lddq, reinterpret_cast<__nv_bfloat16*>(a.dk), a.lddk,

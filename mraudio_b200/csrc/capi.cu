@@ -1,6 +1,10 @@
 // extern "C" surface of libmraudio_b200.so (see include/mraudio_b200.h) + process-wide helpers.
 #include <stdarg.h>
 
+#include <mutex>
+#include <set>
+#include <utility>
+
 #include "common.h"
 
 namespace mra {
@@ -34,6 +38,20 @@ int device_check() {
         return 3;
     }
     cached = 0;
+    return 0;
+}
+
+int ensure_smem_attr(const void* kernel, int bytes, bool max_carveout) {
+    static std::mutex mu;
+    static std::set<std::pair<const void*, int>> done;
+    int dev = 0;
+    MRA_CHECK_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    if (done.count({kernel, dev})) return 0;
+    MRA_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    if (max_carveout)
+        MRA_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    done.insert({kernel, dev});
     return 0;
 }
 
@@ -92,6 +110,18 @@ extern "C" int mra_gemm_ln_bf16(const void* A, int64_t lda, const void* W, int64
     MRA_REQUIRE(N == 768, "mra_gemm_ln_bf16: the fused GEMM + LayerNorm kernel is built for N = 768 (Q-Former hidden size), got %d", N);
     if (int e = device_check()) return e;
     GemmLnArgs a{A, lda, W, ldw, bias, residual, ldr, gamma, beta, y32, ldy32, y16, ldy16, M, K};
+    return launch_gemm_ln_grouped(&a, 1, eps, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mra_gemm_ln_split_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const void* res_hi,
+                                      const void* res_lo, int64_t ldr, const float* gamma, const float* beta, void* y_hi,
+                                      void* y_lo, int64_t ldy, int32_t M, int32_t N, int32_t K, float eps, void* stream) {
+    MRA_REQUIRE(N == 768, "mra_gemm_ln_split_bf16: the fused GEMM + LayerNorm kernel is built for N = 768 (Q-Former hidden size), got %d", N);
+    MRA_REQUIRE(res_hi && res_lo && y_hi && y_lo, "mra_gemm_ln_split_bf16: NULL residual / output");
+    if (int e = device_check()) return e;
+    GemmLnArgs a{A, lda, W, ldw, bias, res_hi, ldr, gamma, beta, nullptr, ldy, y_hi, ldy, M, K};
+    a.res_lo = res_lo;
+    a.y_lo = y_lo;
     return launch_gemm_ln_grouped(&a, 1, eps, reinterpret_cast<cudaStream_t>(stream));
 }
 

@@ -55,6 +55,9 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
 
 int device_check();
 int sm_count();
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize [, PreferredSharedMemoryCarveout = max]) once per (kernel, device):
+// the attribute is per device, and the cache is guarded so that handles on different threads / devices are safe
+int ensure_smem_attr(const void* kernel, int bytes, bool max_carveout = false);
 
 // ---- launchers (each returns 0 / error and bumps *launches when non-null) ----
 struct GemmArgs {
@@ -94,11 +97,15 @@ struct GemmLnArgs {
     const void* A; int64_t lda;        // bf16 [M, K]
     const void* W; int64_t ldw;        // bf16 [768, K]
     const float* bias;                 // fp32 [768] or NULL
-    const float* residual; int64_t ldr;   // fp32 [M, 768]
+    const void* residual; int64_t ldr;    // fp32 [M, 768]  (bf16 hi part in split form)
     const float* gamma; const float* beta;
     float* y32; int64_t ldy32;         // fp32 [M, 768]
     void* y16; int64_t ldy16;          // bf16 [M, 768]
     int M, K;
+    // split residual stream (both non-NULL selects it): `residual` then points at the bf16 hi part (row stride ldr) and
+    // res_lo at the bf16 lo part; the outputs are y16 = hi and y_lo = lo (row stride ldy16), y32 is unused
+    const void* res_lo = nullptr;
+    void* y_lo = nullptr;
 };
 int launch_gemm_ln_grouped(const GemmLnArgs* a, int n, float eps, cudaStream_t s);
 
@@ -128,13 +135,14 @@ int launch_add_frame_pos(const void* x, int in_dtype, const float* pos, void* ou
                          cudaStream_t s);
 // embeddings: LN(cat(query_embeds, word_emb[ids] + pos_emb[:T])) written in the split layout (queries first)
 int launch_embed_layernorm(const float* query_embeds, int q_rows, const int32_t* ids, const void* word_emb,
-                           const void* pos_emb, const float* g, const float* b, float* y32, void* y16, float* pre_out, int rows,
-                           int Nq, int T, int H, int vocab, float eps, cudaStream_t s);
+                           const void* pos_emb, const float* g, const float* b, float* y32, void* y16, void* ylo, float* pre_out,
+                           int rows, int Nq, int T, int H, int vocab, float eps, cudaStream_t s);
 // additive masks (LAVIS get_extended_attention_mask): out[r, j] = (1 - mask[r, j]) * -10000
 int launch_build_enc_mask(const int32_t* enc_mask, float* out, int rows, int Nk, cudaStream_t s);
 // split layout [queries ; text] fp32 -> interleaved [rows, Nq+T, H] fp32
 int launch_prompt_assemble(void* out, int bs, int L, int D, const mra_prompt_segment* segs, int n, cudaStream_t s);
 int launch_gather_last_hidden(const float* split, float* out, int rows, int Nq, int T, int H, cudaStream_t s);
+int launch_gather_last_hidden_split(const void* hi, const void* lo, float* out, int rows, int Nq, int T, int H, cudaStream_t s);
 
 // ---- backward / optimizer (backward.cu)
 struct AttnBwdArgs {

@@ -22,7 +22,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 // x[MAX_VEC][8] holds this lane's elements: vector i covers columns (i*32 + lane)*8 .. +7 (valid when < n).
 __device__ __forceinline__ void ln_normalise_store(float (&x)[MAX_VEC][8], int n, int lane, const float* __restrict__ g,
                                                    const float* __restrict__ b, float eps, float* y32,
-                                                   __nv_bfloat16* y16) {
+                                                   __nv_bfloat16* y16, __nv_bfloat16* ylo = nullptr) {
     const int nvec = n >> 3;
     float sum = 0.f;
 #pragma unroll
@@ -68,6 +68,14 @@ __device__ __forceinline__ void ln_normalise_store(float (&x)[MAX_VEC][8], int n
                 o.z = ptx::pack_bf16x2(y[4], y[5]);
                 o.w = ptx::pack_bf16x2(y[6], y[7]);
                 *reinterpret_cast<uint4*>(y16 + c) = o;
+                if (ylo) {   // split residual stream: lo = bf16(y - hi)
+                    uint4 l;
+                    l.x = ptx::pack_bf16x2(y[0] - ptx::bf16lo(o.x), y[1] - ptx::bf16hi(o.x));
+                    l.y = ptx::pack_bf16x2(y[2] - ptx::bf16lo(o.y), y[3] - ptx::bf16hi(o.y));
+                    l.z = ptx::pack_bf16x2(y[4] - ptx::bf16lo(o.z), y[5] - ptx::bf16hi(o.z));
+                    l.w = ptx::pack_bf16x2(y[6] - ptx::bf16lo(o.w), y[7] - ptx::bf16hi(o.w));
+                    *reinterpret_cast<uint4*>(ylo + c) = l;
+                }
             }
         }
     }
@@ -196,8 +204,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 embed_ln_kernel(const float* __restrict__ query_embeds, int q_rows, const int32_t* __restrict__ ids,
                 const __nv_bfloat16* __restrict__ word_emb, const __nv_bfloat16* __restrict__ pos_emb,
                 const float* __restrict__ g, const float* __restrict__ b, float* __restrict__ y32,
-                __nv_bfloat16* __restrict__ y16, float* __restrict__ pre_out, int rows, int Nq, int T, int H, int vocab,
-                float eps) {
+                __nv_bfloat16* __restrict__ y16, __nv_bfloat16* __restrict__ ylo, float* __restrict__ pre_out, int rows, int Nq,
+                int T, int H, int vocab, float eps) {
     const int64_t orow = static_cast<int64_t>(blockIdx.x) * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     const int64_t nquery = static_cast<int64_t>(rows) * Nq;
@@ -238,7 +246,7 @@ embed_ln_kernel(const float* __restrict__ query_embeds, int q_rows, const int32_
                 *reinterpret_cast<float4*>(pp + 4) = make_float4(v[k][4], v[k][5], v[k][6], v[k][7]);
             }
     }
-    ln_normalise_store(v, H, lane, g, b, eps, y32 + orow * H, y16 + orow * H);
+    ln_normalise_store(v, H, lane, g, b, eps, y32 ? y32 + orow * H : nullptr, y16 + orow * H, ylo ? ylo + orow * H : nullptr);
 }
 
 __global__ void enc_mask_kernel(const int32_t* __restrict__ enc_mask, float* __restrict__ out, int64_t n) {
@@ -259,6 +267,25 @@ __global__ void gather_last_hidden_kernel(const float4* __restrict__ split, floa
     const int64_t srow = i < Nq ? static_cast<int64_t>(r) * Nq + i
                                 : static_cast<int64_t>(rows) * Nq + static_cast<int64_t>(r) * T + (i - Nq);
     out[idx] = split[srow * H4 + c];
+}
+
+// same for the split (hi + lo bf16) residual stream: out = float(hi) + float(lo); 8 elements per thread
+__global__ void gather_last_hidden_split_kernel(const uint4* __restrict__ hi, const uint4* __restrict__ lo, float4* __restrict__ out,
+                                                int rows, int Nq, int T, int H8) {
+    const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int S = Nq + T;
+    const int64_t total = static_cast<int64_t>(rows) * S * H8;
+    if (idx >= total) return;
+    const int c = static_cast<int>(idx % H8);
+    const int64_t tok = idx / H8;
+    const int r = static_cast<int>(tok / S), i = static_cast<int>(tok % S);
+    const int64_t srow = i < Nq ? static_cast<int64_t>(r) * Nq + i
+                                : static_cast<int64_t>(rows) * Nq + static_cast<int64_t>(r) * T + (i - Nq);
+    const uint4 h = hi[srow * H8 + c], l = lo[srow * H8 + c];
+    out[2 * idx] = make_float4(ptx::bf16lo(h.x) + ptx::bf16lo(l.x), ptx::bf16hi(h.x) + ptx::bf16hi(l.x),
+                               ptx::bf16lo(h.y) + ptx::bf16lo(l.y), ptx::bf16hi(h.y) + ptx::bf16hi(l.y));
+    out[2 * idx + 1] = make_float4(ptx::bf16lo(h.z) + ptx::bf16lo(l.z), ptx::bf16hi(h.z) + ptx::bf16hi(l.z),
+                                   ptx::bf16lo(h.w) + ptx::bf16lo(l.w), ptx::bf16hi(h.w) + ptx::bf16hi(l.w));
 }
 
 }  // namespace
@@ -320,15 +347,16 @@ int launch_add_frame_pos(const void* x, int in_dtype, const float* pos, void* ou
 }
 
 int launch_embed_layernorm(const float* query_embeds, int q_rows, const int32_t* ids, const void* word_emb,
-                           const void* pos_emb, const float* g, const float* b, float* y32, void* y16, float* pre_out, int rows,
-                           int Nq, int T, int H, int vocab, float eps, cudaStream_t s) {
+                           const void* pos_emb, const float* g, const float* b, float* y32, void* y16, void* ylo, float* pre_out,
+                           int rows, int Nq, int T, int H, int vocab, float eps, cudaStream_t s) {
     MRA_REQUIRE(H % 8 == 0 && H <= 32 * MAX_VEC * 8, "embedding width %d unsupported", H);
     MRA_REQUIRE(T == 0 || (ids && word_emb && pos_emb), "text tokens given but ids / embedding tables are NULL");
     const int64_t total = static_cast<int64_t>(rows) * (Nq + T);
     const unsigned blocks = static_cast<unsigned>((total + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
     MRA_CHECK_CUDA(launch_pdl(embed_ln_kernel, dim3(blocks), dim3(WARPS_PER_BLOCK * 32), 0, s, query_embeds, q_rows, ids,
                               reinterpret_cast<const __nv_bfloat16*>(word_emb), reinterpret_cast<const __nv_bfloat16*>(pos_emb), g,
-                              b, y32, reinterpret_cast<__nv_bfloat16*>(y16), pre_out, rows, Nq, T, H, vocab, eps));
+                              b, y32, reinterpret_cast<__nv_bfloat16*>(y16), reinterpret_cast<__nv_bfloat16*>(ylo), pre_out, rows,
+                              Nq, T, H, vocab, eps));
     return 0;
 }
 
@@ -392,6 +420,15 @@ int launch_gather_last_hidden(const float* split, float* out, int rows, int Nq, 
     const int64_t n = static_cast<int64_t>(rows) * (Nq + T) * (H / 4);
     gather_last_hidden_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(
         reinterpret_cast<const float4*>(split), reinterpret_cast<float4*>(out), rows, Nq, T, H / 4);
+    MRA_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_gather_last_hidden_split(const void* hi, const void* lo, float* out, int rows, int Nq, int T, int H, cudaStream_t s) {
+    MRA_REQUIRE(H % 8 == 0, "hidden size must be a multiple of 8");
+    const int64_t n = static_cast<int64_t>(rows) * (Nq + T) * (H / 8);
+    gather_last_hidden_split_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(
+        reinterpret_cast<const uint4*>(hi), reinterpret_cast<const uint4*>(lo), reinterpret_cast<float4*>(out), rows, Nq, T, H / 8);
     MRA_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -21,6 +21,13 @@
 #include "common.h"
 #include "ptx.cuh"
 
+// timing experiments (MRA_GEMM_DEBUG) are compiled in only with -DMRA_INSTRUMENT (make INSTRUMENT=1)
+#ifdef MRA_INSTRUMENT
+#define MRA_GEMM_DBG(p) ((p).dbg)
+#else
+#define MRA_GEMM_DBG(p) 0
+#endif
+
 namespace mra {
 
 namespace {
@@ -51,7 +58,7 @@ struct EpiParams {
     // M x N gives few tiles and K is long: the weight gradients, K = number of tokens); needs reduce_add.
     // reduce_add: the epilogue adds its tile into C with TMA reduce-add stores (fp32) instead of storing it.
     int ksplit, kb_per_split, reduce_add;
-    int dbg;   // MRA_GEMM_DEBUG=8: cycles per tile spent waiting for the accumulator vs in the epilogue (one warp of CTA 0)
+    int dbg;   // -DMRA_INSTRUMENT + MRA_GEMM_DEBUG=8: cycles per tile spent waiting for the accumulator vs in the epilogue
 };
 
 __device__ unsigned long long g_gemm_timing[8];
@@ -105,6 +112,19 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // the negative c from flipping the sign of the argument) and the hardware tanh.approx.f32 (relative error 2^-11):
 // 1 MUFU + 7 FMA-pipe instructions per element.  The total error (<= 5e-4 |x|) is an eighth of the bf16 rounding
 // step of the stored result; fp32 outputs keep gelu_erf.
+// the same on a pair of values with packed fp32 instructions: 5 FMA-pipe instructions + 2 MUFU + 2 FMNMX per PAIR
+__device__ __forceinline__ float2 gelu_fast2(float2 x) {
+    float2 u = ptx::mul2(x, x);
+    u.x = fminf(u.x, 64.0f);
+    u.y = fminf(u.y, 64.0f);
+    float2 q = ptx::fma2(make_float2(-3.51534682e-4f, -3.51534682e-4f), u, make_float2(3.70057307e-2f, 3.70057307e-2f));
+    q = ptx::fma2(q, u, make_float2(7.97507813e-1f, 7.97507813e-1f));
+    const float2 a = ptx::mul2(x, q);
+    float2 t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(a.x));
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(a.y));
+    return ptx::mul2(x, ptx::fma2(make_float2(0.5f, 0.5f), t, make_float2(0.5f, 0.5f)));
+}
 __device__ __forceinline__ float gelu_fast(float x) {
     const float u = fminf(x * x, 64.0f);
     float q = fmaf(-3.51534682e-4f, u, 3.70057307e-2f);
@@ -267,7 +287,7 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
             for (int item = first_item; item < total_items; item += item_stride, ++iter) {
                 const int acc = iter & 1;
                 const uint32_t acc_phase = (iter >> 1) & 1;
-                const bool mprof = (p.dbg & 8) && blockIdx.x == 0;
+                const bool mprof = (MRA_GEMM_DBG(p) & 8) && blockIdx.x == 0;
                 long long mt0 = 0, mt1 = 0, mt2 = 0;
                 if (mprof) mt0 = clock64();
                 ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
@@ -347,7 +367,7 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
                 ptx::mbar_arrive_expect_tx(rbar, CHUNK_BYTES);
                 ptx::tma_load_2d(rsrc, tmR, rbar, col_base + member * CH, row0);
             }
-            const bool prof = (p.dbg & 8) && blockIdx.x == 0 && ew == 0 && lane == 0;
+            const bool prof = (MRA_GEMM_DBG(p) & 8) && blockIdx.x == 0 && ew == 0 && lane == 0;
             long long pt0 = 0, pt1 = 0;
             if (prof) pt0 = clock64();
             // Bias of this warp's chunks, fetched BEFORE the wait for the accumulator (the loads used to sit on the critical
@@ -374,38 +394,47 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
                 const int c = member + 2 * ci;
                 if (c >= NCH) break;
                 const int col0 = col_base + c * CH;
-                // the TMA store that last read this warp's staging buffer must have finished reading shared memory
-                if (lane == 0) ptx::tma_store_wait_read<0>();
-                __syncwarp();
-#pragma unroll
                 // all TMEM reads of the chunk are issued before the single wait (one exposed TMEM latency per chunk, not per half)
                 uint32_t racc[RSUB][32];
 #pragma unroll
                 for (int half = 0; half < RSUB; ++half) {
-                    if (p.dbg & 16) {   // experiment: no TMEM reads (results are garbage) -- isolates the drain's cost
+                    if (MRA_GEMM_DBG(p) & 16) {   // experiment: no TMEM reads (results are garbage) -- isolates the drain's cost
 #pragma unroll
                         for (int j = 0; j < 32; ++j) racc[half][j] = 0;
                     } else {
                         ptx::tmem_ld_32x32b_x32(t_row + c * CH + half * 32, racc[half]);
                     }
                 }
-                if (!(p.dbg & 16)) ptx::tmem_ld_wait();
+                if (!(MRA_GEMM_DBG(p) & 16)) ptx::tmem_ld_wait();
 #pragma unroll
                 for (int half = 0; half < RSUB; ++half) {
                     float v[32];
+#ifdef MRA_AB_SCALAR_EPI   // A/B variant: the round-1 scalar bias + GELU arithmetic
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(racc[half][j]);
-                    if (bias != nullptr) {
+                    for (int j = 0; j < 32; ++j) {
+                        v[j] = __uint_as_float(racc[half][j]);
+                        const int idx = half * 32 + j;
+                        if (bias != nullptr) v[j] += __shfl_sync(0xffffffffu, bq[ci][idx % BPL], idx / BPL);
+                        if (GELU) v[j] = OUT_F32 ? gelu_erf(v[j]) : gelu_fast(v[j]);
+                    }
+#else
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
+                    for (int j = 0; j < 32; j += 2) {
+                        // pairs of columns through the packed fp32 pipe (FADD2 / FMUL2 / FFMA2)
+                        float2 x = make_float2(__uint_as_float(racc[half][j]), __uint_as_float(racc[half][j + 1]));
+                        if (bias != nullptr) {
                             const int idx = half * 32 + j;      // column inside the chunk -> (lane, slot) that holds its bias
-                            v[j] += __shfl_sync(0xffffffffu, bq[ci][idx % BPL], idx / BPL);
+                            x = ptx::add2(x, make_float2(__shfl_sync(0xffffffffu, bq[ci][idx % BPL], idx / BPL),
+                                                         __shfl_sync(0xffffffffu, bq[ci][(idx + 1) % BPL], (idx + 1) / BPL)));
                         }
+                        if (GELU) {
+                            if (OUT_F32) x = make_float2(gelu_erf(x.x), gelu_erf(x.y));
+                            else x = gelu_fast2(x);
+                        }
+                        v[j] = x.x;
+                        v[j + 1] = x.y;
                     }
-                    if (GELU) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = OUT_F32 ? gelu_erf(v[j]) : gelu_fast(v[j]);
-                    }
+#endif
                     if (RES) {
                         ptx::mbar_wait(rbar, rphase);
                         rphase ^= 1;
@@ -423,6 +452,12 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
                                 ptx::tma_load_2d(rsrc, tmR, rbar, col_base + nc * CH + nh * 32, row0);
                             }
                         }
+                    }
+                    if (OUT_F32 || half == 0) {
+                        // the TMA store that last read this warp's staging buffer must have finished reading shared memory
+                        // (waited for here, after the TMEM read and the arithmetic of this chunk, not before them)
+                        if (lane == 0) ptx::tma_store_wait_read<0>();
+                        __syncwarp();
                     }
                     if (OUT_F32) {
 #pragma unroll
@@ -640,11 +675,7 @@ template <int BN, int STAGES, bool GELU, bool OUT_F32, bool RES, int CM, int TN 
 int launch_tc_variant(const GemmArgs* ga, int n, cudaStream_t s) {
     using L = SmemLayout<BN, STAGES, RES, U2>;
     auto kern = gemm_tc_kernel<BN, STAGES, GELU, OUT_F32, RES, CM, TN, U2>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        MRA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-        attr_set = true;
-    }
+    if (int e = ensure_smem_attr(reinterpret_cast<const void*>(kern), L::TOTAL)) return e;
     GroupMaps maps;
     EpiParams p;
     p.groups = n;
@@ -706,7 +737,7 @@ int launch_tc_variant(const GemmArgs* ga, int n, cudaStream_t s) {
         const long items = static_cast<long>(total) * p.ksplit;
         const int grid = items < sm_count() ? static_cast<int>(items) : sm_count();
         MRA_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), L::TOTAL, s, maps, p));
-        if (p.dbg & 8) {   // (single-CTA path; the paired paths print below)
+        if (MRA_GEMM_DBG(p) & 8) {   // (single-CTA path; the paired paths print below)
             unsigned long long t[8];
             cudaStreamSynchronize(s);
             cudaMemcpyFromSymbol(t, g_gemm_timing, sizeof(t));
@@ -731,7 +762,7 @@ int launch_tc_variant(const GemmArgs* ga, int n, cudaStream_t s) {
     cfg.attrs = at;
     cfg.numAttrs = 1;
     MRA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, p));
-    if (p.dbg & 8) {
+    if (MRA_GEMM_DBG(p) & 8) {
         unsigned long long t[8];
         cudaStreamSynchronize(s);
         cudaMemcpyFromSymbol(t, g_gemm_timing, sizeof(t));

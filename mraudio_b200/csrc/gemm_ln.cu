@@ -17,8 +17,20 @@
 //       pass B  normalise from registers, * gamma + beta -> fp32 and bf16 copies through swizzled staging + TMA stores
 // (An earlier 2-CTA version with 384 columns per CTA could not double-buffer TMEM and serialised main loop and
 //  epilogue: 92 us on the AO shape against 2 x 64 us unfused; see profiles/.)  Up to 4 grouped problems per launch.
+//
+// SPLIT = true: the residual stream is a PAIR of bf16 tensors (hi = bf16(y), lo = bf16(y - hi); hi + lo carries 16 mantissa
+// bits) instead of fp32 + a bf16 shadow: hi is at the same time the next GEMM's A operand, so a post-LayerNorm element costs
+// 4 B read + 4 B written instead of 4 + 6, the epilogue moves 64-column chunks (one 128-byte line per row and tensor) and
+// pass B needs one staging turnaround per block instead of three.  This is the form the inference forward uses.
 #include "common.h"
 #include "ptx.cuh"
+
+// timing experiments (MRA_LN_DEBUG) are compiled in only with -DMRA_INSTRUMENT (make INSTRUMENT=1)
+#ifdef MRA_INSTRUMENT
+#define MRA_LN_DBG(p) ((p).dbg)
+#else
+#define MRA_LN_DBG(p) 0
+#endif
 
 namespace mra {
 namespace {
@@ -61,7 +73,8 @@ struct LnCfg {
 constexpr int MAX_GROUPS = 4;
 
 struct LnMaps {
-    CUtensorMap a[MAX_GROUPS], b[MAX_GROUPS], r[MAX_GROUPS], c32[MAX_GROUPS], c16[MAX_GROUPS];
+    // r / c32: fp32 residual in / fp32 output (SPLIT: bf16 hi residual / bf16 lo output); rlo: bf16 lo residual (SPLIT only)
+    CUtensorMap a[MAX_GROUPS], b[MAX_GROUPS], r[MAX_GROUPS], rlo[MAX_GROUPS], c32[MAX_GROUPS], c16[MAX_GROUPS];
 };
 struct LnParams {
     const float* bias[MAX_GROUPS];
@@ -72,7 +85,10 @@ struct LnParams {
     int groups;
     int K;
     float eps;
-    int dbg;   // timing experiments only (MRA_LN_DEBUG): 1 = no residual, 2 = no cross-CTA exchange, 4 = no stores, 8 = clocks
+    int dbg;   // timing experiments only (MRA_LN_DEBUG, -DMRA_INSTRUMENT): 1 = no residual, 2 = no cross-CTA exchange,
+               // 4 = no stores, 8 = clocks, 16 = odd clusters start half a block period late (de-phases the store bursts)
+    int stagger_cycles;
+    int prefetch;   // > 0: the CTAs of column slice 0 prefetch the A tile `prefetch` K steps ahead into L2 (MRA_LN_PREFETCH)
 };
 
 __device__ unsigned long long g_ln_timing[16];   // MRA_LN_DEBUG & 8: cycles per epilogue phase (warp 2 / lane 0 of CTA 0)
@@ -109,7 +125,7 @@ __device__ __forceinline__ void decode_blk(const LnParams& p, int blk, int& g, i
     m_blk = blk - p.blk_start[g];
 }
 
-template <bool U2>
+template <bool U2, bool SPLIT>
 __global__ void __cluster_dims__(LnCfg<U2>::CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_ln_kernel(const __grid_constant__ LnMaps maps, const __grid_constant__ LnParams p) {
     using C = LnCfg<U2>;
@@ -145,6 +161,7 @@ gemm_ln_kernel(const __grid_constant__ LnMaps maps, const __grid_constant__ LnPa
             ptx::prefetch_tensormap(&maps.a[g]);
             ptx::prefetch_tensormap(&maps.b[g]);
             ptx::prefetch_tensormap(&maps.r[g]);
+            if (SPLIT) ptx::prefetch_tensormap(&maps.rlo[g]);
             ptx::prefetch_tensormap(&maps.c32[g]);
             ptx::prefetch_tensormap(&maps.c16[g]);
         }
@@ -179,6 +196,10 @@ gemm_ln_kernel(const __grid_constant__ LnMaps maps, const __grid_constant__ LnPa
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
+            if ((MRA_LN_DBG(p) & 16) && (cluster_id & 1)) {   // experiment: de-phase odd clusters
+                const long long t_end = clock64() + p.stagger_cycles;
+                while (clock64() < t_end) {}
+            }
             int stage = 0;
             uint32_t phase = 0;
             for (int blk = cluster_id; blk < total_blks; blk += num_clusters) {
@@ -186,10 +207,14 @@ gemm_ln_kernel(const __grid_constant__ LnMaps maps, const __grid_constant__ LnPa
                 decode_blk(p, blk, g, m_blk);
                 const CUtensorMap* tmA = &maps.a[g];
                 const CUtensorMap* tmB = &maps.b[g];
+                const int a_row = m_blk * C::ROWS + static_cast<int>(mhalf) * BM;
                 for (int kb = 0; kb < k_blocks; ++kb) {
+                    // The A rows usually come from DRAM (the tensor the previous kernel wrote is larger than L2) while the ring
+                    // holds only 3 slabs in flight: one of the three CTAs that read these rows pulls them into L2 ahead of time
+                    if (p.prefetch > 0 && nidx == 0 && kb + p.prefetch < k_blocks && ((kb + p.prefetch) & 1) == 0)
+                        ptx::tma_prefetch_2d(tmA, (kb + p.prefetch) * BK, a_row);   // (256-byte L2 promotion: every 2nd slab)
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* st = smem + stage * STAGE_BYTES;
-                    const int a_row = m_blk * C::ROWS + static_cast<int>(mhalf) * BM;
                     if (U2) {
                         // both pair members' boxes complete on the leader's barrier, which expects the bytes of the pair
                         const uint32_t lead_bar = mapa(ptx::smem_u32(&full_bar[stage]), lead);
@@ -251,13 +276,13 @@ gemm_ln_kernel(const __grid_constant__ LnMaps maps, const __grid_constant__ LnPa
         uint32_t rphase = 0;
         const int row_in_tile = quad * 32 + lane;
         const uint32_t stats_local = ptx::smem_u32(stats);
-        constexpr int NC = NSEG / 32;         // 4 chunks of 32 columns
         int cur_g = -1;
         int iter = 0;
         for (int blk = cluster_id; blk < total_blks; blk += num_clusters, ++iter) {
             int g, m_blk;
             decode_blk(p, blk, g, m_blk);
             const CUtensorMap* tmR = &maps.r[g];
+            const CUtensorMap* tmRlo = &maps.rlo[g];
             const CUtensorMap* tmC32 = &maps.c32[g];
             const CUtensorMap* tmC16 = &maps.c16[g];
             const int Mg = p.M[g];
@@ -265,16 +290,23 @@ gemm_ln_kernel(const __grid_constant__ LnMaps maps, const __grid_constant__ LnPa
             const int row0 = m_blk * C::ROWS + static_cast<int>(mhalf) * BM + quad * 32;
             const int col0 = seg * NSEG;
             const int slot = iter & 1;
-            const bool no_res = p.dbg & 1, no_xchg = p.dbg & 2, no_store = p.dbg & 4;
-            const bool prof = (p.dbg & 8) && blockIdx.x == 0 && ew == 0 && lane == 0;
+            const bool no_res = MRA_LN_DBG(p) & 1, no_xchg = MRA_LN_DBG(p) & 2, no_store = MRA_LN_DBG(p) & 4;
+            const bool prof = (MRA_LN_DBG(p) & 8) && blockIdx.x == 0 && ew == 0 && lane == 0;
             long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
             if (prof) t0 = clock64();
             if (lane == 0 && !no_res) {
-                // first two residual chunks: issued before the accumulator is ready (overlaps the main loop)
+                // first residual chunk(s): issued before the accumulator is ready (overlaps the main loop)
+                if constexpr (SPLIT) {
+                    // 64 columns: hi box -> buffer 0, lo box -> buffer 1, both complete on rbar[0]
+                    ptx::mbar_arrive_expect_tx(&rbar[0], 2 * CHUNK);
+                    ptx::tma_load_2d(my, tmR, &rbar[0], col0, row0);
+                    ptx::tma_load_2d(my + CHUNK, tmRlo, &rbar[0], col0, row0);
+                } else {
 #pragma unroll
-                for (int b = 0; b < 2; ++b) {
-                    ptx::mbar_arrive_expect_tx(&rbar[b], CHUNK);
-                    ptx::tma_load_2d(my + b * CHUNK, tmR, &rbar[b], col0 + b * 32, row0);
+                    for (int b = 0; b < 2; ++b) {
+                        ptx::mbar_arrive_expect_tx(&rbar[b], CHUNK);
+                        ptx::tma_load_2d(my + b * CHUNK, tmR, &rbar[b], col0 + b * 32, row0);
+                    }
                 }
             }
             if (g != cur_g) {
@@ -297,44 +329,87 @@ gemm_ln_kernel(const __grid_constant__ LnMaps maps, const __grid_constant__ LnPa
             ptx::tc_fence_after();
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * NCTA + member * NSEG;
             // ---- pass A: x = acc + bias + residual, kept in registers; row statistics
-            float v[NC][32];
+            float v[NSEG];
             float sum = 0.f, sumsq = 0.f;
+            auto release_accumulator = [&]() {
+                // last TMEM read of this block by this warp: the MMA warp may reuse the accumulator stage
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (U2) ptx::mbar_arrive_cluster(mapa(ptx::smem_u32(&tempty_bar[acc]), lead));   // the pair leader's barrier
+                    else ptx::mbar_arrive(&tempty_bar[acc]);
+                }
+            };
+            if constexpr (SPLIT) {
 #pragma unroll
-            for (int c = 0; c < NC; ++c) {
-                const int b = c & 1;
-                uint32_t r[32];
-                ptx::tmem_ld_32x32b_x32(t_row + c * 32, r);
-                ptx::tmem_ld_wait();
-                if (c == NC - 1) {
-                    // last TMEM read of this block by this warp: the MMA warp may reuse the accumulator stage
-                    ptx::tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) {
-                        if (U2) ptx::mbar_arrive_cluster(mapa(ptx::smem_u32(&tempty_bar[acc]), lead));   // the pair leader's barrier
-                        else ptx::mbar_arrive(&tempty_bar[acc]);
+                for (int cc = 0; cc < NSEG / 64; ++cc) {
+                    uint32_t r[2][32];
+                    ptx::tmem_ld_32x32b_x32(t_row + cc * 64, r[0]);
+                    ptx::tmem_ld_32x32b_x32(t_row + cc * 64 + 32, r[1]);
+                    ptx::tmem_ld_wait();
+                    if (cc == NSEG / 64 - 1) release_accumulator();
+                    if (!no_res) {
+                        ptx::mbar_wait(&rbar[0], rphase & 1u);
+                        rphase ^= 1u;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {   // 16-byte unit j of the row's 128-byte line: columns 8 j .. 8 j + 7 of the chunk
+                        const uint4 hi = ptx::ld_shared_v4(my_s + swz(lane, j));
+                        const uint4 lo = ptx::ld_shared_v4(my_s + CHUNK + swz(lane, j));
+                        const float4 b0 = *reinterpret_cast<const float4*>(bias + cc * 64 + 8 * j);
+                        const float4 b1 = *reinterpret_cast<const float4*>(bias + cc * 64 + 8 * j + 4);
+                        const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
+                        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int idx = 8 * j + 2 * e;   // column inside the 64-column chunk
+                            const float a0 = __uint_as_float(r[idx >> 5][idx & 31]), a1 = __uint_as_float(r[(idx + 1) >> 5][(idx + 1) & 31]);
+                            const float x0 = a0 + bb[2 * e] + (ptx::bf16lo(hw[e]) + ptx::bf16lo(lw[e]));
+                            const float x1 = a1 + bb[2 * e + 1] + (ptx::bf16hi(hw[e]) + ptx::bf16hi(lw[e]));
+                            sum += x0 + x1;
+                            sumsq = fmaf(x0, x0, fmaf(x1, x1, sumsq));
+                            v[cc * 64 + idx] = x0;
+                            v[cc * 64 + idx + 1] = x1;
+                        }
+                    }
+                    __syncwarp();   // every lane has read the residual buffers: refill them
+                    if (lane == 0 && cc + 1 < NSEG / 64 && !no_res) {
+                        ptx::mbar_arrive_expect_tx(&rbar[0], 2 * CHUNK);
+                        ptx::tma_load_2d(my, tmR, &rbar[0], col0 + (cc + 1) * 64, row0);
+                        ptx::tma_load_2d(my + CHUNK, tmRlo, &rbar[0], col0 + (cc + 1) * 64, row0);
                     }
                 }
-                if (!no_res) {
-                    ptx::mbar_wait(&rbar[b], (rphase >> b) & 1u);
-                    rphase ^= 1u << b;
-                }
-                const uint32_t rs = my_s + b * CHUNK;
+            } else {
+                constexpr int NC = NSEG / 32;         // 4 chunks of 32 columns
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 x = ptx::ld_shared_v4f(rs + swz(lane, j));
-                    const float4 bv = *reinterpret_cast<const float4*>(bias + c * 32 + 4 * j);
-                    const float v0 = __uint_as_float(r[4 * j]) + bv.x + x.x;
-                    const float v1 = __uint_as_float(r[4 * j + 1]) + bv.y + x.y;
-                    const float v2 = __uint_as_float(r[4 * j + 2]) + bv.z + x.z;
-                    const float v3 = __uint_as_float(r[4 * j + 3]) + bv.w + x.w;
-                    sum += (v0 + v1) + (v2 + v3);
-                    sumsq = fmaf(v0, v0, fmaf(v1, v1, fmaf(v2, v2, fmaf(v3, v3, sumsq))));
-                    v[c][4 * j] = v0; v[c][4 * j + 1] = v1; v[c][4 * j + 2] = v2; v[c][4 * j + 3] = v3;
-                }
-                __syncwarp();   // every lane has read the residual buffer: refill it
-                if (lane == 0 && c + 2 < NC && !no_res) {
-                    ptx::mbar_arrive_expect_tx(&rbar[b], CHUNK);
-                    ptx::tma_load_2d(my + b * CHUNK, tmR, &rbar[b], col0 + (c + 2) * 32, row0);
+                for (int c = 0; c < NC; ++c) {
+                    const int b = c & 1;
+                    uint32_t r[32];
+                    ptx::tmem_ld_32x32b_x32(t_row + c * 32, r);
+                    ptx::tmem_ld_wait();
+                    if (c == NC - 1) release_accumulator();
+                    if (!no_res) {
+                        ptx::mbar_wait(&rbar[b], (rphase >> b) & 1u);
+                        rphase ^= 1u << b;
+                    }
+                    const uint32_t rs = my_s + b * CHUNK;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 x = ptx::ld_shared_v4f(rs + swz(lane, j));
+                        const float4 bv = *reinterpret_cast<const float4*>(bias + c * 32 + 4 * j);
+                        const float v0 = __uint_as_float(r[4 * j]) + bv.x + x.x;
+                        const float v1 = __uint_as_float(r[4 * j + 1]) + bv.y + x.y;
+                        const float v2 = __uint_as_float(r[4 * j + 2]) + bv.z + x.z;
+                        const float v3 = __uint_as_float(r[4 * j + 3]) + bv.w + x.w;
+                        sum += (v0 + v1) + (v2 + v3);
+                        sumsq = fmaf(v0, v0, fmaf(v1, v1, fmaf(v2, v2, fmaf(v3, v3, sumsq))));
+                        v[c * 32 + 4 * j] = v0; v[c * 32 + 4 * j + 1] = v1; v[c * 32 + 4 * j + 2] = v2; v[c * 32 + 4 * j + 3] = v3;
+                    }
+                    __syncwarp();   // every lane has read the residual buffer: refill it
+                    if (lane == 0 && c + 2 < NC && !no_res) {
+                        ptx::mbar_arrive_expect_tx(&rbar[b], CHUNK);
+                        ptx::tma_load_2d(my + b * CHUNK, tmR, &rbar[b], col0 + (c + 2) * 32, row0);
+                    }
                 }
             }
             if (prof) t2 = clock64();
@@ -373,37 +448,77 @@ gemm_ln_kernel(const __grid_constant__ LnMaps maps, const __grid_constant__ LnPa
                 rstd = rsqrtf(var + p.eps);
             }
             if (prof) t3 = clock64();
-            // ---- pass B: normalise from registers, scale / shift, write fp32 + bf16 copies
-            //      staging: buffer 1 = fp32 chunk (32 columns), buffer 0 = bf16 chunk (64 columns, stored every 2nd chunk)
+            // ---- pass B: normalise from registers, scale / shift, write the output copies
             const float nm = -mean * rstd;
-            uint8_t* o16 = my;
-            uint8_t* o32 = my + CHUNK;
-            const uint32_t o16_s = my_s, o32_s = my_s + CHUNK;
+            if constexpr (SPLIT) {
+                // 64-column chunks: buffer 0 = hi (bf16(y)), buffer 1 = lo (bf16(y - hi)); one 128-byte line per row each
 #pragma unroll
-            for (int c = 0; c < NC; ++c) {
-                if (lane == 0) ptx::tma_store_wait_read<0>();   // the stores that last read the staging buffers are done
-                __syncwarp();
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 gv = *reinterpret_cast<const float4*>(gamma + c * 32 + 4 * j);
-                    const float4 bv = *reinterpret_cast<const float4*>(beta + c * 32 + 4 * j);
-                    const float y0 = fmaf(fmaf(v[c][4 * j], rstd, nm), gv.x, bv.x);
-                    const float y1 = fmaf(fmaf(v[c][4 * j + 1], rstd, nm), gv.y, bv.y);
-                    const float y2 = fmaf(fmaf(v[c][4 * j + 2], rstd, nm), gv.z, bv.z);
-                    const float y3 = fmaf(fmaf(v[c][4 * j + 3], rstd, nm), gv.w, bv.w);
-                    ptx::st_shared_v4f(o32_s + swz(lane, j), y0, y1, y2, y3);
-                    // 8 bytes of bf16 at column 4 j of this chunk: 16-byte unit (c & 1) * 4 + j / 2, half j & 1
-                    ptx::st_shared_v2(o16_s + swz(lane, (c & 1) * 4 + (j >> 1)) + (j & 1) * 8, ptx::pack_bf16x2(y0, y1),
-                                      ptx::pack_bf16x2(y2, y3));
-                }
-                ptx::fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) {
-                    if (row0 < Mg && !no_store) {
-                        ptx::tma_store_2d(tmC32, o32, col0 + c * 32, row0);
-                        if (c & 1) ptx::tma_store_2d(tmC16, o16, col0 + (c - 1) * 32, row0);
+                for (int cc = 0; cc < NSEG / 64; ++cc) {
+                    if (cc > 0) {   // (chunk 0: the buffers held residual chunks whose loads were waited for above)
+                        if (lane == 0) ptx::tma_store_wait_read<0>();
+                        __syncwarp();
                     }
-                    ptx::tma_store_commit();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 g0 = *reinterpret_cast<const float4*>(gamma + cc * 64 + 8 * j);
+                        const float4 g1 = *reinterpret_cast<const float4*>(gamma + cc * 64 + 8 * j + 4);
+                        const float4 e0 = *reinterpret_cast<const float4*>(beta + cc * 64 + 8 * j);
+                        const float4 e1 = *reinterpret_cast<const float4*>(beta + cc * 64 + 8 * j + 4);
+                        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                        const float ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+                        uint32_t hw[4], lw[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float y0 = fmaf(fmaf(v[cc * 64 + 8 * j + 2 * e], rstd, nm), gg[2 * e], ee[2 * e]);
+                            const float y1 = fmaf(fmaf(v[cc * 64 + 8 * j + 2 * e + 1], rstd, nm), gg[2 * e + 1], ee[2 * e + 1]);
+                            hw[e] = ptx::pack_bf16x2(y0, y1);
+                            lw[e] = ptx::pack_bf16x2(y0 - ptx::bf16lo(hw[e]), y1 - ptx::bf16hi(hw[e]));
+                        }
+                        ptx::st_shared_v4(my_s + swz(lane, j), hw[0], hw[1], hw[2], hw[3]);
+                        ptx::st_shared_v4(my_s + CHUNK + swz(lane, j), lw[0], lw[1], lw[2], lw[3]);
+                    }
+                    ptx::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (row0 < Mg && !no_store) {
+                            ptx::tma_store_2d(tmC16, my, col0 + cc * 64, row0);
+                            ptx::tma_store_2d(tmC32, my + CHUNK, col0 + cc * 64, row0);
+                        }
+                        ptx::tma_store_commit();
+                    }
+                }
+            } else {
+                //      staging: buffer 1 = fp32 chunk (32 columns), buffer 0 = bf16 chunk (64 columns, stored every 2nd chunk)
+                constexpr int NC = NSEG / 32;
+                uint8_t* o16 = my;
+                uint8_t* o32 = my + CHUNK;
+                const uint32_t o16_s = my_s, o32_s = my_s + CHUNK;
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    if (lane == 0) ptx::tma_store_wait_read<0>();   // the stores that last read the staging buffers are done
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 gv = *reinterpret_cast<const float4*>(gamma + c * 32 + 4 * j);
+                        const float4 bv = *reinterpret_cast<const float4*>(beta + c * 32 + 4 * j);
+                        const float y0 = fmaf(fmaf(v[c * 32 + 4 * j], rstd, nm), gv.x, bv.x);
+                        const float y1 = fmaf(fmaf(v[c * 32 + 4 * j + 1], rstd, nm), gv.y, bv.y);
+                        const float y2 = fmaf(fmaf(v[c * 32 + 4 * j + 2], rstd, nm), gv.z, bv.z);
+                        const float y3 = fmaf(fmaf(v[c * 32 + 4 * j + 3], rstd, nm), gv.w, bv.w);
+                        ptx::st_shared_v4f(o32_s + swz(lane, j), y0, y1, y2, y3);
+                        // 8 bytes of bf16 at column 4 j of this chunk: 16-byte unit (c & 1) * 4 + j / 2, half j & 1
+                        ptx::st_shared_v2(o16_s + swz(lane, (c & 1) * 4 + (j >> 1)) + (j & 1) * 8, ptx::pack_bf16x2(y0, y1),
+                                          ptx::pack_bf16x2(y2, y3));
+                    }
+                    ptx::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (row0 < Mg && !no_store) {
+                            ptx::tma_store_2d(tmC32, o32, col0 + c * 32, row0);
+                            if (c & 1) ptx::tma_store_2d(tmC16, o16, col0 + (c - 1) * 32, row0);
+                        }
+                        ptx::tma_store_commit();
+                    }
                 }
             }
             if (prof) t4 = clock64();
@@ -428,39 +543,48 @@ gemm_ln_kernel(const __grid_constant__ LnMaps maps, const __grid_constant__ LnPa
     }
 }
 
-template <bool U2>
+template <bool U2, bool SPLIT>
 static int launch_gemm_ln_variant(const GemmLnArgs* ga, int n, float eps, cudaStream_t s) {
     using C = LnCfg<U2>;
-    auto kern = gemm_ln_kernel<U2>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        MRA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_TOTAL));
-        attr_set = true;
-    }
+    auto kern = gemm_ln_kernel<U2, SPLIT>;
+    if (int e = ensure_smem_attr(reinterpret_cast<const void*>(kern), C::SMEM_TOTAL)) return e;
     LnMaps maps;
     LnParams p;
     p.groups = n;
     p.K = ga[0].K;
     p.eps = eps;
     static const int dbg = [] { const char* e = getenv("MRA_LN_DEBUG"); return e ? atoi(e) : 0; }();
+    static const int stagger = [] { const char* e = getenv("MRA_LN_STAGGER"); return e ? atoi(e) : 0; }();
     p.dbg = dbg;
+    p.stagger_cycles = stagger;
+    static const int prefetch = [] { const char* e = getenv("MRA_LN_PREFETCH"); return e ? atoi(e) : 0; }();
+    p.prefetch = prefetch;
     int total = 0;
     for (int g = 0; g < MAX_GROUPS; ++g) {
         if (g < n) {
             const GemmLnArgs& a = ga[g];
             MRA_REQUIRE(a.M > 0 && a.K > 0 && a.K % 8 == 0 && a.K == ga[0].K, "fused GEMM+LayerNorm: bad / mismatching K");
-            MRA_REQUIRE(a.A && a.W && a.residual && a.gamma && a.beta && a.y32 && a.y16, "fused GEMM+LayerNorm: NULL operand");
+            MRA_REQUIRE(a.A && a.W && a.residual && a.gamma && a.beta && a.y16, "fused GEMM+LayerNorm: NULL operand");
+            MRA_REQUIRE(SPLIT ? (a.res_lo && a.y_lo) : (a.y32 != nullptr), "fused GEMM+LayerNorm: NULL residual / output operand");
             if (int e = get_tensor_map(a.A, a.M, a.K, a.lda, BM, BK, 2, &maps.a[g])) return e;
             if (int e = get_tensor_map(a.W, NTOT, a.K, a.ldw, C::B_ROWS, BK, 2, &maps.b[g])) return e;
-            if (int e = get_tensor_map(a.residual, a.M, NTOT, a.ldr, 32, 32, 4, &maps.r[g])) return e;
-            if (int e = get_tensor_map(a.y32, a.M, NTOT, a.ldy32, 32, 32, 4, &maps.c32[g])) return e;
+            if (SPLIT) {
+                if (int e = get_tensor_map(a.residual, a.M, NTOT, a.ldr, 32, 64, 2, &maps.r[g])) return e;
+                if (int e = get_tensor_map(a.res_lo, a.M, NTOT, a.ldr, 32, 64, 2, &maps.rlo[g])) return e;
+                if (int e = get_tensor_map(a.y_lo, a.M, NTOT, a.ldy16, 32, 64, 2, &maps.c32[g])) return e;
+            } else {
+                if (int e = get_tensor_map(a.residual, a.M, NTOT, a.ldr, 32, 32, 4, &maps.r[g])) return e;
+                maps.rlo[g] = maps.r[g];
+                if (int e = get_tensor_map(a.y32, a.M, NTOT, a.ldy32, 32, 32, 4, &maps.c32[g])) return e;
+            }
             if (int e = get_tensor_map(a.y16, a.M, NTOT, a.ldy16, 32, 64, 2, &maps.c16[g])) return e;
             p.bias[g] = a.bias; p.gamma[g] = a.gamma; p.beta[g] = a.beta;
             p.M[g] = a.M;
             p.blk_start[g] = total;
             total += (a.M + C::ROWS - 1) / C::ROWS;
         } else {
-            maps.a[g] = maps.a[0]; maps.b[g] = maps.b[0]; maps.r[g] = maps.r[0]; maps.c32[g] = maps.c32[0]; maps.c16[g] = maps.c16[0];
+            maps.a[g] = maps.a[0]; maps.b[g] = maps.b[0]; maps.r[g] = maps.r[0]; maps.rlo[g] = maps.rlo[0];
+            maps.c32[g] = maps.c32[0]; maps.c16[g] = maps.c16[0];
             p.bias[g] = p.gamma[g] = p.beta[g] = nullptr;
             p.M[g] = 0;
             p.blk_start[g] = total;
@@ -488,16 +612,18 @@ static int launch_gemm_ln_variant(const GemmLnArgs* ga, int n, float eps, cudaSt
     if (clusters > total) clusters = total;
     kern<<<C::CLUSTER * clusters, NUM_THREADS, C::SMEM_TOTAL, s>>>(maps, p);
     MRA_CHECK_CUDA(cudaGetLastError());
+#ifdef MRA_INSTRUMENT
     if (dbg & 8) {
         unsigned long long t[16];
         cudaStreamSynchronize(s);
         cudaMemcpyFromSymbol(t, g_ln_timing, sizeof(t));
         const double nt = t[5] ? double(t[5]) : 1.0;
-        fprintf(stderr, "[gemm_ln U2=%d timing, cycles/tile over %llu tiles] wait-mainloop %.0f | pass1 %.0f | exchange %.0f | pass2 %.0f | drain %.0f\n",
-                int(U2), t[5], t[0] / nt, t[1] / nt, t[2] / nt, t[3] / nt, t[4] / nt);
+        fprintf(stderr, "[gemm_ln U2=%d SPLIT=%d timing, cycles/tile over %llu tiles] wait-mainloop %.0f | pass1 %.0f | exchange %.0f | pass2 %.0f | drain %.0f\n",
+                int(U2), int(SPLIT), t[5], t[0] / nt, t[1] / nt, t[2] / nt, t[3] / nt, t[4] / nt);
         unsigned long long z[16] = {0};
         cudaMemcpyToSymbol(g_ln_timing, z, sizeof(z));
     }
+#endif
     return 0;
 }
 
@@ -505,9 +631,13 @@ static int launch_gemm_ln_variant(const GemmLnArgs* ga, int n, float eps, cudaSt
 
 int launch_gemm_ln_grouped(const GemmLnArgs* ga, int n, float eps, cudaStream_t s) {
     MRA_REQUIRE(n >= 1 && n <= MAX_GROUPS, "fused GEMM+LayerNorm takes 1..%d problems, got %d", MAX_GROUPS, n);
+    const bool split = ga[0].res_lo != nullptr;
+    for (int g = 1; g < n; ++g)
+        MRA_REQUIRE((ga[g].res_lo != nullptr) == split, "fused GEMM+LayerNorm: grouped problems must share the residual form");
     // 1 (default) = 6-CTA clusters with 2-CTA MMAs, 0 = 3-CTA clusters with single-CTA MMAs (A/B runs, tests)
     static const bool u2 = [] { const char* e = getenv("MRA_LN_U2"); return e == nullptr || atoi(e) != 0; }();
-    return u2 ? launch_gemm_ln_variant<true>(ga, n, eps, s) : launch_gemm_ln_variant<false>(ga, n, eps, s);
+    if (split) return u2 ? launch_gemm_ln_variant<true, true>(ga, n, eps, s) : launch_gemm_ln_variant<false, true>(ga, n, eps, s);
+    return u2 ? launch_gemm_ln_variant<true, false>(ga, n, eps, s) : launch_gemm_ln_variant<false, false>(ga, n, eps, s);
 }
 
 }  // namespace mra

@@ -21,6 +21,7 @@ struct mra_qformer {
     int gemm_impl = MRA_GEMM_IMPL_TCGEN05;
     cudaEvent_t layer_done[MRA_MAX_LAYERS] = {};   // optional: recorded by the backward when a layer's gradients are final
     bool fuse_ln = true;   // Linear + residual + LayerNorm in one cluster kernel (MRA_NO_FUSED_LN=1 disables: A/B runs)
+    bool split_res = true; // with fuse_ln: residual stream as a bf16 (hi, lo) pair instead of fp32 (MRA_SPLIT_RESIDUAL=0 disables)
     // optional per-category device timing (CUDA events on the caller's stream), see mra_qformer_profile_*
     int profile_mode = MRA_PROFILE_OFF;
     struct Span { int cat; cudaEvent_t a, b; };
@@ -60,6 +61,10 @@ struct LayerBufs {
 struct Workspace {
     float* x32;             // residual stream: layer input (fp32)
     float* a32;             // residual stream: attention output (fp32)
+    // split residual stream (inference with the fused GEMM+LayerNorm): value = hi + lo with hi = the bf16 GEMM operand
+    // (xb / ab) and lo = bf16(value - hi) kept here; these alias the first half of x32 / a32
+    __nv_bfloat16* xlo;
+    __nv_bfloat16* alo;
     float* pre_e;           // embedding sums before the embedding LayerNorm (saved only)
     __nv_bfloat16* kv;      // [rows*Nk, ncross*2H]
     float* self_mask;       // [rows, S]
@@ -82,6 +87,8 @@ Workspace carve(const mra_qformer* h, int rows, int T, int Nk, uint32_t flags, v
     Workspace w;
     w.x32 = reinterpret_cast<float*>(take(Mtot * H * 4));
     w.a32 = reinterpret_cast<float*>(take(Mtot * H * 4));
+    w.xlo = reinterpret_cast<__nv_bfloat16*>(w.x32);
+    w.alo = reinterpret_cast<__nv_bfloat16*>(w.a32);
     w.pre_e = save ? reinterpret_cast<float*>(take(Mtot * H * 4)) : nullptr;
     w.kv = reinterpret_cast<__nv_bfloat16*>(take(static_cast<size_t>(rows) * Nk * h->n_cross * 2 * H * 2));
     w.self_mask = reinterpret_cast<float*>(take(static_cast<size_t>(rows) * (c.num_query + T) * 4));
@@ -183,6 +190,7 @@ extern "C" int mra_qformer_create(const mra_qformer_config* cfg, mra_qformer_t**
     const char* impl = getenv("MRA_GEMM_IMPL");
     if (impl && std::string(impl) == "simt") h->gemm_impl = MRA_GEMM_IMPL_SIMT_DEBUG;
     if (getenv("MRA_NO_FUSED_LN")) h->fuse_ln = false;
+    if (const char* e = getenv("MRA_SPLIT_RESIDUAL")) h->split_res = atoi(e) != 0;
     *out = h;
     return 0;
 }
@@ -348,11 +356,18 @@ int forward_multi(int n, mra_qformer_t* const* hs, const mra_qformer_io* const* 
     };
     // Linear + residual + LayerNorm in one kernel (gemm_ln.cu) whenever the pre-LayerNorm sums need not be kept
     const bool fuse_ln = !save && H == 768 && h0->gemm_impl == MRA_GEMM_IMPL_TCGEN05 && h0->fuse_ln;
+    // split residual stream: every post-LayerNorm tensor is a bf16 (hi, lo) pair, hi doubling as the next GEMM operand
+    const bool split = fuse_ln && h0->split_res;
     GemmLnArgs gl[4];
     int ngl = 0;
-    auto add_gl = [&](const void* A, int64_t lda, const void* Wt, int64_t ldw, const float* bias, const float* res, const float* g,
-                      const float* b, float* y32, void* y16, int M, int K) {
-        if (M > 0) gl[ngl++] = GemmLnArgs{A, lda, Wt, ldw, bias, res, H, g, b, y32, H, y16, H, M, K};
+    // residual = res32 (fp32) or, in split form, res_hi + res_lo; outputs y32 + y16 or y16 (hi) + y_lo
+    auto add_gl = [&](const void* A, int64_t lda, const void* Wt, int64_t ldw, const float* bias, const float* res32,
+                      const void* res_hi, const void* res_lo, const float* g, const float* b, float* y32, void* y16, void* y_lo,
+                      int M, int K) {
+        if (M <= 0) return;
+        GemmLnArgs a{A, lda, Wt, ldw, bias, split ? res_hi : static_cast<const void*>(res32), H, g, b, split ? nullptr : y32, H, y16, H, M, K};
+        if (split) { a.res_lo = res_lo; a.y_lo = y_lo; }
+        gl[ngl++] = a;
     };
     auto flush_gl = [&]() -> int {
         if (ngl == 0) return 0;
@@ -389,8 +404,8 @@ int forward_multi(int n, mra_qformer_t* const* hs, const mra_qformer_io* const* 
         const auto& W = x.h->w;
         span_begin(MRA_CAT_OTHER);
         MRA_TRY(launch_embed_layernorm(x.io->query_embeds, x.io->q_rows, x.io->input_ids, W.word_emb, W.pos_emb, W.ln_e_g,
-                                       W.ln_e_b, x.ws.x32, x.ws.layer[0].xb, x.ws.pre_e, x.rows, Nq, x.T, H, x.h->cfg.vocab,
-                                       c.ln_eps, s));
+                                       W.ln_e_b, split ? nullptr : x.ws.x32, x.ws.layer[0].xb, split ? x.ws.xlo : nullptr,
+                                       x.ws.pre_e, x.rows, Nq, x.T, H, x.h->cfg.vocab, c.ln_eps, s));
         span_end();
         ++launches;
         if (x.io->attn_mask) {
@@ -433,7 +448,8 @@ int forward_multi(int n, mra_qformer_t* const* hs, const mra_qformer_io* const* 
             const auto& L = cx[i].h->w.layer[l];
             const LayerBufs& B = cx[i].ws.layer[l];
             if (fuse_ln) {
-                add_gl(B.ctx, H, L.w_ao, H, L.b_ao, cx[i].ws.x32, L.ln_a_g, L.ln_a_b, cx[i].ws.a32, B.ab, cx[i].Mtot, H);
+                add_gl(B.ctx, H, L.w_ao, H, L.b_ao, cx[i].ws.x32, B.xb, cx[i].ws.xlo, L.ln_a_g, L.ln_a_b, cx[i].ws.a32, B.ab,
+                       cx[i].ws.alo, cx[i].Mtot, H);
             } else {
                 add(B.ctx, H, L.w_ao, H, L.b_ao, cx[i].ws.x32, H, B.pre_a, H, cx[i].Mtot, H, H, 0, 1);
                 add_ln(B.pre_a, L.ln_a_g, L.ln_a_b, cx[i].ws.a32, B.ab, cx[i].Mtot);
@@ -466,7 +482,8 @@ int forward_multi(int n, mra_qformer_t* const* hs, const mra_qformer_io* const* 
                 const auto& L = cx[i].h->w.layer[l];
                 const LayerBufs& B = cx[i].ws.layer[l];
                 if (fuse_ln) {
-                    add_gl(B.cctx, H, L.w_co, H, L.b_co, cx[i].ws.a32, L.ln_c_g, L.ln_c_b, cx[i].ws.a32, B.ab2, cx[i].Mq, H);
+                    add_gl(B.cctx, H, L.w_co, H, L.b_co, cx[i].ws.a32, B.ab, cx[i].ws.alo, L.ln_c_g, L.ln_c_b, cx[i].ws.a32, B.ab2,
+                           cx[i].ws.alo, cx[i].Mq, H);
                 } else {
                     add(B.cctx, H, L.w_co, H, L.b_co, cx[i].ws.a32, H, B.pre_c, H, cx[i].Mq, H, H, 0, 1);
                     add_ln(B.pre_c, L.ln_c_g, L.ln_c_b, cx[i].ws.a32, B.ab2, cx[i].Mq);
@@ -511,10 +528,11 @@ int forward_multi(int n, mra_qformer_t* const* hs, const mra_qformer_io* const* 
             __nv_bfloat16* xb_next = cx[i].ws.layer[l + 1].xb;
             const size_t o = static_cast<size_t>(cx[i].Mq) * H, oi = static_cast<size_t>(cx[i].Mq) * I;
             if (fuse_ln) {
-                add_gl(B.inter, I, L.w_fq2, I, L.b_fq2, cx[i].ws.a32, L.ln_fq_g, L.ln_fq_b, cx[i].ws.x32, xb_next, cx[i].Mq, I);
+                add_gl(B.inter, I, L.w_fq2, I, L.b_fq2, cx[i].ws.a32, cross ? B.ab2 : B.ab, cx[i].ws.alo, L.ln_fq_g, L.ln_fq_b,
+                       cx[i].ws.x32, xb_next, cx[i].ws.xlo, cx[i].Mq, I);
                 if (text_on[i])
-                    add_gl(B.inter + oi, I, L.w_ft2, I, L.b_ft2, cx[i].ws.a32 + o, L.ln_ft_g, L.ln_ft_b, cx[i].ws.x32 + o,
-                           xb_next + o, cx[i].Mt, I);
+                    add_gl(B.inter + oi, I, L.w_ft2, I, L.b_ft2, cx[i].ws.a32 + o, B.ab + o, cx[i].ws.alo + o, L.ln_ft_g, L.ln_ft_b,
+                           cx[i].ws.x32 + o, xb_next + o, cx[i].ws.xlo + o, cx[i].Mt, I);
             } else {
                 add(B.inter, I, L.w_fq2, I, L.b_fq2, cx[i].ws.a32, H, B.pre_f, H, cx[i].Mq, H, I, 0, 1);
                 add_ln(B.pre_f, L.ln_fq_g, L.ln_fq_b, cx[i].ws.x32, xb_next, cx[i].Mq);
@@ -531,8 +549,16 @@ int forward_multi(int n, mra_qformer_t* const* hs, const mra_qformer_io* const* 
             if (cx[i].Mt > 0 && !text_on[i] && cx[i].io->last_hidden) {
                 // dead last-layer text FFN: keep last_hidden well-defined by passing the attention output through
                 const size_t o = static_cast<size_t>(cx[i].Mq) * H;
-                MRA_CHECK_CUDA(cudaMemcpyAsync(cx[i].ws.x32 + o, cx[i].ws.a32 + o, static_cast<size_t>(cx[i].Mt) * H * 4,
-                                               cudaMemcpyDeviceToDevice, s));
+                if (split) {
+                    MRA_CHECK_CUDA(cudaMemcpyAsync(cx[i].ws.layer[l + 1].xb + o, cx[i].ws.layer[l].ab + o,
+                                                   static_cast<size_t>(cx[i].Mt) * H * 2, cudaMemcpyDeviceToDevice, s));
+                    MRA_CHECK_CUDA(cudaMemcpyAsync(cx[i].ws.xlo + o, cx[i].ws.alo + o, static_cast<size_t>(cx[i].Mt) * H * 2,
+                                                   cudaMemcpyDeviceToDevice, s));
+                    ++launches;
+                } else {
+                    MRA_CHECK_CUDA(cudaMemcpyAsync(cx[i].ws.x32 + o, cx[i].ws.a32 + o, static_cast<size_t>(cx[i].Mt) * H * 4,
+                                                   cudaMemcpyDeviceToDevice, s));
+                }
                 ++launches;
             }
         }
@@ -541,7 +567,12 @@ int forward_multi(int n, mra_qformer_t* const* hs, const mra_qformer_io* const* 
     for (int i = 0; i < n; ++i) {
         if (cx[i].io->last_hidden) {
             span_begin(MRA_CAT_OTHER);
-            MRA_TRY(launch_gather_last_hidden(cx[i].ws.x32, cx[i].io->last_hidden, cx[i].rows, Nq, cx[i].T, H, s));
+            if (split) {
+                MRA_TRY(launch_gather_last_hidden_split(cx[i].ws.layer[c.layers].xb, cx[i].ws.xlo, cx[i].io->last_hidden, cx[i].rows,
+                                                        Nq, cx[i].T, H, s));
+            } else {
+                MRA_TRY(launch_gather_last_hidden(cx[i].ws.x32, cx[i].io->last_hidden, cx[i].rows, Nq, cx[i].T, H, s));
+            }
             span_end();
             ++launches;
         }
@@ -584,7 +615,7 @@ extern "C" int mra_qformer_forward_multi(int32_t n, mra_qformer_t* const* hs, co
 // Backward of mra_qformer_forward(flags | MRA_FWD_SAVE_FOR_BACKWARD) for the Q-Former / projection parameters
 // (encoders frozen: no gradient flows into `enc`).  Gradients are ACCUMULATED into `g` (zero them for a fresh step).
 extern "C" int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, const void* d_llm,
-                                    const mra_qformer_weights* wT, const mra_qformer_grads* g, void* workspace,
+                                    const void* reserved, const mra_qformer_grads* g, void* workspace,
                                     size_t workspace_bytes, void* bwd_workspace, size_t bwd_bytes, void* stream_) {
     MRA_REQUIRE(h && io && d_llm && g && workspace && bwd_workspace, "mra_qformer_backward: NULL argument");
     MRA_REQUIRE(h->has_weights, "mra_qformer_backward: weights not set");
@@ -594,7 +625,7 @@ extern "C" int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, 
     const auto& W = h->w;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
     const int rows = io->rows, T = io->T, Nk = io->Nk, Nq = c.num_query, H = c.hidden, I = c.inter, D = c.llm_dim;
-    (void)wT;   // transposed weight copies are no longer needed (see mraudio_b200.h)
+    MRA_REQUIRE(reserved == nullptr, "mra_qformer_backward: the reserved argument must be NULL");
     MRA_REQUIRE(D > 0 && W.w_proj && g->w_proj && g->b_proj, "mra_qformer_backward needs the projection (llm_dim > 0)");
     Workspace ws = carve(h, rows, T, Nk, io->flags, workspace);
     MRA_REQUIRE(workspace_bytes >= ws.total, "workspace too small: %zu < %zu bytes", workspace_bytes, ws.total);

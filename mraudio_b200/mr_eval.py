@@ -12,8 +12,10 @@ the final reductions are the reference's own numpy expressions (``ap_array.mean(
 2-decimal formatting) evaluated on those records in submission order, so rounded and unrounded metrics match.
 The four identical short/middle/long/full passes of the reference (:184-192) are computed once.
 Multi-GPU: ``score_records_distributed`` scores a rank's shard of queries and gathers fixed-width records to rank 0.
-Highlight-detection metrics (``pred_saliency_scores``; eval/mr_eval.py:219-325) are not produced by mrAudio
-(evaluate.py:50-56) and are not on this path: a submission carrying them raises NotImplementedError.
+Highlight-detection metrics (``pred_saliency_scores``; eval/mr_eval.py:219-325, eval/mr_utils.py:174-221) are never produced
+by mrAudio itself (evaluate.py:50-56) but ``eval_submission`` accepts them: ``eval_highlight`` / ``compute_hl_hit1`` /
+``compute_hl_ap`` / ``mk_gt_scores`` / ``get_ap`` are restated here as host numpy (a few thousand scalar operations per
+query; SURVEY.md 8a row 21 keeps this branch on the host), pinned by fixtures generated with the reference's own functions.
 """
 from __future__ import annotations
 
@@ -178,8 +180,117 @@ def eval_moment_retrieval(submission, ground_truth, verbose=True, _records=None)
     return ret_metrics
 
 
+# ---------------------------------------------------------------------------------------------- highlight detection
+def _precision_recall_curve(y_true: np.ndarray, y_score: np.ndarray):
+    """``sklearn.metrics.precision_recall_curve`` for binary labels (the call of eval/mr_utils.py:208): one point per
+    distinct score in decreasing-threshold order, returned reversed with the final (precision 1, recall 0) point."""
+    y_true = np.asarray(y_true, dtype=np.float64)
+    y_score = np.asarray(y_score, dtype=np.float64)
+    desc = np.argsort(y_score, kind="mergesort")[::-1]
+    y_score, y_true = y_score[desc], y_true[desc]
+    threshold_idxs = np.r_[np.where(np.diff(y_score))[0], y_true.size - 1]
+    tps = np.cumsum(y_true)[threshold_idxs]
+    fps = 1 + threshold_idxs - tps
+    ps = tps + fps
+    precision = np.zeros_like(tps)
+    np.divide(tps, ps, out=precision, where=(ps != 0))
+    recall = np.ones_like(tps) if tps[-1] == 0 else tps / tps[-1]
+    sl = slice(None, None, -1)
+    return np.hstack((precision[sl], 1)), np.hstack((recall[sl], 0)), y_score[threshold_idxs][sl]
+
+
+def get_ap(y_true, y_predict, interpolate=True, point_11=False):
+    """eval/mr_utils.py:174-221: (interpolated) average precision of a binary ranking."""
+    assert len(y_true) == len(y_predict), "Prediction and ground truth need to be of the same length"
+    if len(set(y_true)) == 1:
+        if y_true[0] == 0:
+            return 0  # True labels are all zeros
+        else:
+            return 1
+    else:
+        assert sorted(set(y_true)) == [0, 1], "Ground truth can only contain elements {0,1}"
+    precision, recall, _ = _precision_recall_curve(y_true, y_predict)
+    recall = recall.astype(np.float32)
+    if interpolate:  # Compute the interpolated precision
+        for i in range(1, len(precision)):
+            precision[i] = max(precision[i - 1], precision[i])
+    if point_11:  # Compute the 11-point approximated AP
+        precision_11 = [precision[np.where(recall >= t)[0][-1]] for t in np.arange(0, 1.01, 0.1)]
+        return np.mean(precision_11)
+    indices = np.where(np.diff(recall))
+    return np.mean(precision[indices])
+
+
+def compute_ap_from_tuple(input_tuple):
+    """eval/mr_eval.py:268-281: pad / truncate the predicted scores to the number of clips of the video."""
+    idx, w_idx, y_true, y_predict = input_tuple
+    if len(y_true) < len(y_predict):
+        y_predict = y_predict[: len(y_true)]
+    elif len(y_true) > len(y_predict):
+        _y_predict = np.zeros(len(y_true))
+        _y_predict[: len(y_predict)] = y_predict
+        y_predict = _y_predict
+    score = get_ap(y_true, y_predict)
+    return idx, w_idx, score
+
+
+def compute_hl_hit1(qid2preds, qid2gt_scores_binary):
+    """eval/mr_eval.py:219-234."""
+    qid2max_scored_clip_idx = {k: np.argmax(v["pred_saliency_scores"]) for k, v in qid2preds.items()}
+    hit_scores = np.zeros((len(qid2preds), 3))
+    for idx, qid in enumerate(list(qid2preds.keys())):
+        pred_clip_idx = qid2max_scored_clip_idx[qid]
+        gt_scores_binary = qid2gt_scores_binary[qid]  # (#clips, 3)
+        if pred_clip_idx < len(gt_scores_binary):
+            hit_scores[idx] = gt_scores_binary[pred_clip_idx]
+    # max over the 3 annotators, mean over the queries
+    return float(f"{100 * np.mean(np.max(hit_scores, 1)):.2f}")
+
+
+def compute_hl_ap(qid2preds, qid2gt_scores_binary, num_workers=8, chunksize=50):
+    """eval/mr_eval.py:237-265.  ``num_workers`` / ``chunksize`` are accepted for signature compatibility: the work (3 short
+    rankings per query) runs in-process."""
+    qid2pred_scores = {k: v["pred_saliency_scores"] for k, v in qid2preds.items()}
+    ap_scores = np.zeros((len(qid2preds), 3))  # (#preds, 3)
+    for idx, qid in enumerate(list(qid2preds.keys())):
+        for w_idx in range(3):  # annotation score idx
+            y_true = qid2gt_scores_binary[qid][:, w_idx]
+            y_predict = np.array(qid2pred_scores[qid])
+            _, _, score = compute_ap_from_tuple((idx, w_idx, y_true, y_predict))
+            ap_scores[idx, w_idx] = score
+    return float(f"{100 * np.mean(ap_scores):.2f}")
+
+
+def mk_gt_scores(gt_data, clip_length=2):
+    """eval/mr_eval.py:284-294: saliency scores of the relevant clips scattered over the whole video, (#clips, 3)."""
+    num_clips = int(gt_data["duration"] / clip_length)
+    saliency_scores_full_video = np.zeros((num_clips, 3))
+    relevant_clip_ids = np.array(gt_data["relevant_clip_ids"])
+    saliency_scores_relevant_clips = np.array(gt_data["saliency_scores"])
+    saliency_scores_full_video[relevant_clip_ids] = saliency_scores_relevant_clips
+    return saliency_scores_full_video
+
+
+def eval_highlight(submission, ground_truth, verbose=True):
+    """eval/mr_eval.py:297-325: HL-mAP / HL-Hit1 with positives = clips scored >= Fair (2) / Good (3) / VeryGood (4)."""
+    qid2preds = {d["qid"]: d for d in submission}
+    qid2gt_scores_full_range = {d["qid"]: mk_gt_scores(d) for d in ground_truth}  # scores in range [0, 4]
+    highlight_det_metrics = {}
+    for gt_saliency_score_min, score_name in zip([2, 3, 4], ["Fair", "Good", "VeryGood"]):
+        start_time = time.time()
+        qid2gt_scores_binary = {k: (v >= gt_saliency_score_min).astype(float) for k, v in qid2gt_scores_full_range.items()}
+        hit_at_one = compute_hl_hit1(qid2preds, qid2gt_scores_binary)
+        mean_ap = compute_hl_ap(qid2preds, qid2gt_scores_binary)
+        highlight_det_metrics[f"HL-min-{score_name}"] = {"HL-mAP": mean_ap, "HL-Hit1": hit_at_one}
+        if verbose:
+            print(f"Calculating highlight scores with min score {gt_saliency_score_min} ({score_name})")
+            print(f"Time cost {time.time() - start_time:.2f} seconds")
+    return highlight_det_metrics
+
+
 def eval_submission(submission, ground_truth, verbose=True, match_number=True, _records=None):
-    """eval/mr_eval.py:328-414 (moment-retrieval branch)."""
+    """eval/mr_eval.py:328-414: moment retrieval (GPU scorer) and, when the submission carries ``pred_saliency_scores``,
+    highlight detection (host)."""
     pred_qids = set([e["qid"] for e in submission])
     gt_qids = set([e["qid"] for e in ground_truth])
     if match_number:
@@ -214,8 +325,11 @@ def eval_submission(submission, ground_truth, verbose=True, match_number=True, _
         eval_metrics_brief.update(sorted([(k, v) for k, v in moment_ret_scores_brief.items()], key=lambda x: x[0]))
 
     if "pred_saliency_scores" in submission[0]:
-        raise NotImplementedError("highlight-detection metrics are not on the mrAudio path (evaluate.py:50-56 never "
-                                  "emits pred_saliency_scores); use the reference's eval_highlight for them")
+        highlight_det_scores = eval_highlight(submission, ground_truth, verbose=verbose)
+        eval_metrics.update(highlight_det_scores)
+        highlight_det_scores_brief = dict([(f"{k}-{sub_k.split('-')[1]}", v[sub_k]) for k, v in highlight_det_scores.items()
+                                           for sub_k in v])
+        eval_metrics_brief.update(highlight_det_scores_brief)
 
     final_eval_metrics = OrderedDict()
     final_eval_metrics["brief"] = eval_metrics_brief

@@ -86,6 +86,30 @@ def linear_residual_layernorm(x: torch.Tensor, weight: torch.Tensor, bias: Optio
     return y32, y16
 
 
+def split_residual(x: torch.Tensor):
+    """fp32 -> (hi, lo) bf16 pair of the split residual stream: hi = bf16(x), lo = bf16(x - hi)."""
+    hi = x.to(torch.bfloat16)
+    return hi, (x - hi.float()).to(torch.bfloat16)
+
+
+def linear_residual_layernorm_split(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], res_hi: torch.Tensor,
+                                    res_lo: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
+                                    out: Optional[tuple] = None):
+    """(hi, lo) bf16 pair of LayerNorm(x @ weight.T + bias + (res_hi + res_lo)) * gamma + beta; weight [768, K] bf16.
+    `out` may alias the residual pair (the kernel reads every element before it writes it)."""
+    _need_cuda(x, weight, bias, res_hi, res_lo, gamma, beta)
+    assert x.dtype == weight.dtype == res_hi.dtype == res_lo.dtype == torch.bfloat16
+    M, K = x.shape
+    N = weight.shape[0]
+    assert res_hi.shape == (M, N) and res_lo.shape == (M, N) and res_hi.stride() == res_lo.stride() and res_hi.stride(1) == 1
+    assert x.stride(1) == 1 and weight.stride(1) == 1
+    y_hi, y_lo = out if out is not None else (torch.empty(M, N, device=x.device, dtype=torch.bfloat16) for _ in range(2))
+    check(lib.mra_gemm_ln_split_bf16(ptr(x), x.stride(0), ptr(weight), weight.stride(0), ptr(bias), ptr(res_hi), ptr(res_lo),
+                                     res_hi.stride(0), ptr(gamma), ptr(beta), ptr(y_hi), ptr(y_lo), y_hi.stride(0), M, N, K, eps,
+                                     current_stream()))
+    return y_hi, y_lo
+
+
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, rows: int, heads: int, Sq: int, Sk: int,
               nq_split: int, kv_dense: bool, add_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
     """q [rows*Sq, >=heads*64] (split layout), k/v likewise or dense [rows*Sk, ...]; returns o [rows*Sq, heads*64]."""

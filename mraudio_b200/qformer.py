@@ -144,6 +144,9 @@ def _param_version(mod: nn.Module) -> tuple:
 
 
 def _packed_proj(proj: nn.Linear):
+    tr = getattr(proj, "_mra_trainable", None)
+    if tr is not None:   # under fine-tuning: the trainer's live bf16 operand copy / fp32 master bias (never stale)
+        return tr.proj_operands()
     ver = _param_version(proj)
     cache = getattr(proj, "_mra_pack", None)
     if cache is None or cache[0] != ver:
@@ -163,6 +166,7 @@ class BertModelB200(nn.Module):
         self._handles = {}    # llm_dim -> C handle
         self._pack = None     # (version key, dict of packed tensors, QFormerWeights)
         self._pack_applied = set()
+        self._trainable = None   # TrainableQFormer once the module is being fine-tuned (training.py)
         self._workspace = None
         self.last_launches = 0
         self._profile_mode = _lib.PROFILE_OFF
@@ -189,17 +193,23 @@ class BertModelB200(nn.Module):
             pass
 
     # ------------------------------------------------------------------------------------------------ weight packing
+    def _new_handle(self, llm_dim: int):
+        """A fresh C handle for this configuration (the caller owns it)."""
+        c = self.config
+        cc = _lib.QFormerConfig(hidden=c.hidden_size, layers=c.num_hidden_layers, heads=c.num_attention_heads,
+                                inter=c.intermediate_size, enc_width=c.encoder_width, cross_freq=c.cross_attention_freq,
+                                num_query=c.query_length, llm_dim=llm_dim, vocab=c.vocab_size,
+                                max_pos=c.max_position_embeddings, ln_eps=c.layer_norm_eps)
+        hp = C.c_void_p()
+        check(lib.mra_qformer_create(C.byref(cc), C.byref(hp)))
+        return hp
+
     def _handle(self, llm_dim: int):
+        """The inference handle for this projection width (the trainer has its OWN handle: ``set_weights`` on a shared
+        one would silently re-point training at an inference snapshot)."""
         h = self._handles.get(llm_dim)
         if h is None:
-            c = self.config
-            cc = _lib.QFormerConfig(hidden=c.hidden_size, layers=c.num_hidden_layers, heads=c.num_attention_heads,
-                                    inter=c.intermediate_size, enc_width=c.encoder_width, cross_freq=c.cross_attention_freq,
-                                    num_query=c.query_length, llm_dim=llm_dim, vocab=c.vocab_size,
-                                    max_pos=c.max_position_embeddings, ln_eps=c.layer_norm_eps)
-            hp = C.c_void_p()
-            check(lib.mra_qformer_create(C.byref(cc), C.byref(hp)))
-            h = hp
+            h = self._new_handle(llm_dim)
             self._handles[llm_dim] = h
             check(lib.mra_qformer_profile_mode(h, self._profile_mode))
         return h
@@ -223,7 +233,17 @@ class BertModelB200(nn.Module):
         return ms_tot, n_tot
 
     def _packed(self, proj: Optional[nn.Linear]):
-        ver = (_param_version(self), _param_version(proj) if proj is not None else None)
+        tr = self._trainable
+        if tr is not None and (proj is None or proj is tr.llm_proj):
+            # Under fine-tuning the optimizer updates the flat master / bf16 operand buffers through raw pointers, which
+            # neither moves nor re-versions the parameters: a (data_ptr, _version) cache would serve stale weights to every
+            # validation pass.  Inference therefore reads the trainer's live buffers (refreshed by every adam_step).
+            ver = ("trainable", id(tr))
+            if self._pack is None or self._pack[0] != ver:
+                self._pack = (ver, [tr], tr.weight_struct())
+                self._pack_applied = set()
+            return self._pack[2]
+        ver = (_param_version(self), _param_version(proj) if proj is not None else None, tr.version if tr is not None else 0)
         if self._pack is not None and self._pack[0] == ver:
             return self._pack[2]
         bf = lambda t: t.detach().to(torch.bfloat16).contiguous()

@@ -113,7 +113,10 @@ class TrainableQFormer:
             self._bind(L.output.dense.weight, p + "w_ft2"); self._bind(L.output.dense.bias, p + "b_ft2")
             self._bind(L.output.LayerNorm.weight, p + "ln_ft_g"); self._bind(L.output.LayerNorm.bias, p + "ln_ft_b")
         # (the dgrad GEMMs read the bf16 weights in place through MN-major descriptors: no transposed copies are kept)
-        self._handle = bert._handle(D)
+        # The trainer owns its handle: sharing the inference handle of bert._handles would let a validation pass between
+        # epochs (set_weights with an inference pack) re-point every later training step at a frozen snapshot.
+        self._handle = bert._new_handle(D)
+        self.version = 0                       # bumped whenever the master weights change behind autograd's back
         # ---- gradient buckets for the overlapped all-reduce: [start of layer b, end of the previous bucket), top layers first;
         #      the last bucket also holds the front of the buffer (embeddings, stacked cross K/V, projection, query tokens)
         nl = len(layers)
@@ -139,8 +142,38 @@ class TrainableQFormer:
         self._saved = None
         self.step_count = 0
         self.refresh_operands()
-        bert._pack = None            # the inference path must re-pack from the (moved) parameters
+        # inference through bert / llm_proj now reads these live buffers (see BertModelB200._packed / _packed_proj)
+        bert._trainable = self
+        bert._pack = None
         bert._pack_applied = set()
+        llm_proj._mra_trainable = self
+        llm_proj._mra_pack = None
+
+    def __del__(self):
+        try:
+            lib.mra_qformer_destroy(self._handle)
+        except Exception:
+            pass
+
+    def _params_version(self):
+        ps = list(self.bert.parameters()) + list(self.llm_proj.parameters()) + [self.query_tokens]
+        return tuple(p._version for p in ps)
+
+    def sync_operands(self):
+        """Refresh the bf16 operand copy if a parameter was written through PyTorch since the last refresh
+        (``load_state_dict``, manual ``copy_``): in-place writes bump the parameter's version counter, whereas the
+        optimizer's raw-pointer updates refresh the copy themselves."""
+        v = self._params_version()
+        if v != self._seen_params_version:
+            self.refresh_operands()
+
+    def weight_struct(self):
+        """The C-ABI weight struct over the live training buffers (bf16 operand copy + fp32 vectors)."""
+        return self._structs[0]
+
+    def proj_operands(self):
+        """(bf16 weight, fp32 bias) of llm_proj as the kernels read them: views of the live buffers."""
+        return self._view(self.flat16, "w_proj"), self._view(self.flat, "b_proj")
 
     # ------------------------------------------------------------------------------------------------ flat views
     def _view(self, buf, name, row0=0, nrows=None):
@@ -163,6 +196,8 @@ class TrainableQFormer:
     def refresh_operands(self):
         """bf16 operand copy of the master weights (one cast kernel; ``adam_step`` refreshes it in the same pass)."""
         check(lib.mra_cast_bf16(self.flat.data_ptr(), self.flat16.data_ptr(), self.numel, current_stream()))
+        self.version += 1
+        self._seen_params_version = self._params_version()
         if self._structs is None:
             self._structs = self._build_structs()
             check(lib.mra_qformer_set_weights(self._handle, C.byref(self._structs[0])))
@@ -190,6 +225,7 @@ class TrainableQFormer:
         return _QFormerTrainFn.apply(self, enc, input_ids, attention_mask, self.query_tokens)
 
     def _forward_impl(self, enc, input_ids, attention_mask):
+        self.sync_operands()
         cfg = self.cfg
         dev = enc.device
         rows, Nk, Wd = enc.shape
@@ -260,6 +296,7 @@ class TrainableQFormer:
         """``optimizer.step()`` (+ ``optimizer.zero_grad()`` with ``zero_grad``) and the refresh of the bf16 operand copy
         in ONE pass over the flat buffers."""
         self.step_count += 1
+        self.version += 1
         check(lib.mra_adam_step_fused(self.flat.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
                                       self.exp_avg_sq.data_ptr(), self.flat16.data_ptr(), self.numel, lr, betas[0], betas[1], eps,
                                       weight_decay, self.step_count, grad_scale, int(zero_grad), current_stream()))
@@ -363,9 +400,13 @@ class QFormerTrainer:
         if stepping and world > 1:
             # DDP's gradient averaging, only on optimizer-step iterations (the reference all-reduces on every backward):
             # each modality's backward node launches its bucketed all-reduce on a side stream as its layers finish
-            for st in self.states.values():
-                st.reduce_group, st.reduce_after_backward = self.group, self.overlap_allreduce
+            # (only for the modalities of this step: a flag left set on an absent modality would fire its all-reduce on a
+            #  later, non-stepping iteration and count that gradient world_size times)
+            for m, st in self.states.items():
+                st.reduce_group, st.reduce_after_backward = self.group, self.overlap_allreduce and m in inputs_llm
         (loss / self.accum_grad_iters).backward()                                                                  # :131-133
+        for st in self.states.values():
+            st.reduce_after_backward = False
         if self.parallel_modalities and len(self.mod_streams) > 1:
             # the CUDA backward of each modality ran on its own stream and accumulated into the flat gradient buffers behind
             # autograd's back (no AccumulateGrad node): join explicitly before anything on this stream touches them
@@ -374,10 +415,11 @@ class QFormerTrainer:
         self.iter += 1
         if stepping:
             if world > 1:
-                for st in self.states.values():
-                    if self.overlap_allreduce:
+                for m, st in self.states.items():
+                    if self.overlap_allreduce and st.reduce_done is not None:
                         st.wait_grad_allreduce()
-                    else:                              # one flat all-reduce per modality after the backward (A/B baseline)
+                    else:   # flat all-reduce after the backward: the A/B baseline, and modalities absent from this step
+                            # (their accumulated gradients of earlier iterations still have to be averaged)
                         dist.all_reduce(st.grad, op=dist.ReduceOp.SUM, group=self.group)
             for st in self.states.values():
                 st.adam_step(self.lr, grad_scale=1.0 / world, zero_grad=True)
@@ -419,26 +461,87 @@ class QFormerTrainer:
         grad = {k: v.requires_grad for k, v in self.model.named_parameters()}
         return {k: v for k, v in self.model.state_dict().items() if grad.get(k, False)}
 
+    # ------------------------------------------------------------------------------------------------ checkpoints
+    # ``checkpoint["optimizer"]`` has the layout of ``torch.optim.Adam(model.parameters(), lr=3e-4).state_dict()`` -- what
+    # the reference saves and loads (utils/trainer.py:65,199,255): ``state[i] = {step, exp_avg, exp_avg_sq}`` for the i-th
+    # parameter of ``model.parameters()`` and one ``param_groups`` entry -- so a stock Adam over this module can resume from
+    # it and vice versa.  The moments are views of / copied into the flat buffers; the (shared) step count is per modality.
+    def _param_slices(self):
+        """[(index in model.parameters(), name, state, offset, numel)] for every parameter that lives in a flat buffer."""
+        out = []
+        for i, (name, p) in enumerate(self.model.named_parameters()):
+            for st in self.states.values():
+                off = (p.data_ptr() - st.flat.data_ptr()) // 4
+                if p.device == st.flat.device and 0 <= off < st.numel and p.data_ptr() >= st.flat.data_ptr():
+                    out.append((i, name, st, int(off), p.numel()))
+                    break
+        return out
+
+    def optimizer_state_dict(self, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0):
+        n_params = sum(1 for _ in self.model.parameters())
+        state = {}
+        for i, name, st, off, n in self._param_slices():
+            state[i] = {"step": torch.tensor(float(st.step_count)),
+                        "exp_avg": st.exp_avg[off:off + n].clone(), "exp_avg_sq": st.exp_avg_sq[off:off + n].clone()}
+        shapes = {i: p.shape for i, p in enumerate(self.model.parameters())}
+        for i, d in state.items():
+            d["exp_avg"] = d["exp_avg"].view(shapes[i])
+            d["exp_avg_sq"] = d["exp_avg_sq"].view(shapes[i])
+        if all(st.step_count == 0 for st in self.states.values()):
+            state = {}   # torch's Adam has no per-parameter state before its first step
+        group = {"lr": self.lr, "betas": tuple(betas), "eps": eps, "weight_decay": weight_decay, "amsgrad": False,
+                 "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "decoupled_weight_decay": False, "params": list(range(n_params))}
+        return {"state": state, "param_groups": [group],
+                "param_names": [n for n, _ in self.model.named_parameters()]}   # extra key: makes the indices self-describing
+
+    def load_optimizer_state_dict(self, osd):
+        if not isinstance(osd, dict) or "state" not in osd or "param_groups" not in osd:
+            raise ValueError("checkpoint['optimizer'] is not a torch.optim.Adam state_dict (keys 'state', 'param_groups'); "
+                             "round-1 checkpoints of this package ({modality: {exp_avg, exp_avg_sq, step}}) must be re-saved")
+        names = [n for n, _ in self.model.named_parameters()]
+        ck_names = osd.get("param_names")
+        n_ck = sum(len(g["params"]) for g in osd["param_groups"])
+        if ck_names is None and n_ck != len(names):
+            raise ValueError(f"optimizer state covers {n_ck} parameters but this module has {len(names)}: it was saved over a "
+                             "different parameter list (e.g. the reference's full model incl. the LLM) and carries no "
+                             "'param_names' to map it; resume the Q-Former weights from checkpoint['model'] only")
+        index_of = {n: i for i, n in enumerate(ck_names)} if ck_names is not None else {n: i for i, n in enumerate(names)}
+        steps = {id(st): [] for st in self.states.values()}
+        for _, name, st, off, n in self._param_slices():
+            d = osd["state"].get(index_of.get(name, -1))
+            if d is None:
+                st.exp_avg[off:off + n].zero_()
+                st.exp_avg_sq[off:off + n].zero_()
+                continue
+            if d["exp_avg"].numel() != n:
+                raise ValueError(f"optimizer state of {name}: {tuple(d['exp_avg'].shape)} does not match the parameter")
+            st.exp_avg[off:off + n].copy_(d["exp_avg"].reshape(-1))
+            st.exp_avg_sq[off:off + n].copy_(d["exp_avg_sq"].reshape(-1))
+            steps[id(st)].append(int(float(d["step"])))
+        for st in self.states.values():
+            got = steps[id(st)]
+            st.step_count = max(got) if got else 0
+        if osd["param_groups"]:
+            self.lr = float(osd["param_groups"][0].get("lr", self.lr))
+
     def load_checkpoint(self, path: str) -> int:
-        """``Trainer._load_checkpoint`` (utils/trainer.py:236-260): parameters (``strict=False``: only the trainable ones
-        were saved), Adam moments and step counts; returns the epoch to resume from (``checkpoint["epoch"] + 1``)."""
+        """``Trainer._load_checkpoint`` (utils/trainer.py:236-260): parameters (only the trainable ones were saved), the
+        Adam state and the epoch; returns the epoch to resume from (``checkpoint["epoch"] + 1``)."""
         ckpt = torch.load(path, map_location=next(self.model.parameters()).device)
         with torch.no_grad():
             sd = self.model.state_dict()
             for k, v in ckpt["model"].items():
                 if k in sd:
                     sd[k].copy_(v)          # in place: the parameters are views of the flat master buffers
-        for m, st in self.states.items():
-            o = ckpt["optimizer"][m]
-            st.exp_avg.copy_(o["exp_avg"])
-            st.exp_avg_sq.copy_(o["exp_avg_sq"])
-            st.step_count = int(o["step"])
+        self.load_optimizer_state_dict(ckpt["optimizer"])
+        for st in self.states.values():
             st.refresh_operands()
         return int(ckpt["epoch"]) + 1
 
     def save_checkpoint(self, path: str, cur_epoch: int):
+        """``Trainer._save_checkpoint`` (utils/trainer.py:184-210): {"model": trainable parameters only, "optimizer":
+        Adam state_dict, "scaler": None (bf16 needs no loss scaling), "epoch"}."""
         os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
-        torch.save({"model": self.state_dict_trainable(),
-                    "optimizer": {m: {"exp_avg": s.exp_avg, "exp_avg_sq": s.exp_avg_sq, "step": s.step_count}
-                                  for m, s in self.states.items()},
-                    "scaler": None, "epoch": cur_epoch}, path)
+        torch.save({"model": self.state_dict_trainable(), "optimizer": self.optimizer_state_dict(), "scaler": None,
+                    "epoch": cur_epoch}, path)

@@ -113,6 +113,51 @@ def test_fused_linear_residual_layernorm(M, K):
     assert torch.equal(y32, y32c)
 
 
+@pytest.mark.parametrize("M,K", [(128, 768), (256, 768), (1000, 768), (8192, 768), (4096, 3072), (130, 64), (1, 768), (33000, 768)])
+def test_fused_linear_residual_layernorm_split(M, K):
+    """The same kernel with the residual stream as a bf16 (hi, lo) pair -- the form the inference forward uses: hi + lo must
+    match the fp32 LayerNorm of (x W^T + b + (res_hi + res_lo)) to 16 mantissa bits, hi must be exactly bf16(hi + lo)'s
+    leading part (it is the next GEMM's operand), in-place operation on the residual pair must give the same bits, and
+    rows outside [0, M) must stay untouched."""
+    from mraudio_b200 import ops
+    g = torch.Generator().manual_seed(3 * M + K)
+    N = 768
+    x = torch.randn(M, K, generator=g).to(_dev(), torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) * 0.03).to(_dev(), torch.bfloat16)
+    b = torch.randn(N, generator=g).to(_dev())
+    res = (torch.randn(M, N, generator=g) * 2 + 0.3).to(_dev())
+    gam = (1 + 0.2 * torch.randn(N, generator=g)).to(_dev())
+    bet = (0.3 * torch.randn(N, generator=g)).to(_dev())
+    r_hi, r_lo = ops.split_residual(res)
+    res_q = r_hi.float() + r_lo.float()
+    assert (res_q - res).abs().max().item() <= 2.0 ** -16 * res.abs().max().item()
+    pre = x.float() @ w.float().t() + b + res_q
+    ref = torch.nn.functional.layer_norm(pre, (N,), gam, bet, 1e-12)
+    pad = 32
+    bh = torch.full((M + 2 * pad, N), 7.0, device=_dev(), dtype=torch.bfloat16)
+    bl = torch.full((M + 2 * pad, N), 7.0, device=_dev(), dtype=torch.bfloat16)
+    y_hi, y_lo = ops.linear_residual_layernorm_split(x, w, b, r_hi, r_lo, gam, bet, 1e-12, out=(bh[pad:pad + M], bl[pad:pad + M]))
+    torch.cuda.synchronize()
+    for t in (bh, bl):
+        assert (t[:pad] == 7.0).all() and (t[pad + M:] == 7.0).all()
+    y = y_hi.float() + y_lo.float()
+    scale = max(1.0, ref.abs().max().item())
+    assert (y - ref).abs().max().item() < 2e-4 * scale
+    # hi is the bf16 rounding of the fp32 result the kernel held (|lo| <= half an ulp of hi)
+    assert (y_lo.float().abs() <= y_hi.float().abs() * 2.0 ** -8 + 1e-30).all()
+    # in place on the residual pair (cross-attention output block of the forward): identical bits
+    h2, l2 = r_hi.clone(), r_lo.clone()
+    ops.linear_residual_layernorm_split(x, w, b, h2, l2, gam, bet, 1e-12, out=(h2, l2))
+    torch.cuda.synchronize()
+    assert torch.equal(h2, y_hi) and torch.equal(l2, y_lo)
+    # against the fp32-stream kernel on the same (rounded) residual: same arithmetic up to the output rounding
+    # (the two forms sum the row statistics in a different order, so the last bit of mean / rstd may differ)
+    y32, y16 = ops.linear_residual_layernorm(x, w, b, res_q, gam, bet, 1e-12)
+    assert (y32 - y).abs().max().item() <= 2.0 ** -14 * scale
+    assert (y16.float() - y_hi.float()).abs().max().item() <= 2.0 ** -7 * scale   # at most one bf16 ulp, where a rounding flips
+    assert (y16 != y_hi).float().mean().item() < 1e-2
+
+
 @pytest.mark.parametrize("cm", [1, 2, 3])
 @pytest.mark.parametrize("M,N,K", [(512, 768, 768), (771, 2304, 768), (1280, 3072, 768), (8192, 768, 3072), (640, 9216, 1408)])
 def test_gemm_cluster_multicast_variant(cm, M, N, K):

@@ -178,3 +178,86 @@ def test_checkpoint_resume_and_eval_epoch(tmp_path):
            [(1, [[10, 20]], [[10, 20]]), (2, [[30, 38]], [[0, 8], [30, 40]]), (3, [[-1, -1]], [[4, 6]])]]
     assert res["brief"] == mr_eval.eval_submission(sub, sub, verbose=False)["brief"]
     assert res["brief"]["MR-full-invalid_pred_num"] == 1
+
+
+def _small_trainer(accum=1, lr=1e-3):
+    from mraudio_b200.training import QFormerTrainer
+    from mraudio_b200.xinstructblip import XInstructBLIPQFormers
+    torch.manual_seed(0)
+    model = XInstructBLIPQFormers(modalities=("video", "audio"), encoder_num_features={"video": 128, "audio": 64},
+                                  llm_hidden_size=128, num_hidden_layers=2).cuda()
+    return QFormerTrainer(model, accum_grad_iters=accum, warmup_steps=0, init_lr=lr)
+
+
+def _small_batch(seed=3):
+    g = torch.Generator().manual_seed(seed)
+    feats = {"video": torch.randn(2, 2, 17, 128, generator=g).to(torch.bfloat16).cuda(),
+             "audio": torch.randn(2, 2, 16, 64, generator=g).to(torch.bfloat16).cuda()}
+    ids = torch.randint(1000, 30000, (2, 8), generator=g).cuda()
+    mask = torch.ones(2, 8, dtype=torch.long).cuda()
+    sur = {m: torch.randn(2, 2 * 32, 128, generator=g).cuda() for m in feats}
+    return feats, ids, mask, sur
+
+
+def test_train_then_validate_then_train_uses_live_weights():
+    """Validation between epochs (utils/trainer.py train_epoch / eval_epoch loop): the inference path must (a) see the
+    weights the optimizer has just written through raw pointers and (b) not re-point the training handle at an inference
+    snapshot.  Trainer A validates after every step, trainer B never does: identical losses, and every validation
+    output equals the training forward of the same weights."""
+    feats, ids, mask, sur = _small_batch()
+    a, b = _small_trainer(), _small_trainer()
+    outs = []
+    for it in range(4):
+        la = a.train_step(feats, ids, mask, surrogate=sur)
+        lb = b.train_step(feats, ids, mask, surrogate=sur)
+        assert torch.allclose(la, lb, rtol=1e-4), (it, la.item(), lb.item())
+        with torch.no_grad():
+            inf, _ = a.model.encode_modalities(feats, ids, mask)
+            trn, _ = a.forward_modalities(feats, ids, mask)
+        for m in inf:
+            # same bf16 weights, inference (fused LayerNorm, split residual) vs training (saved activations) forward
+            assert ((inf[m].float() - trn[m].float()).abs().max() / trn[m].float().abs().max()).item() < 2e-2, (it, m)
+        outs.append({m: inf[m].float().clone() for m in inf})
+        a.states["video"]._saved = a.states["audio"]._saved = None
+    # the validation outputs follow the optimizer: they change from step to step
+    assert not torch.equal(outs[0]["video"], outs[-1]["video"])
+    # the two-call projection form reads the live projection weights as well
+    with torch.no_grad():
+        h = torch.randn(3, 32, 768, device="cuda")
+        y = a.model.video_llm_proj(h).float()
+        ref = h.to(torch.bfloat16).float() @ a.model.video_llm_proj.weight.to(torch.bfloat16).float().t() + a.model.video_llm_proj.bias
+    assert ((y - ref).abs().max() / ref.abs().max()).item() < 1e-2
+    for m in a.states:
+        assert torch.allclose(a.states[m].flat, b.states[m].flat, rtol=0, atol=2e-5)
+
+
+def test_checkpoint_optimizer_is_a_torch_adam_state_dict(tmp_path):
+    """checkpoint['optimizer'] has torch.optim.Adam's state_dict layout (what utils/trainer.py:199,255 saves / loads):
+    a stock Adam over the same module loads it, and a state_dict written by a stock Adam resumes here."""
+    feats, ids, mask, sur = _small_batch()
+    a = _small_trainer()
+    for _ in range(3):
+        a.train_step(feats, ids, mask, surrogate=sur)
+    path = str(tmp_path / "c.pth")
+    a.save_checkpoint(path, cur_epoch=0)
+    ck = torch.load(path)
+    osd = ck["optimizer"]
+    assert set(osd) >= {"state", "param_groups"} and osd["param_groups"][0]["lr"] == a.lr
+    params = list(a.model.parameters())
+    opt = torch.optim.Adam(params, lr=3e-4)
+    opt.load_state_dict({"state": osd["state"], "param_groups": osd["param_groups"]})      # stock Adam accepts it
+    name_to_i = {n: i for i, n in enumerate(osd["param_names"])}
+    i = name_to_i["video_Qformer.bert.encoder.layer.1.output_query.dense.weight"]
+    st = opt.state[params[i]]
+    assert float(st["step"]) == 3 and st["exp_avg"].shape == params[i].shape and st["exp_avg"].abs().max().item() > 0
+    # frozen parameters (the modality LayerNorms) carry no state
+    assert name_to_i["video_ln.weight"] not in osd["state"]
+    # the reverse direction: the stock optimizer's state_dict resumes here, moments and step counts intact
+    b = _small_trainer()
+    b.load_optimizer_state_dict(opt.state_dict())
+    for m in a.states:
+        assert b.states[m].step_count == 3
+        assert torch.equal(a.states[m].exp_avg, b.states[m].exp_avg) and torch.equal(a.states[m].exp_avg_sq, b.states[m].exp_avg_sq)
+    # a round-1 style dict is rejected with a clear message
+    with pytest.raises(ValueError, match="state_dict"):
+        b.load_optimizer_state_dict({"video": {"exp_avg": None}})

@@ -5,6 +5,10 @@ import torch
 from mraudio_b200 import ops, _lib
 
 dev = torch.device("cuda:0")
+if os.environ.get("GB_SHORT"):
+    SHORT = {"kv_audio", "qkv", "f1x2", "f2x2", "proj", "f1_nogelu"}
+else:
+    SHORT = None
 SHAPES = [  # name, M, N, K, gelu, f32+res
     ("kv_video", 65792, 9216, 1408, 0, 0), ("kv_audio", 65536, 9216, 768, 0, 0),
     ("qkv", 16384, 2304, 768, 0, 0), ("ao", 16384, 768, 768, 0, 1), ("cq", 8192, 768, 768, 0, 0),
@@ -14,13 +18,15 @@ SHAPES = [  # name, M, N, K, gelu, f32+res
 ]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 for name, M, N, K, gelu, res in SHAPES:
+    if SHORT is not None and name not in SHORT:
+        continue
     x = torch.randn(M, K, device=dev).to(torch.bfloat16)
     w = (torch.randn(N, K, device=dev) * 0.02).to(torch.bfloat16)
     b = torch.randn(N, device=dev)
     r = torch.randn(M, N, device=dev) if res else None
     out = torch.empty(M, N, device=dev, dtype=torch.float32 if res else torch.bfloat16)
-    line = f"{name:9s} M={M:6d} N={N:5d} K={K:5d}"
-    for bn in (-256, 128, 192, 256, 0):
+    line = f"[{os.environ.get('MRA_LIB', 'base')}] {name:9s} M={M:6d} N={N:5d} K={K:5d}"
+    for bn in ((256, 0) if SHORT is not None else (-256, 128, 192, 256, 0)):
         _lib.lib.mra_gemm_cluster_override(1 if bn < 0 else int(os.environ.get('GB_CLUSTER', '3')))   # bn < 0: unpaired kernel at |bn| for comparison
         _lib.lib.mra_gemm_tile_override(abs(bn))
         ts = []
@@ -45,6 +51,8 @@ for name, M, N, K, gelu, res in SHAPES:
     line += f" | cublas(no epi) {min(ts[1:])*1e3:7.1f}us"
     print(line, flush=True)
 
+if SHORT is not None:
+    sys.exit(0)
 print("--- fused Linear + residual + LayerNorm (2-CTA cluster), N = 768")
 for name, M, K in (("ao", 16384, 768), ("ao_x2", 32768, 768), ("co", 8192, 768), ("f2", 8192, 3072), ("f2_x4", 32768, 3072)):
     x = torch.randn(M, K, device=dev).to(torch.bfloat16)
