@@ -158,17 +158,19 @@ int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, const void*
 /* Overlap of the data-parallel gradient all-reduce (DistributedDataParallel, utils/trainer.py:69) with the backward:
  * events[l] (cudaEvent_t, owned by the caller; NULL entries allowed) is recorded on the backward's stream as soon as the
  * gradients of layer l -- and therefore of all layers above it -- are final, so the caller can start the all-reduce of
- * that bucket on another stream while the lower layers are still running.  (The stacked cross-attention K/V gradients,
- * the embeddings and the query tokens are final only when mra_qformer_backward has finished.)  n = 0 clears. */
+ * that bucket on another stream while the lower layers are still running; events[layers] (optional, n = layers + 1) is
+ * recorded when the projection's gradients are final, i.e. after the first launches of the backward.  (The stacked
+ * cross-attention K/V gradients -- ONE weight-gradient GEMM over all cross layers at the end --, the embeddings and the
+ * query tokens are final only when mra_qformer_backward has finished.)  n = 0 clears. */
 int mra_qformer_backward_layer_events(mra_qformer_t* h, void* const* events, int32_t n);
 int mra_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                   float beta2, float eps, float weight_decay, int32_t step, float grad_scale, void* stream);
 /* The same Adam update fused with what always follows it in the fine-tuning loop (utils/trainer.py:137-140): the bf16
  * operand copy of the updated parameters (params_bf16, may be NULL) and optimizer.zero_grad() (zero_grads != 0).
  * n must be a multiple of 4, buffers 16-byte aligned. */
-int mra_adam_step_fused(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* params_bf16, int64_t n, float lr,
-                        float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
-                        int32_t zero_grads, void* stream);
+int mra_adam_step_fused(float* params, float* grads, const void* reduced_grads_bf16, float* exp_avg, float* exp_avg_sq,
+                        void* params_bf16, int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                        int32_t step, float grad_scale, int32_t zero_grads, void* stream);
 int mra_cast_bf16(const float* in, void* out, int64_t n, void* stream);
 
 /* Device-side timing of the launches of mra_qformer_forward with CUDA events recorded on the caller's stream.
@@ -293,7 +295,10 @@ int mra_add_frame_position(const void* x, int32_t in_dtype, const float* pos, vo
  * of compute_mr_r1 (eval/mr_eval.py:97-131) and the IoU helpers (eval/mr_utils.py:16-67), in fp64 with numpy's
  * operation order, nan semantics and argsort tie order.
  *   pred [Q, Pmax, 2] f64, n_pred [Q] (>= 1); gt [Q, Gmax, 2] f64, n_gt [Q] (>= 1); thds [10] f64.
- *   out_ap [Q, 10] f64; out_iou [Q] f64 (top-1 paired IoU); out_invalid [Q] u8 (-1 in top-1 window).
+ *   out_ap [Q, 10] f64; out_iou [Q] f64 (top-1 paired IoU); out_invalid [Q] u8: bit 0 = -1 in the top-1 window;
+ *   bit 1 = "tie-ambiguous": some prediction has exactly the same IoU (>= 0.5) with two different GT windows, the one case
+ *   where the reference's result depends on the (platform-dependent, unstable for >= 4 elements on AVX-512 numpy builds)
+ *   tie order of `tiou_arr.argsort()[::-1]` (eval/mr_utils.py:147); the kernel uses the stable order.
  *   Limits: Pmax <= 256, Gmax <= 64. */
 int mra_mr_score(const double* pred, const int32_t* n_pred, const double* gt, const int32_t* n_gt, const double* thds,
                  int32_t Q, int32_t Pmax, int32_t Gmax, double* out_ap, double* out_iou, uint8_t* out_invalid,

@@ -94,7 +94,7 @@ def _load():
                                          C.c_size_t, vp, C.c_size_t, vp]
     lib.mra_qformer_backward_layer_events.argtypes = [vp, C.POINTER(vp), i32]
     lib.mra_adam_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, vp]
-    lib.mra_adam_step_fused.argtypes = [vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, i32, vp]
+    lib.mra_adam_step_fused.argtypes = [vp, vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, i32, vp]
     lib.mra_cast_bf16.argtypes = [vp, vp, i64, vp]
     lib.mra_qformer_profile_mode.argtypes = [vp, i32]
     lib.mra_qformer_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]

@@ -857,14 +857,22 @@ int launch_embed_bwd(const float* d_emb, const int32_t* ids, float* d_query, int
 // Same update with the two passes that always follow it folded in: the bf16 operand copy of the new parameters (what the
 // GEMMs read) and the reset of the gradient accumulator -- 7 instead of 10 fp32 streams over the 186 M parameters.
 __global__ void __launch_bounds__(256)
-adam_fused_kernel(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
-                  uint2* __restrict__ p16, int64_t n4, float lr, float beta1, float beta2, float eps, float weight_decay, float bc1,
-                  float bc2_sqrt, float grad_scale, int zero_grad) {
+adam_fused_kernel(float4* __restrict__ p, float4* __restrict__ g, const uint2* __restrict__ g16, float4* __restrict__ m,
+                  float4* __restrict__ v, uint2* __restrict__ p16, int64_t n4, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, float bc1, float bc2_sqrt, float grad_scale, int zero_grad) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n4) return;
-    const float4 g4 = g[i], m4 = m[i], v4 = v[i];
+    const float4 m4 = m[i], v4 = v[i];
     float4 p4 = p[i];
-    const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+    float gg[4];
+    if (g16 != nullptr) {   // gradients as reduced over the ranks in bf16 (the fp32 accumulator is only reset)
+        const uint2 gq = g16[i];
+        gg[0] = ptx::bf16lo(gq.x); gg[1] = ptx::bf16hi(gq.x); gg[2] = ptx::bf16lo(gq.y); gg[3] = ptx::bf16hi(gq.y);
+    } else {
+        const float4 g4 = g[i];
+        gg[0] = g4.x; gg[1] = g4.y; gg[2] = g4.z; gg[3] = g4.w;
+    }
+    const float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
     float pp[4] = {p4.x, p4.y, p4.z, p4.w}, mo[4], vo[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -882,18 +890,18 @@ adam_fused_kernel(float4* __restrict__ p, float4* __restrict__ g, float4* __rest
     if (zero_grad) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
-int launch_adam_fused(float* p, float* g, float* m, float* v, void* p16, int64_t n, float lr, float beta1, float beta2, float eps,
-                      float weight_decay, int step, float grad_scale, int zero_grad, cudaStream_t s) {
+int launch_adam_fused(float* p, float* g, const void* g16, float* m, float* v, void* p16, int64_t n, float lr, float beta1, float beta2,
+                      float eps, float weight_decay, int step, float grad_scale, int zero_grad, cudaStream_t s) {
     MRA_REQUIRE(n > 0 && n % 4 == 0 && step >= 1, "fused adam: n must be a positive multiple of 4");
     MRA_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
-                  reinterpret_cast<uintptr_t>(v)) & 15) == 0 && (reinterpret_cast<uintptr_t>(p16) & 7) == 0,
+                  reinterpret_cast<uintptr_t>(v)) & 15) == 0 && ((reinterpret_cast<uintptr_t>(p16) | reinterpret_cast<uintptr_t>(g16)) & 7) == 0,
                 "fused adam: buffers must be 16-byte aligned");
     const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
     const float bc2 = sqrtf(1.f - powf(beta2, static_cast<float>(step)));
     const int64_t n4 = n / 4;
     adam_fused_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, s>>>(
-        reinterpret_cast<float4*>(p), reinterpret_cast<float4*>(g), reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v),
-        reinterpret_cast<uint2*>(p16), n4, lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale, zero_grad);
+        reinterpret_cast<float4*>(p), reinterpret_cast<float4*>(g), reinterpret_cast<const uint2*>(g16), reinterpret_cast<float4*>(m),
+        reinterpret_cast<float4*>(v), reinterpret_cast<uint2*>(p16), n4, lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale, zero_grad);
     MRA_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -110,28 +110,20 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // Same function for bf16 outputs: 0.5 x (1 + erf(x / sqrt 2)) = x * (0.5 + 0.5 tanh(x (a + b x^2 + c x^4))) with (a, b, c)
 // fitted to the erf form (|error| <= 2.6e-5 over all x; x^2 clamped at 64 where tanh has saturated, which also keeps
 // the negative c from flipping the sign of the argument) and the hardware tanh.approx.f32 (relative error 2^-11):
-// 1 MUFU + 7 FMA-pipe instructions per element.  The total error (<= 5e-4 |x|) is an eighth of the bf16 rounding
-// step of the stored result; fp32 outputs keep gelu_erf.
-// the same on a pair of values with packed fp32 instructions: 5 FMA-pipe instructions + 2 MUFU + 2 FMNMX per PAIR
-__device__ __forceinline__ float2 gelu_fast2(float2 x) {
-    float2 u = ptx::mul2(x, x);
-    u.x = fminf(u.x, 64.0f);
-    u.y = fminf(u.y, 64.0f);
-    float2 q = ptx::fma2(make_float2(-3.51534682e-4f, -3.51534682e-4f), u, make_float2(3.70057307e-2f, 3.70057307e-2f));
-    q = ptx::fma2(q, u, make_float2(7.97507813e-1f, 7.97507813e-1f));
-    const float2 a = ptx::mul2(x, q);
-    float2 t;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(a.x));
-    asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(a.y));
-    return ptx::mul2(x, ptx::fma2(make_float2(0.5f, 0.5f), t, make_float2(0.5f, 0.5f)));
-}
-__device__ __forceinline__ float gelu_fast(float x) {
-    const float u = fminf(x * x, 64.0f);
-    float q = fmaf(-3.51534682e-4f, u, 3.70057307e-2f);
-    q = fmaf(q, u, 7.97507813e-1f);
-    float t;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * q));
-    return x * fmaf(0.5f, t, 0.5f);
+// The total error (<= 5e-4 |x|) is an eighth of the bf16 rounding step of the stored result; fp32 outputs keep gelu_erf.
+// Evaluated on a PAIR of values with packed fp32 instructions (FMUL2 / FFMA2): 6 FMA-pipe instructions + 2 MUFU + 2 FMNMX
+// per pair instead of 14 + 2 + 2.
+__device__ __forceinline__ ptx::f32x2_t gelu_fast2(ptx::f32x2_t x) {
+    float u0, u1;
+    ptx::unpack2(ptx::mul2(x, x), u0, u1);
+    const ptx::f32x2_t u = ptx::pack2(fminf(u0, 64.0f), fminf(u1, 64.0f));
+    ptx::f32x2_t q = ptx::fma2(ptx::pack2(-3.51534682e-4f, -3.51534682e-4f), u, ptx::pack2(3.70057307e-2f, 3.70057307e-2f));
+    q = ptx::fma2(q, u, ptx::pack2(7.97507813e-1f, 7.97507813e-1f));
+    float a0, a1, t0, t1;
+    ptx::unpack2(ptx::mul2(x, q), a0, a1);
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(a0));
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(a1));
+    return ptx::mul2(x, ptx::fma2(ptx::pack2(0.5f, 0.5f), ptx::pack2(t0, t1), ptx::pack2(0.5f, 0.5f)));
 }
 
 // byte offset of 16-byte unit `j` of row `r` inside a 32-row x 128-byte chunk buffer with the TMA 128-byte swizzle
@@ -409,32 +401,42 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
 #pragma unroll
                 for (int half = 0; half < RSUB; ++half) {
                     float v[32];
-#ifdef MRA_AB_SCALAR_EPI   // A/B variant: the round-1 scalar bias + GELU arithmetic
+                    if constexpr (!(GELU && !OUT_F32)) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        v[j] = __uint_as_float(racc[half][j]);
-                        const int idx = half * 32 + j;
-                        if (bias != nullptr) v[j] += __shfl_sync(0xffffffffu, bq[ci][idx % BPL], idx / BPL);
-                        if (GELU) v[j] = OUT_F32 ? gelu_erf(v[j]) : gelu_fast(v[j]);
-                    }
-#else
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(racc[half][j]);
+                    if (bias != nullptr) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        // pairs of columns through the packed fp32 pipe (FADD2 / FMUL2 / FFMA2)
-                        float2 x = make_float2(__uint_as_float(racc[half][j]), __uint_as_float(racc[half][j + 1]));
-                        if (bias != nullptr) {
+                        for (int j = 0; j < 32; ++j) {
                             const int idx = half * 32 + j;      // column inside the chunk -> (lane, slot) that holds its bias
-                            x = ptx::add2(x, make_float2(__shfl_sync(0xffffffffu, bq[ci][idx % BPL], idx / BPL),
-                                                         __shfl_sync(0xffffffffu, bq[ci][(idx + 1) % BPL], (idx + 1) / BPL)));
+                            v[j] += __shfl_sync(0xffffffffu, bq[ci][idx % BPL], idx / BPL);
                         }
-                        if (GELU) {
-                            if (OUT_F32) x = make_float2(gelu_erf(x.x), gelu_erf(x.y));
-                            else x = gelu_fast2(x);
-                        }
-                        v[j] = x.x;
-                        v[j + 1] = x.y;
                     }
-#endif
+                    if (GELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                    }
+                    } else {
+                    // bf16 GELU epilogue (FFN-up): pairs of columns through the packed fp32 pipe (FADD2 / FMUL2 / FFMA2) -- this
+                    // epilogue is issue-bound on the FMA pipe: 64.5 vs 67.6 us on the FFN-up shape of a step, same box.  (The
+                    // epilogues without GELU are not: packing them changes nothing.)  The bias test is hoisted out of the loop
+                    // so that the pairs' dependency chains interleave freely.
+                    ptx::f32x2_t xx[16];
+                    if (bias != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            const int idx = half * 32 + j;      // column inside the chunk -> (lane, slot) that holds its bias
+                            xx[j >> 1] = ptx::add2(ptx::pack2(__uint_as_float(racc[half][j]), __uint_as_float(racc[half][j + 1])),
+                                                   ptx::pack2(__shfl_sync(0xffffffffu, bq[ci][idx % BPL], idx / BPL),
+                                                              __shfl_sync(0xffffffffu, bq[ci][(idx + 1) % BPL], (idx + 1) / BPL)));
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2)
+                            xx[j >> 1] = ptx::pack2(__uint_as_float(racc[half][j]), __uint_as_float(racc[half][j + 1]));
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) ptx::unpack2(gelu_fast2(xx[j >> 1]), v[j], v[j + 1]);
+                    }
                     if (RES) {
                         ptx::mbar_wait(rbar, rphase);
                         rphase ^= 1;

@@ -86,9 +86,7 @@ struct LnParams {
     int K;
     float eps;
     int dbg;   // timing experiments only (MRA_LN_DEBUG, -DMRA_INSTRUMENT): 1 = no residual, 2 = no cross-CTA exchange,
-               // 4 = no stores, 8 = clocks, 16 = odd clusters start half a block period late (de-phases the store bursts)
-    int stagger_cycles;
-    int prefetch;   // > 0: the CTAs of column slice 0 prefetch the A tile `prefetch` K steps ahead into L2 (MRA_LN_PREFETCH)
+               // 4 = no stores, 8 = clocks
 };
 
 __device__ unsigned long long g_ln_timing[16];   // MRA_LN_DEBUG & 8: cycles per epilogue phase (warp 2 / lane 0 of CTA 0)
@@ -196,10 +194,6 @@ gemm_ln_kernel(const __grid_constant__ LnMaps maps, const __grid_constant__ LnPa
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
-            if ((MRA_LN_DBG(p) & 16) && (cluster_id & 1)) {   // experiment: de-phase odd clusters
-                const long long t_end = clock64() + p.stagger_cycles;
-                while (clock64() < t_end) {}
-            }
             int stage = 0;
             uint32_t phase = 0;
             for (int blk = cluster_id; blk < total_blks; blk += num_clusters) {
@@ -209,10 +203,6 @@ gemm_ln_kernel(const __grid_constant__ LnMaps maps, const __grid_constant__ LnPa
                 const CUtensorMap* tmB = &maps.b[g];
                 const int a_row = m_blk * C::ROWS + static_cast<int>(mhalf) * BM;
                 for (int kb = 0; kb < k_blocks; ++kb) {
-                    // The A rows usually come from DRAM (the tensor the previous kernel wrote is larger than L2) while the ring
-                    // holds only 3 slabs in flight: one of the three CTAs that read these rows pulls them into L2 ahead of time
-                    if (p.prefetch > 0 && nidx == 0 && kb + p.prefetch < k_blocks && ((kb + p.prefetch) & 1) == 0)
-                        ptx::tma_prefetch_2d(tmA, (kb + p.prefetch) * BK, a_row);   // (256-byte L2 promotion: every 2nd slab)
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* st = smem + stage * STAGE_BYTES;
                     if (U2) {
@@ -554,11 +544,7 @@ static int launch_gemm_ln_variant(const GemmLnArgs* ga, int n, float eps, cudaSt
     p.K = ga[0].K;
     p.eps = eps;
     static const int dbg = [] { const char* e = getenv("MRA_LN_DEBUG"); return e ? atoi(e) : 0; }();
-    static const int stagger = [] { const char* e = getenv("MRA_LN_STAGGER"); return e ? atoi(e) : 0; }();
     p.dbg = dbg;
-    p.stagger_cycles = stagger;
-    static const int prefetch = [] { const char* e = getenv("MRA_LN_PREFETCH"); return e ? atoi(e) : 0; }();
-    p.prefetch = prefetch;
     int total = 0;
     for (int g = 0; g < MAX_GROUPS; ++g) {
         if (g < n) {

@@ -165,19 +165,9 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* des
 // Arrive on a (possibly remote) CTA's mbarrier.  Default semantics (.release at .cta scope): the only ordering the callers
 // need is of tcgen05 operations, which tcgen05.fence::before_thread_sync / ::after_thread_sync provide around the barrier.
 // (With .release.cluster the compiler emits MEMBAR.ALL.GPU + ERRBAR in front of every arrive: ncu attributed 24 % of the
-//  GEMM epilogue's stall samples to it, profiles/r02b_NOTES.md.)
+//  GEMM epilogue's stall samples to it; config-2 step 9.79 -> 9.40 ms on the same box, profiles/r02_NOTES.md.)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
-#ifdef MRA_AB_RELEASE_ARRIVE   // A/B variant: the round-1 form
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
-#else
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
-#endif
-}
-// L2 prefetch of a 2-D tile (no shared-memory destination, no completion tracking)
-__device__ __forceinline__ void tma_prefetch_2d(const void* desc, int32_t crd0, int32_t crd1) {
-    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(desc)), "r"(crd0),
-                 "r"(crd1)
-                 : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {  // whole warp, same warp id in both CTAs
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
@@ -312,28 +302,31 @@ __device__ __forceinline__ void st_global_v8b(void* p, uint32_t a, uint32_t b, u
 }
 
 // ---------------------------------------------------------------- packed fp32 pairs (sm_100: FADD2 / FMUL2 / FFMA2)
-// Two fp32 operations per issued instruction: the epilogues are issue-bound on the FMA pipe (ncu: "selected" /
-// "not_selected" stalls dominate the GELU epilogue).
-__device__ __forceinline__ float2 add2(float2 a, float2 b) {
-    float2 d;
-    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
-        : "=f"(d.x), "=f"(d.y)
-        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+// Two fp32 operations per issued instruction: the GELU epilogue is issue-bound on the FMA pipe (ncu: "selected" /
+// "not_selected" stalls dominate it).  Pairs live in 64-bit registers (f32x2 operands are .b64); pack / unpack are
+// register-pair renamings when the halves are allocated next to each other, which ptxas does for values produced here.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pack2(float lo, float hi) {
+    f32x2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b) {
+    f32x2_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
-__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
-    float2 d;
-    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
-        : "=f"(d.x), "=f"(d.y)
-        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+__device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b) {
+    f32x2_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
-__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
-    float2 d;
-    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
-        "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
-        : "=f"(d.x), "=f"(d.y)
-        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) {
+    f32x2_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
     return d;
 }
 

@@ -19,7 +19,8 @@ struct mra_qformer {
     int cross_slot[MRA_MAX_LAYERS];  // index of the layer's K/V block inside w_ckv, or -1
     int last_launches = 0;
     int gemm_impl = MRA_GEMM_IMPL_TCGEN05;
-    cudaEvent_t layer_done[MRA_MAX_LAYERS] = {};   // optional: recorded by the backward when a layer's gradients are final
+    cudaEvent_t layer_done[MRA_MAX_LAYERS + 1] = {};   // optional: recorded by the backward when a layer's gradients are final
+                                                       // (slot `layers`: the projection's)
     bool fuse_ln = true;   // Linear + residual + LayerNorm in one cluster kernel (MRA_NO_FUSED_LN=1 disables: A/B runs)
     bool split_res = true; // with fuse_ln: residual stream as a bf16 (hi, lo) pair instead of fp32 (MRA_SPLIT_RESIDUAL=0 disables)
     // optional per-category device timing (CUDA events on the caller's stream), see mra_qformer_profile_*
@@ -39,7 +40,6 @@ namespace mra {
 namespace {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-inline int pad8(int v) { return (v + 7) & ~7; }
 
 // Per-layer activation buffers.  Inference: every layer aliases ONE set (activations are dead after the layer).
 // MRA_FWD_SAVE_FOR_BACKWARD: every layer has its own set, kept for mra_qformer_backward.
@@ -133,17 +133,14 @@ struct BwdWorkspace {
     __nv_bfloat16* g_pre16; __nv_bfloat16* g_ctx16;   // [Mtot, H]
     __nv_bfloat16* g_cq16;                        // [Mq, H]
     __nv_bfloat16* g_big16; __nv_bfloat16* g_big2;    // [Mtot, max(I, 3H)]
-    __nv_bfloat16* g_kv16;                        // [rows*Nk, 2H]
-    __nv_bfloat16* t1; __nv_bfloat16* t2;         // transposed operands of the wgrad GEMMs
-    __nv_bfloat16* encT;                          // [W, pad8(rows*Nk)]
+    __nv_bfloat16* g_kv16;                        // [rows*Nk, ncross*2H]: dL/d(keys, values) of ALL cross layers (one wgrad at the end)
     size_t total;
 };
 
 BwdWorkspace carve_bwd(const mra_qformer* h, int rows, int T, int Nk, void* base) {
     const auto& c = h->cfg;
-    const size_t H = c.hidden, I = c.inter, D = c.llm_dim, W = c.enc_width;
+    const size_t H = c.hidden, I = c.inter;
     const size_t Mq = static_cast<size_t>(rows) * c.num_query, Mtot = Mq + static_cast<size_t>(rows) * T;
-    const size_t Mqp = pad8(static_cast<int>(Mq)), Mtp = pad8(static_cast<int>(Mtot)), NKp = pad8(rows * Nk);
     const size_t big = I > 3 * H ? I : 3 * H;
     size_t off = 0;
     auto take = [&](size_t bytes) {
@@ -160,13 +157,7 @@ BwdWorkspace carve_bwd(const mra_qformer* h, int rows, int T, int Nk, void* base
     b.g_cq16 = reinterpret_cast<__nv_bfloat16*>(take(Mq * H * 2));
     b.g_big16 = reinterpret_cast<__nv_bfloat16*>(take(Mtot * big * 2));
     b.g_big2 = reinterpret_cast<__nv_bfloat16*>(take(Mtot * big * 2));
-    b.g_kv16 = reinterpret_cast<__nv_bfloat16*>(take(static_cast<size_t>(rows) * Nk * 2 * H * 2));
-    size_t t1 = big * Mtp;
-    if (D * Mqp > t1) t1 = D * Mqp;
-    if (2 * H * NKp > t1) t1 = 2 * H * NKp;
-    b.t1 = reinterpret_cast<__nv_bfloat16*>(take(t1 * 2));
-    b.t2 = reinterpret_cast<__nv_bfloat16*>(take((I > H ? I : H) * Mtp * 2));
-    b.encT = reinterpret_cast<__nv_bfloat16*>(take(W * NKp * 2));
+    b.g_kv16 = reinterpret_cast<__nv_bfloat16*>(take(static_cast<size_t>(rows) * Nk * h->n_cross * 2 * H * 2));
     b.total = off;
     return b;
 }
@@ -685,6 +676,7 @@ extern "C" int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, 
     // ---- llm_proj
     const __nv_bfloat16* dl = reinterpret_cast<const __nv_bfloat16*>(d_llm);
     if (int e = wgrad(dl, D, ws.layer[c.layers].xb, H, Mq, D, H, g->w_proj, H, g->b_proj)) return e;
+    if (h->layer_done[c.layers]) MRA_CHECK_CUDA(cudaEventRecord(h->layer_done[c.layers], s));   // projection gradients final
     MRA_TRY(gemm(dl, D, W.w_proj, D, nullptr, 0, bw.g_x, H, Mq, H, D, 1));
     if (Mt > 0) {
         MRA_CHECK_CUDA(cudaMemsetAsync(bw.g_x + static_cast<size_t>(Mq) * H, 0, static_cast<size_t>(Mt) * H * 4, s));
@@ -719,8 +711,9 @@ extern "C" int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, 
             if (int e = ln_bwd(bw.g_a, B.pre_c, L.ln_c_g, G.ln_c_g, G.ln_c_b, G.b_co, 0, Mq)) return e;
             if (int e = wgrad(bw.g_pre16, H, B.cctx, H, Mq, H, H, G.w_co, H, nullptr)) return e;
             MRA_TRY(gemm(bw.g_pre16, H, LT.w_co, H, nullptr, 0, bw.g_ctx16, H, Mq, H, H, 0));      // d_cctx
-            AttnBwdArgs a{B.cq, H, kbase, kv_ld, kbase + H, kv_ld, bw.g_ctx16, H, bw.g_cq16, H, bw.g_kv16, 2 * H,
-                          bw.g_kv16 + H, 2 * H, io->enc_mask ? ws.enc_mask : nullptr, rows, c.heads, Nq, Nk, Nq, 1};
+            __nv_bfloat16* gkv = bw.g_kv16 + static_cast<size_t>(slot) * 2 * H;   // this layer's columns of the stacked buffer
+            AttnBwdArgs a{B.cq, H, kbase, kv_ld, kbase + H, kv_ld, bw.g_ctx16, H, bw.g_cq16, H, gkv, kv_ld,
+                          gkv + H, kv_ld, io->enc_mask ? ws.enc_mask : nullptr, rows, c.heads, Nq, Nk, Nq, 1};
             a.o = B.cctx; a.ldof = H;
             a.db_q = G.b_cq;
             a.db_k = g->b_ckv + static_cast<size_t>(slot) * 2 * H;
@@ -729,8 +722,6 @@ extern "C" int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, 
             MRA_TRY(launch_attention_bwd(a, s));
             if (int e = wgrad(bw.g_cq16, H, B.ab, H, Mq, H, H, G.w_cq, H, nullptr)) return e;
             MRA_TRY(gemm(bw.g_cq16, H, LT.w_cq, H, bw.g_pre32, H, bw.g_a, H, Mq, H, H, 1));         // -> grad of LN_a out (query rows)
-            if (int e = wgrad(bw.g_kv16, 2 * H, reinterpret_cast<const __nv_bfloat16*>(io->enc), c.enc_width, NK, 2 * H, c.enc_width,
-                              g->w_ckv + static_cast<size_t>(slot) * 2 * H * c.enc_width, c.enc_width, nullptr)) return e;
         }
         // ---- self-attention block (all rows)
         if (int e = ln_bwd(bw.g_a, B.pre_a, L.ln_a_g, G.ln_a_g, G.ln_a_b, G.b_ao, 0, Mtot)) return e;
@@ -750,6 +741,12 @@ extern "C" int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, 
         // the gradients of layers >= l (except the stacked cross K/V weights) are final: a bucketed all-reduce may start
         if (h->layer_done[l]) MRA_CHECK_CUDA(cudaEventRecord(h->layer_done[l], s));
     }
+    // ---- stacked cross-attention K/V weights of ALL cross layers: dW_ckv [ncross*2H, W] += g_kv^T . enc in ONE GEMM (the
+    //      encoder tokens are read once, as in the forward, and the launch fills the machine: ncross*2H x W output tiles)
+    if (h->n_cross > 0) {
+        if (int e = wgrad(bw.g_kv16, kv_ld, reinterpret_cast<const __nv_bfloat16*>(io->enc), c.enc_width, NK, kv_ld, c.enc_width,
+                          g->w_ckv, c.enc_width, nullptr)) return e;
+    }
     // ---- embeddings
     if (int e = ln_bwd(bw.g_x, ws.pre_e, W.ln_e_g, g->ln_e_g, g->ln_e_b, nullptr, 0, Mtot)) return e;
     MRA_TRY(launch_embed_bwd(bw.g_pre32, io->input_ids, g->query_tokens, io->q_rows, g->word_emb, g->pos_emb, rows, Nq, T, H,
@@ -760,8 +757,8 @@ extern "C" int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, 
 }
 
 extern "C" int mra_qformer_backward_layer_events(mra_qformer_t* h, void* const* events, int32_t n) {
-    MRA_REQUIRE(h != nullptr && n >= 0 && n <= MRA_MAX_LAYERS && (events != nullptr || n == 0), "mra_qformer_backward_layer_events: bad arguments");
-    for (int l = 0; l < MRA_MAX_LAYERS; ++l) h->layer_done[l] = l < n ? reinterpret_cast<cudaEvent_t>(events[l]) : nullptr;
+    MRA_REQUIRE(h != nullptr && n >= 0 && n <= MRA_MAX_LAYERS + 1 && (events != nullptr || n == 0), "mra_qformer_backward_layer_events: bad arguments");
+    for (int l = 0; l <= MRA_MAX_LAYERS; ++l) h->layer_done[l] = l < n ? reinterpret_cast<cudaEvent_t>(events[l]) : nullptr;
     return 0;
 }
 
@@ -774,13 +771,13 @@ extern "C" int mra_adam_step(float* params, const float* grads, float* exp_avg, 
                        reinterpret_cast<cudaStream_t>(stream));
 }
 
-extern "C" int mra_adam_step_fused(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* params_bf16, int64_t n,
-                                   float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
-                                   float grad_scale, int32_t zero_grads, void* stream) {
+extern "C" int mra_adam_step_fused(float* params, float* grads, const void* reduced_grads_bf16, float* exp_avg, float* exp_avg_sq,
+                                   void* params_bf16, int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                                   int32_t step, float grad_scale, int32_t zero_grads, void* stream) {
     MRA_REQUIRE(params && grads && exp_avg && exp_avg_sq, "mra_adam_step_fused: NULL argument");
     if (int e = device_check()) return e;
-    return launch_adam_fused(params, grads, exp_avg, exp_avg_sq, params_bf16, n, lr, beta1, beta2, eps, weight_decay, step,
-                             grad_scale, zero_grads, reinterpret_cast<cudaStream_t>(stream));
+    return launch_adam_fused(params, grads, reduced_grads_bf16, exp_avg, exp_avg_sq, params_bf16, n, lr, beta1, beta2, eps,
+                             weight_decay, step, grad_scale, zero_grads, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int mra_cast_bf16(const float* in, void* out, int64_t n, void* stream) {

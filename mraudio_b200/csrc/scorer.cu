@@ -70,6 +70,7 @@ mr_score_kernel(const double* __restrict__ pred, const int32_t* __restrict__ n_p
     }
     double iou[GMAX];
     int order[GMAX];
+    bool tie_ambiguous = false;
     for (int idx = 0; idx < np_; ++idx) {
         const double p0 = P[2 * idx], p1 = P[2 * idx + 1];
         for (int j = 0; j < ng; ++j) iou[j] = cross_iou(p0, p1, G[2 * j], G[2 * j + 1]);
@@ -82,6 +83,16 @@ mr_score_kernel(const double* __restrict__ pred, const int32_t* __restrict__ n_p
                 --k;
             }
             order[k] = j;
+        }
+        // Two DIFFERENT ground-truth windows with exactly the same IoU (>= the lowest threshold, or nan) for one prediction:
+        // which of them is matched first is decided by the tie order of numpy's argsort, which is an unstable SIMD sort on
+        // AVX-512 / AVX2 builds for >= 4 elements, i.e. the reference's own result is platform-dependent for this query.
+        // This kernel uses the stable order; the query is flagged (bit 1 of out_invalid) so that callers can tell.
+        for (int k = 0; k + 1 < ng; ++k) {
+            const int j1 = order[k], j2 = order[k + 1];
+            const double v1 = iou[j1], v2 = iou[j2];
+            const bool eq = v1 == v2 || (v1 != v1 && v2 != v2);
+            if (eq && !(v1 < thd[0]) && (G[2 * j1] != G[2 * j2] || G[2 * j1 + 1] != G[2 * j2 + 1])) tie_ambiguous = true;
         }
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
@@ -148,7 +159,7 @@ mr_score_kernel(const double* __restrict__ pred, const int32_t* __restrict__ n_p
         if (inter < 0.0) inter = 0.0;
         const double uni = fmax(p1, g1) - fmin(p0, g0);
         out_iou[q] = (uni != 0.0) ? inter / uni : 0.0;
-        out_invalid[q] = (p0 == -1.0 || p1 == -1.0) ? 1 : 0;
+        out_invalid[q] = ((p0 == -1.0 || p1 == -1.0) ? 1 : 0) | (tie_ambiguous ? 2 : 0);
     }
 }
 

@@ -68,7 +68,8 @@ def pack_windows(submission: List[dict], ground_truth: List[dict]):
 
 
 def score_records(submission: List[dict], ground_truth: List[dict], device=None) -> Dict[str, np.ndarray]:
-    """Per-query records in submission order, computed on the GPU: ``ap`` [Q,10], ``iou`` [Q], ``invalid`` [Q]."""
+    """Per-query records in submission order, computed on the GPU: ``ap`` [Q,10], ``iou`` [Q], ``invalid`` [Q], and
+    ``tie_ambiguous`` [Q] (queries whose reference result depends on numpy's platform-dependent argsort tie order)."""
     if not torch.cuda.is_available():
         raise MraError("mraudio_b200.mr_eval needs a CUDA device (no CPU fallback)")
     device = torch.device(device if device is not None else "cuda")
@@ -77,7 +78,10 @@ def score_records(submission: List[dict], ground_truth: List[dict], device=None)
         return {"ap": np.zeros((0, 10)), "iou": np.zeros(0), "invalid": np.zeros(0, dtype=bool)}
     to = lambda a: torch.from_numpy(a).pin_memory().to(device, non_blocking=True)
     ap, iou, inv = ops.mr_score(to(pred), to(npred), to(gt), to(ngt), torch.tensor(IOU_THDS, dtype=torch.float64, device=device))
-    return {"ap": ap.cpu().numpy(), "iou": iou.cpu().numpy(), "invalid": inv.cpu().numpy().astype(bool)}
+    flags = inv.cpu().numpy()
+    # bit 1: the query's result depends on numpy's argsort tie order (see include/mraudio_b200.h, mra_mr_score)
+    return {"ap": ap.cpu().numpy(), "iou": iou.cpu().numpy(), "invalid": (flags & 1).astype(bool),
+            "tie_ambiguous": (flags & 2).astype(bool)}
 
 
 def gather_records(rec: Dict[str, np.ndarray], order: np.ndarray, group=None, device=None):

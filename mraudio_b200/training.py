@@ -117,22 +117,35 @@ class TrainableQFormer:
         # epochs (set_weights with an inference pack) re-point every later training step at a frozen snapshot.
         self._handle = bert._new_handle(D)
         self.version = 0                       # bumped whenever the master weights change behind autograd's back
-        # ---- gradient buckets for the overlapped all-reduce: [start of layer b, end of the previous bucket), top layers first;
-        #      the last bucket also holds the front of the buffer (embeddings, stacked cross K/V, projection, query tokens)
+        # ---- gradient buckets for the overlapped all-reduce, in the order in which the backward finalises them:
+        #      the projection (first launches of the backward), then pairs of layers from the top, then what is final only at
+        #      the end (embeddings, stacked cross K/V, query tokens).  Each entry: (event index | None = end of backward,
+        #      [(lo, hi) ranges of the flat buffer]).  12 layers -> 8 buckets; the tail holds ~20 % of the elements (the word
+        #      embedding table alone is 12.6 %) and is the only part whose exchange cannot overlap the backward.
         nl = len(layers)
-        cuts = sorted({nl * 2 // 3, nl // 3} - {0}, reverse=True)           # 12 layers -> buckets from layer 8 and layer 4
-        self.buckets: List[Tuple[Optional[int], int, int]] = []            # (layer whose "done" event gates it | None, lo, hi)
+        self.buckets: List[Tuple[Optional[int], List[Tuple[int, int]]]] = []
+        proj_lo, proj_hi = self.seg["w_proj"][0], self.seg["query_tokens"][0]
+        self.buckets.append((nl, [(proj_lo, proj_hi)]))
         hi = self.numel
-        for b in cuts:
+        step = 2 if nl >= 4 else 1
+        for b in range(nl - step, -1, -step):
             lo = self.seg[f"L{b}.w_qkv"][0]
-            self.buckets.append((b, lo, hi))
+            self.buckets.append((b, [(lo, hi)]))
             hi = lo
-        self.buckets.append((None, 0, hi))
-        self.layer_events = [torch.cuda.Event() for _ in range(nl)]
+        if hi > self.seg["L0.w_qkv"][0]:                                    # odd layer count: the remaining bottom layer(s)
+            self.buckets.append((0, [(self.seg["L0.w_qkv"][0], hi)]))
+            hi = self.seg["L0.w_qkv"][0]
+        self.buckets.append((None, [(0, proj_lo), (proj_hi, hi)]))
+        self.layer_events = [torch.cuda.Event() for _ in range(nl + 1)]    # [nl] = projection gradients final
         for e in self.layer_events:
             e.record()                                                     # creates the underlying cudaEvent_t
-        ev = (C.c_void_p * nl)(*[e.cuda_event for e in self.layer_events])
-        check(lib.mra_qformer_backward_layer_events(self._handle, ev, nl))
+        ev = (C.c_void_p * (nl + 1))(*[e.cuda_event for e in self.layer_events])
+        check(lib.mra_qformer_backward_layer_events(self._handle, ev, nl + 1))
+        # gradient exchange dtype: bf16 halves the bytes on NVLink (fp32 accumulation on every rank, bf16 on the wire --
+        # the usual DDP compression hook); fp32 keeps the exchange exact (used by the equivalence checks)
+        self.grad_comm_dtype = torch.bfloat16
+        self.grad16 = None                      # bf16 staging / result of the exchange (allocated on first use)
+        self._reduced_bf16 = False              # the last exchange left its result in grad16
         self.comm_stream = torch.cuda.Stream(dev)
         self.reduce_group = None
         self.reduce_after_backward = False     # set by the trainer on optimizer-step iterations when world > 1
@@ -265,22 +278,39 @@ class TrainableQFormer:
         if self.reduce_after_backward:
             self.launch_grad_allreduce()
 
-    def launch_grad_allreduce(self):
-        """DDP's gradient all-reduce (utils/trainer.py:69), bucketed and overlapped: the bucket of the top layers starts on
-        ``comm_stream`` as soon as the backward has recorded that layer's event, while the lower layers (and the other
-        modality's backward) are still running on the compute stream.  Sum semantics; ``adam_step(grad_scale=1/world)``
-        turns it into DDP's mean.  ``wait_grad_allreduce`` makes the current stream wait for it."""
+    def _exchange(self, lo: int, hi: int):
+        """all-reduce (sum) of one range of the flat gradient buffer on the current (communication) stream"""
         import torch.distributed as dist
+        if self.grad_comm_dtype == torch.bfloat16:
+            if self.grad16 is None:
+                self.grad16 = torch.empty(self.numel, device=self.grad.device, dtype=torch.bfloat16)
+            check(lib.mra_cast_bf16(self.grad.data_ptr() + lo * 4, self.grad16.data_ptr() + lo * 2, hi - lo, current_stream()))
+            dist.all_reduce(self.grad16[lo:hi], op=dist.ReduceOp.SUM, group=self.reduce_group)
+        else:
+            dist.all_reduce(self.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.reduce_group)
+
+    def launch_grad_allreduce(self):
+        """DDP's gradient all-reduce (utils/trainer.py:69), bucketed and overlapped: a bucket starts on ``comm_stream`` as soon
+        as the backward has recorded the event that makes it final, while the lower layers (and the other modality's
+        backward) are still running on the compute stream.  Sum semantics; ``adam_step(grad_scale=1/world)`` turns it into
+        DDP's mean.  ``wait_grad_allreduce`` makes the current stream wait for it."""
         main = torch.cuda.current_stream()
         tail = torch.cuda.Event()
         tail.record(main)                      # end of this backward: gates the last bucket
         with torch.cuda.stream(self.comm_stream):
-            for layer, lo, hi in self.buckets:
-                self.comm_stream.wait_event(self.layer_events[layer] if layer is not None else tail)
-                dist.all_reduce(self.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.reduce_group)
+            for ev, ranges in self.buckets:
+                self.comm_stream.wait_event(self.layer_events[ev] if ev is not None else tail)
+                for lo, hi in ranges:
+                    self._exchange(lo, hi)
             self.reduce_done = torch.cuda.Event()
             self.reduce_done.record(self.comm_stream)
+        self._reduced_bf16 = self.grad_comm_dtype == torch.bfloat16
         self.reduce_after_backward = False
+
+    def flat_grad_allreduce(self):
+        """one exchange of the whole buffer on the current stream, after the backward (the A/B baseline of the overlap)"""
+        self._exchange(0, self.numel)
+        self._reduced_bf16 = self.grad_comm_dtype == torch.bfloat16
 
     def wait_grad_allreduce(self):
         if self.reduce_done is not None:
@@ -297,7 +327,9 @@ class TrainableQFormer:
         in ONE pass over the flat buffers."""
         self.step_count += 1
         self.version += 1
-        check(lib.mra_adam_step_fused(self.flat.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
+        g16 = self.grad16.data_ptr() if self._reduced_bf16 else None      # gradients as exchanged in bf16 (else the fp32 buffer)
+        self._reduced_bf16 = False
+        check(lib.mra_adam_step_fused(self.flat.data_ptr(), self.grad.data_ptr(), g16, self.exp_avg.data_ptr(),
                                       self.exp_avg_sq.data_ptr(), self.flat16.data_ptr(), self.numel, lr, betas[0], betas[1], eps,
                                       weight_decay, self.step_count, grad_scale, int(zero_grad), current_stream()))
 
@@ -333,7 +365,8 @@ class QFormerTrainer:
     (out of scope); the default is the surrogate ``sum(inputs_llm * G)`` used by the parity tests and the benchmark."""
 
     def __init__(self, model, max_epoch: int = 1, accum_grad_iters: int = 2, init_lr: float = 3e-4, warmup_steps: int = 1000,
-                 loss_fn=None, group=None, overlap_allreduce: bool = True, parallel_modalities: bool = True):
+                 loss_fn=None, group=None, overlap_allreduce: bool = True, parallel_modalities: bool = True,
+                 grad_comm_dtype: torch.dtype = torch.bfloat16):
         self.model = model
         model.freeze_qformers(False)
         self.states = {m: TrainableQFormer(getattr(model, f"{m}_Qformer"), getattr(model, f"{m}_query_tokens"),
@@ -342,6 +375,8 @@ class QFormerTrainer:
         self.loss_fn = loss_fn
         self.group = group
         self.overlap_allreduce = overlap_allreduce
+        self.allreduce_enabled = True       # False: skip the gradient exchange (bench.py measures its exposed cost that way)
+        self.set_grad_comm_dtype(grad_comm_dtype)
         # At fine-tuning batch sizes (64 rows per modality) most launches fill a fraction of the 148 SMs, so the video and
         # the audio Q-Former run on two streams: autograd replays each modality's backward on the stream of its forward.
         # (For the large-batch inference forward the opposite holds -- DESIGN.md section 4 -- and one stream is used.)
@@ -350,6 +385,12 @@ class QFormerTrainer:
         self.mod_streams = {m: torch.cuda.Stream(dev) for m in model.modalities}
         self.iter = 0
         self.lr = init_lr
+
+    def set_grad_comm_dtype(self, dtype: torch.dtype):
+        """bf16 (default: 0.74 GB per step for both Q-Formers) or fp32 (1.49 GB, exact) gradient exchange"""
+        assert dtype in (torch.bfloat16, torch.float32)
+        for st in self.states.values():
+            st.grad_comm_dtype = dtype
 
     def _world(self):
         import torch.distributed as dist
@@ -386,8 +427,11 @@ class QFormerTrainer:
             torch.cuda.current_stream().wait_stream(side)
         return inputs_llm, atts_llm
 
-    def train_step(self, feats, input_ids, attention_mask, samples=None, cur_epoch: int = 0, surrogate: Optional[Dict[str, torch.Tensor]] = None):
-        """One iteration of the reference's inner loop.  Returns the (unscaled) loss tensor."""
+    def train_step(self, feats, input_ids, attention_mask, samples=None, cur_epoch: int = 0, surrogate: Optional[Dict[str, torch.Tensor]] = None,
+                   apply_optimizer: bool = True):
+        """One iteration of the reference's inner loop.  Returns the (unscaled) loss tensor.  ``apply_optimizer=False`` stops
+        after the gradient all-reduce of a stepping iteration (the flat gradient buffers then hold the SUM over ranks):
+        used by the data-parallel equivalence checks."""
         import torch.distributed as dist
         self.lr = warmup_cosine_lr(cur_epoch, self.iter, self.max_epoch, self.init_lr, 0.0, self.warmup_steps)   # :127
         inputs_llm, atts_llm = self.forward_modalities(feats, input_ids, attention_mask)
@@ -397,7 +441,8 @@ class QFormerTrainer:
             loss = sum((inputs_llm[m].float() * surrogate[m]).sum() for m in inputs_llm)
         world = self._world()
         stepping = (self.iter + 1) % self.accum_grad_iters == 0                                                    # :137
-        if stepping and world > 1:
+        reduce = stepping and world > 1 and self.allreduce_enabled
+        if reduce:
             # DDP's gradient averaging, only on optimizer-step iterations (the reference all-reduces on every backward):
             # each modality's backward node launches its bucketed all-reduce on a side stream as its layers finish
             # (only for the modalities of this step: a flag left set on an absent modality would fire its all-reduce on a
@@ -414,15 +459,22 @@ class QFormerTrainer:
                 torch.cuda.current_stream().wait_stream(side)
         self.iter += 1
         if stepping:
-            if world > 1:
+            if reduce:
                 for m, st in self.states.items():
                     if self.overlap_allreduce and st.reduce_done is not None:
                         st.wait_grad_allreduce()
                     else:   # flat all-reduce after the backward: the A/B baseline, and modalities absent from this step
                             # (their accumulated gradients of earlier iterations still have to be averaged)
-                        dist.all_reduce(st.grad, op=dist.ReduceOp.SUM, group=self.group)
-            for st in self.states.values():
-                st.adam_step(self.lr, grad_scale=1.0 / world, zero_grad=True)
+                        st.reduce_group = self.group
+                        st.flat_grad_allreduce()
+                if not apply_optimizer:
+                    for st in self.states.values():       # leave the exchanged SUM in the fp32 buffers for the caller
+                        if st._reduced_bf16:
+                            st.grad.copy_(st.grad16)
+                            st._reduced_bf16 = False
+            if apply_optimizer:
+                for st in self.states.values():
+                    st.adam_step(self.lr, grad_scale=1.0 / world, zero_grad=True)
         return loss.detach()
 
     def eval_epoch(self, generations, group=None):

@@ -52,6 +52,11 @@ def make_scorer_golden():
     cases["int_ties_200"] = synth_submission(200, seed=11, duration=20, clip_len=2, max_pred=8, max_gt=6)
     cases["float_150"] = synth_submission(150, seed=3, float_windows=True)
     cases["many_invalid_64"] = synth_submission(64, seed=5, invalid_frac=0.5)
+    # 17..64 ground-truth windows per query (beyond numpy's insertion-sort range of 16 elements): float windows, so equal
+    # IoUs come only from duplicated windows; and the integer grid, where DIFFERENT windows can tie exactly -- there the
+    # reference's result depends on the tie order of this numpy build's (AVX-512) argsort, see oracle/mr_eval_oracle.py
+    cases["many_gt_float_120"] = synth_submission(120, seed=13, max_pred=10, max_gt=64, float_windows=True)
+    cases["many_gt_int_120"] = synth_submission(120, seed=17, duration=150, max_pred=10, max_gt=40)
     # SURVEY.md 8(a) known-answer vectors
     cases["kat_two_queries"] = (
         [{"qid": "a", "pred_relevant_windows": [[10, 20], [30, 40]]}, {"qid": "b", "pred_relevant_windows": [[-1, -1]]}],

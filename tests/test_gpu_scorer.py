@@ -88,3 +88,27 @@ def test_edge_cases():
         mr_eval.eval_submission(sub[:1], gt, verbose=False)
     out = mr_eval.eval_submission(sub[:1], gt, verbose=False, match_number=False)
     assert out["brief"]["MR-full-invalid_pred_num"] == 1
+
+
+def test_many_gt_windows_and_tie_ambiguity_flag():
+    """Up to 64 ground-truth windows per query (the kernel's limit) -- the reference-generated fixtures many_gt_* above are
+    matched bit for bit -- and the one ill-defined situation is flagged: a prediction with EXACTLY the same IoU >= 0.5 with
+    two different GT windows (the reference resolves it by numpy's argsort tie order, which is unstable for >= 4 elements on
+    AVX-512 builds; the kernel uses the stable order)."""
+    from mraudio_b200 import mr_eval
+    from mraudio_b200._lib import MraError
+    sub = [{"qid": 0, "pred_relevant_windows": [[10, 20], [4, 20]]},      # IoU 2/3 with both [5, 20] and [10, 25]: ambiguous
+           {"qid": 1, "pred_relevant_windows": [[10, 20]]},               # equal IoU only with DUPLICATED windows: well defined
+           {"qid": 2, "pred_relevant_windows": [[10, 20]]},               # equal IoU below every threshold (0): irrelevant
+           {"qid": 3, "pred_relevant_windows": [[0, 2]]}]
+    gt = [{"qid": 0, "relevant_windows": [[5, 20], [10, 25], [40, 50], [60, 70]]},
+          {"qid": 1, "relevant_windows": [[10, 20], [10, 20], [40, 50], [60, 70]]},
+          {"qid": 2, "relevant_windows": [[30, 40], [50, 60], [70, 80], [10, 19]]},
+          {"qid": 3, "relevant_windows": [[2 * i, 2 * i + 2] for i in range(64)]}]
+    rec = mr_eval.score_records(sub, gt)
+    assert rec["tie_ambiguous"].tolist() == [True, False, False, False]
+    assert not rec["invalid"].any()
+    ora = mo.score_records(sub, gt)
+    assert _eq(rec["ap"], ora["ap"]) and _eq(rec["iou"], ora["iou"])
+    with pytest.raises(MraError):   # 65 windows: over the kernel's limit, refused loudly
+        mr_eval.score_records(sub[3:], [{"qid": 3, "relevant_windows": [[2 * i, 2 * i + 2] for i in range(65)]}])
