@@ -458,8 +458,11 @@ def run_b200(args):
         del pipe, host_feats, feats, model
         torch.cuda.empty_cache()
         sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import contextlib
+        import io
         import secondary
-        sec = secondary.run_all(world, rank, dev)
+        with contextlib.redirect_stdout(io.StringIO()):     # (eval_submission prints its split sizes like the reference does)
+            sec = secondary.run_all(world, rank, dev)
         wd.cancel()
         emit(sec)
     else:

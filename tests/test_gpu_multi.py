@@ -60,6 +60,31 @@ def _worker(rank, world, port, q):
         torch.cuda.synchronize()
         flat2 = torch.cat([s.flat for s in tr2.states.values()])
         same = same and torch.allclose(flat, flat2, rtol=0, atol=2e-5) and not torch.equal(flat2, torch.zeros_like(flat2))
+        # ---- the defining property of DistributedDataParallel (utils/trainer.py:69): the all-reduced gradient of the ranks'
+        #      shards == the gradient of the whole batch on one rank (same prompt for every video: the reference tiles prompts
+        #      frame-major over the rows, so with different prompts the pairing would depend on the batch size); fp32 exchange
+        #      to 1e-4 (summation order only), bf16 exchange to bf16 rounding
+        ids1 = ids[:1].expand(B, -1).contiguous()
+        for comm, tol in ((torch.float32, 1e-4), (torch.bfloat16, 1e-2)):
+            tr.set_grad_comm_dtype(comm)
+            for st in tr.states.values():
+                st.zero_grad()
+            tr.train_step({m: t[lo:hi].cuda() for m, t in feats.items()}, ids1[lo:hi].cuda(), mask[lo:hi].cuda(),
+                          surrogate={m: t[lo:hi].cuda() for m, t in sur.items()}, apply_optimizer=False)
+            torch.cuda.synchronize()
+            g_ddp = {m: st.grad.clone() for m, st in tr.states.items()}
+            for st in tr.states.values():
+                st.zero_grad()
+            tr.allreduce_enabled = False
+            tr.train_step({m: t.cuda() for m, t in feats.items()}, ids1.cuda(), mask.cuda(), surrogate={m: t.cuda() for m, t in sur.items()},
+                          apply_optimizer=False)
+            tr.allreduce_enabled = True
+            torch.cuda.synchronize()
+            for m, st in tr.states.items():
+                err = ((g_ddp[m] - st.grad).abs().max() / st.grad.abs().max()).item()
+                same = same and err < tol and st.grad.abs().max().item() > 0
+            for st in tr.states.values():
+                st.zero_grad()
         # ---- scorer: NCCL gather of scored moments == single-process result
         sub, gt = mo.synth_submission(333, seed=9)
         lo, hi = shard_range(len(sub), rank, world)

@@ -32,7 +32,9 @@ def _oracle_grads(cfg, w, ids, atts, enc, G):
     return y.detach(), {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in wr.items()}
 
 
-@pytest.mark.parametrize("rows,T,Nk,W,layers", [(3, 8, 20, 64, 2), (2, 32, 257, 1408, 3), (5, 0, 40, 768, 2)])
+# the last case is BASELINE.json config 4 at its per-GPU size: 8 videos x 8 frames = 64 rows of 257 x 1408 tokens, 12 layers
+@pytest.mark.parametrize("rows,T,Nk,W,layers", [(3, 8, 20, 64, 2), (2, 32, 257, 1408, 3), (5, 0, 40, 768, 2),
+                                                 (64, 32, 257, 1408, 12)])
 def test_backward_matches_oracle_autograd(rows, T, Nk, W, layers):
     from mraudio_b200.training import TrainableQFormer
     D = 256

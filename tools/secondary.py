@@ -53,11 +53,14 @@ class Ctx:
         return self.max_over_ranks(e0.elapsed_time(e1) / steps)
 
 
-def _train_batch(B, F, T, seed, dev, scale=1e-3):
+def _train_batch(B, F, T, seed, dev, scale=1e-3, text_seed=None):
     g = torch.Generator().manual_seed(seed)
     feats = {"video": torch.randn(B, F, 257, 1408, generator=g).to(torch.bfloat16).to(dev),
              "audio": torch.randn(B, F, 256, 768, generator=g).to(torch.bfloat16).to(dev)}
-    ids = torch.randint(1000, 30000, (B, T), generator=g).to(dev)
+    if text_seed is None:
+        ids = torch.randint(1000, 30000, (B, T), generator=g).to(dev)
+    else:   # the same instruction prompt for every video (of every rank)
+        ids = torch.randint(1000, 30000, (1, T), generator=torch.Generator().manual_seed(text_seed)).expand(B, T).contiguous().to(dev)
     mask = torch.ones(B, T, dtype=torch.long, device=dev)
     sur = {m: (torch.randn(B, F * 32, 4096, generator=g) * scale).to(dev) for m in feats}
     return feats, ids, mask, sur
@@ -75,36 +78,20 @@ def cfg4_finetune(cx: Ctx, steps=8, warmup=3):
     out = {"workload": "finetune.py step on cached features: 8 videos x 8 frames per GPU, video + audio Q-Former + llm_proj, "
                        "fwd + bwd + gradient all-reduce + Adam (372 M parameters), surrogate loss (LLM out of scope)",
            "n_gpus": cx.world}
-    ms = cx.timed(step, steps, warmup)
-    out["ms_per_step"] = ms
-    out["clips_per_s_all_gpus"] = cx.world * B * F / (ms * 1e-3)
-    out["backward_launches"] = sum(s.last_backward_launches for s in tr.states.values())
-    numel = sum(s.numel for s in tr.states.values())
-    out["grad_allreduce"] = {"dtype": "bf16 (fp32 master weights / Adam state)", "buckets_per_modality": len(next(iter(tr.states.values())).buckets),
-                             "nccl_bytes_per_step": (numel * 2) if cx.world > 1 else 0}
     if cx.world > 1:
-        tr.allreduce_enabled = False
-        ms_no = cx.timed(step, steps, 2)
-        tr.allreduce_enabled = True
-        tr.overlap_allreduce = False
-        ms_flat = cx.timed(step, steps, 2)
-        tr.overlap_allreduce = True
-        out["ms_per_step_without_allreduce"] = ms_no
-        out["exposed_allreduce_ms"] = ms - ms_no
-        out["ms_per_step_flat_allreduce_after_backward"] = ms_flat
-        # ---- data-parallel equivalence on a small batch: mean over ranks of the shard gradients == gradient of the whole
-        #      batch (fp32 exchange for this check; the sum-loss makes the whole-batch gradient the SUM of the shard gradients)
+        # ---- data-parallel equivalence on a small batch, BEFORE anything lets the replicas drift: mean over ranks of the shard
+        #      gradients == gradient of the whole batch (fp32 exchange for this check; with the sum-loss the whole-batch
+        #      gradient is the SUM of the shard gradients).  Every video carries the same prompt: the reference tiles the
+        #      prompt frame-major over the (video, frame) rows (models/xinstructblip.py:287-289), so with DIFFERENT prompts
+        #      per video the pairing of prompt and row depends on the batch size, and a shard would not compute the same
+        #      function as the whole batch.
         Bc = 2
         tr.set_grad_comm_dtype(torch.float32)
-        shard = _train_batch(Bc, F, T, 1000 + cx.rank, cx.dev)
-        for st in tr.states.values():
-            st.zero_grad()
+        parts = [_train_batch(Bc, F, T, 1000 + r, cx.dev, text_seed=77) for r in range(cx.world)]
+        shard = parts[cx.rank]
         tr.train_step(shard[0], shard[1], shard[2], surrogate=shard[3], apply_optimizer=False)
         torch.cuda.synchronize()
-        sample = {m: torch.randint(0, st.numel, (1 << 16,), generator=torch.Generator().manual_seed(5)).to(cx.dev)
-                  for m, st in tr.states.items()}
-        g_ddp = {m: st.grad[sample[m]].clone() for m, st in tr.states.items()}
-        parts = [_train_batch(Bc, F, T, 1000 + r, cx.dev) for r in range(cx.world)]
+        g_ddp = {m: st.grad.clone() for m, st in tr.states.items()}
         whole = ({m: torch.cat([p[0][m] for p in parts]) for m in parts[0][0]}, torch.cat([p[1] for p in parts]),
                  torch.cat([p[2] for p in parts]), {m: torch.cat([p[3][m] for p in parts]) for m in parts[0][3]})
         for st in tr.states.values():
@@ -115,15 +102,33 @@ def cfg4_finetune(cx: Ctx, steps=8, warmup=3):
         torch.cuda.synchronize()
         worst = 0.0
         for m, st in tr.states.items():
-            ref = st.grad[sample[m]]
-            worst = max(worst, ((g_ddp[m] - ref).abs().max() / ref.abs().max()).item())
+            worst = max(worst, ((g_ddp[m] - st.grad).abs().max() / st.grad.abs().max()).item())
         worst = cx.max_over_ranks(worst)
+        # (recorded, not raised: a failed check must not take the headline line down; tests/test_gpu_multi.py asserts it)
         out["ddp_equivalence"] = {"check": f"all-reduced gradient of {cx.world} shards of {Bc} videos == gradient of the {cx.world * Bc}-video batch "
-                                           "on one rank, 65 536 sampled parameters per modality, fp32 exchange",
-                                  "max_rel_err": worst, "tolerance": 1e-4, "ok": bool(worst < 1e-4)}
-        assert worst < 1e-4, f"data-parallel gradient differs from the whole-batch gradient: {worst}"
+                                           "computed on one rank, all 186 M parameters of each modality, fp32 exchange, max-norm relative",
+                                  "max_rel_err": worst, "tolerance": 1e-5, "ok": bool(worst < 1e-5)}
         for st in tr.states.values():
             st.zero_grad()
+        del g_ddp, parts, whole, shard
+        tr.set_grad_comm_dtype(torch.bfloat16)
+    ms = cx.timed(step, steps, warmup)
+    out["ms_per_step"] = ms
+    out["clips_per_s_all_gpus"] = cx.world * B * F / (ms * 1e-3)
+    out["backward_launches"] = sum(s.last_backward_launches for s in tr.states.values())
+    numel = sum(s.numel for s in tr.states.values())
+    out["grad_allreduce"] = {"dtype": "bf16 (fp32 master weights / Adam state)", "buckets_per_modality": len(next(iter(tr.states.values())).buckets),
+                             "nccl_bytes_per_step": (numel * 2) if cx.world > 1 else 0}
+    if cx.world > 1:
+        tr.overlap_allreduce = False
+        out["ms_per_step_flat_allreduce_after_backward"] = cx.timed(step, steps, 2)
+        tr.overlap_allreduce = True
+        tr.allreduce_enabled = False      # last: without the exchange the replicas drift apart
+        ms_no = cx.timed(step, steps, 2)
+        tr.allreduce_enabled = True
+        out["ms_per_step_without_allreduce"] = ms_no
+        out["exposed_allreduce_ms"] = ms - ms_no
+        out["scaling_vs_no_exchange"] = ms_no / ms
     del tr, model
     torch.cuda.empty_cache()
     return out
@@ -217,8 +222,6 @@ def run_all(world, rank, dev):
     for name, fn in (("cfg4_finetune_step", cfg4_finetune), ("cfg5_eval_sweep", cfg5_sweep), ("cfg3_videollama_v1", cfg3_videollama)):
         try:
             out[name] = fn(cx)
-        except AssertionError:
-            raise
         except Exception as e:   # a secondary measurement must not take the headline down with it
             out[name] = {"error": f"{type(e).__name__}: {e}"}
             torch.cuda.empty_cache()
