@@ -109,6 +109,15 @@ typedef struct mra_qformer_io {
     int32_t llm_frames;
     int32_t reserved0;
     int64_t llm_ld, llm_frame_stride, llm_video_stride;
+    /* Training-mode dropout (model.train() of utils/trainer.py:110; BertConfig hidden_dropout_prob = attention_probs_dropout_prob
+     * = 0.1): with dropout_p > 0 -- only together with MRA_FWD_SAVE_FOR_BACKWARD -- the embeddings' LayerNorm output, the
+     * attention probabilities (self and cross) and the output of every attention-output / FFN-output Linear (before the
+     * residual add) are dropped with a counter-based Philox mask derived from dropout_seed (never stored: mra_qformer_backward
+     * regenerates it from the same io).  Effective probability round(p * 256) / 256, see csrc/dropout.cuh.  The text length
+     * T must be a multiple of 32 (pad the prompt and mask the padding) so that the TMA attention kernels cover the shape. */
+    float dropout_p;
+    uint32_t reserved1;
+    uint64_t dropout_seed;
 } mra_qformer_io;
 
 /* Replaces `{modality}_Qformer.bert(input_ids, attention_mask=, query_embeds=, encoder_hidden_states=,

@@ -241,6 +241,7 @@ struct TmaParams {
     int q_n0, q_n1;   // query tokens per row in segment 0 / 1
     int k_n0, k_n1;   // key tokens per row in segment 0 / 1
     int nchunks;      // ceil(Sk / 64)
+    DropoutParams drop;   // thr8 != 0: training-mode dropout on the attention probabilities (dropout.cuh)
 };
 
 constexpr int TMA_STAGES = 2;
@@ -411,14 +412,27 @@ attention_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant
             // ---- P = exp2(S - m), row sums, pack to bf16 A fragments
             uint32_t pf[4][4];
             float ls[2] = {0.f, 0.f};
+            // training-mode dropout: the softmax normaliser (row sum) is that of the UNdropped probabilities; the values that
+            // go into P V are masked and rescaled.  One Philox call covers this thread's 16 values of a query row and chunk.
+            const bool dropping = p.drop.thr8 != 0;
+            uint4 rb0 = make_uint4(0, 0, 0, 0), rb1 = rb0;
+            if (dropping) {
+                const uint64_t rh = static_cast<uint64_t>(r) * p.heads + head;
+                rb0 = dropout_bytes(p.drop, ((rh * p.Sq + (qr0 + g)) * p.nchunks + kc) * 4 + t);
+                rb1 = dropout_bytes(p.drop, ((rh * p.Sq + (qr0 + g + 8)) * p.nchunks + kc) * 4 + t);
+            }
 #pragma unroll
             for (int nt = 0; nt < 8; ++nt) {
-                const float p0 = exp2f(s[nt][0] - m_run[0]);
-                const float p1 = exp2f(s[nt][1] - m_run[0]);
-                const float p2 = exp2f(s[nt][2] - m_run[1]);
-                const float p3 = exp2f(s[nt][3] - m_run[1]);
+                float p0 = exp2f(s[nt][0] - m_run[0]);
+                float p1 = exp2f(s[nt][1] - m_run[0]);
+                float p2 = exp2f(s[nt][2] - m_run[1]);
+                float p3 = exp2f(s[nt][3] - m_run[1]);
                 ls[0] += p0 + p1;
                 ls[1] += p2 + p3;
+                if (dropping) {
+                    p0 *= dropout_mult(p.drop, rb0, 2 * nt); p1 *= dropout_mult(p.drop, rb0, 2 * nt + 1);
+                    p2 *= dropout_mult(p.drop, rb1, 2 * nt); p3 *= dropout_mult(p.drop, rb1, 2 * nt + 1);
+                }
                 const int j = nt >> 1;
                 if ((nt & 1) == 0) {
                     pf[j][0] = ptx::pack_bf16x2(p0, p1);
@@ -553,6 +567,7 @@ int prepare_tma_problem(const AttnArgs& a, int slot, TmaMaps& maps, TmaParams2& 
     p.q_n0 = split_q ? a.nq_split : a.Sq; p.q_n1 = split_q ? a.Sq - a.nq_split : 0;
     p.k_n0 = split_k ? a.nq_split : a.Sk; p.k_n1 = split_k ? a.Sk - a.nq_split : 0;
     p.nchunks = (a.Sk + 63) / 64;
+    p.drop = a.drop;
     const int width = a.heads * HD;
     const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(a.q);
     const __nv_bfloat16* k = reinterpret_cast<const __nv_bfloat16*>(a.k);
@@ -621,6 +636,8 @@ int launch_attention(const AttnArgs& a, cudaStream_t s) {
         const int e = try_launch_attention_tma(&a, 1, s);
         if (e >= 0) return e;
     }
+    MRA_REQUIRE(a.drop.thr8 == 0, "attention dropout needs a shape the TMA kernel covers (Sq <= 256, Sk <= 4096, text length a "
+                                  "multiple of 32): Sq=%d Sk=%d split=%d", a.Sq, a.Sk, a.nq_split);
     Params p{reinterpret_cast<const __nv_bfloat16*>(a.q), a.ldq, reinterpret_cast<const __nv_bfloat16*>(a.k), a.ldk,
              reinterpret_cast<const __nv_bfloat16*>(a.v), a.ldv, reinterpret_cast<__nv_bfloat16*>(a.o), a.ldo,
              a.add_mask, a.rows, a.heads, a.Sq, a.Sk, a.nq_split, a.kv_dense};

@@ -89,7 +89,8 @@ template <int LNB_MAXV, bool DBIAS>
 __global__ void __launch_bounds__(LNB_WARPS * 32)
 ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ pre, const float* __restrict__ gamma,
               float* __restrict__ dx32, __nv_bfloat16* __restrict__ dx16, float* __restrict__ dgamma,
-              float* __restrict__ dbeta, float* __restrict__ dbias, int rows, int n, float eps) {
+              float* __restrict__ dbeta, float* __restrict__ dbias, int rows, int n, float eps, const DropoutParams drop_out,
+              const DropoutParams drop_in, int row0) {
     __shared__ float red[LNB_WARPS][256];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nvec = n >> 3;
@@ -115,6 +116,11 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ pre, const
                 x[i][0] = a.x; x[i][1] = a.y; x[i][2] = a.z; x[i][3] = a.w; x[i][4] = b.x; x[i][5] = b.y; x[i][6] = b.z; x[i][7] = b.w;
                 const float4 c = *reinterpret_cast<const float4*>(dr + vi * 8), e4 = *reinterpret_cast<const float4*>(dr + vi * 8 + 4);
                 d[i][0] = c.x; d[i][1] = c.y; d[i][2] = c.z; d[i][3] = c.w; d[i][4] = e4.x; d[i][5] = e4.y; d[i][6] = e4.z; d[i][7] = e4.w;
+                if (drop_in.thr8 != 0) {   // dropout sat on this LayerNorm's output (embeddings): mask the incoming gradient
+                    const uint4 rb = dropout_bytes(drop_in, static_cast<uint64_t>(row0 + row) * nvec + vi);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) d[i][e] *= dropout_mult(drop_in, rb, e);
+                }
 #pragma unroll
                 for (int e = 0; e < 8; ++e) sum += x[i][e];
             }
@@ -154,14 +160,22 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ pre, const
             if (vi < nvec) {
                 float o[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    o[e] = rstd * (d[i][e] - c1 - x[i][e] * c2);
-                    if (DBIAS) ax[i][e] += o[e];
-                }
+                for (int e = 0; e < 8; ++e) o[e] = rstd * (d[i][e] - c1 - x[i][e] * c2);
                 if (dx32) {
                     float* p = dx32 + static_cast<int64_t>(row) * n + vi * 8;
                     *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
                     *reinterpret_cast<float4*>(p + 4) = make_float4(o[4], o[5], o[6], o[7]);
+                }
+                if (drop_out.thr8 != 0) {
+                    // dropout sat between the producing Linear and the residual add: the Linear's output gradient (dx16, and
+                    // the bias gradient summed from it) is the masked one; dx32 above -- the residual path -- is not
+                    const uint4 rb = dropout_bytes(drop_out, static_cast<uint64_t>(row0 + row) * nvec + vi);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) o[e] *= dropout_mult(drop_out, rb, e);
+                }
+                if (DBIAS) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) ax[i][e] += o[e];
                 }
                 if (dx16) {
                     uint4 u;
@@ -354,6 +368,7 @@ struct AttnBwdTcParams {
     AttnBwdParams b;
     const __nv_bfloat16* o; int64_t ldof;   // forward output (context) of the same attention
     float* db_q; float* db_k; float* db_v;  // optional fused bias gradients of the q / k / v projections: [heads * 64] column sums
+    DropoutParams drop;                     // the forward's attention-probability dropout (mask regenerated here)
 };
 constexpr int ABT_LD = 72;
 constexpr int ABT_WARPS = 8;
@@ -451,8 +466,9 @@ attn_bwd_tc_kernel(const AttnBwdTcParams pp) {
         d += __shfl_xor_sync(0xffffffffu, d, 2);
         d += __shfl_xor_sync(0xffffffffu, d, 4);
         if (c == 0) sDelta[i] = d;
-        if (pp.db_v) {
-            // bias gradient of the value projection: sum_j dV_j = sum_q (sum_j P_qj) dO_q = sum_q dO_q (softmax rows sum to 1)
+        if (pp.db_v && pp.drop.thr8 == 0) {
+            // bias gradient of the value projection: sum_j dV_j = sum_q (sum_j P_qj) dO_q = sum_q dO_q (softmax rows sum to 1;
+            // with dropout the rows of the masked P do not: the column sums of the dV tiles are taken in phase 2 instead)
             float e8[8];
 #pragma unroll
             for (int k = 0; k < 4; ++k) { e8[2 * k] = ptx::bf16lo(dd[k]); e8[2 * k + 1] = ptx::bf16hi(dd[k]); }
@@ -539,6 +555,16 @@ attn_bwd_tc_kernel(const AttnBwdTcParams pp) {
         const int i0 = qt * 16 + g, i1 = i0 + 8;
         const float m0 = sMx[i0], m1 = sMx[i1], il0 = sIl[i0], il1 = sIl[i1], d0 = sDelta[i0], d1 = sDelta[i1];
         const int nt_end = min(ch * 4 + 4, nK8);
+        // forward dropout mask of this thread's elements: one Philox call per query row and 64-key chunk (a 32-key item lies
+        // inside one chunk); O = (P o M c) V  =>  dV = (P o M c)^T dO,  dP = (dO V^T) o M c,  delta = dO . O unchanged
+        const bool dropping = pp.drop.thr8 != 0;
+        uint4 rb0 = make_uint4(0, 0, 0, 0), rb1 = rb0;
+        if (dropping) {
+            const uint64_t rh = static_cast<uint64_t>(r) * p.heads + head;
+            const int nchunks = (p.Sk + 63) >> 6, kc = ch >> 1;
+            rb0 = dropout_bytes(pp.drop, ((rh * p.Sq + i0) * nchunks + kc) * 4 + t);
+            rb1 = dropout_bytes(pp.drop, ((rh * p.Sq + i1) * nchunks + kc) * 4 + t);
+        }
         for (int nt = ch * 4; nt < nt_end; ++nt) {
             float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
             const __nv_bfloat16* kb = sK + (nt * 8 + g) * ABT_LD + 2 * t;
@@ -552,10 +578,21 @@ attn_bwd_tc_kernel(const AttnBwdTcParams pp) {
             const float p0 = exp2f(fmaf(s[0], scale2, k0) - m0) * il0, p1 = exp2f(fmaf(s[1], scale2, k1) - m0) * il0;
             const float p2 = exp2f(fmaf(s[2], scale2, k0) - m1) * il1, p3 = exp2f(fmaf(s[3], scale2, k1) - m1) * il1;
             const int c = nt * 8 + 2 * t;
-            *reinterpret_cast<uint32_t*>(sP + i0 * ldp + c) = ptx::pack_bf16x2(p0, p1);
-            *reinterpret_cast<uint32_t*>(sP + i1 * ldp + c) = ptx::pack_bf16x2(p2, p3);
-            *reinterpret_cast<uint32_t*>(sDS + i0 * ldp + c) = ptx::pack_bf16x2(p0 * (dp[0] - d0), p1 * (dp[1] - d0));
-            *reinterpret_cast<uint32_t*>(sDS + i1 * ldp + c) = ptx::pack_bf16x2(p2 * (dp[2] - d1), p3 * (dp[3] - d1));
+            float k0m = 1.f, k1m = 1.f, k2m = 1.f, k3m = 1.f;
+            if (dropping) {
+                const int nl = nt & 7;   // 8-key tile inside the 64-key chunk (dynamic index: select the byte at run time)
+                const uint32_t w0 = nl < 2 ? rb0.x : (nl < 4 ? rb0.y : (nl < 6 ? rb0.z : rb0.w));
+                const uint32_t w1 = nl < 2 ? rb1.x : (nl < 4 ? rb1.y : (nl < 6 ? rb1.z : rb1.w));
+                const int sh = (nl & 1) * 16;
+                k0m = ((w0 >> sh) & 0xFFu) >= pp.drop.thr8 ? pp.drop.scale : 0.f;
+                k1m = ((w0 >> (sh + 8)) & 0xFFu) >= pp.drop.thr8 ? pp.drop.scale : 0.f;
+                k2m = ((w1 >> sh) & 0xFFu) >= pp.drop.thr8 ? pp.drop.scale : 0.f;
+                k3m = ((w1 >> (sh + 8)) & 0xFFu) >= pp.drop.thr8 ? pp.drop.scale : 0.f;
+            }
+            *reinterpret_cast<uint32_t*>(sP + i0 * ldp + c) = ptx::pack_bf16x2(p0 * k0m, p1 * k1m);
+            *reinterpret_cast<uint32_t*>(sP + i1 * ldp + c) = ptx::pack_bf16x2(p2 * k2m, p3 * k3m);
+            *reinterpret_cast<uint32_t*>(sDS + i0 * ldp + c) = ptx::pack_bf16x2(p0 * (dp[0] * k0m - d0), p1 * (dp[1] * k1m - d0));
+            *reinterpret_cast<uint32_t*>(sDS + i1 * ldp + c) = ptx::pack_bf16x2(p2 * (dp[2] * k2m - d1), p3 * (dp[3] * k3m - d1));
         }
     }
     __syncthreads();
@@ -610,6 +647,7 @@ attn_bwd_tc_kernel(const AttnBwdTcParams pp) {
                     abt_mma(acc[2 * dp + 1], a, bf[2], bf[3]);
                 }
             }
+            if (!is_dk && pp.db_v && pp.drop.thr8 != 0) abt_colsum(acc, 1.0f, sCol + 128, lane);   // (see the staging loop)
             const float sc = is_dk ? 0.125f : 1.0f;
             __nv_bfloat16* out = is_dk ? p.dk : p.dv;
             const int64_t ld = is_dk ? p.lddk : p.lddv;
@@ -718,8 +756,10 @@ int launch_colsum(const void* in, int64_t ld, int R, int C, float* colsum, cudaS
 }
 
 int launch_ln_bwd(const float* dy, const float* pre, const float* gamma, float* dx32, void* dx16, float* dgamma, float* dbeta,
-                  float* dbias, int rows, int n, float eps, cudaStream_t s) {
+                  float* dbias, int rows, int n, float eps, cudaStream_t s, const DropoutParams* drop_out, const DropoutParams* drop_in,
+                  int row0) {
     MRA_REQUIRE(rows > 0 && n % 8 == 0 && n <= 32 * LNB_MAXV_WIDE * 8, "layernorm backward width %d unsupported", n);
+    const DropoutParams dout = drop_out ? *drop_out : DropoutParams(), din = drop_in ? *drop_in : DropoutParams();
     MRA_REQUIRE(dbias == nullptr || (n <= 32 * LNB_MAXV_H * 8 && dgamma != nullptr),
                 "layernorm backward: the fused bias gradient needs width <= %d and dgamma", 32 * LNB_MAXV_H * 8);
     int blocks = (rows + LNB_WARPS - 1) / LNB_WARPS;
@@ -727,9 +767,11 @@ int launch_ln_bwd(const float* dy, const float* pre, const float* gamma, float* 
     if (blocks > cap) blocks = cap;
     __nv_bfloat16* d16 = reinterpret_cast<__nv_bfloat16*>(dx16);
     if (n <= 32 * LNB_MAXV_H * 8)
-        ln_bwd_kernel<LNB_MAXV_H, true><<<blocks, LNB_WARPS * 32, 0, s>>>(dy, pre, gamma, dx32, d16, dgamma, dbeta, dbias, rows, n, eps);
+        ln_bwd_kernel<LNB_MAXV_H, true><<<blocks, LNB_WARPS * 32, 0, s>>>(dy, pre, gamma, dx32, d16, dgamma, dbeta, dbias, rows, n, eps,
+                                                                          dout, din, row0);
     else
-        ln_bwd_kernel<LNB_MAXV_WIDE, false><<<blocks, LNB_WARPS * 32, 0, s>>>(dy, pre, gamma, dx32, d16, dgamma, dbeta, nullptr, rows, n, eps);
+        ln_bwd_kernel<LNB_MAXV_WIDE, false><<<blocks, LNB_WARPS * 32, 0, s>>>(dy, pre, gamma, dx32, d16, dgamma, dbeta, nullptr, rows, n,
+                                                                              eps, dout, din, row0);
     MRA_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -817,11 +859,13 @@ int launch_attention_bwd(const AttnBwdArgs& a, cudaStream_t s) {
                             reinterpret_cast<const __nv_bfloat16*>(a.v), a.ldv, reinterpret_cast<const __nv_bfloat16*>(a.d_o), a.ldo,
                             reinterpret_cast<__nv_bfloat16*>(a.dq), a.lddq, reinterpret_cast<__nv_bfloat16*>(a.dk), a.lddk,
                             reinterpret_cast<__nv_bfloat16*>(a.dv), a.lddv, a.add_mask, a.rows, a.heads, a.Sq, a.Sk, a.nq_split, a.kv_dense},
-                           reinterpret_cast<const __nv_bfloat16*>(a.o), a.ldof, a.db_q, a.db_k, a.db_v};
+                           reinterpret_cast<const __nv_bfloat16*>(a.o), a.ldof, a.db_q, a.db_k, a.db_v, a.drop};
         attn_bwd_tc_kernel<<<static_cast<unsigned>(a.rows) * a.heads, ABT_WARPS * 32, tc_smem, s>>>(pp);
         MRA_CHECK_CUDA(cudaGetLastError());
         return 0;
     }
+    MRA_REQUIRE(a.drop.thr8 == 0, "attention backward with dropout needs the tensor-core kernel (forward output given, tiles within "
+                                  "220 KiB of shared memory): Sq=%d Sk=%d", a.Sq, a.Sk);
     const size_t smem = static_cast<size_t>(2 * a.Sq + 2 * a.Sk) * AB_LD * 2 + 16 + static_cast<size_t>(a.Sq) * a.Sk * 8;
     MRA_REQUIRE(smem <= 220 * 1024, "attention backward: Sq=%d x Sk=%d needs %zu bytes of shared memory (max 220 KiB)", a.Sq, a.Sk, smem);
     if (int e = ensure_smem_attr(reinterpret_cast<const void*>(attn_bwd_kernel), 220 * 1024)) return e;

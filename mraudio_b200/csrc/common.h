@@ -9,6 +9,7 @@
 #include <string>
 
 #include "../../include/mraudio_b200.h"
+#include "dropout.cuh"
 
 namespace mra {
 
@@ -79,6 +80,10 @@ struct GemmArgs {
     int64_t c_frame_stride = 0, c_batch_stride = 0;
     // (set by the launcher) split of the K range into separate work items + TMA reduce-add epilogue, see gemm.cu
     int ksplit = 1, reduce_add = 0;
+    // training-mode dropout on (A W^T + bias) BEFORE the residual is added (BertSelfOutput / BertOutput): needs the fp32
+    // output + residual epilogue; drop_row0 = index of this problem's first row in the split token layout
+    DropoutParams drop;
+    int drop_row0 = 0;
 };
 int launch_gemm_tc(const GemmArgs& a, cudaStream_t s);
 int launch_gemm_tc_grouped(const GemmArgs* a, int n, cudaStream_t s);   // n <= 4 problems sharing N, K, epilogue kind
@@ -116,6 +121,7 @@ struct AttnArgs {
     void* o; int64_t ldo;
     const float* add_mask;
     int rows, heads, Sq, Sk, nq_split, kv_dense;
+    DropoutParams drop;   // training-mode dropout on the attention probabilities (TMA kernel only)
 };
 int launch_attention(const AttnArgs& a, cudaStream_t s);
 int launch_attention_pair(const AttnArgs* a, int n, cudaStream_t s, int* launches);   // n <= 2, one launch when possible
@@ -136,7 +142,8 @@ int launch_add_frame_pos(const void* x, int in_dtype, const float* pos, void* ou
 // embeddings: LN(cat(query_embeds, word_emb[ids] + pos_emb[:T])) written in the split layout (queries first)
 int launch_embed_layernorm(const float* query_embeds, int q_rows, const int32_t* ids, const void* word_emb,
                            const void* pos_emb, const float* g, const float* b, float* y32, void* y16, void* ylo, float* pre_out,
-                           int rows, int Nq, int T, int H, int vocab, float eps, cudaStream_t s);
+                           int rows, int Nq, int T, int H, int vocab, float eps, cudaStream_t s,
+                           const DropoutParams* drop = nullptr);
 // additive masks (LAVIS get_extended_attention_mask): out[r, j] = (1 - mask[r, j]) * -10000
 int launch_build_enc_mask(const int32_t* enc_mask, float* out, int rows, int Nk, cudaStream_t s);
 // split layout [queries ; text] fp32 -> interleaved [rows, Nq+T, H] fp32
@@ -160,12 +167,17 @@ struct AttnBwdArgs {
     // all tokens; the tensor-core kernel produces them in the same pass
     float* db_q = nullptr; float* db_k = nullptr; float* db_v = nullptr;
     int64_t n_q_tokens = 0, n_k_tokens = 0;      // total token rows of dq and of dk / dv (for the fallback column-sum pass)
+    DropoutParams drop;   // the forward's attention-probability dropout (tensor-core kernel only)
 };
 int launch_attention_bwd(const AttnBwdArgs& a, cudaStream_t s);
 int launch_transpose(const void* in, int64_t ld_in, void* out, int64_t ld_out, int R, int C, float* colsum, cudaStream_t s);
 int launch_colsum(const void* in, int64_t ld, int R, int C, float* colsum, cudaStream_t s);
+// drop_out: dropout sat between the producing Linear and the residual add (dx16 and dbias get the masked gradient, dx32 --
+// the residual path -- does not); drop_in: dropout sat on the LayerNorm's OUTPUT (embeddings): dy is masked on load.
+// row0 = index of the first row in the split token layout.
 int launch_ln_bwd(const float* dy, const float* pre, const float* gamma, float* dx32, void* dx16, float* dgamma, float* dbeta,
-                  float* dbias, int rows, int n, float eps, cudaStream_t s);
+                  float* dbias, int rows, int n, float eps, cudaStream_t s, const DropoutParams* drop_out = nullptr,
+                  const DropoutParams* drop_in = nullptr, int row0 = 0);
 int launch_gelu_bwd_colsum(const void* z, const void* dy, void* dz, float* colsum, int rows, int cols, cudaStream_t s);
 int launch_gelu_fwd(const void* z, void* out, int64_t n, cudaStream_t s);
 int launch_gelu_bwd(const void* z, const void* dy, void* dz, int64_t n, cudaStream_t s);

@@ -22,7 +22,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 // x[MAX_VEC][8] holds this lane's elements: vector i covers columns (i*32 + lane)*8 .. +7 (valid when < n).
 __device__ __forceinline__ void ln_normalise_store(float (&x)[MAX_VEC][8], int n, int lane, const float* __restrict__ g,
                                                    const float* __restrict__ b, float eps, float* y32,
-                                                   __nv_bfloat16* y16, __nv_bfloat16* ylo = nullptr) {
+                                                   __nv_bfloat16* y16, __nv_bfloat16* ylo = nullptr,
+                                                   const DropoutParams* drop = nullptr, int64_t drop_row = 0) {
     const int nvec = n >> 3;
     float sum = 0.f;
 #pragma unroll
@@ -57,6 +58,11 @@ __device__ __forceinline__ void ln_normalise_store(float (&x)[MAX_VEC][8], int n
             y[5] = (x[i][5] - mean) * rstd * g1.y + b1.y;
             y[6] = (x[i][6] - mean) * rstd * g1.z + b1.z;
             y[7] = (x[i][7] - mean) * rstd * g1.w + b1.w;
+            if (drop != nullptr) {   // training-mode dropout on the LayerNorm output (embeddings)
+                const uint4 rb = dropout_bytes(*drop, static_cast<uint64_t>(drop_row) * nvec + vi);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) y[e] *= dropout_mult(*drop, rb, e);
+            }
             if (y32) {
                 *reinterpret_cast<float4*>(y32 + c) = make_float4(y[0], y[1], y[2], y[3]);
                 *reinterpret_cast<float4*>(y32 + c + 4) = make_float4(y[4], y[5], y[6], y[7]);
@@ -205,7 +211,7 @@ embed_ln_kernel(const float* __restrict__ query_embeds, int q_rows, const int32_
                 const __nv_bfloat16* __restrict__ word_emb, const __nv_bfloat16* __restrict__ pos_emb,
                 const float* __restrict__ g, const float* __restrict__ b, float* __restrict__ y32,
                 __nv_bfloat16* __restrict__ y16, __nv_bfloat16* __restrict__ ylo, float* __restrict__ pre_out, int rows, int Nq,
-                int T, int H, int vocab, float eps) {
+                int T, int H, int vocab, float eps, const DropoutParams drop) {
     const int64_t orow = static_cast<int64_t>(blockIdx.x) * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     const int64_t nquery = static_cast<int64_t>(rows) * Nq;
@@ -246,7 +252,8 @@ embed_ln_kernel(const float* __restrict__ query_embeds, int q_rows, const int32_
                 *reinterpret_cast<float4*>(pp + 4) = make_float4(v[k][4], v[k][5], v[k][6], v[k][7]);
             }
     }
-    ln_normalise_store(v, H, lane, g, b, eps, y32 ? y32 + orow * H : nullptr, y16 + orow * H, ylo ? ylo + orow * H : nullptr);
+    ln_normalise_store(v, H, lane, g, b, eps, y32 ? y32 + orow * H : nullptr, y16 + orow * H, ylo ? ylo + orow * H : nullptr,
+                       drop.thr8 ? &drop : nullptr, orow);
 }
 
 __global__ void enc_mask_kernel(const int32_t* __restrict__ enc_mask, float* __restrict__ out, int64_t n) {
@@ -348,7 +355,7 @@ int launch_add_frame_pos(const void* x, int in_dtype, const float* pos, void* ou
 
 int launch_embed_layernorm(const float* query_embeds, int q_rows, const int32_t* ids, const void* word_emb,
                            const void* pos_emb, const float* g, const float* b, float* y32, void* y16, void* ylo, float* pre_out,
-                           int rows, int Nq, int T, int H, int vocab, float eps, cudaStream_t s) {
+                           int rows, int Nq, int T, int H, int vocab, float eps, cudaStream_t s, const DropoutParams* drop) {
     MRA_REQUIRE(H % 8 == 0 && H <= 32 * MAX_VEC * 8, "embedding width %d unsupported", H);
     MRA_REQUIRE(T == 0 || (ids && word_emb && pos_emb), "text tokens given but ids / embedding tables are NULL");
     const int64_t total = static_cast<int64_t>(rows) * (Nq + T);
@@ -356,7 +363,7 @@ int launch_embed_layernorm(const float* query_embeds, int q_rows, const int32_t*
     MRA_CHECK_CUDA(launch_pdl(embed_ln_kernel, dim3(blocks), dim3(WARPS_PER_BLOCK * 32), 0, s, query_embeds, q_rows, ids,
                               reinterpret_cast<const __nv_bfloat16*>(word_emb), reinterpret_cast<const __nv_bfloat16*>(pos_emb), g,
                               b, y32, reinterpret_cast<__nv_bfloat16*>(y16), reinterpret_cast<__nv_bfloat16*>(ylo), pre_out, rows,
-                              Nq, T, H, vocab, eps));
+                              Nq, T, H, vocab, eps, drop ? *drop : DropoutParams()));
     return 0;
 }
 

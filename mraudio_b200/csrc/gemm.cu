@@ -58,6 +58,8 @@ struct EpiParams {
     // M x N gives few tiles and K is long: the weight gradients, K = number of tokens); needs reduce_add.
     // reduce_add: the epilogue adds its tile into C with TMA reduce-add stores (fp32) instead of storing it.
     int ksplit, kb_per_split, reduce_add;
+    DropoutParams drop;               // thr8 != 0: dropout on (acc + bias) before the residual add (fp32 + residual epilogue)
+    int drop_row0[MAX_GROUPS];        // first row of each group in the split token layout
     int dbg;   // -DMRA_INSTRUMENT + MRA_GEMM_DEBUG=8: cycles per tile spent waiting for the accumulator vs in the epilogue
 };
 
@@ -437,6 +439,19 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
 #pragma unroll
                     for (int j = 0; j < 32; j += 2) ptx::unpack2(gelu_fast2(xx[j >> 1]), v[j], v[j + 1]);
                     }
+                    if constexpr (RES && OUT_F32) {
+                        if (p.drop.thr8 != 0) {
+                            // training-mode dropout of BertSelfOutput / BertOutput: on the Linear's output, before the residual
+                            const uint64_t grow = static_cast<uint64_t>(p.drop_row0[g] + row0 + lane);
+                            const uint64_t base = grow * static_cast<uint64_t>(p.N >> 3) + ((col0 + half * 32) >> 3);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const uint4 rb = dropout_bytes(p.drop, base + q);
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) v[8 * q + e] *= dropout_mult(p.drop, rb, e);
+                            }
+                        }
+                    }
                     if (RES) {
                         ptx::mbar_wait(rbar, rphase);
                         rphase ^= 1;
@@ -684,6 +699,8 @@ int launch_tc_variant(const GemmArgs* ga, int n, cudaStream_t s) {
     p.N = ga[0].N;
     p.K = ga[0].K;
     p.reduce_add = ga[0].reduce_add;
+    p.drop = ga[0].drop;
+    MRA_REQUIRE(p.drop.thr8 == 0 || (RES && OUT_F32 && !GELU && TN == 0), "GEMM dropout needs the fp32 + residual epilogue");
     static const int dbg_env = [] { const char* e = getenv("MRA_GEMM_DEBUG"); return e ? atoi(e) : 0; }();
     p.dbg = dbg_env;
     {
@@ -723,12 +740,14 @@ int launch_tc_variant(const GemmArgs* ga, int n, cudaStream_t s) {
             }
             p.bias[g] = a.bias;
             p.M[g] = a.M;
+            p.drop_row0[g] = a.drop_row0;
             p.tile_start[g] = total;
             total += (((a.M + BM - 1) / BM + CM - 1) / CM) * n_tiles;   // work items: m-block pairs when CM == 2
         } else {
             maps.a[g] = maps.a[0]; maps.b[g] = maps.b[0]; maps.c[g] = maps.c[0]; maps.r[g] = maps.r[0];
             p.bias[g] = nullptr;
             p.M[g] = 0;
+            p.drop_row0[g] = 0;
             p.c_frames[g] = 0;
             p.tile_start[g] = total;
         }

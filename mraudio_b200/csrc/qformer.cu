@@ -41,6 +41,20 @@ namespace {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// dropout parameters of a call (thr8 == 0: off), see dropout.cuh
+inline DropoutParams dropout_base(const mra_qformer_io* io) {
+    DropoutParams d;
+    if (io->dropout_p > 0.f) {
+        int thr = static_cast<int>(io->dropout_p * 256.0f + 0.5f);
+        thr = thr < 1 ? 1 : (thr > 255 ? 255 : thr);
+        d.thr8 = static_cast<uint32_t>(thr);
+        d.scale = 256.0f / static_cast<float>(256 - thr);
+        d.seed_lo = static_cast<uint32_t>(io->dropout_seed);
+        d.seed_hi = static_cast<uint32_t>(io->dropout_seed >> 32);
+    }
+    return d;
+}
+
 // Per-layer activation buffers.  Inference: every layer aliases ONE set (activations are dead after the layer).
 // MRA_FWD_SAVE_FOR_BACKWARD: every layer has its own set, kept for mra_qformer_backward.
 struct LayerBufs {
@@ -305,6 +319,13 @@ int forward_multi(int n, mra_qformer_t* const* hs, const mra_qformer_io* const* 
         x.self_mask = x.enc_mask = nullptr;
     }
     const bool save = cx[0].save;
+    const DropoutParams drop0 = dropout_base(ios[0]);
+    if (drop0.thr8 != 0) {
+        MRA_REQUIRE(n == 1 && save, "dropout_p > 0 needs MRA_FWD_SAVE_FOR_BACKWARD and one Q-Former per call (the training forward)");
+        MRA_REQUIRE(ios[0]->dropout_p < 1.f && ios[0]->T % 32 == 0, "dropout: p must be < 1 and the text length a multiple of 32 (T=%d)", ios[0]->T);
+    }
+    auto dsite = [&](int site, int layer) { return drop0.thr8 != 0 ? dropout_site(drop0, site, layer) : DropoutParams(); };
+    const DropoutParams drop_emb = dsite(DROP_EMB, 0);
     int launches = 0;
     // profiling spans (recorded on the first handle): MRA_PROFILE_DOMINANT brackets only GEMM launches, _ALL every launch
     int cur_cat = -1;
@@ -396,7 +417,8 @@ int forward_multi(int n, mra_qformer_t* const* hs, const mra_qformer_io* const* 
         span_begin(MRA_CAT_OTHER);
         MRA_TRY(launch_embed_layernorm(x.io->query_embeds, x.io->q_rows, x.io->input_ids, W.word_emb, W.pos_emb, W.ln_e_g,
                                        W.ln_e_b, split ? nullptr : x.ws.x32, x.ws.layer[0].xb, split ? x.ws.xlo : nullptr,
-                                       x.ws.pre_e, x.rows, Nq, x.T, H, x.h->cfg.vocab, c.ln_eps, s));
+                                       x.ws.pre_e, x.rows, Nq, x.T, H, x.h->cfg.vocab, c.ln_eps, s,
+                                       drop0.thr8 != 0 ? &drop_emb : nullptr));
         span_end();
         ++launches;
         if (x.io->attn_mask) {
@@ -430,6 +452,7 @@ int forward_multi(int n, mra_qformer_t* const* hs, const mra_qformer_io* const* 
                 const LayerBufs& B = cx[i].ws.layer[l];
                 aa[i] = AttnArgs{B.qkv, 3 * H, B.qkv + H, 3 * H, B.qkv + 2 * H, 3 * H, B.ctx, H, cx[i].self_mask, cx[i].rows, c.heads,
                                  cx[i].S, cx[i].S, Nq, 0};
+                aa[i].drop = dsite(DROP_SELF_PROBS, l);
             }
             span_begin(MRA_CAT_ATTENTION);
             MRA_TRY(launch_attention_pair(aa, n, s, &launches));
@@ -443,6 +466,7 @@ int forward_multi(int n, mra_qformer_t* const* hs, const mra_qformer_io* const* 
                        cx[i].ws.alo, cx[i].Mtot, H);
             } else {
                 add(B.ctx, H, L.w_ao, H, L.b_ao, cx[i].ws.x32, H, B.pre_a, H, cx[i].Mtot, H, H, 0, 1);
+                if (ng > 0) ga[ng - 1].drop = dsite(DROP_SELF_OUT, l);
                 add_ln(B.pre_a, L.ln_a_g, L.ln_a_b, cx[i].ws.a32, B.ab, cx[i].Mtot);
             }
         }
@@ -464,6 +488,7 @@ int forward_multi(int n, mra_qformer_t* const* hs, const mra_qformer_io* const* 
                     const __nv_bfloat16* kbase = cx[i].ws.kv + static_cast<size_t>(cx[i].h->cross_slot[l]) * 2 * H;
                     aa[i] = AttnArgs{B.cq, H, kbase, cx[i].kv_ld, kbase + H, cx[i].kv_ld, B.cctx, H, cx[i].enc_mask, cx[i].rows,
                                      c.heads, Nq, cx[i].Nk, Nq, 1};
+                    aa[i].drop = dsite(DROP_CROSS_PROBS, l);
                 }
                 span_begin(MRA_CAT_ATTENTION);
                 MRA_TRY(launch_attention_pair(aa, n, s, &launches));
@@ -477,6 +502,7 @@ int forward_multi(int n, mra_qformer_t* const* hs, const mra_qformer_io* const* 
                            cx[i].ws.alo, cx[i].Mq, H);
                 } else {
                     add(B.cctx, H, L.w_co, H, L.b_co, cx[i].ws.a32, H, B.pre_c, H, cx[i].Mq, H, H, 0, 1);
+                    if (ng > 0) ga[ng - 1].drop = dsite(DROP_CROSS_OUT, l);
                     add_ln(B.pre_c, L.ln_c_g, L.ln_c_b, cx[i].ws.a32, B.ab2, cx[i].Mq);
                 }
             }
@@ -526,9 +552,11 @@ int forward_multi(int n, mra_qformer_t* const* hs, const mra_qformer_io* const* 
                            cx[i].ws.x32 + o, xb_next + o, cx[i].ws.xlo + o, cx[i].Mt, I);
             } else {
                 add(B.inter, I, L.w_fq2, I, L.b_fq2, cx[i].ws.a32, H, B.pre_f, H, cx[i].Mq, H, I, 0, 1);
+                if (ng > 0) ga[ng - 1].drop = dsite(DROP_FFN_OUT, l);
                 add_ln(B.pre_f, L.ln_fq_g, L.ln_fq_b, cx[i].ws.x32, xb_next, cx[i].Mq);
                 if (text_on[i]) {
                     add(B.inter + oi, I, L.w_ft2, I, L.b_ft2, cx[i].ws.a32 + o, H, B.pre_f + o, H, cx[i].Mt, H, I, 0, 1);
+                    if (ng > 0) { ga[ng - 1].drop = dsite(DROP_FFN_OUT, l); ga[ng - 1].drop_row0 = cx[i].Mq; }   // text rows follow the queries
                     add_ln(B.pre_f + o, L.ln_ft_g, L.ln_ft_b, cx[i].ws.x32 + o, xb_next + o, cx[i].Mt);
                 }
             }
@@ -628,6 +656,8 @@ extern "C" int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, 
     const int kv_ld = h->n_cross * 2 * H;
     const int NK = rows * Nk;
     const bool skip_dead = (io->flags & MRA_FWD_SKIP_DEAD_TEXT_FFN) != 0;
+    const DropoutParams drop0 = dropout_base(io);   // the forward's dropout: every mask is regenerated from (seed, site, layer)
+    auto dsite = [&](int site, int layer) { return drop0.thr8 != 0 ? dropout_site(drop0, site, layer) : DropoutParams(); };
     int launches = 0;
 #define MRA_TRY(expr)            \
     do {                         \
@@ -654,16 +684,19 @@ extern "C" int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, 
     };
     // LayerNorm backward of a post-LN block; dbias = bias gradient of the Linear feeding the LayerNorm (fused column sums)
     auto ln_bwd = [&](const float* dy, const float* pre, const float* gamma, float* dgam, float* dbet, float* dbias, size_t r0,
-                      int n) -> int {
+                      int n, const DropoutParams& dout, const DropoutParams& din) -> int {
         const size_t o = r0 * H;
-        MRA_TRY(launch_ln_bwd(dy + o, pre + o, gamma, bw.g_pre32 + o, bw.g_pre16 + o, dgam, dbet, dbias, n, H, c.ln_eps, s));
+        MRA_TRY(launch_ln_bwd(dy + o, pre + o, gamma, bw.g_pre32 + o, bw.g_pre16 + o, dgam, dbet, dbias, n, H, c.ln_eps, s,
+                              dout.thr8 ? &dout : nullptr, din.thr8 ? &din : nullptr, static_cast<int>(r0)));
         return 0;
     };
+    const DropoutParams no_drop;
     // FFN backward over rows [r0, r0+n): g_out = bw.g_x rows -> g_in accumulated into bw.g_a rows
     auto ffn_bwd = [&](const LayerBufs& B, const __nv_bfloat16* in16, size_t r0, int n, const void* w1T, const void* w2T,
-                       const float* gamma, float* g_w1, float* g_b1, float* g_w2, float* g_b2, float* g_gam, float* g_bet) -> int {
+                       const float* gamma, float* g_w1, float* g_b1, float* g_w2, float* g_b2, float* g_gam, float* g_bet,
+                       int layer) -> int {
         const size_t o = r0 * H, oi = r0 * I;
-        if (int e = ln_bwd(bw.g_x, B.pre_f, gamma, g_gam, g_bet, g_b2, r0, n)) return e;
+        if (int e = ln_bwd(bw.g_x, B.pre_f, gamma, g_gam, g_bet, g_b2, r0, n, dsite(DROP_FFN_OUT, layer), no_drop)) return e;
         if (int e = wgrad(bw.g_pre16 + o, H, B.inter + oi, I, n, H, I, g_w2, I, nullptr)) return e;
         MRA_TRY(gemm(bw.g_pre16 + o, H, w2T, H, nullptr, 0, bw.g_big16, I, n, I, H, 0));          // d_inter
         if (g_b1 != nullptr) MRA_TRY(launch_gelu_bwd_colsum(B.z + oi, bw.g_big16, bw.g_big2, g_b1, n, I, s));   // dz (+ db1)
@@ -692,7 +725,7 @@ extern "C" int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, 
         const bool cross = h->cross_slot[l] >= 0;
         // ---- FFN_query (rows < Mq) and FFN_text
         if (int e = ffn_bwd(B, cross ? B.ab2 : B.ab, 0, Mq, LT.w_fq1, LT.w_fq2, L.ln_fq_g, G.w_fq1, G.b_fq1, G.w_fq2, G.b_fq2,
-                            G.ln_fq_g, G.ln_fq_b)) return e;
+                            G.ln_fq_g, G.ln_fq_b, l)) return e;
         if (Mt > 0) {
             const size_t o = static_cast<size_t>(Mq) * H;
             if (last && skip_dead) {
@@ -701,20 +734,21 @@ extern "C" int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, 
             } else {
                 MRA_REQUIRE(LT.w_ft1 && LT.w_ft2 && G.w_ft1 && G.w_ft2, "layer %d: text FFN weights / grads missing", l);
                 if (int e = ffn_bwd(B, B.ab, Mq, Mt, LT.w_ft1, LT.w_ft2, L.ln_ft_g, G.w_ft1, G.b_ft1, G.w_ft2, G.b_ft2,
-                                    G.ln_ft_g, G.ln_ft_b)) return e;
+                                    G.ln_ft_g, G.ln_ft_b, l)) return e;
             }
         }
         // ---- cross-attention block (query rows): g_a[:Mq] is the gradient w.r.t. LN_c's output
         if (cross) {
             const int slot = h->cross_slot[l];
             const __nv_bfloat16* kbase = ws.kv + static_cast<size_t>(slot) * 2 * H;
-            if (int e = ln_bwd(bw.g_a, B.pre_c, L.ln_c_g, G.ln_c_g, G.ln_c_b, G.b_co, 0, Mq)) return e;
+            if (int e = ln_bwd(bw.g_a, B.pre_c, L.ln_c_g, G.ln_c_g, G.ln_c_b, G.b_co, 0, Mq, dsite(DROP_CROSS_OUT, l), no_drop)) return e;
             if (int e = wgrad(bw.g_pre16, H, B.cctx, H, Mq, H, H, G.w_co, H, nullptr)) return e;
             MRA_TRY(gemm(bw.g_pre16, H, LT.w_co, H, nullptr, 0, bw.g_ctx16, H, Mq, H, H, 0));      // d_cctx
             __nv_bfloat16* gkv = bw.g_kv16 + static_cast<size_t>(slot) * 2 * H;   // this layer's columns of the stacked buffer
             AttnBwdArgs a{B.cq, H, kbase, kv_ld, kbase + H, kv_ld, bw.g_ctx16, H, bw.g_cq16, H, gkv, kv_ld,
                           gkv + H, kv_ld, io->enc_mask ? ws.enc_mask : nullptr, rows, c.heads, Nq, Nk, Nq, 1};
             a.o = B.cctx; a.ldof = H;
+            a.drop = dsite(DROP_CROSS_PROBS, l);
             a.db_q = G.b_cq;
             a.db_k = g->b_ckv + static_cast<size_t>(slot) * 2 * H;
             a.db_v = a.db_k + H;
@@ -724,7 +758,7 @@ extern "C" int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, 
             MRA_TRY(gemm(bw.g_cq16, H, LT.w_cq, H, bw.g_pre32, H, bw.g_a, H, Mq, H, H, 1));         // -> grad of LN_a out (query rows)
         }
         // ---- self-attention block (all rows)
-        if (int e = ln_bwd(bw.g_a, B.pre_a, L.ln_a_g, G.ln_a_g, G.ln_a_b, G.b_ao, 0, Mtot)) return e;
+        if (int e = ln_bwd(bw.g_a, B.pre_a, L.ln_a_g, G.ln_a_g, G.ln_a_b, G.b_ao, 0, Mtot, dsite(DROP_SELF_OUT, l), no_drop)) return e;
         if (int e = wgrad(bw.g_pre16, H, B.ctx, H, Mtot, H, H, G.w_ao, H, nullptr)) return e;
         MRA_TRY(gemm(bw.g_pre16, H, LT.w_ao, H, nullptr, 0, bw.g_ctx16, H, Mtot, H, H, 0));         // d_ctx
         {
@@ -732,6 +766,7 @@ extern "C" int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, 
                           bw.g_big16 + H, 3 * H, bw.g_big16 + 2 * H, 3 * H, io->attn_mask ? ws.self_mask : nullptr,
                           rows, c.heads, S, S, Nq, 0};
             a.o = B.ctx; a.ldof = H;
+            a.drop = dsite(DROP_SELF_PROBS, l);
             a.db_q = G.b_qkv; a.db_k = G.b_qkv + H; a.db_v = G.b_qkv + 2 * H;
             a.n_q_tokens = a.n_k_tokens = Mtot;
             MRA_TRY(launch_attention_bwd(a, s));
@@ -748,7 +783,7 @@ extern "C" int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, 
                           g->w_ckv, c.enc_width, nullptr)) return e;
     }
     // ---- embeddings
-    if (int e = ln_bwd(bw.g_x, ws.pre_e, W.ln_e_g, g->ln_e_g, g->ln_e_b, nullptr, 0, Mtot)) return e;
+    if (int e = ln_bwd(bw.g_x, ws.pre_e, W.ln_e_g, g->ln_e_g, g->ln_e_b, nullptr, 0, Mtot, no_drop, dsite(DROP_EMB, 0))) return e;
     MRA_TRY(launch_embed_bwd(bw.g_pre32, io->input_ids, g->query_tokens, io->q_rows, g->word_emb, g->pos_emb, rows, Nq, T, H,
                              c.vocab, s));
 #undef MRA_TRY

@@ -146,10 +146,9 @@ class TrainableQFormer:
         self.grad_comm_dtype = torch.bfloat16
         self.grad16 = None                      # bf16 staging / result of the exchange (allocated on first use)
         self._reduced_bf16 = False              # the last exchange left its result in grad16
-        self.comm_stream = torch.cuda.Stream(dev)
         self.reduce_group = None
-        self.reduce_after_backward = False     # set by the trainer on optimizer-step iterations when world > 1
-        self.reduce_done: Optional[torch.cuda.Event] = None
+        self.backward_done = torch.cuda.Event()       # recorded on the backward's stream when mra_qformer_backward is enqueued
+        self.backward_ran = False
         self._structs = None
         self._ws = self._bws = None
         self._saved = None
@@ -232,13 +231,28 @@ class TrainableQFormer:
         return W, G
 
     # ------------------------------------------------------------------------------------------------ forward / backward
-    def forward(self, enc: torch.Tensor, input_ids: Optional[torch.Tensor], attention_mask: Optional[torch.Tensor]) -> torch.Tensor:
+    def forward(self, enc: torch.Tensor, input_ids: Optional[torch.Tensor], attention_mask: Optional[torch.Tensor],
+                dropout_p: float = 0.0, dropout_seed: int = 0) -> torch.Tensor:
         """Training forward (activations kept): returns ``llm_proj(Qformer.bert(...).last_hidden_state[:, :Nq])`` as
-        bf16 ``[rows, Nq, D]`` attached to autograd; ``.backward()`` accumulates into the flat gradient buffer."""
+        bf16 ``[rows, Nq, D]`` attached to autograd; ``.backward()`` accumulates into the flat gradient buffer.
+
+        ``dropout_p > 0`` = ``model.train()`` of the reference (utils/trainer.py:110): Philox dropout on the embeddings, the
+        attention probabilities and the attention-output / FFN-output Linears, mask regenerated (not stored) by the backward.
+        The text is padded to a multiple of 32 tokens with masked-out padding (TMA attention kernels)."""
+        self._dropout = (float(dropout_p), int(dropout_seed))
         return _QFormerTrainFn.apply(self, enc, input_ids, attention_mask, self.query_tokens)
 
     def _forward_impl(self, enc, input_ids, attention_mask):
         self.sync_operands()
+        drop_p, drop_seed = getattr(self, "_dropout", (0.0, 0))
+        self._dropout = (0.0, 0)
+        if drop_p > 0.0 and input_ids is not None and input_ids.shape[1] % 32 != 0:
+            pad = 32 - input_ids.shape[1] % 32
+            Nq0 = self.cfg.query_length
+            if attention_mask is None:
+                attention_mask = torch.ones(input_ids.shape[0], Nq0 + input_ids.shape[1], dtype=torch.long, device=input_ids.device)
+            input_ids = torch.nn.functional.pad(input_ids, (0, pad), value=0)
+            attention_mask = torch.nn.functional.pad(attention_mask, (0, pad), value=0)
         cfg = self.cfg
         dev = enc.device
         rows, Nk, Wd = enc.shape
@@ -259,7 +273,8 @@ class TrainableQFormer:
         out = torch.empty(rows * Nq, self.D, device=dev, dtype=torch.bfloat16)
         io = _lib.QFormerIO(enc=enc_b.data_ptr(), input_ids=_lib.ptr(ids), attn_mask=_lib.ptr(amask), enc_mask=None,
                             query_embeds=self._ptr(self.flat, "query_tokens", 4), q_rows=self.query_tokens.shape[0],
-                            rows=rows, T=T, Nk=Nk, flags=flags, last_hidden=None, llm_out=out.data_ptr())
+                            rows=rows, T=T, Nk=Nk, flags=flags, last_hidden=None, llm_out=out.data_ptr(),
+                            dropout_p=drop_p, dropout_seed=drop_seed & 0xFFFFFFFFFFFFFFFF)
         check(lib.mra_qformer_forward(self._handle, C.byref(io), self._ws.data_ptr(), self._ws.numel(), current_stream()))
         self._saved = (io, enc_b, ids, amask, rows, T, Nk)
         return out.view(rows, Nq, self.D)
@@ -275,8 +290,8 @@ class TrainableQFormer:
                                        self._ws.numel(), self._bws.data_ptr(), self._bws.numel(), current_stream()))
         self.last_backward_launches = lib.mra_qformer_last_launch_count(self._handle)
         self._saved = None
-        if self.reduce_after_backward:
-            self.launch_grad_allreduce()
+        self.backward_done.record(torch.cuda.current_stream())
+        self.backward_ran = True
 
     def _exchange(self, lo: int, hi: int):
         """all-reduce (sum) of one range of the flat gradient buffer on the current (communication) stream"""
@@ -289,33 +304,19 @@ class TrainableQFormer:
         else:
             dist.all_reduce(self.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.reduce_group)
 
-    def launch_grad_allreduce(self):
-        """DDP's gradient all-reduce (utils/trainer.py:69), bucketed and overlapped: a bucket starts on ``comm_stream`` as soon
-        as the backward has recorded the event that makes it final, while the lower layers (and the other modality's
-        backward) are still running on the compute stream.  Sum semantics; ``adam_step(grad_scale=1/world)`` turns it into
-        DDP's mean.  ``wait_grad_allreduce`` makes the current stream wait for it."""
-        main = torch.cuda.current_stream()
-        tail = torch.cuda.Event()
-        tail.record(main)                      # end of this backward: gates the last bucket
-        with torch.cuda.stream(self.comm_stream):
-            for ev, ranges in self.buckets:
-                self.comm_stream.wait_event(self.layer_events[ev] if ev is not None else tail)
-                for lo, hi in ranges:
-                    self._exchange(lo, hi)
-            self.reduce_done = torch.cuda.Event()
-            self.reduce_done.record(self.comm_stream)
+    def exchange_bucket(self, k: int, comm_stream: torch.cuda.Stream):
+        """Enqueue the all-reduce of bucket ``k`` on ``comm_stream`` behind the event that makes its gradients final."""
+        ev, ranges = self.buckets[k]
+        comm_stream.wait_event(self.layer_events[ev] if ev is not None else self.backward_done)
+        with torch.cuda.stream(comm_stream):
+            for lo, hi in ranges:
+                self._exchange(lo, hi)
         self._reduced_bf16 = self.grad_comm_dtype == torch.bfloat16
-        self.reduce_after_backward = False
 
     def flat_grad_allreduce(self):
         """one exchange of the whole buffer on the current stream, after the backward (the A/B baseline of the overlap)"""
         self._exchange(0, self.numel)
         self._reduced_bf16 = self.grad_comm_dtype == torch.bfloat16
-
-    def wait_grad_allreduce(self):
-        if self.reduce_done is not None:
-            torch.cuda.current_stream().wait_event(self.reduce_done)
-            self.reduce_done = None
 
     # ------------------------------------------------------------------------------------------------ optimizer
     def zero_grad(self):
@@ -350,6 +351,11 @@ class _QFormerTrainFn(torch.autograd.Function):
         return None, None, None, None, None
 
 
+def dist_rank() -> int:
+    import torch.distributed as dist
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
 def warmup_cosine_lr(cur_epoch: int, cur_step: int, max_epoch: int, init_lr: float = 3e-4, min_lr: float = 0.0,
                      warmup_steps: int = 1000, warmup_start_lr: float = 1e-8) -> float:
     """LAVIS ``LinearWarmupCosineLRScheduler.step`` (utils/trainer.py:66,127): linear warm-up over the first
@@ -366,7 +372,7 @@ class QFormerTrainer:
 
     def __init__(self, model, max_epoch: int = 1, accum_grad_iters: int = 2, init_lr: float = 3e-4, warmup_steps: int = 1000,
                  loss_fn=None, group=None, overlap_allreduce: bool = True, parallel_modalities: bool = True,
-                 grad_comm_dtype: torch.dtype = torch.bfloat16):
+                 grad_comm_dtype: torch.dtype = torch.bfloat16, dropout: Optional[float] = 0.0, seed: int = 0):
         self.model = model
         model.freeze_qformers(False)
         self.states = {m: TrainableQFormer(getattr(model, f"{m}_Qformer"), getattr(model, f"{m}_query_tokens"),
@@ -375,6 +381,10 @@ class QFormerTrainer:
         self.loss_fn = loss_fn
         self.group = group
         self.overlap_allreduce = overlap_allreduce
+        # dropout: 0.0 (default: the parity configuration) or a probability; None = the Q-Former config's
+        # hidden_dropout_prob (0.1), i.e. the reference's model.train() (utils/trainer.py:110)
+        self.dropout = dropout
+        self.seed = seed
         self.allreduce_enabled = True       # False: skip the gradient exchange (bench.py measures its exposed cost that way)
         self.set_grad_comm_dtype(grad_comm_dtype)
         # At fine-tuning batch sizes (64 rows per modality) most launches fill a fraction of the 148 SMs, so the video and
@@ -383,6 +393,7 @@ class QFormerTrainer:
         self.parallel_modalities = parallel_modalities
         dev = next(model.parameters()).device
         self.mod_streams = {m: torch.cuda.Stream(dev) for m in model.modalities}
+        self.comm_stream = torch.cuda.Stream(dev)     # ONE stream for the gradient exchange of all modalities
         self.iter = 0
         self.lr = init_lr
 
@@ -411,16 +422,22 @@ class QFormerTrainer:
             tmask = attention_mask.repeat(num, 1)
             q_atts = torch.ones(enc.shape[0], model.num_query_token, dtype=tmask.dtype, device=tmask.device)
             full_mask = torch.cat([q_atts, tmask], 1)
+            p_drop = getattr(model, f"{m}_Qformer").config.hidden_dropout_prob if self.dropout is None else self.dropout
+            # one dropout stream per (trainer seed, iteration, modality, rank): ranks and modalities draw independent masks
+            dkw = {}
+            if p_drop and p_drop > 0.0:
+                rank = dist_rank() if self._world() > 1 else 0
+                dkw = dict(dropout_p=p_drop, dropout_seed=((self.seed * 1000003 + self.iter) * 64 + model.modalities.index(m)) * 4096 + rank)
             if self.parallel_modalities and len(model.modalities) > 1:
                 main, side = torch.cuda.current_stream(), self.mod_streams[m]
                 side.wait_stream(main)                      # inputs prepared on the main stream
                 with torch.cuda.stream(side):
-                    y = self.states[m].forward(enc, ids, full_mask)
+                    y = self.states[m].forward(enc, ids, full_mask, **dkw)
                 for t in (enc, ids, full_mask):
                     t.record_stream(side)
                 joins.append(side)
             else:
-                y = self.states[m].forward(enc, ids, full_mask)
+                y = self.states[m].forward(enc, ids, full_mask, **dkw)
             inputs_llm[m] = y.reshape(bs, num, model.num_query_token, -1).view(bs, num * model.num_query_token, -1)
             atts_llm[m] = torch.ones(inputs_llm[m].size()[:-1], dtype=torch.long, device=y.device)
         for side in joins:                                  # the loss is computed on the main stream
@@ -442,30 +459,38 @@ class QFormerTrainer:
         world = self._world()
         stepping = (self.iter + 1) % self.accum_grad_iters == 0                                                    # :137
         reduce = stepping and world > 1 and self.allreduce_enabled
-        if reduce:
-            # DDP's gradient averaging, only on optimizer-step iterations (the reference all-reduces on every backward):
-            # each modality's backward node launches its bucketed all-reduce on a side stream as its layers finish
-            # (only for the modalities of this step: a flag left set on an absent modality would fire its all-reduce on a
-            #  later, non-stepping iteration and count that gradient world_size times)
-            for m, st in self.states.items():
-                st.reduce_group, st.reduce_after_backward = self.group, self.overlap_allreduce and m in inputs_llm
-        (loss / self.accum_grad_iters).backward()                                                                  # :131-133
         for st in self.states.values():
-            st.reduce_after_backward = False
+            st.backward_ran = False
+        (loss / self.accum_grad_iters).backward()                                                                  # :131-133
+        # (the CUDA backward of each modality ran on its own stream and accumulated into the flat gradient buffers behind
+        #  autograd's back -- no AccumulateGrad node: the streams are joined explicitly below)
+        if reduce:
+            # DDP's gradient averaging (utils/trainer.py:69), only on optimizer-step iterations (the reference all-reduces on
+            # every backward).  By now the whole backward of every modality is ENQUEUED (the host runs far ahead of the GPU)
+            # and has recorded, per bucket, the event that makes its gradients final.  The buckets of all modalities go on
+            # one communication stream in the order in which they become ready -- projection, top layers, ..., tail of
+            # modality A, tail of modality B alternating -- so that no modality's exchange queues behind another's tail.
+            # Sum semantics; adam_step(grad_scale = 1 / world) turns it into DDP's mean.
+            for st in self.states.values():
+                st.reduce_group = self.group
+            live = [st for st in self.states.values() if st.backward_ran]
+            if self.overlap_allreduce and live:
+                for k in range(max(len(st.buckets) for st in live)):
+                    for st in live:
+                        if k < len(st.buckets):
+                            st.exchange_bucket(k, self.comm_stream)
         if self.parallel_modalities and len(self.mod_streams) > 1:
-            # the CUDA backward of each modality ran on its own stream and accumulated into the flat gradient buffers behind
-            # autograd's back (no AccumulateGrad node): join explicitly before anything on this stream touches them
             for side in self.mod_streams.values():
                 torch.cuda.current_stream().wait_stream(side)
         self.iter += 1
         if stepping:
             if reduce:
-                for m, st in self.states.items():
-                    if self.overlap_allreduce and st.reduce_done is not None:
-                        st.wait_grad_allreduce()
-                    else:   # flat all-reduce after the backward: the A/B baseline, and modalities absent from this step
-                            # (their accumulated gradients of earlier iterations still have to be averaged)
-                        st.reduce_group = self.group
+                if self.overlap_allreduce:
+                    torch.cuda.current_stream().wait_stream(self.comm_stream)
+                for st in self.states.values():
+                    if not (self.overlap_allreduce and st.backward_ran):
+                        # flat all-reduce after the backward: the A/B baseline, and modalities absent from this step (their
+                        # accumulated gradients of earlier iterations still have to be averaged)
                         st.flat_grad_allreduce()
                 if not apply_optimizer:
                     for st in self.states.values():       # leave the exchanged SUM in the fp32 buffers for the caller

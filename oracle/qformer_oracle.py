@@ -147,8 +147,77 @@ def _layernorm(x, g, b, eps):
     return F.layer_norm(x, (x.shape[-1],), g, b, eps)
 
 
-def _attention(q, k, v, add_mask, nheads, emu):
-    """q:[R,Sq,H] k,v:[R,Sk,H] add_mask:[R,Sk] or None -> [R,Sq,H].  scores/8 + mask -> softmax -> PV."""
+# ---------------------------------------------------------------------------------------------------------------------
+# Training-mode dropout (model.train() of utils/trainer.py:110; HF port modeling_instructblip.py:530,551,608,781).  The CUDA
+# path draws its masks from a counter-based Philox4x32-10 stream (mraudio_b200/csrc/dropout.cuh); this is the same generator
+# in numpy with the same (seed, site, layer, element) -> byte mapping, so forward and gradients can be compared with the
+# IDENTICAL mask.  Sites: 1 embeddings, 2 self-attention probs, 3 cross-attention probs, 4 self-output, 5 cross-output,
+# 6 FFN output.
+# ---------------------------------------------------------------------------------------------------------------------
+DROP_EMB, DROP_SELF_PROBS, DROP_CROSS_PROBS, DROP_SELF_OUT, DROP_CROSS_OUT, DROP_FFN_OUT = 1, 2, 3, 4, 5, 6
+
+
+def _philox4x32_10(c0, c1, c2, c3, k0, k1):
+    import numpy as np
+    M = np.uint64(0xFFFFFFFF)
+    c0, c1, c2, c3 = (np.asarray(c, dtype=np.uint64) & M for c in (c0, c1, c2, c3))
+    k0, k1 = np.uint64(k0) & M, np.uint64(k1) & M
+    for _ in range(10):
+        p0 = np.uint64(0xD2511F53) * c0
+        p1 = np.uint64(0xCD9E8D57) * c2
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & M, p1 >> np.uint64(32), p1 & M
+        c0, c1, c2, c3 = hi1 ^ c1 ^ k0, lo1, hi0 ^ c3 ^ k1, lo0
+        k0 = (k0 + np.uint64(0x9E3779B9)) & M
+        k1 = (k1 + np.uint64(0xBB67AE85)) & M
+    return c0, c1, c2, c3
+
+
+def dropout_bytes(seed: int, site: int, layer: int, idx):
+    """uint8 [..., 16]: the 16 random bytes of call ``idx`` of the stream (site, layer) -- dropout.cuh::dropout_bytes"""
+    import numpy as np
+    idx = np.asarray(idx, dtype=np.uint64)
+    w = _philox4x32_10(idx & np.uint64(0xFFFFFFFF), idx >> np.uint64(32), np.full(idx.shape, site * 256 + layer, np.uint64),
+                       np.full(idx.shape, 0x6d72, np.uint64), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    out = np.empty(idx.shape + (16,), dtype=np.uint8)
+    for k in range(16):
+        out[..., k] = ((w[k // 4] >> np.uint64(8 * (k % 4))) & np.uint64(0xFF)).astype(np.uint8)
+    return out
+
+
+def dropout_params(p: float):
+    """(thr8, scale): an element is kept iff its byte >= thr8 = round(256 p); kept values are scaled by 256 / (256 - thr8)"""
+    thr = min(255, max(1, int(p * 256.0 + 0.5)))
+    return thr, 256.0 / (256 - thr)
+
+
+def hidden_dropout_mult(p: float, seed: int, site: int, layer: int, m_index: torch.Tensor, H: int) -> torch.Tensor:
+    """multiplier [..., H] for tokens whose split-layout row indices are ``m_index`` [...] (queries of all rows first, then
+    text): element (m, n) -> call m * (H / 8) + n / 8, byte n % 8"""
+    import numpy as np
+    thr, scale = dropout_params(p)
+    m = m_index.numpy().astype(np.uint64)
+    idx = m[..., None] * np.uint64(H // 8) + np.arange(H // 8, dtype=np.uint64)
+    b = dropout_bytes(seed, site, layer, idx)[..., :8]                 # [..., H/8, 8]
+    keep = (b >= thr).reshape(m.shape + (H,))
+    return torch.from_numpy(keep.astype(np.float32) * np.float32(scale))
+
+
+def attention_dropout_mult(p: float, seed: int, site: int, layer: int, rows: int, heads: int, Sq: int, Sk: int) -> torch.Tensor:
+    """multiplier [rows, heads, Sq, Sk]: element (r, h, i, j) -> call (((r heads + h) Sq + i) ceil(Sk / 64) + j / 64) 4 + (j % 8) / 2,
+    byte ((j % 64) / 8) 2 + j % 2"""
+    import numpy as np
+    thr, scale = dropout_params(p)
+    nch = (Sk + 63) // 64
+    r, h, i, j = np.meshgrid(np.arange(rows), np.arange(heads), np.arange(Sq), np.arange(Sk), indexing="ij")
+    idx = (((r * heads + h) * Sq + i) * nch + j // 64) * 4 + (j % 8) // 2
+    byte = ((j % 64) // 8) * 2 + j % 2
+    b = dropout_bytes(seed, site, layer, idx.astype(np.uint64))
+    sel = np.take_along_axis(b, byte[..., None].astype(np.int64), axis=-1)[..., 0]
+    return torch.from_numpy((sel >= thr).astype(np.float32) * np.float32(scale))
+
+
+def _attention(q, k, v, add_mask, nheads, emu, drop_mult=None):
+    """q:[R,Sq,H] k,v:[R,Sk,H] add_mask:[R,Sk] or None -> [R,Sq,H].  scores/8 + mask -> softmax -> (dropout) -> PV."""
     R, Sq, H = q.shape
     Sk = k.shape[1]
     d = H // nheads
@@ -164,9 +233,10 @@ def _attention(q, k, v, add_mask, nheads, emu):
         # row sum afterwards
         m = s.max(dim=-1, keepdim=True).values
         e = torch.exp(s - m)
-        o = torch.matmul(_r(e, True), vh) / e.sum(dim=-1, keepdim=True)
+        ed = e if drop_mult is None else e * drop_mult
+        o = torch.matmul(_r(ed, True), vh) / e.sum(dim=-1, keepdim=True)
     else:
-        o = torch.matmul(p, vh)
+        o = torch.matmul(p if drop_mult is None else p * drop_mult, vh)
     return o.permute(0, 2, 1, 3).reshape(R, Sq, H)
 
 
@@ -174,7 +244,7 @@ def qformer_bert(w: Dict[str, torch.Tensor], cfg: QFormerOracleConfig,
                  input_ids: Optional[torch.Tensor], attention_mask: Optional[torch.Tensor],
                  query_embeds: torch.Tensor, encoder_hidden_states: torch.Tensor,
                  encoder_attention_mask: Optional[torch.Tensor] = None,
-                 emulate_bf16: bool = False, skip_dead_text_ffn: bool = False) -> torch.Tensor:
+                 emulate_bf16: bool = False, skip_dead_text_ffn: bool = False, dropout=None) -> torch.Tensor:
     """``Qformer.bert(input_ids, attention_mask=, query_embeds=, encoder_hidden_states=, encoder_attention_mask=,
     return_dict=True).last_hidden_state`` -> [rows, Nq+T, H]   (call site models/xinstructblip.py:286-293)."""
     emu = emulate_bf16
@@ -184,6 +254,22 @@ def qformer_bert(w: Dict[str, torch.Tensor], cfg: QFormerOracleConfig,
     rows = encoder_hidden_states.shape[0]
     query_embeds = query_embeds.expand(rows, -1, -1).to(torch.float32)
     enc = encoder_hidden_states.to(torch.float32)
+    H = cfg.hidden_size
+    Tn = input_ids.shape[1] if (input_ids is not None and cfg.has_text) else 0
+    # ``dropout = (p, seed)``: training mode with the CUDA path's counter-based masks (see above); None = eval
+    r_idx = torch.arange(rows)[:, None]
+    m_query = r_idx * Nq + torch.arange(Nq)[None, :]                                   # split-layout row of query token (r, i)
+    m_text = rows * Nq + r_idx * Tn + torch.arange(Tn)[None, :]                        # ... of text token (r, j)
+    m_all = torch.cat([m_query, m_text], dim=1)
+
+    def hdrop(site, layer, m_index):
+        return None if dropout is None else hidden_dropout_mult(dropout[0], dropout[1], site, layer, m_index, H)
+
+    def adrop(site, layer, Sq, Sk):
+        return None if dropout is None else attention_dropout_mult(dropout[0], dropout[1], site, layer, rows, nh, Sq, Sk)
+
+    def dropped(y, mult):
+        return y if mult is None else y * mult
 
     # --- embeddings: LN(cat(query_embeds, word_emb[ids] + pos_emb[0:T]))
     if input_ids is not None and cfg.has_text:
@@ -196,7 +282,8 @@ def qformer_bert(w: Dict[str, torch.Tensor], cfg: QFormerOracleConfig,
         x = query_embeds
     # residual stream x / a / aq stays fp32 (the CUDA path keeps an fp32 copy next to the bf16 GEMM operand copy);
     # tag "ln" is only for the error study in DESIGN.md
-    x = _r(_layernorm(x, w["bert.embeddings.LayerNorm.weight"], w["bert.embeddings.LayerNorm.bias"], eps), emu, "ln")
+    x = _layernorm(x, w["bert.embeddings.LayerNorm.weight"], w["bert.embeddings.LayerNorm.bias"], eps)
+    x = _r(dropped(x, hdrop(DROP_EMB, 0, m_all)), emu, "ln")
 
     # --- masks: (1 - m) * -10000 on keys (LAVIS get_extended_attention_mask); encoder mask inverted the same way
     if attention_mask is None:
@@ -221,27 +308,28 @@ def qformer_bert(w: Dict[str, torch.Tensor], cfg: QFormerOracleConfig,
         q = _r(lin(x, p + "attention.self.query"), emu)
         k = _r(lin(x, p + "attention.self.key"), emu)
         v = _r(lin(x, p + "attention.self.value"), emu)
-        ctx = _attention(q, k, v, self_mask, nh, emu)
-        a = ln(lin(ctx, p + "attention.output.dense") + x, p + "attention.output.LayerNorm")
+        ctx = _attention(q, k, v, self_mask, nh, emu, adrop(DROP_SELF_PROBS, i, Nq + T, Nq + T))
+        a = ln(dropped(lin(ctx, p + "attention.output.dense"), hdrop(DROP_SELF_OUT, i, m_all)) + x, p + "attention.output.LayerNorm")
 
         aq = a[:, :Nq]
         if cfg.has_cross(i):
             cq = _r(lin(aq, p + "crossattention.self.query"), emu)
             ck = _r(lin(enc, p + "crossattention.self.key"), emu)
             cv = _r(lin(enc, p + "crossattention.self.value"), emu)
-            cctx = _attention(cq, ck, cv, enc_mask, nh, emu)
-            aq = ln(lin(cctx, p + "crossattention.output.dense") + aq, p + "crossattention.output.LayerNorm")
+            cctx = _attention(cq, ck, cv, enc_mask, nh, emu, adrop(DROP_CROSS_PROBS, i, Nq, enc.shape[1]))
+            aq = ln(dropped(lin(cctx, p + "crossattention.output.dense"), hdrop(DROP_CROSS_OUT, i, m_query)) + aq,
+                    p + "crossattention.output.LayerNorm")
 
         # FFN_query
         h = F.gelu(lin(aq, p + "intermediate_query.dense"))
-        yq = ln(lin(h, p + "output_query.dense") + aq, p + "output_query.LayerNorm")
+        yq = ln(dropped(lin(h, p + "output_query.dense"), hdrop(DROP_FFN_OUT, i, m_query)) + aq, p + "output_query.LayerNorm")
         if T > 0:
             at = a[:, Nq:]
             if last and skip_dead_text_ffn:
                 yt = at  # layer-11 text FFN output is never read by the hot path (models/xinstructblip.py:303)
             else:
                 h = F.gelu(lin(at, p + "intermediate.dense"))
-                yt = ln(lin(h, p + "output.dense") + at, p + "output.LayerNorm")
+                yt = ln(dropped(lin(h, p + "output.dense"), hdrop(DROP_FFN_OUT, i, m_text)) + at, p + "output.LayerNorm")
             x = torch.cat([yq, yt], dim=1)
         else:
             x = yq
