@@ -550,7 +550,7 @@ int launch_tma_variant(const TmaMaps& maps, const TmaParams2& pp, unsigned grid,
     auto kern = attention_tma_kernel<NWARPS>;
     // same L1 / shared-memory split as the GEMM kernels around it: no SM reconfiguration between launches
     if (int e = ensure_smem_attr(reinterpret_cast<const void*>(kern), 160 * 1024, true)) return e;
-    MRA_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(NWARPS * 32), smem, s, maps, pp));
+    MRA_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(NWARPS * 32), smem, s, 1, maps, pp));
     return 0;
 }
 
@@ -647,9 +647,9 @@ int launch_attention(const AttnArgs& a, cudaStream_t s) {
     if (int e = ensure_smem_attr(reinterpret_cast<const void*>(attention_kernel<2>), 96 * 1024)) return e;
     if (int e = ensure_smem_attr(reinterpret_cast<const void*>(attention_kernel<4>), 96 * 1024)) return e;
     if (a.Sq <= 32)
-        MRA_CHECK_CUDA(launch_pdl(attention_kernel<2>, dim3(grid), dim3(64), smem, s, p));
+        MRA_CHECK_CUDA(launch_pdl(attention_kernel<2>, dim3(grid), dim3(64), smem, s, 1, p));
     else
-        MRA_CHECK_CUDA(launch_pdl(attention_kernel<4>, dim3(grid), dim3(128), smem, s, p));
+        MRA_CHECK_CUDA(launch_pdl(attention_kernel<4>, dim3(grid), dim3(128), smem, s, 1, p));
     return 0;
 }
 

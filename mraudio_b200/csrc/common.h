@@ -36,21 +36,34 @@ void set_error(const char* fmt, ...);
 // its prologue (barrier init, TMEM allocation, descriptor prefetch), and blocks in ptx::griddep_wait() until the
 // predecessor has completed and flushed.  EVERY kernel launched through this helper must call ptx::griddep_wait()
 // before touching global memory.
+// MRA_PDL=0 disables (A/B).  Round 1 measured no gain (only the unpaired kernels took part); with every kernel of the chain
+// taking part -- the 2-CTA GEMMs and the fused GEMM+LayerNorm included -- see profiles/r02_NOTES.md.
+inline bool pdl_enabled() {
+    static const bool enabled = [] { const char* e = getenv("MRA_PDL"); return e == nullptr || atoi(e) != 0; }();
+    return enabled;
+}
+// cluster_x > 1: launch with that (1-D) thread-block cluster size
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, int cluster_x, Args&&... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
-    // Measured on B200 (round 1): no gain for this launch chain (the gaps are kernel tails, not launch latency) and it
-    // slows the three-stream host pipeline, so it is opt-in (MRA_PDL=1) until the fused kernels shorten the tails.
-    static const bool enabled = getenv("MRA_PDL") != nullptr;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if (cluster_x > 1) {
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = cluster_x; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (pdl_enabled()) {
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
     cfg.attrs = at;
-    cfg.numAttrs = enabled ? 1 : 0;
+    cfg.numAttrs = na;
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 

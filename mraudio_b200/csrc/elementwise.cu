@@ -320,7 +320,7 @@ int launch_layernorm_grouped(const LnSegment* segs, int nseg, int n, float eps, 
     for (int i = nseg; i <= 4; ++i) grp.start[i] = total;
     grp.n = nseg;
     const int blocks = (total + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
-    MRA_CHECK_CUDA(launch_pdl(layernorm_grouped_kernel, dim3(blocks), dim3(WARPS_PER_BLOCK * 32), 0, s, grp, n, eps));
+    MRA_CHECK_CUDA(launch_pdl(layernorm_grouped_kernel, dim3(blocks), dim3(WARPS_PER_BLOCK * 32), 0, s, 1, grp, n, eps));
     return 0;
 }
 
@@ -360,7 +360,7 @@ int launch_embed_layernorm(const float* query_embeds, int q_rows, const int32_t*
     MRA_REQUIRE(T == 0 || (ids && word_emb && pos_emb), "text tokens given but ids / embedding tables are NULL");
     const int64_t total = static_cast<int64_t>(rows) * (Nq + T);
     const unsigned blocks = static_cast<unsigned>((total + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
-    MRA_CHECK_CUDA(launch_pdl(embed_ln_kernel, dim3(blocks), dim3(WARPS_PER_BLOCK * 32), 0, s, query_embeds, q_rows, ids,
+    MRA_CHECK_CUDA(launch_pdl(embed_ln_kernel, dim3(blocks), dim3(WARPS_PER_BLOCK * 32), 0, s, 1, query_embeds, q_rows, ids,
                               reinterpret_cast<const __nv_bfloat16*>(word_emb), reinterpret_cast<const __nv_bfloat16*>(pos_emb), g,
                               b, y32, reinterpret_cast<__nv_bfloat16*>(y16), reinterpret_cast<__nv_bfloat16*>(ylo), pre_out, rows,
                               Nq, T, H, vocab, eps, drop ? *drop : DropoutParams()));

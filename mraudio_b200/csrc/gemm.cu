@@ -757,7 +757,7 @@ int launch_tc_variant(const GemmArgs* ga, int n, cudaStream_t s) {
     if (CM == 1) {
         const long items = static_cast<long>(total) * p.ksplit;
         const int grid = items < sm_count() ? static_cast<int>(items) : sm_count();
-        MRA_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), L::TOTAL, s, maps, p));
+        MRA_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), L::TOTAL, s, 1, maps, p));
         if (MRA_GEMM_DBG(p) & 8) {   // (single-CTA path; the paired paths print below)
             unsigned long long t[8];
             cudaStreamSynchronize(s);
@@ -772,17 +772,7 @@ int launch_tc_variant(const GemmArgs* ga, int n, cudaStream_t s) {
         return 0;
     }
     const int clusters = total < sm_count() / CM ? total : sm_count() / CM;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(clusters * CM);
-    cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = L::TOTAL;
-    cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = CM; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    MRA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, p));
+    MRA_CHECK_CUDA(launch_pdl(kern, dim3(clusters * CM), dim3(NUM_THREADS), L::TOTAL, s, CM, maps, p));
     if (MRA_GEMM_DBG(p) & 8) {
         unsigned long long t[8];
         cudaStreamSynchronize(s);

@@ -189,6 +189,9 @@ gemm_ln_kernel(const __grid_constant__ LnMaps maps, const __grid_constant__ LnPa
     ptx::tc_fence_after();
     cluster_sync_all();   // the peers' barriers are initialised before anyone signals them remotely
     const uint32_t tmem_base = *tmem_ptr_smem;
+    // everything above overlapped the tail of the previous kernel in the stream (programmatic dependent launch)
+    ptx::griddep_wait();
+    ptx::griddep_launch_dependents();
 
     if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");   // producer / MMA warpgroup gives up registers
     if (warp == 0) {
@@ -596,8 +599,8 @@ static int launch_gemm_ln_variant(const GemmLnArgs* ga, int n, float eps, cudaSt
     }
     int clusters = max_clusters;
     if (clusters > total) clusters = total;
-    kern<<<C::CLUSTER * clusters, NUM_THREADS, C::SMEM_TOTAL, s>>>(maps, p);
-    MRA_CHECK_CUDA(cudaGetLastError());
+    // (the cluster size is the kernel's compile-time __cluster_dims__: no launch attribute for it)
+    MRA_CHECK_CUDA(launch_pdl(kern, dim3(C::CLUSTER * clusters), dim3(NUM_THREADS), C::SMEM_TOTAL, s, 1, maps, p));
 #ifdef MRA_INSTRUMENT
     if (dbg & 8) {
         unsigned long long t[16];
