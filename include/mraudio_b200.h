@@ -168,7 +168,9 @@ int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, const void*
  * events[l] (cudaEvent_t, owned by the caller; NULL entries allowed) is recorded on the backward's stream as soon as the
  * gradients of layer l -- and therefore of all layers above it -- are final, so the caller can start the all-reduce of
  * that bucket on another stream while the lower layers are still running; events[layers] (optional, n = layers + 1) is
- * recorded when the projection's gradients are final, i.e. after the first launches of the backward.  (The stacked
+ * recorded when the projection's gradients are final, i.e. after the first launches of the backward.  At each event the
+ * WEIGHTS of those layers (of the projection) are also no longer read by this backward: the caller may run the optimizer
+ * update of the bucket -- rewriting the bf16 operands in place -- behind the event.  (The stacked
  * cross-attention K/V gradients -- ONE weight-gradient GEMM over all cross layers at the end --, the embeddings and the
  * query tokens are final only when mra_qformer_backward has finished.)  n = 0 clears. */
 int mra_qformer_backward_layer_events(mra_qformer_t* h, void* const* events, int32_t n);
@@ -180,6 +182,14 @@ int mra_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
 int mra_adam_step_fused(float* params, float* grads, const void* reduced_grads_bf16, float* exp_avg, float* exp_avg_sq,
                         void* params_bf16, int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
                         int32_t step, float grad_scale, int32_t zero_grads, void* stream);
+/* mra_adam_step_fused with the per-step scalars read from DEVICE memory -- hyper_dev[4] = {lr, 1 - beta1^step,
+ * sqrt(1 - beta2^step), grad_scale}, 16-byte aligned -- so that the launch can be captured in a CUDA graph and replayed
+ * while the learning-rate schedule (utils/trainer.py:127) and the step count advance.  mra_adam_hyper fills the four values
+ * on the host exactly as mra_adam_step_fused derives them (bit-identical updates). */
+int mra_adam_step_fused_dyn(float* params, float* grads, const void* reduced_grads_bf16, float* exp_avg, float* exp_avg_sq,
+                            void* params_bf16, int64_t n, float beta1, float beta2, float eps, float weight_decay,
+                            int32_t zero_grads, const float* hyper_dev, void* stream);
+void mra_adam_hyper(float lr, float beta1, float beta2, int32_t step, float grad_scale, float* out4);
 int mra_cast_bf16(const float* in, void* out, int64_t n, void* stream);
 
 /* Device-side timing of the launches of mra_qformer_forward with CUDA events recorded on the caller's stream.

@@ -95,6 +95,9 @@ def _load():
     lib.mra_qformer_backward_layer_events.argtypes = [vp, C.POINTER(vp), i32]
     lib.mra_adam_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, vp]
     lib.mra_adam_step_fused.argtypes = [vp, vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, i32, vp]
+    lib.mra_adam_step_fused_dyn.argtypes = [vp, vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, vp, vp]
+    lib.mra_adam_hyper.argtypes = [f32, f32, f32, i32, f32, C.POINTER(C.c_float)]
+    lib.mra_adam_hyper.restype = None
     lib.mra_cast_bf16.argtypes = [vp, vp, i64, vp]
     lib.mra_qformer_profile_mode.argtypes = [vp, i32]
     lib.mra_qformer_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
@@ -135,7 +138,7 @@ lib = _LazyLib()
 # every symbol include/mraudio_b200.h declares (checked by tests/test_capi_symbols.py)
 EXPORTED_SYMBOLS = (
     "mra_last_error", "mra_version", "mra_device_check", "mra_qformer_create", "mra_qformer_set_weights",
-    "mra_qformer_destroy", "mra_qformer_workspace_bytes", "mra_qformer_forward", "mra_qformer_forward_multi", "mra_qformer_last_launch_count", "mra_qformer_backward_workspace_bytes", "mra_qformer_backward", "mra_qformer_backward_layer_events", "mra_adam_step", "mra_adam_step_fused",
+    "mra_qformer_destroy", "mra_qformer_workspace_bytes", "mra_qformer_forward", "mra_qformer_forward_multi", "mra_qformer_last_launch_count", "mra_qformer_backward_workspace_bytes", "mra_qformer_backward", "mra_qformer_backward_layer_events", "mra_adam_step", "mra_adam_step_fused", "mra_adam_step_fused_dyn", "mra_adam_hyper",
     "mra_cast_bf16",
     "mra_qformer_profile_mode", "mra_qformer_profile_read",
     "mra_gemm_bf16", "mra_wgrad_bf16", "mra_dgrad_bf16", "mra_gemm_ln_bf16", "mra_gemm_ln_split_bf16", "mra_gemm_tile_override", "mra_gemm_cluster_override", "mra_attention", "mra_attention_impl_override", "mra_layernorm", "mra_modality_layernorm", "mra_add_frame_position", "mra_prompt_assemble", "mra_mr_score",

@@ -903,9 +903,12 @@ int launch_embed_bwd(const float* d_emb, const int32_t* ids, float* d_query, int
 __global__ void __launch_bounds__(256)
 adam_fused_kernel(float4* __restrict__ p, float4* __restrict__ g, const uint2* __restrict__ g16, float4* __restrict__ m,
                   float4* __restrict__ v, uint2* __restrict__ p16, int64_t n4, float lr, float beta1, float beta2, float eps,
-                  float weight_decay, float bc1, float bc2_sqrt, float grad_scale, int zero_grad) {
+                  float weight_decay, float bc1, float bc2_sqrt, float grad_scale, int zero_grad, const float* __restrict__ dyn) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n4) return;
+    if (dyn != nullptr) {   // per-step scalars from device memory: the launch can be replayed from a CUDA graph
+        lr = __ldg(dyn); bc1 = __ldg(dyn + 1); bc2_sqrt = __ldg(dyn + 2); grad_scale = __ldg(dyn + 3);
+    }
     const float4 m4 = m[i], v4 = v[i];
     float4 p4 = p[i];
     float gg[4];
@@ -935,8 +938,9 @@ adam_fused_kernel(float4* __restrict__ p, float4* __restrict__ g, const uint2* _
 }
 
 int launch_adam_fused(float* p, float* g, const void* g16, float* m, float* v, void* p16, int64_t n, float lr, float beta1, float beta2,
-                      float eps, float weight_decay, int step, float grad_scale, int zero_grad, cudaStream_t s) {
-    MRA_REQUIRE(n > 0 && n % 4 == 0 && step >= 1, "fused adam: n must be a positive multiple of 4");
+                      float eps, float weight_decay, int step, float grad_scale, int zero_grad, cudaStream_t s, const float* dyn) {
+    MRA_REQUIRE(n > 0 && n % 4 == 0 && (step >= 1 || dyn != nullptr), "fused adam: n must be a positive multiple of 4");
+    if (dyn != nullptr) step = 1;   // (lr, bias corrections and gradient scale are read from `dyn` by the kernel)
     MRA_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
                   reinterpret_cast<uintptr_t>(v)) & 15) == 0 && ((reinterpret_cast<uintptr_t>(p16) | reinterpret_cast<uintptr_t>(g16)) & 7) == 0,
                 "fused adam: buffers must be 16-byte aligned");
@@ -945,9 +949,17 @@ int launch_adam_fused(float* p, float* g, const void* g16, float* m, float* v, v
     const int64_t n4 = n / 4;
     adam_fused_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, s>>>(
         reinterpret_cast<float4*>(p), reinterpret_cast<float4*>(g), reinterpret_cast<const uint2*>(g16), reinterpret_cast<float4*>(m),
-        reinterpret_cast<float4*>(v), reinterpret_cast<uint2*>(p16), n4, lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale, zero_grad);
+        reinterpret_cast<float4*>(v), reinterpret_cast<uint2*>(p16), n4, lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale, zero_grad,
+        dyn);
     MRA_CHECK_CUDA(cudaGetLastError());
     return 0;
+}
+
+void adam_hyper(float lr, float beta1, float beta2, int step, float grad_scale, float* out4) {
+    out4[0] = lr;
+    out4[1] = 1.f - powf(beta1, static_cast<float>(step));
+    out4[2] = sqrtf(1.f - powf(beta2, static_cast<float>(step)));
+    out4[3] = grad_scale;
 }
 
 int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,

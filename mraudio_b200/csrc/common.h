@@ -197,7 +197,9 @@ int launch_gelu_bwd(const void* z, const void* dy, void* dz, int64_t n, cudaStre
 int launch_embed_bwd(const float* d_emb, const int32_t* ids, float* d_query, int q_rows, float* d_word, float* d_pos, int rows,
                      int Nq, int T, int H, int vocab, cudaStream_t s);
 int launch_adam_fused(float* p, float* g, const void* g16, float* m, float* v, void* p16, int64_t n, float lr, float beta1, float beta2,
-                      float eps, float weight_decay, int step, float grad_scale, int zero_grad, cudaStream_t s);
+                      float eps, float weight_decay, int step, float grad_scale, int zero_grad, cudaStream_t s, const float* dyn = nullptr);
+// {lr, 1 - beta1^step, sqrt(1 - beta2^step), grad_scale}: what launch_adam_fused derives on the host, for the `dyn` form
+void adam_hyper(float lr, float beta1, float beta2, int step, float grad_scale, float* out4);
 int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                 float weight_decay, int step, float grad_scale, cudaStream_t s);
 int launch_cast_bf16(const float* in, void* out, int64_t n, cudaStream_t s);

@@ -709,8 +709,9 @@ extern "C" int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, 
     // ---- llm_proj
     const __nv_bfloat16* dl = reinterpret_cast<const __nv_bfloat16*>(d_llm);
     if (int e = wgrad(dl, D, ws.layer[c.layers].xb, H, Mq, D, H, g->w_proj, H, g->b_proj)) return e;
-    if (h->layer_done[c.layers]) MRA_CHECK_CUDA(cudaEventRecord(h->layer_done[c.layers], s));   // projection gradients final
     MRA_TRY(gemm(dl, D, W.w_proj, D, nullptr, 0, bw.g_x, H, Mq, H, D, 1));
+    // projection gradients final AND its weights no longer read by this backward (the optimizer may rewrite them)
+    if (h->layer_done[c.layers]) MRA_CHECK_CUDA(cudaEventRecord(h->layer_done[c.layers], s));
     if (Mt > 0) {
         MRA_CHECK_CUDA(cudaMemsetAsync(bw.g_x + static_cast<size_t>(Mq) * H, 0, static_cast<size_t>(Mt) * H * 4, s));
         ++launches;
@@ -813,6 +814,20 @@ extern "C" int mra_adam_step_fused(float* params, float* grads, const void* redu
     if (int e = device_check()) return e;
     return launch_adam_fused(params, grads, reduced_grads_bf16, exp_avg, exp_avg_sq, params_bf16, n, lr, beta1, beta2, eps,
                              weight_decay, step, grad_scale, zero_grads, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mra_adam_step_fused_dyn(float* params, float* grads, const void* reduced_grads_bf16, float* exp_avg, float* exp_avg_sq,
+                                       void* params_bf16, int64_t n, float beta1, float beta2, float eps, float weight_decay,
+                                       int32_t zero_grads, const float* hyper_dev, void* stream) {
+    MRA_REQUIRE(params && grads && exp_avg && exp_avg_sq && hyper_dev, "mra_adam_step_fused_dyn: NULL argument");
+    MRA_REQUIRE((reinterpret_cast<uintptr_t>(hyper_dev) & 15) == 0, "mra_adam_step_fused_dyn: hyper_dev must be 16-byte aligned");
+    if (int e = device_check()) return e;
+    return launch_adam_fused(params, grads, reduced_grads_bf16, exp_avg, exp_avg_sq, params_bf16, n, 0.f, beta1, beta2, eps,
+                             weight_decay, 1, 1.f, zero_grads, reinterpret_cast<cudaStream_t>(stream), hyper_dev);
+}
+
+extern "C" void mra_adam_hyper(float lr, float beta1, float beta2, int32_t step, float grad_scale, float* out4) {
+    if (out4) adam_hyper(lr, beta1, beta2, step, grad_scale, out4);
 }
 
 extern "C" int mra_cast_bf16(const float* in, void* out, int64_t n, void* stream) {

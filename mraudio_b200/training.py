@@ -334,6 +334,31 @@ class TrainableQFormer:
                                       self.exp_avg_sq.data_ptr(), self.flat16.data_ptr(), self.numel, lr, betas[0], betas[1], eps,
                                       weight_decay, self.step_count, grad_scale, int(zero_grad), current_stream()))
 
+    def begin_bucketed_step(self):
+        """Start an optimizer step that is applied bucket by bucket (``adam_bucket``): one step count for all buckets."""
+        self.step_count += 1
+        self.version += 1
+
+    def adam_bucket(self, k: int, lr: float, grad_scale: float = 1.0, betas=(0.9, 0.999), eps: float = 1e-8,
+                    weight_decay: float = 0.0, zero_grad: bool = True, reduced_bf16: bool = False, hyper_dev: Optional[int] = None):
+        """``adam_step`` restricted to the flat-buffer ranges of gradient bucket ``k`` (same arithmetic per element), on the
+        current stream.  Called behind the event that makes the bucket's gradients final (and behind its exchange), so the
+        update of the top layers runs under the backward of the lower ones: the backward's launches at fine-tuning batch
+        sizes leave most SMs and nearly all of the HBM bandwidth idle, which is what this 28-bytes-per-parameter pass needs.
+        The bf16 operand copy of a bucket is rewritten here too: no kernel of this step reads those weights any more."""
+        for lo, hi in self.buckets[k][1]:
+            g16 = self.grad16.data_ptr() + lo * 2 if reduced_bf16 else None
+            if hyper_dev is not None:   # lr / bias corrections / gradient scale from device memory (CUDA-graph replay)
+                check(lib.mra_adam_step_fused_dyn(self.flat.data_ptr() + lo * 4, self.grad.data_ptr() + lo * 4, g16,
+                                                  self.exp_avg.data_ptr() + lo * 4, self.exp_avg_sq.data_ptr() + lo * 4,
+                                                  self.flat16.data_ptr() + lo * 2, hi - lo, betas[0], betas[1], eps, weight_decay,
+                                                  int(zero_grad), hyper_dev, current_stream()))
+                continue
+            check(lib.mra_adam_step_fused(self.flat.data_ptr() + lo * 4, self.grad.data_ptr() + lo * 4, g16,
+                                          self.exp_avg.data_ptr() + lo * 4, self.exp_avg_sq.data_ptr() + lo * 4,
+                                          self.flat16.data_ptr() + lo * 2, hi - lo, lr, betas[0], betas[1], eps, weight_decay,
+                                          self.step_count, grad_scale, int(zero_grad), current_stream()))
+
 
 class _QFormerTrainFn(torch.autograd.Function):
     """Autograd node of one modality's Q-Former + projection.  The parameter gradients are accumulated by the CUDA
@@ -365,6 +390,127 @@ def warmup_cosine_lr(cur_epoch: int, cur_step: int, max_epoch: int, init_lr: flo
     return (init_lr - min_lr) * 0.5 * (1.0 + math.cos(math.pi * cur_epoch / max_epoch)) + min_lr
 
 
+class _StepGraphs:
+    """The captured CUDA graphs of one input shape of ``QFormerTrainer.train_step``: ``fwd`` (input preparation + the
+    training forward of every modality on its stream) and, per (stepping, reduce) variant, the backward of every modality
+    on its stream + the bucketed gradient exchange + the per-bucket Adam update on the communication stream.  Inputs,
+    projected outputs and their gradients live in static buffers; the optimizer's per-step scalars in device memory."""
+
+    def __init__(self, tr: "QFormerTrainer", mods, feats, input_ids, attention_mask):
+        self.tr, self.mods = tr, mods
+        dev = next(tr.model.parameters()).device
+        self.feats = {m: torch.empty(feats[m].shape, dtype=feats[m].dtype, device=dev) for m in mods}
+        self.ids = torch.empty(input_ids.shape, dtype=input_ids.dtype, device=dev)
+        self.mask = torch.empty(attention_mask.shape, dtype=attention_mask.dtype, device=dev)
+        for m in mods:
+            self.feats[m].copy_(feats[m])
+        self.ids.copy_(input_ids)
+        self.mask.copy_(attention_mask)
+        self.hyper_host = {m: torch.zeros(4, dtype=torch.float32) for m in mods}   # pageable: the H2D copy below stages it before returning
+        self.hyper_dev = {m: torch.zeros(4, dtype=torch.float32, device=dev) for m in mods}
+        self.bwd: Dict[tuple, torch.cuda.CUDAGraph] = {}
+        self.keep = []
+        # eager warm-up of exactly what is captured (lazy initialisation: kernel attributes, workspaces, tensor maps): the
+        # backward runs on a zero gradient, i.e. accumulates nothing, and no optimizer step is taken
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            y = self._forward()
+            for m in mods:
+                tr.states[m]._backward_impl(torch.zeros(y[m].shape, dtype=torch.bfloat16, device=dev))
+            self._join()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.fwd = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.fwd, capture_error_mode="thread_local"):
+            self.y = self._forward()
+            self._join()
+        self.saved = {m: tr.states[m]._saved for m in mods}
+        self.ws = [(tr.states[m]._ws, tr.states[m]._bws) for m in mods]      # the graphs hold raw pointers into these
+        Nq = tr.model.num_query_token
+        self.dy = {m: torch.zeros(self.y[m].shape[0] * self.y[m].shape[1], self.y[m].shape[2], dtype=torch.bfloat16, device=dev)
+                   for m in mods}
+
+    def _forward(self):
+        """``QFormerTrainer.forward_modalities`` on the static inputs (no autograd node, no record_stream)."""
+        tr, model = self.tr, self.tr.model
+        main = torch.cuda.current_stream()
+        ys, self._sides = {}, []
+        for m in self.mods:
+            enc = model.fold_frames(m, self.feats[m], apply_ln=False)
+            bs = self.ids.shape[0]
+            num = enc.shape[0] // bs
+            ids = self.ids.repeat(num, 1)
+            tmask = self.mask.repeat(num, 1)
+            q_atts = torch.ones(enc.shape[0], model.num_query_token, dtype=tmask.dtype, device=tmask.device)
+            full_mask = torch.cat([q_atts, tmask], 1)
+            st = tr.states[m]
+            st._dropout = (0.0, 0)
+            if tr.parallel_modalities and len(self.mods) > 1:
+                side = tr.mod_streams[m]
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    y = st._forward_impl(enc, ids, full_mask)
+                self._sides.append(side)
+            else:
+                y = st._forward_impl(enc, ids, full_mask)
+            self.keep += [enc, ids, full_mask]
+            ys[m] = y.reshape(bs, num * model.num_query_token, -1)
+        return ys
+
+    def _join(self):
+        for side in self._sides:
+            torch.cuda.current_stream().wait_stream(side)
+
+    def _capture_backward(self, stepping: bool, reduce: bool, world: int) -> torch.cuda.CUDAGraph:
+        tr = self.tr
+        assert not reduce, "the gradient exchange is not captured (single-process replay only)"
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, pool=self.fwd.pool(), capture_error_mode="thread_local"):
+            main = torch.cuda.current_stream()
+            sides = []
+            for m in self.mods:
+                st = tr.states[m]
+                st._saved = self.saved[m]
+                if tr.parallel_modalities and len(self.mods) > 1:
+                    side = tr.mod_streams[m]
+                    side.wait_stream(main)
+                    with torch.cuda.stream(side):
+                        st._backward_impl(self.dy[m])
+                    sides.append(side)
+                else:
+                    st._backward_impl(self.dy[m])
+            live = [tr.states[m] for m in self.mods]
+            if stepping:
+                for k in range(max(len(st.buckets) for st in live)):
+                    for m, st in zip(self.mods, live):
+                        if k >= len(st.buckets):
+                            continue
+                        ev = st.buckets[k][0]
+                        tr.comm_stream.wait_event(st.layer_events[ev] if ev is not None else st.backward_done)
+                        with torch.cuda.stream(tr.comm_stream):
+                            st.adam_bucket(k, 0.0, zero_grad=True, hyper_dev=self.hyper_dev[m].data_ptr())
+                main.wait_stream(tr.comm_stream)
+            for side in sides:
+                main.wait_stream(side)
+        return g
+
+    def replay_backward(self, stepping: bool, reduce: bool, world: int):
+        tr = self.tr
+        key = (stepping, reduce, tuple(tr.states[m].grad_comm_dtype for m in self.mods))
+        g = self.bwd.get(key)
+        if g is None:
+            g = self.bwd[key] = self._capture_backward(stepping, reduce, world)
+        if stepping:
+            for m in self.mods:
+                st = tr.states[m]
+                st.begin_bucketed_step()
+                lib.mra_adam_hyper(tr.lr, 0.9, 0.999, st.step_count, 1.0 / world,
+                                   C.cast(self.hyper_host[m].data_ptr(), C.POINTER(C.c_float)))
+                self.hyper_dev[m].copy_(self.hyper_host[m])
+        g.replay()
+
+
 class QFormerTrainer:
     """The hot-path slice of ``utils/trainer.py::Trainer`` for ``XInstructBLIPQFormers``: ``train_step`` = one iteration of
     ``train_epoch`` (:124-140).  ``loss_fn(inputs_llm, atts_llm, samples) -> scalar`` stands in for the frozen LLM's loss
@@ -372,7 +518,8 @@ class QFormerTrainer:
 
     def __init__(self, model, max_epoch: int = 1, accum_grad_iters: int = 2, init_lr: float = 3e-4, warmup_steps: int = 1000,
                  loss_fn=None, group=None, overlap_allreduce: bool = True, parallel_modalities: bool = True,
-                 grad_comm_dtype: torch.dtype = torch.bfloat16, dropout: Optional[float] = 0.0, seed: int = 0):
+                 grad_comm_dtype: torch.dtype = torch.bfloat16, dropout: Optional[float] = 0.0, seed: int = 0,
+                 cuda_graph: bool = False):
         self.model = model
         model.freeze_qformers(False)
         self.states = {m: TrainableQFormer(getattr(model, f"{m}_Qformer"), getattr(model, f"{m}_query_tokens"),
@@ -386,6 +533,10 @@ class QFormerTrainer:
         self.dropout = dropout
         self.seed = seed
         self.allreduce_enabled = True       # False: skip the gradient exchange (bench.py measures its exposed cost that way)
+        # Adam per gradient bucket behind the backward, on the communication stream (TrainableQFormer.adam_bucket), instead of
+        # one pass after it.  Off by default: measured neutral on B200 (13.77 vs 13.77 ms at 1 GPU, 14.95 vs 14.77 ms at 2 --
+        # the backward's launches do not leave the HBM bandwidth idle that the update needs); the CUDA-graph replay uses it.
+        self.overlap_optimizer = False
         self.set_grad_comm_dtype(grad_comm_dtype)
         # At fine-tuning batch sizes (64 rows per modality) most launches fill a fraction of the 148 SMs, so the video and
         # the audio Q-Former run on two streams: autograd replays each modality's backward on the stream of its forward.
@@ -396,6 +547,14 @@ class QFormerTrainer:
         self.comm_stream = torch.cuda.Stream(dev)     # ONE stream for the gradient exchange of all modalities
         self.iter = 0
         self.lr = init_lr
+        # cuda_graph: replay the step from two captured CUDA graphs (forward | backward + gradient exchange + optimizer)
+        # around the eagerly evaluated loss.  The ~800 launches of a config-4 step take the host ~10 ms to issue against
+        # ~14 ms on the device, so the streams of the two modalities starve each other; a replay costs the host two
+        # launches.  One pair of graphs per input shape (batches of a fixed shape: pad the text to a fixed length); needs
+        # dropout 0 and falls back to the eager path otherwise.
+        self.cuda_graph = cuda_graph
+        self._graphs: Dict[tuple, "_StepGraphs"] = {}
+        self.max_graphs = 4
 
     def set_grad_comm_dtype(self, dtype: torch.dtype):
         """bf16 (default: 0.74 GB per step for both Q-Formers) or fp32 (1.49 GB, exact) gradient exchange"""
@@ -451,6 +610,8 @@ class QFormerTrainer:
         used by the data-parallel equivalence checks."""
         import torch.distributed as dist
         self.lr = warmup_cosine_lr(cur_epoch, self.iter, self.max_epoch, self.init_lr, 0.0, self.warmup_steps)   # :127
+        if self.cuda_graph and apply_optimizer and self._graph_eligible(feats):
+            return self._train_step_graphed(feats, input_ids, attention_mask, samples, surrogate)
         inputs_llm, atts_llm = self.forward_modalities(feats, input_ids, attention_mask)
         if self.loss_fn is not None:
             loss = self.loss_fn(inputs_llm, atts_llm, samples)
@@ -459,35 +620,54 @@ class QFormerTrainer:
         world = self._world()
         stepping = (self.iter + 1) % self.accum_grad_iters == 0                                                    # :137
         reduce = stepping and world > 1 and self.allreduce_enabled
+        # optimizer applied bucket by bucket behind the backward (see TrainableQFormer.adam_bucket)
+        bucketed_opt = stepping and apply_optimizer and self.overlap_allreduce and self.overlap_optimizer
         for st in self.states.values():
             st.backward_ran = False
         (loss / self.accum_grad_iters).backward()                                                                  # :131-133
         # (the CUDA backward of each modality ran on its own stream and accumulated into the flat gradient buffers behind
         #  autograd's back -- no AccumulateGrad node: the streams are joined explicitly below)
-        if reduce:
+        live = [st for st in self.states.values() if st.backward_ran]
+        bucketed = set()
+        if (reduce or bucketed_opt) and self.overlap_allreduce and live:
             # DDP's gradient averaging (utils/trainer.py:69), only on optimizer-step iterations (the reference all-reduces on
             # every backward).  By now the whole backward of every modality is ENQUEUED (the host runs far ahead of the GPU)
             # and has recorded, per bucket, the event that makes its gradients final.  The buckets of all modalities go on
             # one communication stream in the order in which they become ready -- projection, top layers, ..., tail of
-            # modality A, tail of modality B alternating -- so that no modality's exchange queues behind another's tail.
-            # Sum semantics; adam_step(grad_scale = 1 / world) turns it into DDP's mean.
-            for st in self.states.values():
+            # modality A, tail of modality B alternating -- so that no modality's exchange queues behind another's tail;
+            # each bucket's Adam update follows its exchange on the same stream, under the rest of the backward.
+            # Sum semantics; grad_scale = 1 / world turns it into DDP's mean.
+            for st in live:
                 st.reduce_group = self.group
-            live = [st for st in self.states.values() if st.backward_ran]
-            if self.overlap_allreduce and live:
-                for k in range(max(len(st.buckets) for st in live)):
-                    for st in live:
-                        if k < len(st.buckets):
-                            st.exchange_bucket(k, self.comm_stream)
+                if bucketed_opt:
+                    st.begin_bucketed_step()
+                    bucketed.add(id(st))
+            for k in range(max(len(st.buckets) for st in live)):
+                for st in live:
+                    if k >= len(st.buckets):
+                        continue
+                    if reduce:
+                        st.exchange_bucket(k, self.comm_stream)
+                    else:
+                        ev = st.buckets[k][0]
+                        self.comm_stream.wait_event(st.layer_events[ev] if ev is not None else st.backward_done)
+                    if bucketed_opt:
+                        with torch.cuda.stream(self.comm_stream):
+                            st.adam_bucket(k, self.lr, grad_scale=1.0 / world, zero_grad=True,
+                                           reduced_bf16=reduce and st.grad_comm_dtype == torch.bfloat16)
+            if bucketed_opt:
+                for st in live:
+                    st._reduced_bf16 = False
         if self.parallel_modalities and len(self.mod_streams) > 1:
             for side in self.mod_streams.values():
                 torch.cuda.current_stream().wait_stream(side)
         self.iter += 1
         if stepping:
+            if (reduce and self.overlap_allreduce) or bucketed:
+                torch.cuda.current_stream().wait_stream(self.comm_stream)
             if reduce:
-                if self.overlap_allreduce:
-                    torch.cuda.current_stream().wait_stream(self.comm_stream)
                 for st in self.states.values():
+                    st.reduce_group = self.group
                     if not (self.overlap_allreduce and st.backward_ran):
                         # flat all-reduce after the backward: the A/B baseline, and modalities absent from this step (their
                         # accumulated gradients of earlier iterations still have to be averaged)
@@ -499,7 +679,53 @@ class QFormerTrainer:
                             st._reduced_bf16 = False
             if apply_optimizer:
                 for st in self.states.values():
-                    st.adam_step(self.lr, grad_scale=1.0 / world, zero_grad=True)
+                    if id(st) not in bucketed:
+                        st.adam_step(self.lr, grad_scale=1.0 / world, zero_grad=True)
+        return loss.detach()
+
+    # ------------------------------------------------------------------------------------------------ CUDA-graph replay
+    def _graph_eligible(self, feats) -> bool:
+        for m in self.model.modalities:
+            if m in feats:
+                p = getattr(self.model, f"{m}_Qformer").config.hidden_dropout_prob if self.dropout is None else self.dropout
+                if p and p > 0.0:
+                    return False      # the dropout seed of an iteration is a launch argument: not replayable
+        if self._world() > 1:
+            return False          # single-process only: a captured NCCL exchange hung at 2 ranks (profiles/r02_NOTES.md);
+                                  # the eager step keeps the exchange overlapped with the backward
+        return self.overlap_allreduce and all(t.is_cuda or t.is_pinned() for t in feats.values())
+
+    def _train_step_graphed(self, feats, input_ids, attention_mask, samples, surrogate):
+        world = self._world()
+        stepping = (self.iter + 1) % self.accum_grad_iters == 0
+        reduce = stepping and world > 1 and self.allreduce_enabled
+        mods = tuple(m for m in self.model.modalities if m in feats)
+        key = (mods, tuple((tuple(feats[m].shape), feats[m].dtype) for m in mods), tuple(input_ids.shape),
+               tuple(attention_mask.shape), self.parallel_modalities)
+        G = self._graphs.get(key)
+        if G is None:
+            if len(self._graphs) >= self.max_graphs:
+                self._graphs.pop(next(iter(self._graphs)))
+            G = self._graphs[key] = _StepGraphs(self, mods, feats, input_ids, attention_mask)
+        for m in mods:
+            if feats[m].data_ptr() != G.feats[m].data_ptr():
+                G.feats[m].copy_(feats[m], non_blocking=True)
+            self.states[m].sync_operands()
+        G.ids.copy_(input_ids, non_blocking=True)
+        G.mask.copy_(attention_mask, non_blocking=True)
+        G.fwd.replay()
+        # the loss stays eager (any user function of the projected query tokens: the frozen LLM in the reference)
+        leaf = {m: G.y[m].detach().requires_grad_(True) for m in mods}
+        atts = {m: torch.ones(leaf[m].size()[:-1], dtype=torch.long, device=leaf[m].device) for m in mods}
+        if self.loss_fn is not None:
+            loss = self.loss_fn(leaf, atts, samples)
+        else:
+            loss = sum((leaf[m].float() * surrogate[m]).sum() for m in mods)
+        grads = torch.autograd.grad(loss / self.accum_grad_iters, [leaf[m] for m in mods])
+        for m, g in zip(mods, grads):
+            G.dy[m].copy_(g.reshape(G.dy[m].shape))
+        G.replay_backward(stepping, reduce, world)
+        self.iter += 1
         return loss.detach()
 
     def eval_epoch(self, generations, group=None):
