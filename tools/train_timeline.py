@@ -59,3 +59,11 @@ for e in ev_:
 print(f"span {prev_end - t0:.0f} us, kernels {len(ev_)}, busy {sum(a[1] for a in agg.values()):.0f} us, gaps {sum(a[2] for a in agg.values()):.0f} us")
 for k, (n, d, gp) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f"{k:72s} n={n:4d} dur={d:8.1f} avg={d / n:7.1f} gap_before_tot={gp:7.1f}")
+
+seqs = collections.OrderedDict()
+for e in ev_:
+    n = e.name.replace("void ", "").replace("(anonymous namespace)::", "").replace("mra::", "").split("(")[0][:40]
+    if "attn_bwd" in n or "ln_bwd" in n or "attention_tma" in n:
+        seqs.setdefault(n, []).append(round(e.time_range.end - e.time_range.start, 1))
+for n, l in seqs.items():
+    print("per-launch us", n, l)
