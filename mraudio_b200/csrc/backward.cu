@@ -369,6 +369,7 @@ struct AttnBwdTcParams {
     const __nv_bfloat16* o; int64_t ldof;   // forward output (context) of the same attention
     float* db_q; float* db_k; float* db_v;  // optional fused bias gradients of the q / k / v projections: [heads * 64] column sums
     DropoutParams drop;                     // the forward's attention-probability dropout (mask regenerated here)
+    int kc;                                 // keys per resident chunk: the padded key count, or a multiple of 64 below it
 };
 constexpr int ABT_LD = 72;
 constexpr int ABT_WARPS = 8;
@@ -421,32 +422,38 @@ __device__ __forceinline__ void abt_colsum(const float (&acc)[8][4], float scale
     }
 }
 
-__global__ void __launch_bounds__(ABT_WARPS * 32)
+__global__ void __launch_bounds__(ABT_WARPS * 32, 3)
 attn_bwd_tc_kernel(const AttnBwdTcParams pp) {
     const AttnBwdParams& p = pp.b;
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    const int Sqp = (p.Sq + 15) & ~15, Skp = (p.Sk + 15) & ~15, ldp = Skp + 8;
+    // Keys are processed in chunks of KC (a multiple of 64 when there is more than one chunk; the whole padded key range
+    // otherwise): only one chunk of K / V / P / dS is resident, so the cross-attention form (257 keys: chunks of 128) takes
+    // 74 KiB instead of 125 KiB of shared memory -- three CTAs per SM instead of one -- and key counts beyond one CTA's
+    // shared memory (1024 keys of the Video-LLaMA-style Q-Former) stay on the tensor cores.
+    const int Sqp = (p.Sq + 15) & ~15, Skp = (p.Sk + 15) & ~15, KC = pp.kc, NC = (Skp + KC - 1) / KC, ldp = KC + 8;
     __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_raw);     // [Sqp][72]
     __nv_bfloat16* sDO = sQ + Sqp * ABT_LD;                             // [Sqp][72]
-    __nv_bfloat16* sK = sDO + Sqp * ABT_LD;                             // [Skp][72]
-    __nv_bfloat16* sV = sK + Skp * ABT_LD;                              // [Skp][72]
-    __nv_bfloat16* sP = sV + Skp * ABT_LD;                              // [Sqp][ldp]
+    __nv_bfloat16* sK = sDO + Sqp * ABT_LD;                             // [KC][72]   current key chunk
+    __nv_bfloat16* sV = sK + KC * ABT_LD;                               // [KC][72]
+    __nv_bfloat16* sP = sV + KC * ABT_LD;                               // [Sqp][ldp]
     __nv_bfloat16* sDS = sP + Sqp * ldp;                                // [Sqp][ldp]
     float* sMask = reinterpret_cast<float*>(sDS + Sqp * ldp);           // [Skp]   additive mask * log2e, -inf on padding keys
     float* sDelta = sMask + Skp;                                        // [Sqp]
     float* sMx = sDelta + Sqp;                                          // [Sqp]   row max (log2 domain)
     float* sIl = sMx + Sqp;                                             // [Sqp]   1 / row sum
-    float* sPM = sIl + Sqp;                                             // [ABT_WARPS][Sqp] partial max
+    float* sPM = sIl + Sqp;                                             // [ABT_WARPS][Sqp] partial max (running over the chunks)
     float* sPL = sPM + ABT_WARPS * Sqp;                                 // [ABT_WARPS][Sqp] partial sum
     float* sCol = sPL + ABT_WARPS * Sqp;                                // [3][64] column sums of dQ / dK / dV (bias gradients)
+    float* sDQ = sCol + 192;                                            // [Sqp][64] dQ accumulated over the chunks (NC > 1 only)
     const int head = blockIdx.x % p.heads, r = blockIdx.x / p.heads;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     constexpr int NT = ABT_WARPS * 32;
     const bool q_dense = p.nq_split >= p.Sq;
 
     if (tid < 192) sCol[tid] = 0.f;
+    for (int i = tid; i < ABT_WARPS * Sqp; i += NT) { sPM[i] = -INFINITY; sPL[i] = 0.f; }
     __syncthreads();
-    // ---- stage Q, dO (+ delta = dO . O), K, V; rows past the end are zero
+    // ---- stage Q, dO (+ delta = dO . O); rows past the end are zero
     for (int idx = tid; idx < Sqp * 8; idx += NT) {
         const int i = idx >> 3, c = idx & 7;
         uint4 qv = make_uint4(0, 0, 0, 0), dv = qv, ov = qv;
@@ -483,57 +490,68 @@ attn_bwd_tc_kernel(const AttnBwdTcParams pp) {
             }
         }
     }
-    for (int idx = tid; idx < Skp * 8; idx += NT) {
-        const int j = idx >> 3, c = idx & 7;
-        uint4 kv = make_uint4(0, 0, 0, 0), vv = kv;
-        if (j < p.Sk) {
-            const int64_t gj = tok_index(r, j, p.rows, p.nq_split, p.Sk, p.kv_dense != 0);
-            kv = *reinterpret_cast<const uint4*>(p.k + gj * p.ldk + head * 64 + c * 8);
-            vv = *reinterpret_cast<const uint4*>(p.v + gj * p.ldv + head * 64 + c * 8);
-        }
-        *reinterpret_cast<uint4*>(sK + j * ABT_LD + c * 8) = kv;
-        *reinterpret_cast<uint4*>(sV + j * ABT_LD + c * 8) = vv;
-    }
     for (int j = tid; j < Skp; j += NT)
         sMask[j] = j < p.Sk ? (p.add_mask ? p.add_mask[static_cast<int64_t>(r) * p.Sk + j] * ABT_LOG2E : 0.f) : -INFINITY;
-    __syncthreads();
+    // keys [k0, k0 + kn) -> sK (and sV): rows past the end of the row's keys are zero
+    auto stage_kv = [&](int k0, int kn, bool with_v) {
+        for (int idx = tid; idx < kn * 8; idx += NT) {
+            const int jl = idx >> 3, c = idx & 7, j = k0 + jl;
+            uint4 kv = make_uint4(0, 0, 0, 0), vv = kv;
+            if (j < p.Sk) {
+                const int64_t gj = tok_index(r, j, p.rows, p.nq_split, p.Sk, p.kv_dense != 0);
+                kv = *reinterpret_cast<const uint4*>(p.k + gj * p.ldk + head * 64 + c * 8);
+                if (with_v) vv = *reinterpret_cast<const uint4*>(p.v + gj * p.ldv + head * 64 + c * 8);
+            }
+            *reinterpret_cast<uint4*>(sK + jl * ABT_LD + c * 8) = kv;
+            if (with_v) *reinterpret_cast<uint4*>(sV + jl * ABT_LD + c * 8) = vv;
+        }
+    };
 
-    const int nQT = Sqp >> 4, nK8 = Skp >> 3, nKT = Skp >> 4;
+    const int nQT = Sqp >> 4;
     const float scale2 = 0.125f * ABT_LOG2E;
-    // ---- phase 0: row max / sum
+    // ---- pass 1 over the key chunks: row max / sum (running partials per (query tile, key split) in sPM / sPL)
     const int nsplit = nQT >= ABT_WARPS ? 1 : ABT_WARPS / nQT;
-    for (int item = warp; item < nQT * nsplit; item += ABT_WARPS) {
-        const int qt = item / nsplit, sp = item - qt * nsplit;
-        uint32_t qf[4][4];
-        abt_load_a(qf, sQ, qt * 16, g, t);
-        float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
-        for (int nt = sp; nt < nK8; nt += nsplit) {
-            float s[4] = {0.f, 0.f, 0.f, 0.f};
-            const __nv_bfloat16* kb = sK + (nt * 8 + g) * ABT_LD + 2 * t;
+    for (int ck = 0; ck < NC; ++ck) {
+        const int k0 = ck * KC, kn = min(KC, Skp - k0), nK8 = kn >> 3;
+        if (ck > 0) __syncthreads();              // everybody is done with the previous chunk's keys
+        stage_kv(k0, kn, NC == 1);                // a single chunk stays resident for pass 2: stage V with it
+        __syncthreads();
+        for (int item = warp; item < nQT * nsplit; item += ABT_WARPS) {
+            const int qt = item / nsplit, sp = item - qt * nsplit;
+            uint32_t qf[4][4];
+            abt_load_a(qf, sQ, qt * 16, g, t);
+            float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+            for (int nt = sp; nt < nK8; nt += nsplit) {
+                float s[4] = {0.f, 0.f, 0.f, 0.f};
+                const __nv_bfloat16* kb = sK + (nt * 8 + g) * ABT_LD + 2 * t;
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-                abt_mma(s, qf[ks], *reinterpret_cast<const uint32_t*>(kb + ks * 16), *reinterpret_cast<const uint32_t*>(kb + ks * 16 + 8));
-            const float k0 = sMask[nt * 8 + 2 * t], k1 = sMask[nt * 8 + 2 * t + 1];
-            const float v[4] = {fmaf(s[0], scale2, k0), fmaf(s[1], scale2, k1), fmaf(s[2], scale2, k0), fmaf(s[3], scale2, k1)};
+                for (int ks = 0; ks < 4; ++ks)
+                    abt_mma(s, qf[ks], *reinterpret_cast<const uint32_t*>(kb + ks * 16), *reinterpret_cast<const uint32_t*>(kb + ks * 16 + 8));
+                const float k0m = sMask[k0 + nt * 8 + 2 * t], k1m = sMask[k0 + nt * 8 + 2 * t + 1];
+                const float v[4] = {fmaf(s[0], scale2, k0m), fmaf(s[1], scale2, k1m), fmaf(s[2], scale2, k0m), fmaf(s[3], scale2, k1m)};
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const float mn = fmaxf(m[h], fmaxf(v[2 * h], v[2 * h + 1]));
-                if (mn != -INFINITY) {
-                    l[h] = l[h] * exp2f(m[h] - mn) + exp2f(v[2 * h] - mn) + exp2f(v[2 * h + 1] - mn);
-                    m[h] = mn;
+                for (int h = 0; h < 2; ++h) {
+                    const float mn = fmaxf(m[h], fmaxf(v[2 * h], v[2 * h + 1]));
+                    if (mn != -INFINITY) {
+                        l[h] = l[h] * exp2f(m[h] - mn) + exp2f(v[2 * h] - mn) + exp2f(v[2 * h + 1] - mn);
+                        m[h] = mn;
+                    }
                 }
             }
-        }
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < 2; ++h) {
 #pragma unroll
-            for (int o = 1; o <= 2; o <<= 1) {
-                const float m2 = __shfl_xor_sync(0xffffffffu, m[h], o), l2 = __shfl_xor_sync(0xffffffffu, l[h], o);
-                abt_merge(m[h], l[h], m2, l2);
-            }
-            if (t == 0) {
-                sPM[sp * Sqp + qt * 16 + g + 8 * h] = m[h];
-                sPL[sp * Sqp + qt * 16 + g + 8 * h] = l[h];
+                for (int o = 1; o <= 2; o <<= 1) {
+                    const float m2 = __shfl_xor_sync(0xffffffffu, m[h], o), l2 = __shfl_xor_sync(0xffffffffu, l[h], o);
+                    abt_merge(m[h], l[h], m2, l2);
+                }
+                if (t == 0) {   // (the same warp owns this (split, row) entry in every chunk)
+                    const int e = sp * Sqp + qt * 16 + g + 8 * h;
+                    float rm = sPM[e], rl = sPL[e];
+                    abt_merge(rm, rl, m[h], l[h]);
+                    sPM[e] = rm;
+                    sPL[e] = rl;
+                }
             }
         }
     }
@@ -544,121 +562,150 @@ attn_bwd_tc_kernel(const AttnBwdTcParams pp) {
         sMx[i] = m == -INFINITY ? 0.f : m;
         sIl[i] = l > 0.f ? 1.f / l : 0.f;
     }
-    __syncthreads();
-    // ---- phase 1: P and dS tiles (16 queries x 32 keys per item) -> shared memory, bf16
-    const int nCH = (nK8 + 3) >> 2;
-    for (int item = warp; item < nQT * nCH; item += ABT_WARPS) {
-        const int qt = item / nCH, ch = item - qt * nCH;
-        uint32_t qf[4][4], df[4][4];
-        abt_load_a(qf, sQ, qt * 16, g, t);
-        abt_load_a(df, sDO, qt * 16, g, t);
-        const int i0 = qt * 16 + g, i1 = i0 + 8;
-        const float m0 = sMx[i0], m1 = sMx[i1], il0 = sIl[i0], il1 = sIl[i1], d0 = sDelta[i0], d1 = sDelta[i1];
-        const int nt_end = min(ch * 4 + 4, nK8);
-        // forward dropout mask of this thread's elements: one Philox call per query row and 64-key chunk (a 32-key item lies
-        // inside one chunk); O = (P o M c) V  =>  dV = (P o M c)^T dO,  dP = (dO V^T) o M c,  delta = dO . O unchanged
-        const bool dropping = pp.drop.thr8 != 0;
-        uint4 rb0 = make_uint4(0, 0, 0, 0), rb1 = rb0;
-        if (dropping) {
-            const uint64_t rh = static_cast<uint64_t>(r) * p.heads + head;
-            const int nchunks = (p.Sk + 63) >> 6, kc = ch >> 1;
-            rb0 = dropout_bytes(pp.drop, ((rh * p.Sq + i0) * nchunks + kc) * 4 + t);
-            rb1 = dropout_bytes(pp.drop, ((rh * p.Sq + i1) * nchunks + kc) * 4 + t);
-        }
-        for (int nt = ch * 4; nt < nt_end; ++nt) {
-            float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
-            const __nv_bfloat16* kb = sK + (nt * 8 + g) * ABT_LD + 2 * t;
-            const __nv_bfloat16* vb = sV + (nt * 8 + g) * ABT_LD + 2 * t;
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-                abt_mma(s, qf[ks], *reinterpret_cast<const uint32_t*>(kb + ks * 16), *reinterpret_cast<const uint32_t*>(kb + ks * 16 + 8));
-                abt_mma(dp, df[ks], *reinterpret_cast<const uint32_t*>(vb + ks * 16), *reinterpret_cast<const uint32_t*>(vb + ks * 16 + 8));
-            }
-            const float k0 = sMask[nt * 8 + 2 * t], k1 = sMask[nt * 8 + 2 * t + 1];
-            const float p0 = exp2f(fmaf(s[0], scale2, k0) - m0) * il0, p1 = exp2f(fmaf(s[1], scale2, k1) - m0) * il0;
-            const float p2 = exp2f(fmaf(s[2], scale2, k0) - m1) * il1, p3 = exp2f(fmaf(s[3], scale2, k1) - m1) * il1;
-            const int c = nt * 8 + 2 * t;
-            float k0m = 1.f, k1m = 1.f, k2m = 1.f, k3m = 1.f;
-            if (dropping) {
-                const int nl = nt & 7;   // 8-key tile inside the 64-key chunk (dynamic index: select the byte at run time)
-                const uint32_t w0 = nl < 2 ? rb0.x : (nl < 4 ? rb0.y : (nl < 6 ? rb0.z : rb0.w));
-                const uint32_t w1 = nl < 2 ? rb1.x : (nl < 4 ? rb1.y : (nl < 6 ? rb1.z : rb1.w));
-                const int sh = (nl & 1) * 16;
-                k0m = ((w0 >> sh) & 0xFFu) >= pp.drop.thr8 ? pp.drop.scale : 0.f;
-                k1m = ((w0 >> (sh + 8)) & 0xFFu) >= pp.drop.thr8 ? pp.drop.scale : 0.f;
-                k2m = ((w1 >> sh) & 0xFFu) >= pp.drop.thr8 ? pp.drop.scale : 0.f;
-                k3m = ((w1 >> (sh + 8)) & 0xFFu) >= pp.drop.thr8 ? pp.drop.scale : 0.f;
-            }
-            *reinterpret_cast<uint32_t*>(sP + i0 * ldp + c) = ptx::pack_bf16x2(p0 * k0m, p1 * k1m);
-            *reinterpret_cast<uint32_t*>(sP + i1 * ldp + c) = ptx::pack_bf16x2(p2 * k2m, p3 * k3m);
-            *reinterpret_cast<uint32_t*>(sDS + i0 * ldp + c) = ptx::pack_bf16x2(p0 * (dp[0] * k0m - d0), p1 * (dp[1] * k1m - d0));
-            *reinterpret_cast<uint32_t*>(sDS + i1 * ldp + c) = ptx::pack_bf16x2(p2 * (dp[2] * k2m - d1), p3 * (dp[3] * k3m - d1));
-        }
-    }
-    __syncthreads();
-    // ---- phase 2: one 16 x 64 output tile per item: dQ tiles, then dK tiles, then dV tiles
+    // ---- pass 2 over the key chunks
     const int lrow = ((lane >> 3) & 1) * 8 + (lane & 7), lcol = (lane >> 4) * 8;     // ldmatrix.trans of a [reduction][dim] tile (B)
     const int arow = ((lane >> 4) & 1) * 8 + (lane & 7), acol = ((lane >> 3) & 1) * 8;   // ... of a [query][key] tile (A^T)
-    for (int item = warp; item < nQT + 2 * nKT; item += ABT_WARPS) {
-        float acc[8][4];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-        if (item < nQT) {
-            const int i0 = item * 16 + g, i1 = i0 + 8;
-            for (int kt = 0; kt < nKT; ++kt) {
-                uint32_t a[4];
-                const __nv_bfloat16* ab = sDS + i0 * ldp + kt * 16 + 2 * t;
-                a[0] = *reinterpret_cast<const uint32_t*>(ab);
-                a[1] = *reinterpret_cast<const uint32_t*>(ab + 8 * ldp);
-                a[2] = *reinterpret_cast<const uint32_t*>(ab + 8);
-                a[3] = *reinterpret_cast<const uint32_t*>(ab + 8 * ldp + 8);
-#pragma unroll
-                for (int dp = 0; dp < 4; ++dp) {
-                    uint32_t bf[4];
-                    abt_ldsm_t(bf, sK + (kt * 16 + lrow) * ABT_LD + dp * 16 + lcol);
-                    abt_mma(acc[2 * dp], a, bf[0], bf[1]);
-                    abt_mma(acc[2 * dp + 1], a, bf[2], bf[3]);
-                }
+    for (int ck = 0; ck < NC; ++ck) {
+        const int k0 = ck * KC, kn = min(KC, Skp - k0), nK8 = kn >> 3, nKT = kn >> 4;
+        const bool last_chunk = ck == NC - 1;
+        __syncthreads();                          // statistics written / previous chunk's phase 2 done
+        if (NC > 1) {
+            stage_kv(k0, kn, true);
+            __syncthreads();
+        }
+        // ---- phase 1: P and dS tiles (16 queries x 32 keys per item) -> shared memory, bf16
+        const int nCH = (nK8 + 3) >> 2;
+        for (int item = warp; item < nQT * nCH; item += ABT_WARPS) {
+            const int qt = item / nCH, ch = item - qt * nCH;
+            uint32_t qf[4][4], df[4][4];
+            abt_load_a(qf, sQ, qt * 16, g, t);
+            abt_load_a(df, sDO, qt * 16, g, t);
+            const int i0 = qt * 16 + g, i1 = i0 + 8;
+            const float m0 = sMx[i0], m1 = sMx[i1], il0 = sIl[i0], il1 = sIl[i1], d0 = sDelta[i0], d1 = sDelta[i1];
+            const int nt_end = min(ch * 4 + 4, nK8);
+            // forward dropout mask of this thread's elements: one Philox call per query row and 64-key chunk of the row (a
+            // 32-key item lies inside one: k0 is a multiple of 64); O = (P o M c) V  =>  dV = (P o M c)^T dO,
+            // dP = (dO V^T) o M c,  delta = dO . O unchanged
+            const bool dropping = pp.drop.thr8 != 0;
+            uint4 rb0 = make_uint4(0, 0, 0, 0), rb1 = rb0;
+            if (dropping) {
+                const uint64_t rh = static_cast<uint64_t>(r) * p.heads + head;
+                const int nchunks = (p.Sk + 63) >> 6, kc = (k0 >> 6) + (ch >> 1);
+                rb0 = dropout_bytes(pp.drop, ((rh * p.Sq + i0) * nchunks + kc) * 4 + t);
+                rb1 = dropout_bytes(pp.drop, ((rh * p.Sq + i1) * nchunks + kc) * 4 + t);
             }
-            if (pp.db_q) abt_colsum(acc, 0.125f, sCol, lane);
+            for (int nt = ch * 4; nt < nt_end; ++nt) {
+                float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
+                const __nv_bfloat16* kb = sK + (nt * 8 + g) * ABT_LD + 2 * t;
+                const __nv_bfloat16* vb = sV + (nt * 8 + g) * ABT_LD + 2 * t;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int i = h ? i1 : i0;
-                if (i < p.Sq) {
-                    __nv_bfloat16* dst = p.dq + tok_index(r, i, p.rows, p.nq_split, p.Sq, q_dense) * p.lddq + head * 64 + 2 * t;
-#pragma unroll
-                    for (int nt = 0; nt < 8; ++nt)
-                        *reinterpret_cast<uint32_t*>(dst + nt * 8) = ptx::pack_bf16x2(acc[nt][2 * h] * 0.125f, acc[nt][2 * h + 1] * 0.125f);
+                for (int ks = 0; ks < 4; ++ks) {
+                    abt_mma(s, qf[ks], *reinterpret_cast<const uint32_t*>(kb + ks * 16), *reinterpret_cast<const uint32_t*>(kb + ks * 16 + 8));
+                    abt_mma(dp, df[ks], *reinterpret_cast<const uint32_t*>(vb + ks * 16), *reinterpret_cast<const uint32_t*>(vb + ks * 16 + 8));
                 }
-            }
-        } else {
-            const bool is_dk = item < nQT + nKT;
-            const int kt = item - nQT - (is_dk ? 0 : nKT);
-            const __nv_bfloat16* lhs = is_dk ? sDS : sP;     // [query][key], read transposed
-            const __nv_bfloat16* rhs = is_dk ? sQ : sDO;     // [query][dim]
-            for (int qt = 0; qt < nQT; ++qt) {
-                uint32_t a[4];
-                abt_ldsm_t(a, lhs + (qt * 16 + arow) * ldp + kt * 16 + acol);
-#pragma unroll
-                for (int dp = 0; dp < 4; ++dp) {
-                    uint32_t bf[4];
-                    abt_ldsm_t(bf, rhs + (qt * 16 + lrow) * ABT_LD + dp * 16 + lcol);
-                    abt_mma(acc[2 * dp], a, bf[0], bf[1]);
-                    abt_mma(acc[2 * dp + 1], a, bf[2], bf[3]);
+                const float k0m = sMask[k0 + nt * 8 + 2 * t], k1m = sMask[k0 + nt * 8 + 2 * t + 1];
+                const float p0 = exp2f(fmaf(s[0], scale2, k0m) - m0) * il0, p1 = exp2f(fmaf(s[1], scale2, k1m) - m0) * il0;
+                const float p2 = exp2f(fmaf(s[2], scale2, k0m) - m1) * il1, p3 = exp2f(fmaf(s[3], scale2, k1m) - m1) * il1;
+                const int c = nt * 8 + 2 * t;
+                float d0m = 1.f, d1m = 1.f, d2m = 1.f, d3m = 1.f;
+                if (dropping) {
+                    const int nl = nt & 7;   // 8-key tile inside the 64-key chunk (dynamic index: select the byte at run time)
+                    const uint32_t w0 = nl < 2 ? rb0.x : (nl < 4 ? rb0.y : (nl < 6 ? rb0.z : rb0.w));
+                    const uint32_t w1 = nl < 2 ? rb1.x : (nl < 4 ? rb1.y : (nl < 6 ? rb1.z : rb1.w));
+                    const int sh = (nl & 1) * 16;
+                    d0m = ((w0 >> sh) & 0xFFu) >= pp.drop.thr8 ? pp.drop.scale : 0.f;
+                    d1m = ((w0 >> (sh + 8)) & 0xFFu) >= pp.drop.thr8 ? pp.drop.scale : 0.f;
+                    d2m = ((w1 >> sh) & 0xFFu) >= pp.drop.thr8 ? pp.drop.scale : 0.f;
+                    d3m = ((w1 >> (sh + 8)) & 0xFFu) >= pp.drop.thr8 ? pp.drop.scale : 0.f;
                 }
+                *reinterpret_cast<uint32_t*>(sP + i0 * ldp + c) = ptx::pack_bf16x2(p0 * d0m, p1 * d1m);
+                *reinterpret_cast<uint32_t*>(sP + i1 * ldp + c) = ptx::pack_bf16x2(p2 * d2m, p3 * d3m);
+                *reinterpret_cast<uint32_t*>(sDS + i0 * ldp + c) = ptx::pack_bf16x2(p0 * (dp[0] * d0m - d0), p1 * (dp[1] * d1m - d0));
+                *reinterpret_cast<uint32_t*>(sDS + i1 * ldp + c) = ptx::pack_bf16x2(p2 * (dp[2] * d2m - d1), p3 * (dp[3] * d3m - d1));
             }
-            if (!is_dk && pp.db_v && pp.drop.thr8 != 0) abt_colsum(acc, 1.0f, sCol + 128, lane);   // (see the staging loop)
-            const float sc = is_dk ? 0.125f : 1.0f;
-            __nv_bfloat16* out = is_dk ? p.dk : p.dv;
-            const int64_t ld = is_dk ? p.lddk : p.lddv;
+        }
+        __syncthreads();
+        // ---- phase 2: one 16 x 64 output tile per item: dQ tiles (accumulated over the chunks), then this chunk's dK and dV tiles
+        for (int item = warp; item < nQT + 2 * nKT; item += ABT_WARPS) {
+            float acc[8][4];
+            if (item < nQT) {
+                const int i0 = item * 16 + g, i1 = i0 + 8;
+                float* dq0 = sDQ + i0 * 64 + 2 * t;
+                float* dq1 = sDQ + i1 * 64 + 2 * t;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int j = kt * 16 + g + 8 * h;
-                if (j < p.Sk) {
-                    __nv_bfloat16* dst = out + tok_index(r, j, p.rows, p.nq_split, p.Sk, p.kv_dense != 0) * ld + head * 64 + 2 * t;
+                for (int nt = 0; nt < 8; ++nt) {
+                    if (ck > 0) {
+                        const float2 a0 = *reinterpret_cast<const float2*>(dq0 + nt * 8), a1 = *reinterpret_cast<const float2*>(dq1 + nt * 8);
+                        acc[nt][0] = a0.x; acc[nt][1] = a0.y; acc[nt][2] = a1.x; acc[nt][3] = a1.y;
+                    } else {
+                        acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+                    }
+                }
+                for (int kt = 0; kt < nKT; ++kt) {
+                    uint32_t a[4];
+                    const __nv_bfloat16* ab = sDS + i0 * ldp + kt * 16 + 2 * t;
+                    a[0] = *reinterpret_cast<const uint32_t*>(ab);
+                    a[1] = *reinterpret_cast<const uint32_t*>(ab + 8 * ldp);
+                    a[2] = *reinterpret_cast<const uint32_t*>(ab + 8);
+                    a[3] = *reinterpret_cast<const uint32_t*>(ab + 8 * ldp + 8);
 #pragma unroll
-                    for (int nt = 0; nt < 8; ++nt)
-                        *reinterpret_cast<uint32_t*>(dst + nt * 8) = ptx::pack_bf16x2(acc[nt][2 * h] * sc, acc[nt][2 * h + 1] * sc);
+                    for (int dp = 0; dp < 4; ++dp) {
+                        uint32_t bf[4];
+                        abt_ldsm_t(bf, sK + (kt * 16 + lrow) * ABT_LD + dp * 16 + lcol);
+                        abt_mma(acc[2 * dp], a, bf[0], bf[1]);
+                        abt_mma(acc[2 * dp + 1], a, bf[2], bf[3]);
+                    }
+                }
+                if (!last_chunk) {
+#pragma unroll
+                    for (int nt = 0; nt < 8; ++nt) {
+                        *reinterpret_cast<float2*>(dq0 + nt * 8) = make_float2(acc[nt][0], acc[nt][1]);
+                        *reinterpret_cast<float2*>(dq1 + nt * 8) = make_float2(acc[nt][2], acc[nt][3]);
+                    }
+                    continue;
+                }
+                if (pp.db_q) abt_colsum(acc, 0.125f, sCol, lane);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int i = h ? i1 : i0;
+                    if (i < p.Sq) {
+                        __nv_bfloat16* dst = p.dq + tok_index(r, i, p.rows, p.nq_split, p.Sq, q_dense) * p.lddq + head * 64 + 2 * t;
+#pragma unroll
+                        for (int nt = 0; nt < 8; ++nt)
+                            *reinterpret_cast<uint32_t*>(dst + nt * 8) = ptx::pack_bf16x2(acc[nt][2 * h] * 0.125f, acc[nt][2 * h + 1] * 0.125f);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+                const bool is_dk = item < nQT + nKT;
+                const int kt = item - nQT - (is_dk ? 0 : nKT);
+                const __nv_bfloat16* lhs = is_dk ? sDS : sP;     // [query][key], read transposed
+                const __nv_bfloat16* rhs = is_dk ? sQ : sDO;     // [query][dim]
+                for (int qt = 0; qt < nQT; ++qt) {
+                    uint32_t a[4];
+                    abt_ldsm_t(a, lhs + (qt * 16 + arow) * ldp + kt * 16 + acol);
+#pragma unroll
+                    for (int dp = 0; dp < 4; ++dp) {
+                        uint32_t bf[4];
+                        abt_ldsm_t(bf, rhs + (qt * 16 + lrow) * ABT_LD + dp * 16 + lcol);
+                        abt_mma(acc[2 * dp], a, bf[0], bf[1]);
+                        abt_mma(acc[2 * dp + 1], a, bf[2], bf[3]);
+                    }
+                }
+                if (!is_dk && pp.db_v && pp.drop.thr8 != 0) abt_colsum(acc, 1.0f, sCol + 128, lane);   // (see the staging loop)
+                const float sc = is_dk ? 0.125f : 1.0f;
+                __nv_bfloat16* out = is_dk ? p.dk : p.dv;
+                const int64_t ld = is_dk ? p.lddk : p.lddv;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int j = k0 + kt * 16 + g + 8 * h;
+                    if (j < p.Sk) {
+                        __nv_bfloat16* dst = out + tok_index(r, j, p.rows, p.nq_split, p.Sk, p.kv_dense != 0) * ld + head * 64 + 2 * t;
+#pragma unroll
+                        for (int nt = 0; nt < 8; ++nt)
+                            *reinterpret_cast<uint32_t*>(dst + nt * 8) = ptx::pack_bf16x2(acc[nt][2 * h] * sc, acc[nt][2 * h + 1] * sc);
+                    }
                 }
             }
         }
@@ -842,9 +889,26 @@ int launch_gelu_bwd(const void* z, const void* dy, void* dz, int64_t n, cudaStre
     return 0;
 }
 
-static size_t attn_bwd_tc_smem(int Sq, int Sk) {
-    const size_t Sqp = (Sq + 15) & ~15, Skp = (Sk + 15) & ~15, ldp = Skp + 8;
-    return (2 * Sqp + 2 * Skp) * ABT_LD * 2 + 2 * Sqp * ldp * 2 + (Skp + 3 * Sqp + 2 * ABT_WARPS * Sqp + 192) * 4;
+static size_t attn_bwd_tc_smem(int Sq, int Sk, int kc) {
+    const size_t Sqp = (Sq + 15) & ~15, Skp = (Sk + 15) & ~15, ldp = kc + 8;
+    const size_t dq = Skp > static_cast<size_t>(kc) ? Sqp * 64 : 0;
+    return (2 * Sqp + 2 * kc) * ABT_LD * 2 + 2 * Sqp * ldp * 2 + (Skp + 3 * Sqp + 2 * ABT_WARPS * Sqp + 192 + dq) * 4;
+}
+// Keys per resident chunk: everything when the padded key count is <= 192 (self-attention, short encoders); otherwise
+// equal chunks of a multiple of 64 keys (the dropout mask is generated per 64-key chunk), at most 128 -- and fewer if the
+// query tile is large -- so that the CTA stays within 220 KiB.  Measured on the cross-attention form (32 queries x 257 keys,
+// 768 CTAs): whole key range resident 126 us (125 KiB, one CTA per SM), chunks of 192 keys 103 us (two per SM), 128 keys
+// 84 us (74 KiB, three per SM), 64 keys 97 us.  0: no chunk size fits (the fp32 CUDA-core kernel takes over).
+static int attn_bwd_tc_chunk(int Sq, int Sk) {
+    static const int forced = [] { const char* e = getenv("MRA_ATTN_BWD_KC"); return e ? atoi(e) : 0; }();
+    const int Skp = (Sk + 15) & ~15;
+    if (Skp <= 192 && attn_bwd_tc_smem(Sq, Sk, Skp) <= 220 * 1024) return Skp;
+    for (int cap = forced > 0 ? forced : 128; cap >= 64; cap -= 64) {
+        const int nc = (Skp + cap - 1) / cap;
+        const int kc = (((Skp + nc - 1) / nc) + 63) & ~63;
+        if (kc < Skp && attn_bwd_tc_smem(Sq, Sk, kc) <= 220 * 1024) return kc;
+    }
+    return 0;
 }
 
 int launch_attention_bwd(const AttnBwdArgs& a, cudaStream_t s) {
@@ -852,14 +916,15 @@ int launch_attention_bwd(const AttnBwdArgs& a, cudaStream_t s) {
     // tensor-core kernel when the forward output is available and the tiles fit in shared memory; MRA_ATTN_BWD_SIMT=1
     // forces the fp32 CUDA-core kernel (tests compare the two)
     static const bool force_simt = getenv("MRA_ATTN_BWD_SIMT") != nullptr;
-    const size_t tc_smem = attn_bwd_tc_smem(a.Sq, a.Sk);
-    if (a.o != nullptr && !force_simt && tc_smem <= 220 * 1024) {
+    const int kc = attn_bwd_tc_chunk(a.Sq, a.Sk);
+    const size_t tc_smem = kc > 0 ? attn_bwd_tc_smem(a.Sq, a.Sk, kc) : 0;
+    if (a.o != nullptr && !force_simt && kc > 0) {
         if (int e = ensure_smem_attr(reinterpret_cast<const void*>(attn_bwd_tc_kernel), 220 * 1024)) return e;
         AttnBwdTcParams pp{{reinterpret_cast<const __nv_bfloat16*>(a.q), a.ldq, reinterpret_cast<const __nv_bfloat16*>(a.k), a.ldk,
                             reinterpret_cast<const __nv_bfloat16*>(a.v), a.ldv, reinterpret_cast<const __nv_bfloat16*>(a.d_o), a.ldo,
                             reinterpret_cast<__nv_bfloat16*>(a.dq), a.lddq, reinterpret_cast<__nv_bfloat16*>(a.dk), a.lddk,
                             reinterpret_cast<__nv_bfloat16*>(a.dv), a.lddv, a.add_mask, a.rows, a.heads, a.Sq, a.Sk, a.nq_split, a.kv_dense},
-                           reinterpret_cast<const __nv_bfloat16*>(a.o), a.ldof, a.db_q, a.db_k, a.db_v, a.drop};
+                           reinterpret_cast<const __nv_bfloat16*>(a.o), a.ldof, a.db_q, a.db_k, a.db_v, a.drop, kc};
         attn_bwd_tc_kernel<<<static_cast<unsigned>(a.rows) * a.heads, ABT_WARPS * 32, tc_smem, s>>>(pp);
         MRA_CHECK_CUDA(cudaGetLastError());
         return 0;

@@ -52,7 +52,8 @@ def _build(cfg, w, llm_dim):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("rows,T,Nk,W,layers,p", [(3, 32, 64, 64, 2, 0.1), (2, 32, 257, 1408, 3, 0.1), (4, 0, 40, 768, 2, 0.25)])
+@pytest.mark.parametrize("rows,T,Nk,W,layers,p", [(3, 32, 64, 64, 2, 0.1), (2, 32, 257, 1408, 3, 0.1), (4, 0, 40, 768, 2, 0.25),
+                                                        (2, 32, 600, 64, 2, 0.1)])
 def test_dropout_forward_and_gradients_match_oracle_under_the_same_mask(rows, T, Nk, W, layers, p):
     from mraudio_b200.training import TrainableQFormer
     D, seed = 256, 20261018 + rows

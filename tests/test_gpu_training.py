@@ -33,8 +33,10 @@ def _oracle_grads(cfg, w, ids, atts, enc, G):
 
 
 # the last case is BASELINE.json config 4 at its per-GPU size: 8 videos x 8 frames = 64 rows of 257 x 1408 tokens, 12 layers
+# (2, 32, 600, 64, 2): four resident key chunks in the attention backward (257 keys: two); (2, 96, 200, 64, 2): 128-token
+# self-attention rows (eight 16-query tiles) with 200 keys in two chunks
 @pytest.mark.parametrize("rows,T,Nk,W,layers", [(3, 8, 20, 64, 2), (2, 32, 257, 1408, 3), (5, 0, 40, 768, 2),
-                                                 (64, 32, 257, 1408, 12)])
+                                                 (2, 32, 600, 64, 2), (2, 96, 200, 64, 2), (64, 32, 257, 1408, 12)])
 def test_backward_matches_oracle_autograd(rows, T, Nk, W, layers):
     from mraudio_b200.training import TrainableQFormer
     D = 256
