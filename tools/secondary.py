@@ -129,6 +129,11 @@ def cfg4_finetune(cx: Ctx, steps=8, warmup=3):
         out["ms_per_step_without_allreduce"] = ms_no
         out["exposed_allreduce_ms"] = ms - ms_no
         out["scaling_vs_no_exchange"] = ms_no / ms
+    else:
+        # single process: the same step replayed from CUDA graphs (forward | eager loss | backward + per-bucket Adam)
+        tr.cuda_graph = True
+        out["ms_per_step_cuda_graph_replay"] = cx.timed(step, steps, 3)
+        tr.cuda_graph = False
     del tr, model
     torch.cuda.empty_cache()
     return out
