@@ -286,6 +286,20 @@ int mra_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const 
                   int64_t ldo, const float* add_mask, int32_t rows, int32_t heads, int32_t Sq, int32_t Sk,
                   int32_t nq_split, int32_t kv_dense, void* stream);
 
+/* The same core on HEAD-MAJOR operands, the layout the inference forward uses between the QKV / cross-K/V Linear and
+ * the attention core: head h of q starts at q + h*hsq and its token rows are ldq elements apart (likewise k, v), so with
+ * ldq = 64 and hsq = tokens*64 every (row, head) tile is one contiguous run of bytes.  hs* = 0 means 64 (heads side by
+ * side in a row: exactly mra_attention).  All strides in elements, multiples of 8. */
+int mra_attention_strided(const void* q, int64_t ldq, int64_t hsq, const void* k, int64_t ldk, int64_t hsk, const void* v,
+                          int64_t ldv, int64_t hsv, void* o, int64_t ldo, const float* add_mask, int32_t rows,
+                          int32_t heads, int32_t Sq, int32_t Sk, int32_t nq_split, int32_t kv_dense, void* stream);
+
+/* C = A W^T + bias written head-major: bf16 C[N/64][M][64], i.e. column n of output row m at C + ((n/64)*M + m)*64 + n%64
+ * (N % 64 == 0).  Producer side of mra_attention_strided: the fused QKV projection (HF port :499-510) and the stacked
+ * cross-attention K/V projection write this form in the inference forward. */
+int mra_gemm_head_major_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int32_t M,
+                             int32_t N, int32_t K, void* stream);
+
 /* Test aid: generic != 0 forces the register-staged generic attention kernel instead of the TMA-pipelined one (which
  * covers Sq <= 256, Sk <= 4096 and split points that are multiples of 32; other shapes always use the generic one). */
 int mra_attention_impl_override(int32_t generic);

@@ -29,6 +29,7 @@ struct Params {
     __nv_bfloat16* o; int64_t ldo;
     const float* add_mask;
     int rows, heads, Sq, Sk, nq_split, kv_dense;
+    int64_t hsq, hsk, hsv;   // head strides (elements): 64 = heads side by side in a row, else the head-major layout
 };
 
 __device__ __forceinline__ int64_t split_index(int r, int i, int rows, int nsplit, int S) {
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(NWARPS * 32) attention_kernel(const Params p) 
         uint4 val = make_uint4(0, 0, 0, 0);
         if (i < p.Sq) {
             const int64_t gi = split_index(r, i, p.rows, p.nq_split, p.Sq);
-            val = *reinterpret_cast<const uint4*>(p.q + gi * p.ldq + head * HD + c * 8);
+            val = *reinterpret_cast<const uint4*>(p.q + gi * p.ldq + head * p.hsq + c * 8);
         }
         *reinterpret_cast<uint4*>(sQ + i * LDS_ROW + c * 8) = val;
     }
@@ -111,8 +112,8 @@ __global__ void __launch_bounds__(NWARPS * 32) attention_kernel(const Params p) 
                 if (key < p.Sk) {
                     const int64_t gi = p.kv_dense ? static_cast<int64_t>(r) * p.Sk + key
                                                   : split_index(r, key, p.rows, p.nq_split, p.Sk);
-                    kv = *reinterpret_cast<const uint4*>(p.k + gi * p.ldk + head * HD + c * 8);
-                    vv = *reinterpret_cast<const uint4*>(p.v + gi * p.ldv + head * HD + c * 8);
+                    kv = *reinterpret_cast<const uint4*>(p.k + gi * p.ldk + head * p.hsk + c * 8);
+                    vv = *reinterpret_cast<const uint4*>(p.v + gi * p.ldv + head * p.hsv + c * 8);
                 }
                 *reinterpret_cast<uint4*>(sK + j * LDS_ROW + c * 8) = kv;
                 *reinterpret_cast<uint4*>(sV + j * LDS_ROW + c * 8) = vv;
@@ -230,10 +231,16 @@ __global__ void __launch_bounds__(NWARPS * 32) attention_kernel(const Params p) 
 
 // =====================================================================================================================
 // TMA-pipelined variant (the one the forward uses): same math, but Q / K / V tiles arrive as 128B-swizzled 32 x 64 boxes
-// through cp.async.bulk.tensor (3-D tensor maps [row][token][column], so tokens past the end of a row are zero-filled
-// by the TMA unit and never fetched), K/V chunks of 64 keys flow through a STAGES-deep mbarrier ring, and fragments are
-// read with ldmatrix from the swizzled tiles (bank-conflict free).  One CTA per (row, head), one warp per 16 queries.
-// The token axis may consist of two segments ("split" layout: query tokens of all rows first, text tokens after them).
+// through cp.async.bulk.tensor (4-D tensor maps [head][row][token][64 columns], so tokens past the end of a row are
+// zero-filled by the TMA unit and never fetched), K/V chunks of 64 keys flow through an mbarrier ring of `stages` slots
+// (one for the single-chunk self-attention: more CTAs per SM), and fragments are read with ldmatrix from the swizzled
+// tiles (bank-conflict free).  One CTA per (row, head), one warp per 16 queries.  The token axis may consist of two
+// segments ("split" layout: query tokens of all rows first, text tokens after them).  The head axis has its own stride:
+// 64 elements when the heads sit side by side in a [tokens, heads * 64] matrix, tokens * 64 in the HEAD-MAJOR layout the
+// inference forward lets the QKV / cross-K/V GEMMs write ([head][token][64]: every 32-token box is 4 KiB of
+// consecutive bytes and a (row, head) tile one contiguous run, instead of 128-byte pieces at the matrix pitch).
+// The output rows leave through the finished Q tile: every warp parks its 16 x 64 results in the swizzled tile and writes
+// them back as full 128-byte lines (16 bytes per lane) instead of 4-byte pieces.
 struct TmaParams {
     __nv_bfloat16* o; int64_t ldo;
     const float* add_mask;
@@ -244,15 +251,16 @@ struct TmaParams {
     DropoutParams drop;   // thr8 != 0: training-mode dropout on the attention probabilities (dropout.cuh)
 };
 
-constexpr int TMA_STAGES = 2;
+constexpr int TMA_STAGES_MAX = 3;
 constexpr int BOX_BYTES = 32 * 128;          // 32 tokens x 64 bf16
 constexpr int STAGE_BYTES_ATT = 4 * BOX_BYTES;  // K lo, K hi, V lo, V hi
 
-__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* desc, uint64_t* bar, int32_t c0, int32_t c1, int32_t c2) {
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* desc, uint64_t* bar, int32_t c0, int32_t c1, int32_t c2,
+                                            int32_t c3) {
     asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
             ptx::smem_u32(smem_dst)),
-        "l"(reinterpret_cast<uint64_t>(desc)), "r"(ptx::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        "l"(reinterpret_cast<uint64_t>(desc)), "r"(ptx::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
@@ -275,10 +283,18 @@ struct TmaMaps {
 struct TmaParams2 {
     TmaParams p[2];
     int split;           // first block of problem 1 (== grid size when there is one problem)
+    int stages;          // slots of the K/V ring in shared memory: min(chunks, TMA_STAGES_MAX)
+    int o_stage;         // != 0: O rows leave through the Q tile as full 128-byte lines (needs 16-byte aligned output rows)
 };
 
+// resident CTAs per SM the register allocation is sized for (shared memory allows as many for the step's shapes)
+#ifndef MRA_ATT_MINB4
+#define MRA_ATT_MINB4 4
+#endif
+template <int NWARPS> struct AttOcc { static constexpr int MINB = NWARPS == 2 ? 7 : (NWARPS == 4 ? MRA_ATT_MINB4 : 1); };
+
 template <int NWARPS>
-__global__ void __launch_bounds__(NWARPS * 32)
+__global__ void __launch_bounds__(NWARPS * 32, AttOcc<NWARPS>::MINB)
 attention_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaParams2 pp) {
     const int prob = static_cast<int>(blockIdx.x) >= pp.split ? 1 : 0;
     const TmaParams& p = pp.p[prob];
@@ -292,10 +308,11 @@ attention_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr int QBOXES = (NWARPS * 16 + 31) / 32;
+    const int nstages = pp.stages;
     uint8_t* sQ = smem;                                         // QBOXES boxes
-    uint8_t* sKV = smem + QBOXES * BOX_BYTES;                   // TMA_STAGES x (K 64x64, V 64x64)
-    float* sMask = reinterpret_cast<float*>(sKV + TMA_STAGES * STAGE_BYTES_ATT);   // [nchunks * 64]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sMask + p.nchunks * 64);          // q_full, full[TMA_STAGES]
+    uint8_t* sKV = smem + QBOXES * BOX_BYTES;                   // nstages x (K 64x64, V 64x64)
+    float* sMask = reinterpret_cast<float*>(sKV + nstages * STAGE_BYTES_ATT);   // [nchunks * 64]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sMask + p.nchunks * 64);       // q_full, full[nstages]
 
     const int head = bid % p.heads;
     const int r = bid / p.heads;
@@ -305,14 +322,16 @@ attention_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant
 
     auto load_kv_chunk = [&](int kc, int stage) {
         uint8_t* dst = sKV + stage * STAGE_BYTES_ATT;
-        ptx::mbar_arrive_expect_tx(&bars[1 + stage], STAGE_BYTES_ATT);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        // boxes that start past the last key are neither fetched nor waited for (their shared memory is never read:
+        // the tail chunk's MMAs stop at the last 16-key group that holds a key)
+        const int nbox = (p.Sk - kc * 64 + 31) / 32 >= 2 ? 2 : 1;
+        ptx::mbar_arrive_expect_tx(&bars[1 + stage], 2 * nbox * BOX_BYTES);
+        for (int h = 0; h < nbox; ++h) {
             const int key0 = kc * 64 + h * 32;
             const bool seg1 = p.k_n1 > 0 && key0 >= p.k_n0;
-            const int tok = seg1 ? key0 - p.k_n0 : key0;   // past the end -> zero fill
-            tma_load_3d(dst + h * BOX_BYTES, seg1 ? tmK1 : tmK0, &bars[1 + stage], head * HD, tok, r);
-            tma_load_3d(dst + (2 + h) * BOX_BYTES, seg1 ? tmV1 : tmV0, &bars[1 + stage], head * HD, tok, r);
+            const int tok = seg1 ? key0 - p.k_n0 : key0;   // past the end of the row -> zero fill
+            tma_load_4d(dst + h * BOX_BYTES, seg1 ? tmK1 : tmK0, &bars[1 + stage], 0, tok, r, head);
+            tma_load_4d(dst + (2 + h) * BOX_BYTES, seg1 ? tmV1 : tmV0, &bars[1 + stage], 0, tok, r, head);
         }
     };
 
@@ -320,7 +339,7 @@ attention_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant
         ptx::prefetch_tensormap(tmQ0);
         ptx::prefetch_tensormap(tmK0);
         ptx::prefetch_tensormap(tmV0);
-        for (int i = 0; i < 1 + TMA_STAGES; ++i) ptx::mbar_init(&bars[i], 1);
+        for (int i = 0; i < 1 + nstages; ++i) ptx::mbar_init(&bars[i], 1);
         ptx::fence_mbar_init();
     }
     ptx::griddep_wait();               // the producers of q / k / v have completed
@@ -331,9 +350,9 @@ attention_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant
         for (int b = 0; b < QBOXES; ++b) {
             const int q0 = b * 32;
             const bool seg1 = p.q_n1 > 0 && q0 >= p.q_n0;
-            tma_load_3d(sQ + b * BOX_BYTES, seg1 ? tmQ1 : tmQ0, &bars[0], head * HD, seg1 ? q0 - p.q_n0 : q0, r);
+            tma_load_4d(sQ + b * BOX_BYTES, seg1 ? tmQ1 : tmQ0, &bars[0], 0, seg1 ? q0 - p.q_n0 : q0, r, head);
         }
-        for (int s = 0; s < TMA_STAGES && s < p.nchunks; ++s) load_kv_chunk(s, s);
+        for (int s = 0; s < nstages && s < p.nchunks; ++s) load_kv_chunk(s, s);
     }
     // additive mask (log2 domain); -inf past the last key
     for (int j = tid; j < p.nchunks * 64; j += NT) {
@@ -346,40 +365,42 @@ attention_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant
     const float scale_log2 = 0.125f * LOG2E;
     const int qr0 = warp * 16;
     const bool active = qr0 < p.Sq;
-    uint32_t qf[4][4];
+    const uint32_t qb = ptx::smem_u32(sQ);
+    const int qrow = qr0 + (lane & 7) + ((lane >> 3) & 1) * 8;
     ptx::mbar_wait(&bars[0], 0);
-    {
-        const uint32_t qb = ptx::smem_u32(sQ);
-        const int row = qr0 + (lane & 7) + ((lane >> 3) & 1) * 8;
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) ldmatrix_x4(qf[ks], tile_addr(qb, row, ks * 2 + (lane >> 4)));
-    }
     float o_acc[8][4];
     float m_run[2] = {-INFINITY, -INFINITY};
     float l_run[2] = {0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < 8; ++i) { o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.f; }
 
+    int stage = 0;
+    uint32_t phase = 0;
     for (int kc = 0; kc < p.nchunks; ++kc) {
-        const int stage = kc % TMA_STAGES;
-        ptx::mbar_wait(&bars[1 + stage], (kc / TMA_STAGES) & 1);
+        ptx::mbar_wait(&bars[1 + stage], phase);
         if (active) {
             const uint32_t kb = ptx::smem_u32(sKV + stage * STAGE_BYTES_ATT);
             const uint32_t vb = kb + 2 * BOX_BYTES;
             const float* mk = sMask + kc * 64;
-            // ---- S = Q K^T for 16 rows x 64 keys
+            const int nvalid = p.Sk - kc * 64;   // keys of this chunk (>= 64 except in the tail chunk)
+            // ---- S = Q K^T for 16 rows x 64 keys (Q fragments re-read from the tile per chunk: 16 registers fewer held)
+            uint32_t qf[4][4];
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) ldmatrix_x4(qf[ks], tile_addr(qb, qrow, ks * 2 + (lane >> 4)));
             float s[8][4];
 #pragma unroll
             for (int np = 0; np < 4; ++np) {    // pairs of 8-key tiles
                 s[2 * np][0] = s[2 * np][1] = s[2 * np][2] = s[2 * np][3] = 0.f;
                 s[2 * np + 1][0] = s[2 * np + 1][1] = s[2 * np + 1][2] = s[2 * np + 1][3] = 0.f;
-                const int key = np * 16 + (lane & 7) + (lane >> 4) * 8;
+                if (np * 16 < nvalid) {         // (warp-uniform) 16-key groups past the last key: the mask makes them -inf
+                    const int key = np * 16 + (lane & 7) + (lane >> 4) * 8;
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    uint32_t kf[4];
-                    ldmatrix_x4(kf, tile_addr(kb, key, ks * 2 + ((lane >> 3) & 1)));
-                    mma_bf16_16816(s[2 * np], qf[ks], kf[0], kf[1]);
-                    mma_bf16_16816(s[2 * np + 1], qf[ks], kf[2], kf[3]);
+                    for (int ks = 0; ks < 4; ++ks) {
+                        uint32_t kf[4];
+                        ldmatrix_x4(kf, tile_addr(kb, key, ks * 2 + ((lane >> 3) & 1)));
+                        mma_bf16_16816(s[2 * np], qf[ks], kf[0], kf[1]);
+                        mma_bf16_16816(s[2 * np + 1], qf[ks], kf[2], kf[3]);
+                    }
                 }
             }
             // ---- scale + mask (log2 domain), chunk row max
@@ -447,18 +468,23 @@ attention_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant
             // ---- O += P V   (V^T fragments through ldmatrix.trans from the row-major [key][dim] tile)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {          // 16 keys per step
-                const int key = j * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                if (j * 16 < nvalid) {             // (warp-uniform) P is exactly zero past the last key
+                    const int key = j * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
 #pragma unroll
-                for (int dp = 0; dp < 4; ++dp) {   // pairs of 8-wide dim tiles
-                    uint32_t vf[4];
-                    ldmatrix_x4_t(vf, tile_addr(vb, key, dp * 2 + (lane >> 4)));
-                    mma_bf16_16816(o_acc[2 * dp], pf[j], vf[0], vf[1]);
-                    mma_bf16_16816(o_acc[2 * dp + 1], pf[j], vf[2], vf[3]);
+                    for (int dp = 0; dp < 4; ++dp) {   // pairs of 8-wide dim tiles
+                        uint32_t vf[4];
+                        ldmatrix_x4_t(vf, tile_addr(vb, key, dp * 2 + (lane >> 4)));
+                        mma_bf16_16816(o_acc[2 * dp], pf[j], vf[0], vf[1]);
+                        mma_bf16_16816(o_acc[2 * dp + 1], pf[j], vf[2], vf[3]);
+                    }
                 }
             }
         }
-        __syncthreads();   // every warp is done with this stage
-        if (tid == 0 && kc + TMA_STAGES < p.nchunks) load_kv_chunk(kc + TMA_STAGES, stage);
+        if (kc + nstages < p.nchunks) {
+            __syncthreads();   // every warp is done with this stage
+            if (tid == 0) load_kv_chunk(kc + nstages, stage);
+        }
+        if (++stage == nstages) { stage = 0; phase ^= 1; }
     }
     if (active) {
 #pragma unroll
@@ -467,18 +493,42 @@ attention_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant
             l_run[h] += __shfl_xor_sync(0xffffffffu, l_run[h], 2);
         }
         const float inv[2] = {1.f / l_run[0], 1.f / l_run[1]};
+        auto out_row = [&](int i) -> __nv_bfloat16* {
+            const int64_t grow = (p.q_n1 > 0 && i >= p.q_n0)
+                                     ? static_cast<int64_t>(p.rows) * p.q_n0 + static_cast<int64_t>(r) * p.q_n1 + (i - p.q_n0)
+                                     : static_cast<int64_t>(r) * p.q_n0 + i;
+            return p.o + grow * p.ldo + head * HD;
+        };
+        if (pp.o_stage) {
+            // this warp's 16 rows of the Q tile are finished (only this warp ever read them): park O there, then write
+            // each row back as one 128-byte line (8 lanes x 16 bytes)
+            __syncwarp();
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int i = qr0 + g + h * 8;
-            if (i < p.Sq) {
-                const int64_t grow = (p.q_n1 > 0 && i >= p.q_n0)
-                                         ? static_cast<int64_t>(p.rows) * p.q_n0 + static_cast<int64_t>(r) * p.q_n1 + (i - p.q_n0)
-                                         : static_cast<int64_t>(r) * p.q_n0 + i;
-                __nv_bfloat16* op = p.o + grow * p.ldo + head * HD + 2 * t;
+            for (int h = 0; h < 2; ++h) {
+                const int row = qr0 + g + h * 8;
 #pragma unroll
                 for (int nt = 0; nt < 8; ++nt)
-                    *reinterpret_cast<uint32_t*>(op + nt * 8) =
-                        ptx::pack_bf16x2(o_acc[nt][2 * h] * inv[h], o_acc[nt][2 * h + 1] * inv[h]);
+                    ptx::st_shared_b32(tile_addr(qb, row, nt) + 4 * t,
+                                       ptx::pack_bf16x2(o_acc[nt][2 * h] * inv[h], o_acc[nt][2 * h + 1] * inv[h]));
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int row = qr0 + i * 4 + (lane >> 3);
+                const uint4 val = ptx::ld_shared_v4(tile_addr(qb, row, lane & 7));
+                if (row < p.Sq) *reinterpret_cast<uint4*>(out_row(row) + (lane & 7) * 8) = val;
+            }
+        } else {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int i = qr0 + g + h * 8;
+                if (i < p.Sq) {
+                    __nv_bfloat16* op = out_row(i) + 2 * t;
+#pragma unroll
+                    for (int nt = 0; nt < 8; ++nt)
+                        *reinterpret_cast<uint32_t*>(op + nt * 8) =
+                            ptx::pack_bf16x2(o_acc[nt][2 * h] * inv[h], o_acc[nt][2 * h + 1] * inv[h]);
+                }
             }
         }
     }
@@ -501,25 +551,29 @@ EncodeTiledFn attn_encode_fn() {
     return fn;
 }
 
-struct Map3Key {
-    const void* ptr; int64_t ld; int width, ntok, rows;
-    bool operator==(const Map3Key& o) const { return ptr == o.ptr && ld == o.ld && width == o.width && ntok == o.ntok && rows == o.rows; }
+struct Map4Key {
+    const void* ptr; int64_t ld, hs; int ntok, rows, heads;
+    bool operator==(const Map4Key& o) const {
+        return ptr == o.ptr && ld == o.ld && hs == o.hs && ntok == o.ntok && rows == o.rows && heads == o.heads;
+    }
 };
-struct Map3Hash {
-    size_t operator()(const Map3Key& k) const {
+struct Map4Hash {
+    size_t operator()(const Map4Key& k) const {
         size_t h = reinterpret_cast<size_t>(k.ptr);
         h = h * 1000003u ^ static_cast<size_t>(k.ld);
-        h = h * 1000003u ^ static_cast<size_t>(k.width * 31 + k.ntok);
+        h = h * 1000003u ^ static_cast<size_t>(k.hs);
+        h = h * 1000003u ^ static_cast<size_t>(k.heads * 31 + k.ntok);
         h = h * 1000003u ^ static_cast<size_t>(k.rows);
         return h;
     }
 };
 
-// bf16 [rows][ntok][width] view with token stride ld (elements) and row stride ntok*ld; box {64, 32, 1}, 128B swizzle.
-int get_map3(const void* ptr, int64_t ld, int width, int ntok, int rows, CUtensorMap* out) {
+// bf16 [heads][rows][ntok][64] view: token stride ld, row stride ntok * ld, head stride hs (all in elements; hs = 64 when the
+// heads sit side by side in one [tokens, heads * 64] matrix); box {64, 32, 1, 1}, 128B swizzle.
+int get_map4(const void* ptr, int64_t ld, int64_t hs, int ntok, int rows, int heads, CUtensorMap* out) {
     static std::mutex mu;
-    static std::unordered_map<Map3Key, CUtensorMap, Map3Hash> cache;
-    Map3Key key{ptr, ld, width, ntok, rows};
+    static std::unordered_map<Map4Key, CUtensorMap, Map4Hash> cache;
+    Map4Key key{ptr, ld, hs, ntok, rows, heads};
     {
         std::lock_guard<std::mutex> g(mu);
         auto it = cache.find(key);
@@ -527,12 +581,13 @@ int get_map3(const void* ptr, int64_t ld, int width, int ntok, int rows, CUtenso
     }
     EncodeTiledFn enc = attn_encode_fn();
     MRA_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
-    cuuint64_t gdim[3] = {static_cast<cuuint64_t>(width), static_cast<cuuint64_t>(ntok), static_cast<cuuint64_t>(rows)};
-    cuuint64_t gstride[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(ld) * 2 * ntok};
-    cuuint32_t box[3] = {64, 32, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
+    cuuint64_t gdim[4] = {static_cast<cuuint64_t>(HD), static_cast<cuuint64_t>(ntok), static_cast<cuuint64_t>(rows),
+                          static_cast<cuuint64_t>(heads)};
+    cuuint64_t gstride[3] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(ld) * 2 * ntok, static_cast<cuuint64_t>(hs) * 2};
+    cuuint32_t box[4] = {64, 32, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
     CUtensorMap m;
-    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstride, box, estr,
+    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstride, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MRA_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (attention) failed with CUresult %d", (int)r);
@@ -568,32 +623,41 @@ int prepare_tma_problem(const AttnArgs& a, int slot, TmaMaps& maps, TmaParams2& 
     p.k_n0 = split_k ? a.nq_split : a.Sk; p.k_n1 = split_k ? a.Sk - a.nq_split : 0;
     p.nchunks = (a.Sk + 63) / 64;
     p.drop = a.drop;
-    const int width = a.heads * HD;
+    const int64_t hsq = a.hsq ? a.hsq : HD, hsk = a.hsk ? a.hsk : HD, hsv = a.hsv ? a.hsv : HD;
     const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(a.q);
     const __nv_bfloat16* k = reinterpret_cast<const __nv_bfloat16*>(a.k);
     const __nv_bfloat16* v = reinterpret_cast<const __nv_bfloat16*>(a.v);
     CUtensorMap* m = &maps.m[slot * 6];
-    if (int e = get_map3(q, a.ldq, width, p.q_n0, a.rows, &m[0])) return e;
+    if (int e = get_map4(q, a.ldq, hsq, p.q_n0, a.rows, a.heads, &m[0])) return e;
     m[1] = m[0];
     if (p.q_n1 > 0)
-        if (int e = get_map3(q + static_cast<int64_t>(a.rows) * p.q_n0 * a.ldq, a.ldq, width, p.q_n1, a.rows, &m[1])) return e;
-    if (int e = get_map3(k, a.ldk, width, p.k_n0, a.rows, &m[2])) return e;
+        if (int e = get_map4(q + static_cast<int64_t>(a.rows) * p.q_n0 * a.ldq, a.ldq, hsq, p.q_n1, a.rows, a.heads, &m[1])) return e;
+    if (int e = get_map4(k, a.ldk, hsk, p.k_n0, a.rows, a.heads, &m[2])) return e;
     m[3] = m[2];
     if (p.k_n1 > 0)
-        if (int e = get_map3(k + static_cast<int64_t>(a.rows) * p.k_n0 * a.ldk, a.ldk, width, p.k_n1, a.rows, &m[3])) return e;
-    if (int e = get_map3(v, a.ldv, width, p.k_n0, a.rows, &m[4])) return e;
+        if (int e = get_map4(k + static_cast<int64_t>(a.rows) * p.k_n0 * a.ldk, a.ldk, hsk, p.k_n1, a.rows, a.heads, &m[3])) return e;
+    if (int e = get_map4(v, a.ldv, hsv, p.k_n0, a.rows, a.heads, &m[4])) return e;
     m[5] = m[4];
     if (p.k_n1 > 0)
-        if (int e = get_map3(v + static_cast<int64_t>(a.rows) * p.k_n0 * a.ldv, a.ldv, width, p.k_n1, a.rows, &m[5])) return e;
+        if (int e = get_map4(v + static_cast<int64_t>(a.rows) * p.k_n0 * a.ldv, a.ldv, hsv, p.k_n1, a.rows, a.heads, &m[5])) return e;
     return 0;
+}
+
+// tuning switches (A/B runs): MRA_ATT_STAGES = slots of the K/V ring (1..3, default 2), MRA_ATT_OSTAGE=0 = 4-byte output stores
+int att_env(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
 }
 
 // one launch for `n` (1 or 2) problems with the same number of query warps; -1 = not covered by the TMA kernel
 int try_launch_attention_tma(const AttnArgs* a, int n, cudaStream_t s) {
+    static const int max_stages = [] { const int v = att_env("MRA_ATT_STAGES", 2); return v < 1 ? 1 : (v > TMA_STAGES_MAX ? TMA_STAGES_MAX : v); }();
+    static const int o_stage_on = att_env("MRA_ATT_OSTAGE", 1);
     TmaMaps maps;
     TmaParams2 pp;
     int nw = 0, nchunks = 0;
     unsigned grid = 0;
+    bool o_aligned = true;
     for (int i = 0; i < n; ++i) {
         const int e = prepare_tma_problem(a[i], i, maps, pp);
         if (e != 0) return e;
@@ -604,15 +668,18 @@ int try_launch_attention_tma(const AttnArgs* a, int n, cudaStream_t s) {
         nchunks = pp.p[i].nchunks > nchunks ? pp.p[i].nchunks : nchunks;
         if (i == 0) pp.split = static_cast<int>(a[i].rows) * a[i].heads;
         grid += static_cast<unsigned>(a[i].rows) * a[i].heads;
+        o_aligned = o_aligned && (reinterpret_cast<uintptr_t>(a[i].o) & 15) == 0 && a[i].ldo % 8 == 0;
     }
     if (n == 1) {
         pp.p[1] = pp.p[0];
         for (int i = 0; i < 6; ++i) maps.m[6 + i] = maps.m[i];
         pp.split = static_cast<int>(grid);
     }
+    pp.stages = nchunks < max_stages ? nchunks : max_stages;
+    pp.o_stage = (o_stage_on && o_aligned) ? 1 : 0;
     const int qboxes = (nw * 16 + 31) / 32;
-    const size_t smem = static_cast<size_t>(qboxes) * BOX_BYTES + TMA_STAGES * STAGE_BYTES_ATT + static_cast<size_t>(nchunks) * 64 * 4 +
-                        (1 + TMA_STAGES) * 8 + 1024;
+    const size_t smem = static_cast<size_t>(qboxes) * BOX_BYTES + pp.stages * STAGE_BYTES_ATT + static_cast<size_t>(nchunks) * 64 * 4 +
+                        (1 + pp.stages) * 8 + 1024;
     if (nw == 2) return launch_tma_variant<2>(maps, pp, grid, smem, s);
     if (nw == 4) return launch_tma_variant<4>(maps, pp, grid, smem, s);
     if (nw == 8) return launch_tma_variant<8>(maps, pp, grid, smem, s);
@@ -628,6 +695,8 @@ int launch_attention(const AttnArgs& a, cudaStream_t s) {
     MRA_REQUIRE(a.rows > 0 && a.heads > 0 && a.Sq > 0 && a.Sk > 0, "attention with empty dimension");
     MRA_REQUIRE(a.Sq <= 512, "attention supports at most 512 query tokens per row, got %d", a.Sq);
     MRA_REQUIRE(a.ldq % 8 == 0 && a.ldk % 8 == 0 && a.ldv % 8 == 0 && a.ldo % 2 == 0, "attention strides must be 16-byte rows");
+    MRA_REQUIRE(a.hsq % 8 == 0 && a.hsk % 8 == 0 && a.hsv % 8 == 0 && a.hsq >= 0 && a.hsk >= 0 && a.hsv >= 0,
+                "attention head strides must be multiples of 8 elements");
     MRA_REQUIRE(((reinterpret_cast<uintptr_t>(a.q) | reinterpret_cast<uintptr_t>(a.k) | reinterpret_cast<uintptr_t>(a.v)) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(a.o) & 3) == 0,
                 "attention operands must be 16-byte aligned");
@@ -640,7 +709,8 @@ int launch_attention(const AttnArgs& a, cudaStream_t s) {
                                   "multiple of 32): Sq=%d Sk=%d split=%d", a.Sq, a.Sk, a.nq_split);
     Params p{reinterpret_cast<const __nv_bfloat16*>(a.q), a.ldq, reinterpret_cast<const __nv_bfloat16*>(a.k), a.ldk,
              reinterpret_cast<const __nv_bfloat16*>(a.v), a.ldv, reinterpret_cast<__nv_bfloat16*>(a.o), a.ldo,
-             a.add_mask, a.rows, a.heads, a.Sq, a.Sk, a.nq_split, a.kv_dense};
+             a.add_mask, a.rows, a.heads, a.Sq, a.Sk, a.nq_split, a.kv_dense,
+             a.hsq ? a.hsq : HD, a.hsk ? a.hsk : HD, a.hsv ? a.hsv : HD};
     const int sq_pad = (a.Sq + 15) & ~15;
     const size_t smem = static_cast<size_t>(sq_pad + 2 * KC) * LDS_ROW * 2 + KC * sizeof(float);
     const unsigned grid = static_cast<unsigned>(a.rows) * a.heads;

@@ -146,6 +146,25 @@ extern "C" int mra_attention(const void* q, int64_t ldq, const void* k, int64_t 
     return launch_attention(a, reinterpret_cast<cudaStream_t>(stream));
 }
 
+extern "C" int mra_attention_strided(const void* q, int64_t ldq, int64_t hsq, const void* k, int64_t ldk, int64_t hsk, const void* v,
+                                     int64_t ldv, int64_t hsv, void* o, int64_t ldo, const float* add_mask, int32_t rows,
+                                     int32_t heads, int32_t Sq, int32_t Sk, int32_t nq_split, int32_t kv_dense, void* stream) {
+    MRA_REQUIRE(q && k && v && o, "mra_attention_strided: NULL operand");
+    if (int e = device_check()) return e;
+    AttnArgs a{q, ldq, k, ldk, v, ldv, o, ldo, add_mask, rows, heads, Sq, Sk, nq_split, kv_dense};
+    a.hsq = hsq; a.hsk = hsk; a.hsv = hsv;
+    return launch_attention(a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mra_gemm_head_major_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int32_t M,
+                                        int32_t N, int32_t K, void* stream) {
+    MRA_REQUIRE(A && W && C, "mra_gemm_head_major_bf16: NULL operand");
+    if (int e = device_check()) return e;
+    GemmArgs a{A, lda, W, ldw, bias, nullptr, 0, C, N, M, N, K, 0, 0};
+    a.c_head_major = 1;
+    return launch_gemm_tc(a, reinterpret_cast<cudaStream_t>(stream));
+}
+
 extern "C" int mra_attention_impl_override(int32_t generic) {
     set_attention_impl_override(generic);
     return 0;

@@ -91,6 +91,9 @@ struct GemmArgs {
     // into their slot of the interleaved LLM prompt (models/xinstructblip.py:359-366).  bf16 output, M % 32 == 0.
     int c_frames = 0;
     int64_t c_frame_stride = 0, c_batch_stride = 0;
+    // c_head_major != 0: C is [N / 64][M][64] bf16 (slot n / 64 of output row m at C + ((n / 64) * M + m) * 64): the layout
+    // the attention kernel reads Q / K / V heads from as contiguous tiles.  N % 64 == 0, ldc ignored.
+    int c_head_major = 0;
     // (set by the launcher) split of the K range into separate work items + TMA reduce-add epilogue, see gemm.cu
     int ksplit = 1, reduce_add = 0;
     // training-mode dropout on (A W^T + bias) BEFORE the residual is added (BertSelfOutput / BertOutput): needs the fp32
@@ -107,6 +110,7 @@ int get_tensor_map(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int 
 // bf16 [batch][frames][32][cols] with element strides (batch_stride, frame_stride, ld, 1); box {64 cols, 32 rows, 1, 1}
 int get_tensor_map_scatter(const void* ptr, int64_t batch, int64_t frames, int64_t cols, int64_t ld, int64_t frame_stride,
                            int64_t batch_stride, CUtensorMap* out);
+int get_tensor_map_head_major(const void* ptr, int64_t rows, int64_t cols, CUtensorMap* out);
 void set_gemm_tile_override(int bn);
 void set_gemm_cluster_override(int cm);   // 1 = never pair CTAs, 2 = pair along M when possible (default)
 
@@ -135,6 +139,9 @@ struct AttnArgs {
     const float* add_mask;
     int rows, heads, Sq, Sk, nq_split, kv_dense;
     DropoutParams drop;   // training-mode dropout on the attention probabilities (TMA kernel only)
+    // head strides in elements; 0 = the heads sit side by side in a row (head h at column 64 h).  Head-major operands
+    // ([head][token][64], written by the GEMM epilogue's c_head_major form): ld = 64, head stride = tokens * 64.
+    int64_t hsq = 0, hsk = 0, hsv = 0;
 };
 int launch_attention(const AttnArgs& a, cudaStream_t s);
 int launch_attention_pair(const AttnArgs* a, int n, cudaStream_t s, int* launches);   // n <= 2, one launch when possible

@@ -50,7 +50,8 @@ struct GroupMaps {
 struct EpiParams {
     const float* bias[MAX_GROUPS];
     int M[MAX_GROUPS];
-    int c_frames[MAX_GROUPS];         // > 0: the C map of this group is the 4-D scatter map (GemmArgs::c_frames)
+    int c_frames[MAX_GROUPS];         // > 0: the C map of this group is the 4-D scatter map (GemmArgs::c_frames);
+                                      // < 0: the 3-D head-major map (GemmArgs::c_head_major)
     int tile_start[MAX_GROUPS + 1];   // first tile index of each group (tiles of a group: m-block major, n fastest)
     int groups;
     int N, K;
@@ -509,6 +510,9 @@ gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ E
                                 const int rf = row0 >> 5;
                                 ptx::tma_store_4d(tmC, odst, col0, 0, rf % cf, rf / cf);
                                 scattered = true;
+                            } else if (cf < 0) {   // head-major C: this 64-column chunk is 32 full rows of slot col0 / 64
+                                ptx::tma_store_3d(tmC, odst, 0, row0, col0 >> 6);
+                                scattered = true;
                             }
                         }
                         if (!scattered) {
@@ -686,6 +690,23 @@ int get_tensor_map_scatter(const void* ptr, int64_t batch, int64_t frames, int64
     return 0;
 }
 
+// bf16 [cols / 64][rows][64]: 64-column slot c / 64 of output row r at ptr + ((c / 64) * rows + r) * 64; box {64, 32, 1}
+int get_tensor_map_head_major(const void* ptr, int64_t rows, int64_t cols, CUtensorMap* out) {
+    EncodeTiledFn enc = get_encode_fn();
+    MRA_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+    MRA_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && rows > 0 && cols > 0 && cols % 64 == 0,
+                "head-major output: pointer must be 16-byte aligned, cols a multiple of 64");
+    cuuint64_t gdim[3] = {64, static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(cols / 64)};
+    cuuint64_t gstride[2] = {128, static_cast<cuuint64_t>(rows) * 128};
+    cuuint32_t box[3] = {64, 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MRA_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (head-major output) failed with CUresult %d", (int)r);
+    return 0;
+}
+
 namespace {
 
 template <int BN, int STAGES, bool GELU, bool OUT_F32, bool RES, int CM, int TN = 0, bool U2 = false>
@@ -726,8 +747,11 @@ int launch_tc_variant(const GemmArgs* ga, int n, cudaStream_t s) {
                 if (int e = get_tensor_map(a.A, a.M, a.K, a.lda, BM, BK, 2, &maps.a[g])) return e;
                 if (int e = get_tensor_map(a.W, a.N, a.K, a.ldw, BN / CM, BK, 2, &maps.b[g])) return e;
             }
-            p.c_frames[g] = a.c_frames;
-            if (a.c_frames > 0) {
+            p.c_frames[g] = a.c_head_major ? -1 : a.c_frames;
+            if (a.c_head_major) {
+                MRA_REQUIRE(!OUT_F32 && a.c_frames == 0 && a.N % 64 == 0, "head-major output needs bf16 C and N a multiple of 64 (N=%d)", a.N);
+                if (int e = get_tensor_map_head_major(a.C, a.M, a.N, &maps.c[g])) return e;
+            } else if (a.c_frames > 0) {
                 MRA_REQUIRE(!OUT_F32 && a.M % 32 == 0 && (a.M / 32) % a.c_frames == 0,
                             "scatter output needs bf16 C and M = videos * frames * 32 (M=%d frames=%d)", a.M, a.c_frames);
                 if (int e = get_tensor_map_scatter(a.C, a.M / 32 / a.c_frames, a.c_frames, a.N, a.ldc, a.c_frame_stride,

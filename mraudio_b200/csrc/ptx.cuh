@@ -87,6 +87,12 @@ __device__ __forceinline__ void tma_reduce_add_2d(const void* desc, const void* 
                  "r"(smem_u32(smem_src)), "r"(crd0), "r"(crd1)
                  : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const void* desc, const void* smem_src, int32_t crd0, int32_t crd1, int32_t crd2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(desc)),
+                 "r"(smem_u32(smem_src)), "r"(crd0), "r"(crd1), "r"(crd2)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_store_4d(const void* desc, const void* smem_src, int32_t crd0, int32_t crd1, int32_t crd2,
                                              int32_t crd3) {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
@@ -268,6 +274,9 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 }
 __device__ __forceinline__ void st_shared_v4f(uint32_t addr, float a, float b, float c, float d) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void st_shared_b32(uint32_t addr, uint32_t a) {
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(a) : "memory");
 }
 __device__ __forceinline__ void st_shared_v2(uint32_t addr, uint32_t a, uint32_t b) {
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");

@@ -23,6 +23,8 @@ struct mra_qformer {
                                                        // (slot `layers`: the projection's)
     bool fuse_ln = true;   // Linear + residual + LayerNorm in one cluster kernel (MRA_NO_FUSED_LN=1 disables: A/B runs)
     bool split_res = true; // with fuse_ln: residual stream as a bf16 (hi, lo) pair instead of fp32 (MRA_SPLIT_RESIDUAL=0 disables)
+    bool head_major = true; // inference forward: QKV / cross-K/V GEMMs write [head][token][64] for the attention kernel's TMA
+                            // boxes (MRA_HEAD_MAJOR=0 disables: A/B runs); the save-for-backward forward keeps [token][heads * 64]
     // optional per-category device timing (CUDA events on the caller's stream), see mra_qformer_profile_*
     int profile_mode = MRA_PROFILE_OFF;
     struct Span { int cat; cudaEvent_t a, b; };
@@ -196,6 +198,7 @@ extern "C" int mra_qformer_create(const mra_qformer_config* cfg, mra_qformer_t**
     if (impl && std::string(impl) == "simt") h->gemm_impl = MRA_GEMM_IMPL_SIMT_DEBUG;
     if (getenv("MRA_NO_FUSED_LN")) h->fuse_ln = false;
     if (const char* e = getenv("MRA_SPLIT_RESIDUAL")) h->split_res = atoi(e) != 0;
+    if (const char* e = getenv("MRA_HEAD_MAJOR")) h->head_major = atoi(e) != 0;
     *out = h;
     return 0;
 }
@@ -370,6 +373,9 @@ int forward_multi(int n, mra_qformer_t* const* hs, const mra_qformer_io* const* 
     const bool fuse_ln = !save && H == 768 && h0->gemm_impl == MRA_GEMM_IMPL_TCGEN05 && h0->fuse_ln;
     // split residual stream: every post-LayerNorm tensor is a bf16 (hi, lo) pair, hi doubling as the next GEMM operand
     const bool split = fuse_ln && h0->split_res;
+    // head-major Q / K / V: only the attention kernel reads these tensors in the inference forward (the backward's kernels
+    // read the [token][heads * 64] form, so the save-for-backward forward keeps it)
+    const bool hm = !save && c.hidden == c.heads * 64 && h0->gemm_impl == MRA_GEMM_IMPL_TCGEN05 && h0->head_major;
     GemmLnArgs gl[4];
     int ngl = 0;
     // residual = res32 (fp32) or, in split form, res_hi + res_lo; outputs y32 + y16 or y16 (hi) + y_lo
@@ -433,6 +439,7 @@ int forward_multi(int n, mra_qformer_t* const* hs, const mra_qformer_io* const* 
         }
         const int Wd = x.h->cfg.enc_width;
         add(x.io->enc, Wd, W.w_ckv, Wd, W.b_ckv, nullptr, 0, x.ws.kv, x.kv_ld, x.rows * x.Nk, x.kv_ld, Wd, 0, 0);
+        if (hm && ng > 0) ga[ng - 1].c_head_major = 1;
         MRA_TRY(flush(MRA_CAT_GEMM_CROSS_KV));
     }
 
@@ -444,6 +451,7 @@ int forward_multi(int n, mra_qformer_t* const* hs, const mra_qformer_io* const* 
             const auto& L = cx[i].h->w.layer[l];
             const LayerBufs& B = cx[i].ws.layer[l];
             add(B.xb, H, L.w_qkv, H, L.b_qkv, nullptr, 0, B.qkv, 3 * H, cx[i].Mtot, 3 * H, H, 0, 0);
+            if (hm && ng > 0) ga[ng - 1].c_head_major = 1;
         }
         MRA_TRY(flush(MRA_CAT_GEMM));
         {
@@ -452,6 +460,12 @@ int forward_multi(int n, mra_qformer_t* const* hs, const mra_qformer_io* const* 
                 const LayerBufs& B = cx[i].ws.layer[l];
                 aa[i] = AttnArgs{B.qkv, 3 * H, B.qkv + H, 3 * H, B.qkv + 2 * H, 3 * H, B.ctx, H, cx[i].self_mask, cx[i].rows, c.heads,
                                  cx[i].S, cx[i].S, Nq, 0};
+                if (hm) {   // qkv = [3 * heads][Mtot][64]: Q heads, then K heads, then V heads
+                    const int64_t hs = static_cast<int64_t>(cx[i].Mtot) * 64;
+                    aa[i].q = B.qkv; aa[i].k = B.qkv + c.heads * hs; aa[i].v = B.qkv + 2 * c.heads * hs;
+                    aa[i].ldq = aa[i].ldk = aa[i].ldv = 64;
+                    aa[i].hsq = aa[i].hsk = aa[i].hsv = hs;
+                }
                 aa[i].drop = dsite(DROP_SELF_PROBS, l);
             }
             span_begin(MRA_CAT_ATTENTION);
@@ -488,6 +502,13 @@ int forward_multi(int n, mra_qformer_t* const* hs, const mra_qformer_io* const* 
                     const __nv_bfloat16* kbase = cx[i].ws.kv + static_cast<size_t>(cx[i].h->cross_slot[l]) * 2 * H;
                     aa[i] = AttnArgs{B.cq, H, kbase, cx[i].kv_ld, kbase + H, cx[i].kv_ld, B.cctx, H, cx[i].enc_mask, cx[i].rows,
                                      c.heads, Nq, cx[i].Nk, Nq, 1};
+                    if (hm) {   // kv = [cross layers * 2 * heads][rows * Nk][64]: per cross layer K heads, then V heads
+                        const int64_t hs = static_cast<int64_t>(cx[i].rows) * cx[i].Nk * 64;
+                        aa[i].k = cx[i].ws.kv + static_cast<int64_t>(cx[i].h->cross_slot[l]) * 2 * c.heads * hs;
+                        aa[i].v = reinterpret_cast<const __nv_bfloat16*>(aa[i].k) + c.heads * hs;
+                        aa[i].ldk = aa[i].ldv = 64;
+                        aa[i].hsk = aa[i].hsv = hs;
+                    }
                     aa[i].drop = dsite(DROP_CROSS_PROBS, l);
                 }
                 span_begin(MRA_CAT_ATTENTION);

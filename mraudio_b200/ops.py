@@ -123,6 +123,36 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, rows: int, head
     return o
 
 
+def linear_head_major(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """x @ weight.T + bias written head-major: bf16 [N // 64, M, 64] (slot n // 64 holds columns 64*(n//64) .. of every row)."""
+    _need_cuda(x, weight, bias)
+    assert x.dtype == weight.dtype == torch.bfloat16 and x.stride(1) == 1 and weight.stride(1) == 1
+    M, K = x.shape
+    N = weight.shape[0]
+    assert N % 64 == 0 and weight.shape[1] == K
+    out = torch.empty(N // 64, M, 64, device=x.device, dtype=torch.bfloat16)
+    check(lib.mra_gemm_head_major_bf16(ptr(x), x.stride(0), ptr(weight), weight.stride(0), ptr(bias), ptr(out), M, N, K,
+                                       current_stream()))
+    return out
+
+
+def attention_head_major(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, rows: int, Sq: int, Sk: int, nq_split: int,
+                         kv_dense: bool, add_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q / k / v: head-major [heads, tokens, 64] (views of ``linear_head_major`` output); returns o [rows*Sq, heads*64]."""
+    _need_cuda(q, k, v, add_mask)
+    assert q.dtype == k.dtype == v.dtype == torch.bfloat16
+    heads = q.shape[0]
+    for t in (q, k, v):
+        assert t.dim() == 3 and t.shape[0] == heads and t.shape[2] == 64 and t.stride(2) == 1
+    o = torch.empty(rows * Sq, heads * 64, device=q.device, dtype=torch.bfloat16)
+    if add_mask is not None:
+        assert add_mask.dtype == torch.float32 and add_mask.shape == (rows, Sk) and add_mask.is_contiguous()
+    check(lib.mra_attention_strided(ptr(q), q.stride(1), q.stride(0), ptr(k), k.stride(1), k.stride(0), ptr(v), v.stride(1),
+                                    v.stride(0), ptr(o), o.stride(0), ptr(add_mask), rows, heads, Sq, Sk, nq_split,
+                                    int(kv_dense), current_stream()))
+    return o
+
+
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float):
     """fp32 [rows, n] -> (fp32, bf16) LayerNorm outputs."""
     _need_cuda(x, gamma, beta)

@@ -325,6 +325,78 @@ def test_self_attention_split_layout(rows, Nq, T, attn_impl):
     assert _rel(got, ref) < 1.5e-2
 
 
+@pytest.mark.parametrize("M,N,K", [(32 * 257, 1536, 1408), (777, 2304, 768), (100, 64, 64), (4096, 9216, 768)])
+def test_gemm_head_major_output(M, N, K):
+    """The head-major epilogue ([N / 64][M][64], what the inference forward hands to the attention kernel) holds exactly
+    the values of the row-major bf16 GEMM: same accumulation, only the TMA store coordinates differ."""
+    from mraudio_b200 import ops
+    g = torch.Generator().manual_seed(M + N)
+    x = torch.randn(M, K, generator=g).to(_dev(), torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) * 0.03).to(_dev(), torch.bfloat16)
+    b = torch.randn(N, generator=g).to(_dev())
+    guard = torch.full((N // 64 + 2, M, 64), 7.0, device=_dev(), dtype=torch.bfloat16)   # slots 0 and -1 must stay untouched
+    hm = ops.linear_head_major(x, w, b)
+    ref = ops.linear(x, w, b)
+    assert torch.equal(hm.permute(1, 0, 2).reshape(M, N), ref)
+    from mraudio_b200 import _lib
+    _lib.check(_lib.lib.mra_gemm_head_major_bf16(_lib.ptr(x), x.stride(0), _lib.ptr(w), w.stride(0), _lib.ptr(b),
+                                                 guard[1:].data_ptr(), M, N, K, _lib.current_stream()))
+    assert torch.equal(guard[1:-1], hm) and bool((guard[0] == 7.0).all()) and bool((guard[-1] == 7.0).all())
+
+
+@pytest.mark.parametrize("rows,Sq,Sk,heads", [(3, 32, 257, 12), (2, 32, 256, 12), (4, 17, 100, 3), (2, 64, 300, 4), (5, 32, 8, 12)])
+def test_cross_attention_head_major_equals_row_major(rows, Sq, Sk, heads, attn_impl):
+    from mraudio_b200 import ops
+    g = torch.Generator().manual_seed(rows * 10 + Sk)
+    H = heads * 64
+    q = torch.randn(rows * Sq, H, generator=g).to(_dev(), torch.bfloat16)
+    kv = torch.randn(rows * Sk, 2 * H, generator=g).to(_dev(), torch.bfloat16)
+    mask = torch.zeros(rows, Sk)
+    mask[0, Sk // 2:] = -10000.0
+    mask = mask.to(_dev())
+    ref = ops.attention(q, kv[:, :H], kv[:, H:], rows, heads, Sq, Sk, Sq, True, mask)
+    kv_hm = kv.view(rows * Sk, 2 * heads, 64).permute(1, 0, 2).contiguous()       # [2 * heads][tokens][64]
+    q_hm = q.view(rows * Sq, heads, 64).permute(1, 0, 2).contiguous()
+    o = ops.attention_head_major(q_hm, kv_hm[:heads], kv_hm[heads:], rows, Sq, Sk, Sq, True, mask)
+    assert torch.equal(o, ref)
+    # mixed: row-major queries (stride 64 between heads), head-major keys / values -- the cross-attention of the forward
+    o2 = ops.attention_head_major(q.view(rows * Sq, heads, 64).permute(1, 0, 2), kv_hm[:heads], kv_hm[heads:], rows, Sq, Sk, Sq,
+                                  True, mask)
+    assert torch.equal(o2, ref)
+
+
+@pytest.mark.parametrize("rows,Nq,T", [(3, 32, 32), (2, 32, 0), (4, 32, 13), (2, 32, 128), (3, 64, 40)])
+def test_self_attention_head_major_equals_row_major(rows, Nq, T, attn_impl):
+    from mraudio_b200 import ops
+    heads, H = 12, 768
+    S = Nq + T
+    g = torch.Generator().manual_seed(rows + 3 * T)
+    split = torch.randn(rows * S, 3 * H, generator=g).to(_dev(), torch.bfloat16)   # split layout: query rows, then text rows
+    mask = torch.zeros(rows, S)
+    if T > 3:
+        mask[1, Nq + T // 2:] = -10000.0
+    mask = mask.to(_dev())
+    ref = ops.attention(split[:, :H], split[:, H:2 * H], split[:, 2 * H:], rows, heads, S, S, Nq, False, mask)
+    hm = split.view(rows * S, 3 * heads, 64).permute(1, 0, 2).contiguous()         # [3 * heads][tokens][64]
+    o = ops.attention_head_major(hm[:heads], hm[heads:2 * heads], hm[2 * heads:], rows, S, S, Nq, False, mask)
+    assert torch.equal(o, ref)
+
+
+def test_attention_unaligned_output_rows_take_the_narrow_store_path():
+    """Output rows that are not 16-byte aligned cannot leave as 128-byte lines: same values through the 4-byte stores."""
+    from mraudio_b200 import _lib, ops
+    rows, Sq, Sk, heads, H = 2, 32, 257, 2, 128
+    g = torch.Generator().manual_seed(5)
+    q = torch.randn(rows * Sq, H, generator=g).to(_dev(), torch.bfloat16)
+    kv = torch.randn(rows * Sk, 2 * H, generator=g).to(_dev(), torch.bfloat16)
+    ref = ops.attention(q, kv[:, :H], kv[:, H:], rows, heads, Sq, Sk, Sq, True, None)
+    buf = torch.zeros(rows * Sq, H + 2, device=_dev(), dtype=torch.bfloat16)
+    o = buf[:, 2:]                                       # rows start 4 bytes off a 16-byte boundary, pitch 260 bytes
+    _lib.check(_lib.lib.mra_attention(_lib.ptr(q), H, _lib.ptr(kv), 2 * H, kv[:, H:].data_ptr(), 2 * H, o.data_ptr(), H + 2, None,
+                                      rows, heads, Sq, Sk, Sq, 1, _lib.current_stream()))
+    assert torch.equal(o, ref) and bool((buf[:, :2] == 0).all())
+
+
 @pytest.mark.parametrize("rows,n", [(1, 768), (1000, 768), (77, 1408), (5, 1024), (9, 8)])
 def test_layernorm(rows, n):
     from mraudio_b200 import ops
