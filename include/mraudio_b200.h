@@ -300,6 +300,15 @@ int mra_attention_strided(const void* q, int64_t ldq, int64_t hsq, const void* k
 int mra_gemm_head_major_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int32_t M,
                              int32_t N, int32_t K, void* stream);
 
+/* ctx = SelfAttention(x W_qkv^T + b_qkv): the fused Q/K/V Linear of a Q-Former block and its attention core in ONE kernel
+ * (Q, K, V never reach HBM), for rows of 32 query + 32 text tokens in the split layout and heads of 64:
+ *   x bf16 [rows*64, K] (the 32 query tokens of every row first, then the 32 text tokens of every row), w bf16
+ *   [3*heads*64, K] (Q rows, K rows, V rows), bias fp32 [3*heads*64] or NULL, add_mask fp32 [rows, 64] or NULL,
+ *   ctx bf16 [rows*64, heads*64] (row order of x, 16-byte aligned rows).  Bit-equal to mra_gemm_bf16 followed by
+ *   mra_attention.  Replaces BertSelfAttention query/key/value + core (HF port modeling_instructblip.py:499-538). */
+int mra_qkv_attention_bf16(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias, const float* add_mask,
+                           void* ctx, int64_t ldo, int32_t rows, int32_t heads, int32_t K, void* stream);
+
 /* Test aid: generic != 0 forces the register-staged generic attention kernel instead of the TMA-pipelined one (which
  * covers Sq <= 256, Sk <= 4096 and split points that are multiples of 32; other shapes always use the generic one). */
 int mra_attention_impl_override(int32_t generic);

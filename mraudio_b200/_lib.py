@@ -111,6 +111,7 @@ def _load():
     lib.mra_attention.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.mra_attention_strided.argtypes = [vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, i64, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.mra_gemm_head_major_bf16.argtypes = [vp, i64, vp, i64, vp, vp, i32, i32, i32, vp]
+    lib.mra_qkv_attention_bf16.argtypes = [vp, i64, vp, i64, vp, vp, vp, i64, i32, i32, i32, vp]
     lib.mra_attention_impl_override.argtypes = [i32]
     lib.mra_layernorm.argtypes = [vp, vp, vp, vp, vp, i32, i32, f32, vp]
     lib.mra_modality_layernorm.argtypes = [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp]
@@ -143,7 +144,7 @@ EXPORTED_SYMBOLS = (
     "mra_qformer_destroy", "mra_qformer_workspace_bytes", "mra_qformer_forward", "mra_qformer_forward_multi", "mra_qformer_last_launch_count", "mra_qformer_backward_workspace_bytes", "mra_qformer_backward", "mra_qformer_backward_layer_events", "mra_adam_step", "mra_adam_step_fused", "mra_adam_step_fused_dyn", "mra_adam_hyper",
     "mra_cast_bf16",
     "mra_qformer_profile_mode", "mra_qformer_profile_read",
-    "mra_gemm_bf16", "mra_wgrad_bf16", "mra_dgrad_bf16", "mra_gemm_ln_bf16", "mra_gemm_ln_split_bf16", "mra_gemm_tile_override", "mra_gemm_cluster_override", "mra_attention", "mra_attention_strided", "mra_gemm_head_major_bf16", "mra_attention_impl_override", "mra_layernorm", "mra_modality_layernorm", "mra_add_frame_position", "mra_prompt_assemble", "mra_mr_score",
+    "mra_gemm_bf16", "mra_wgrad_bf16", "mra_dgrad_bf16", "mra_gemm_ln_bf16", "mra_gemm_ln_split_bf16", "mra_gemm_tile_override", "mra_gemm_cluster_override", "mra_attention", "mra_attention_strided", "mra_gemm_head_major_bf16", "mra_qkv_attention_bf16", "mra_attention_impl_override", "mra_layernorm", "mra_modality_layernorm", "mra_add_frame_position", "mra_prompt_assemble", "mra_mr_score",
 )
 
 

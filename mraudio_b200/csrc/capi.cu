@@ -165,6 +165,14 @@ extern "C" int mra_gemm_head_major_bf16(const void* A, int64_t lda, const void* 
     return launch_gemm_tc(a, reinterpret_cast<cudaStream_t>(stream));
 }
 
+extern "C" int mra_qkv_attention_bf16(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias, const float* add_mask,
+                                      void* ctx, int64_t ldo, int32_t rows, int32_t heads, int32_t K, void* stream) {
+    MRA_REQUIRE(x && w && ctx, "mra_qkv_attention_bf16: NULL operand");
+    if (int e = device_check()) return e;
+    QkvAttnArgs a{x, ldx, w, ldw, bias, ctx, ldo, add_mask, rows, heads, K};
+    return launch_qkv_attention(&a, 1, reinterpret_cast<cudaStream_t>(stream));
+}
+
 extern "C" int mra_attention_impl_override(int32_t generic) {
     set_attention_impl_override(generic);
     return 0;

@@ -147,6 +147,17 @@ int launch_attention(const AttnArgs& a, cudaStream_t s);
 int launch_attention_pair(const AttnArgs* a, int n, cudaStream_t s, int* launches);   // n <= 2, one launch when possible
 void set_attention_impl_override(int generic);
 
+// fused Q/K/V projection + self-attention core for rows of 32 query + 32 text tokens in the split layout (qkv_attn.cu)
+struct QkvAttnArgs {
+    const void* x; int64_t ldx;      // bf16 [rows * 64, K]: the query tokens of all rows, then the text tokens of all rows
+    const void* w; int64_t ldw;      // bf16 [3 * heads * 64, K]: Q rows, K rows, V rows (the fused QKV Linear)
+    const float* bias;               // fp32 [3 * heads * 64] or NULL
+    void* ctx; int64_t ldo;          // bf16 [rows * 64, heads * 64] out, same row order as x
+    const float* add_mask;           // fp32 [rows, 64] added to the scaled scores, or NULL
+    int rows, heads, K;
+};
+int launch_qkv_attention(const QkvAttnArgs* a, int n, cudaStream_t s);   // n <= 2 problems in one launch
+
 int launch_layernorm(const float* x, const float* g, const float* b, float* y32, void* y16, int rows, int n, float eps,
                      cudaStream_t s);
 struct LnSegment {

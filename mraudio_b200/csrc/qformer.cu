@@ -23,6 +23,8 @@ struct mra_qformer {
                                                        // (slot `layers`: the projection's)
     bool fuse_ln = true;   // Linear + residual + LayerNorm in one cluster kernel (MRA_NO_FUSED_LN=1 disables: A/B runs)
     bool split_res = true; // with fuse_ln: residual stream as a bf16 (hi, lo) pair instead of fp32 (MRA_SPLIT_RESIDUAL=0 disables)
+    bool fuse_qkv_attn = true; // inference forward with 32 queries + 32 text tokens per row: QKV Linear + self-attention core in
+                               // one kernel, qkv never reaches HBM (qkv_attn.cu; MRA_FUSE_QKV_ATTN=0 disables: A/B runs)
     bool head_major = true; // inference forward: QKV / cross-K/V GEMMs write [head][token][64] for the attention kernel's TMA
                             // boxes (MRA_HEAD_MAJOR=0 disables: A/B runs); the save-for-backward forward keeps [token][heads * 64]
     // optional per-category device timing (CUDA events on the caller's stream), see mra_qformer_profile_*
@@ -199,6 +201,7 @@ extern "C" int mra_qformer_create(const mra_qformer_config* cfg, mra_qformer_t**
     if (getenv("MRA_NO_FUSED_LN")) h->fuse_ln = false;
     if (const char* e = getenv("MRA_SPLIT_RESIDUAL")) h->split_res = atoi(e) != 0;
     if (const char* e = getenv("MRA_HEAD_MAJOR")) h->head_major = atoi(e) != 0;
+    if (const char* e = getenv("MRA_FUSE_QKV_ATTN")) h->fuse_qkv_attn = atoi(e) != 0;
     *out = h;
     return 0;
 }
@@ -376,6 +379,9 @@ int forward_multi(int n, mra_qformer_t* const* hs, const mra_qformer_io* const* 
     // head-major Q / K / V: only the attention kernel reads these tensors in the inference forward (the backward's kernels
     // read the [token][heads * 64] form, so the save-for-backward forward keeps it)
     const bool hm = !save && c.hidden == c.heads * 64 && h0->gemm_impl == MRA_GEMM_IMPL_TCGEN05 && h0->head_major;
+    // QKV Linear + self-attention core in one kernel when every context has the 32 + 32 token geometry
+    bool fuse_qa = !save && c.hidden == c.heads * 64 && Nq == 32 && h0->gemm_impl == MRA_GEMM_IMPL_TCGEN05 && h0->fuse_qkv_attn;
+    for (int i = 0; i < n; ++i) fuse_qa = fuse_qa && cx[i].T == 32;
     GemmLnArgs gl[4];
     int ngl = 0;
     // residual = res32 (fp32) or, in split form, res_hi + res_lo; outputs y32 + y16 or y16 (hi) + y_lo
@@ -447,30 +453,43 @@ int forward_multi(int n, mra_qformer_t* const* hs, const mra_qformer_io* const* 
         const bool last = l == c.layers - 1;
         const bool cross = h0->cross_slot[l] >= 0;
         // ---- self-attention over queries || text
-        for (int i = 0; i < n; ++i) {
-            const auto& L = cx[i].h->w.layer[l];
-            const LayerBufs& B = cx[i].ws.layer[l];
-            add(B.xb, H, L.w_qkv, H, L.b_qkv, nullptr, 0, B.qkv, 3 * H, cx[i].Mtot, 3 * H, H, 0, 0);
-            if (hm && ng > 0) ga[ng - 1].c_head_major = 1;
-        }
-        MRA_TRY(flush(MRA_CAT_GEMM));
-        {
-            AttnArgs aa[MAX_CTX];
+        if (fuse_qa) {
+            QkvAttnArgs qa[MAX_CTX];
             for (int i = 0; i < n; ++i) {
+                const auto& L = cx[i].h->w.layer[l];
                 const LayerBufs& B = cx[i].ws.layer[l];
-                aa[i] = AttnArgs{B.qkv, 3 * H, B.qkv + H, 3 * H, B.qkv + 2 * H, 3 * H, B.ctx, H, cx[i].self_mask, cx[i].rows, c.heads,
-                                 cx[i].S, cx[i].S, Nq, 0};
-                if (hm) {   // qkv = [3 * heads][Mtot][64]: Q heads, then K heads, then V heads
-                    const int64_t hs = static_cast<int64_t>(cx[i].Mtot) * 64;
-                    aa[i].q = B.qkv; aa[i].k = B.qkv + c.heads * hs; aa[i].v = B.qkv + 2 * c.heads * hs;
-                    aa[i].ldq = aa[i].ldk = aa[i].ldv = 64;
-                    aa[i].hsq = aa[i].hsk = aa[i].hsv = hs;
-                }
-                aa[i].drop = dsite(DROP_SELF_PROBS, l);
+                qa[i] = QkvAttnArgs{B.xb, H, L.w_qkv, H, L.b_qkv, B.ctx, H, cx[i].self_mask, cx[i].rows, c.heads, H};
             }
-            span_begin(MRA_CAT_ATTENTION);
-            MRA_TRY(launch_attention_pair(aa, n, s, &launches));
+            span_begin(MRA_CAT_GEMM);
+            MRA_TRY(launch_qkv_attention(qa, n, s));
             span_end();
+            ++launches;
+        } else {
+            for (int i = 0; i < n; ++i) {
+                const auto& L = cx[i].h->w.layer[l];
+                const LayerBufs& B = cx[i].ws.layer[l];
+                add(B.xb, H, L.w_qkv, H, L.b_qkv, nullptr, 0, B.qkv, 3 * H, cx[i].Mtot, 3 * H, H, 0, 0);
+                if (hm && ng > 0) ga[ng - 1].c_head_major = 1;
+            }
+            MRA_TRY(flush(MRA_CAT_GEMM));
+            {
+                AttnArgs aa[MAX_CTX];
+                for (int i = 0; i < n; ++i) {
+                    const LayerBufs& B = cx[i].ws.layer[l];
+                    aa[i] = AttnArgs{B.qkv, 3 * H, B.qkv + H, 3 * H, B.qkv + 2 * H, 3 * H, B.ctx, H, cx[i].self_mask, cx[i].rows, c.heads,
+                                     cx[i].S, cx[i].S, Nq, 0};
+                    if (hm) {   // qkv = [3 * heads][Mtot][64]: Q heads, then K heads, then V heads
+                        const int64_t hs = static_cast<int64_t>(cx[i].Mtot) * 64;
+                        aa[i].q = B.qkv; aa[i].k = B.qkv + c.heads * hs; aa[i].v = B.qkv + 2 * c.heads * hs;
+                        aa[i].ldq = aa[i].ldk = aa[i].ldv = 64;
+                        aa[i].hsq = aa[i].hsk = aa[i].hsv = hs;
+                    }
+                    aa[i].drop = dsite(DROP_SELF_PROBS, l);
+                }
+                span_begin(MRA_CAT_ATTENTION);
+                MRA_TRY(launch_attention_pair(aa, n, s, &launches));
+                span_end();
+            }
         }
         for (int i = 0; i < n; ++i) {
             const auto& L = cx[i].h->w.layer[l];

@@ -153,6 +153,23 @@ def attention_head_major(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, rows
     return o
 
 
+def qkv_self_attention(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], rows: int,
+                       add_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Fused QKV Linear + self-attention core: x [rows*64, K] in the split layout (32 query tokens of every row, then the 32
+    text tokens of every row), weight [3*H, K]; returns ctx [rows*64, H] in the same row order."""
+    _need_cuda(x, weight, bias, add_mask)
+    assert x.dtype == weight.dtype == torch.bfloat16 and x.stride(1) == 1 and weight.stride(1) == 1
+    M, K = x.shape
+    H = weight.shape[0] // 3
+    assert M == rows * 64 and weight.shape == (3 * H, K) and H % 64 == 0
+    if add_mask is not None:
+        assert add_mask.dtype == torch.float32 and add_mask.shape == (rows, 64) and add_mask.is_contiguous()
+    ctx = torch.empty(M, H, device=x.device, dtype=torch.bfloat16)
+    check(lib.mra_qkv_attention_bf16(ptr(x), x.stride(0), ptr(weight), weight.stride(0), ptr(bias), ptr(add_mask), ptr(ctx),
+                                     ctx.stride(0), rows, H // 64, K, current_stream()))
+    return ctx
+
+
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float):
     """fp32 [rows, n] -> (fp32, bf16) LayerNorm outputs."""
     _need_cuda(x, gamma, beta)

@@ -382,6 +382,43 @@ def test_self_attention_head_major_equals_row_major(rows, Nq, T, attn_impl):
     assert torch.equal(o, ref)
 
 
+@pytest.mark.parametrize("rows,heads,K,masked", [(1, 12, 768, False), (2, 12, 768, True), (3, 12, 768, True), (4, 12, 768, False),
+                                                 (5, 4, 256, True), (37, 12, 768, True), (256, 12, 768, True)])
+def test_fused_qkv_attention_equals_linear_then_attention(rows, heads, K, masked):
+    """csrc/qkv_attn.cu: the QKV Linear and the self-attention core in one kernel (Q / K / V stay in shared memory) computes
+    exactly what the two launches it replaces compute: same fp32 accumulation + bias + bf16 rounding of q / k / v, same
+    flash step.  Covers clip blocks cut at the tail (rows not a multiple of 4 / 2), a second geometry, and the text mask."""
+    from mraudio_b200 import ops
+    H = heads * 64
+    g = torch.Generator().manual_seed(rows * 7 + heads)
+    x = torch.randn(rows * 64, K, generator=g).to(_dev(), torch.bfloat16)          # split layout: query rows, then text rows
+    w = (torch.randn(3 * H, K, generator=g) * 0.05).to(_dev(), torch.bfloat16)
+    b = (torch.randn(3 * H, generator=g) * 0.5).to(_dev())
+    mask = None
+    if masked:
+        mask = torch.zeros(rows, 64)
+        mask[rows // 2, 32 + 11:] = -10000.0
+        mask[0, 60:] = -10000.0
+        mask = mask.to(_dev())
+    guard = torch.full((rows * 64 + 16, H), 3.0, device=_dev(), dtype=torch.bfloat16)
+    qkv = ops.linear(x, w, b)
+    ref = ops.attention(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], rows, heads, 64, 64, 32, False, mask)
+    got = ops.qkv_self_attention(x, w, b, rows, mask)
+    assert torch.equal(got, ref)
+    # nothing written outside [rows * 64, H], also when the last clip block is cut
+    from mraudio_b200 import _lib
+    out = guard[8:8 + rows * 64]
+    _lib.check(_lib.lib.mra_qkv_attention_bf16(_lib.ptr(x), K, _lib.ptr(w), K, _lib.ptr(b), _lib.ptr(mask), out.data_ptr(), H, rows,
+                                               heads, K, _lib.current_stream()))
+    assert torch.equal(out, ref) and bool((guard[:8] == 3.0).all()) and bool((guard[8 + rows * 64:] == 3.0).all())
+    # against the fp32 definition
+    xs = torch.cat([x[:rows * 32].view(rows, 32, K), x[rows * 32:].view(rows, 32, K)], 1).float()
+    full = xs @ w.float().t() + b
+    r32 = _ref_attention(full[..., :H], full[..., H:2 * H], full[..., 2 * H:], mask, heads)
+    got3 = torch.cat([got[:rows * 32].view(rows, 32, H), got[rows * 32:].view(rows, 32, H)], 1)
+    assert _rel(got3, r32) < 1.5e-2
+
+
 def test_attention_unaligned_output_rows_take_the_narrow_store_path():
     """Output rows that are not 16-byte aligned cannot leave as 128-byte lines: same values through the 4-byte stores."""
     from mraudio_b200 import _lib, ops

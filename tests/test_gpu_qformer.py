@@ -142,6 +142,37 @@ def test_split_residual_stream_matches_fp32_residual_stream(monkeypatch):
     assert not torch.equal(outs["1"][0], outs["0"][0])   # the two modes really ran different kernels
 
 
+@pytest.mark.parametrize("rows", [3, 10])
+def test_fused_qkv_attention_forward_equals_unfused_forward(monkeypatch, rows):
+    """The inference forward runs the QKV Linear + self-attention core as one kernel when every row has 32 + 32 tokens
+    (csrc/qkv_attn.cu) and hands head-major Q / K / V to the attention kernel otherwise (MRA_FUSE_QKV_ATTN=0; row-major with
+    MRA_HEAD_MAJOR=0).  All three forms compute identical values: the outputs are bit-equal."""
+    cfg = qo.QFormerOracleConfig(encoder_width=1408, num_hidden_layers=4)
+    w = qo.init_qformer_weights(cfg, seed=7, randomize_ln_and_bias=True, llm_dim=512)
+    g = torch.Generator().manual_seed(8)
+    T, Nk = 32, 257
+    enc = torch.randn(rows, Nk, 1408, generator=g).to(torch.bfloat16)
+    ids = torch.randint(1000, 30000, (rows, T), generator=g)
+    atts = torch.ones(rows, 32 + T, dtype=torch.long)
+    atts[1, 32 + 20:] = 0
+    outs, launches = {}, {}
+    for mode in (("1", "1"), ("0", "1"), ("0", "0")):
+        monkeypatch.setenv("MRA_FUSE_QKV_ATTN", mode[0])
+        monkeypatch.setenv("MRA_HEAD_MAJOR", mode[1])
+        model, proj = _build(cfg, w, llm_dim=512)
+        with torch.no_grad():
+            o = model.bert(ids.cuda(), attention_mask=atts.cuda(), query_embeds=w["query_tokens"].cuda(),
+                           encoder_hidden_states=enc.cuda(), return_dict=True, llm_proj=proj)
+        outs[mode] = (o.last_hidden_state.float().cpu(), o.llm_inputs.float().cpu())
+        launches[mode] = model.bert.last_launches
+    assert launches[("1", "1")] == launches[("0", "1")] - cfg.num_hidden_layers    # one launch less per layer
+    for mode in (("0", "1"), ("0", "0")):
+        assert torch.equal(outs[mode][0], outs[("1", "1")][0]) and torch.equal(outs[mode][1], outs[("1", "1")][1]), mode
+    with torch.no_grad():
+        ref32 = qo.qformer_bert(w, cfg, ids, atts, w["query_tokens"], enc.float(), None)
+    assert _rel(outs[("1", "1")][0][:, :32], ref32[:, :32]) < TOL_FP32_REF
+
+
 def test_forward_is_deterministic_and_linear_in_projection():
     cfg = qo.QFormerOracleConfig(encoder_width=768, num_hidden_layers=2)
     w = qo.init_qformer_weights(cfg, seed=0, llm_dim=256)
