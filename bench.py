@@ -80,14 +80,17 @@ def load_ncu_traffic():
     if best is None:
         return None, None
     path, rows = best
-    plain = ["cross_kv_video (gemm_tc_kernel, 2-CTA MMA)", "cross_kv_audio (gemm_tc_kernel, 2-CTA MMA)", "qkv_grouped (gemm_tc_kernel)",
-             "cross_q (gemm_tc_kernel)"]
+    fused_qa = any("qkv_attn_kernel" in r["Kernel Name"] for r in rows)   # QKV Linear + self-attention core in one kernel
+    plain = ["cross_kv_video (gemm_tc_kernel, 2-CTA MMA)", "cross_kv_audio (gemm_tc_kernel, 2-CTA MMA)"] + \
+            ([] if fused_qa else ["qkv_grouped (gemm_tc_kernel)"]) + ["cross_q (gemm_tc_kernel)"]
     lns = ["attn_out+LN (gemm_ln_kernel)", "cross_out+LN (gemm_ln_kernel)", "ffn_down+LN (gemm_ln_kernel)"]
-    atts = ["self_attention (attention_tma_kernel<4>)", "cross_attention (attention_tma_kernel<2>)"]
+    atts = ([] if fused_qa else ["self_attention (attention_tma_kernel<4>)"]) + ["cross_attention (attention_tma_kernel<2>)"]
     out = {}
     for r in rows:
         k = r["Kernel Name"]
-        if "gemm_ln_kernel" in k:
+        if "qkv_attn_kernel" in k:
+            name = "qkv+self_attention (qkv_attn_kernel)" if "qkv+self_attention (qkv_attn_kernel)" not in out else None
+        elif "gemm_ln_kernel" in k:
             name = lns.pop(0) if lns else None
         elif "gemm_tc_kernel<256, 6, 1," in k:
             name = "ffn_up GELU (gemm_tc_kernel)" if "ffn_up GELU (gemm_tc_kernel)" not in out else None
@@ -409,7 +412,7 @@ def run_b200(args):
         lin, core, kv = lin + a * clips, core + b * clips, kv + c * clips
     dead = dead_text_ffn_flops_per_row(T) * clips * len(MODAL)       # skipped by the CUDA path (both modalities)
     lin_exec = lin - dead
-    # dominant kernel = gemm_tc_kernel + gemm_ln_kernel (every Linear); per-launch figures are flops-weighted over a step
+    # dominant kernel = gemm_tc_kernel + gemm_ln_kernel + qkv_attn_kernel (every Linear); per-launch figures are flops-weighted over a step
     gemm_ms = (prof_ms[0] + prof_ms[1]) / args.steps
     gemm_n = (prof_n[0] + prof_n[1]) // args.steps
     burst, sustained = peaks["bf16_tflops"], peaks["bf16_tflops_sustained"]
@@ -443,14 +446,15 @@ def run_b200(args):
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
                      "frac_of_sustained_peak": achieved / sustained, "peak_sustained": sustained,
                      "achieved_note": "EXECUTED Linear flops of a step (algorithmic minus the skipped dead text FFN) / CUDA-event time of "
-                                      "all gemm_tc_kernel + gemm_ln_kernel launches of the step",
+                                      "all gemm_tc_kernel + gemm_ln_kernel + qkv_attn_kernel launches of the step (the last one also computes the self-attention core, "
+                                      "whose flops are NOT in the numerator)",
                      "traffic": (ncu_caps or {}).get("cross_kv_video (gemm_tc_kernel, 2-CTA MMA)", {}).get("dram_bytes_per_launch"),
                      "traffic_note": f"dram read+write bytes of the largest launch (cross-K/V GEMM, video: 1.42 GB algorithmic) from "
                                      f"{ncu_src}; other captured launch types in ncu_captures",
                      "ncu_captures": ncu_caps,
                      "peak_source": peak_src + ": burst figure as the denominator (the 0.1-0.2 s timed region runs near burst clocks); "
                                                "the sustained figure is given beside it",
-                     "kernel": "tcgen05 Linear kernels gemm_tc_kernel + gemm_ln_kernel (all launches of a step, flops-weighted)",
+                     "kernel": "tcgen05 Linear kernels gemm_tc_kernel + gemm_ln_kernel + qkv_attn_kernel (all launches of a step, flops-weighted)",
                      "launches_per_step": gemm_n, "ms_per_step_in_kernel": gemm_ms, "ms_per_step_instrumented": ms_instr,
                      "executed_tflop_per_step": lin_exec / 1e12, "algorithmic_tflop_per_step": lin / 1e12,
                      "cross_kv_launch": {"tflop": kv / 1e12, "ms": kv_ms, "achieved": kv / (kv_ms * 1e-3) / 1e12 if kv_ms else 0.0}},

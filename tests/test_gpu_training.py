@@ -214,7 +214,9 @@ def test_train_then_validate_then_train_uses_live_weights():
     for it in range(4):
         la = a.train_step(feats, ids, mask, surrogate=sur)
         lb = b.train_step(feats, ids, mask, surrogate=sur)
-        assert torch.allclose(la, lb, rtol=1e-4), (it, la.item(), lb.item())
+        # (from the third step on two identical trainers differ by the order of the gradient reduce-adds: see the note in
+        #  test_overlapped_optimizer_matches_one_pass_training)
+        assert torch.allclose(la, lb, rtol=1e-4 if it < 2 else 1e-3), (it, la.item(), lb.item())
         with torch.no_grad():
             inf, _ = a.model.encode_modalities(feats, ids, mask)
             trn, _ = a.forward_modalities(feats, ids, mask)
@@ -313,10 +315,14 @@ def test_overlapped_optimizer_matches_one_pass_training():
     feats, ids, mask, sur = _small_batch()
     a, b = _small_trainer(lr=1e-4), _small_trainer(lr=1e-4)
     a.overlap_optimizer, b.overlap_optimizer = True, False
+    # Tolerance = the run-to-run noise of ONE path: the weight gradients are summed by TMA reduce-add (split-K), whose order is
+    # not fixed, so two identical trainers drift apart from the third step on (measured over 6 x 2 runs on a B200: steps 0 / 1
+    # bit-equal, later steps up to 9.6e-5 relative for the same path twice, up to 1.2e-4 overlapped vs one-pass).  A missing
+    # stream dependency lets Adam read half-written gradients: orders of magnitude above this.
     for it in range(5):
         la = a.train_step(feats, ids, mask, surrogate=sur)
         lb = b.train_step(feats, ids, mask, surrogate=sur)
-        assert torch.allclose(la, lb, rtol=1e-4), (it, la.item(), lb.item())
+        assert torch.allclose(la, lb, rtol=1e-6 if it < 2 else 1e-3), (it, la.item(), lb.item())
     torch.cuda.synchronize()
     for m in a.states:
         assert a.states[m].step_count == b.states[m].step_count == 5
