@@ -746,6 +746,51 @@ extern "C" int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, 
         return 0;
     };
 
+    // FFN_query and FFN_text backward of one layer TOGETHER (rows [0, Mq) and [Mq, Mq + Mt), Mq == Mt): the two chains are
+    // independent and have the same shapes, so every GEMM of the pair is ONE grouped launch (gemm.cu takes up to four problems
+    // with their own operands): 4 launches fewer per layer; the step is bound by its ~800 small launches (profiles/r02_NOTES.md)
+    auto gemm2 = [&](GemmArgs a0, GemmArgs a1) -> int {
+        GemmArgs pair[2] = {a0, a1};
+        return launch_gemm_tc_grouped(pair, 2, s);
+    };
+    auto ffn_bwd_pair = [&](const LayerBufs& B, const __nv_bfloat16* in16_q, const mra_qformer_layer_weights& LW, const mra_qformer_layer_grads& G,
+                            int layer) -> int {
+        const size_t o = static_cast<size_t>(Mq) * H, oi = static_cast<size_t>(Mq) * I;
+        const DropoutParams dout = dsite(DROP_FFN_OUT, layer);
+        if (int e = ln_bwd(bw.g_x, B.pre_f, LW.ln_fq_g, G.ln_fq_g, G.ln_fq_b, G.b_fq2, 0, Mq, dout, no_drop)) return e;
+        if (int e = ln_bwd(bw.g_x, B.pre_f, LW.ln_ft_g, G.ln_ft_g, G.ln_ft_b, G.b_ft2, Mq, Mt, dout, no_drop)) return e;
+        {   // dW2 += d_pre^T inter  (query | text)
+            GemmArgs a{bw.g_pre16, H, B.inter, I, nullptr, G.w_fq2, I, G.w_fq2, I, H, I, Mq, 0, 1};
+            GemmArgs b{bw.g_pre16 + o, H, B.inter + oi, I, nullptr, G.w_ft2, I, G.w_ft2, I, H, I, Mt, 0, 1};
+            a.tn = b.tn = 1;
+            MRA_TRY(gemm2(a, b));
+        }
+        {   // d_inter = d_pre W2
+            GemmArgs a{bw.g_pre16, H, LW.w_fq2, I, nullptr, nullptr, 0, bw.g_big16, I, Mq, I, H, 0, 0};
+            GemmArgs b{bw.g_pre16 + o, H, LW.w_ft2, I, nullptr, nullptr, 0, bw.g_big16 + oi, I, Mt, I, H, 0, 0};
+            a.tn = b.tn = 2;
+            MRA_TRY(gemm2(a, b));
+        }
+        if (G.b_fq1 != nullptr) MRA_TRY(launch_gelu_bwd_colsum(B.z, bw.g_big16, bw.g_big2, G.b_fq1, Mq, I, s));   // dz (+ db1)
+        else MRA_TRY(launch_gelu_bwd(B.z, bw.g_big16, bw.g_big2, static_cast<int64_t>(Mq) * I, s));
+        if (G.b_ft1 != nullptr) MRA_TRY(launch_gelu_bwd_colsum(B.z + oi, bw.g_big16 + oi, bw.g_big2 + oi, G.b_ft1, Mt, I, s));
+        else MRA_TRY(launch_gelu_bwd(B.z + oi, bw.g_big16 + oi, bw.g_big2 + oi, static_cast<int64_t>(Mt) * I, s));
+        {   // dW1 += dz^T x
+            GemmArgs a{bw.g_big2, I, in16_q, H, nullptr, G.w_fq1, H, G.w_fq1, H, I, H, Mq, 0, 1};
+            GemmArgs b{bw.g_big2 + oi, I, B.ab + o, H, nullptr, G.w_ft1, H, G.w_ft1, H, I, H, Mt, 0, 1};
+            a.tn = b.tn = 1;
+            MRA_TRY(gemm2(a, b));
+        }
+        {   // d_x = dz W1 + the residual path
+            GemmArgs a{bw.g_big2, I, LW.w_fq1, H, nullptr, bw.g_pre32, H, bw.g_a, H, Mq, H, I, 0, 1};
+            GemmArgs b{bw.g_big2 + oi, I, LW.w_ft1, H, nullptr, bw.g_pre32 + o, H, bw.g_a + o, H, Mt, H, I, 0, 1};
+            a.tn = b.tn = 2;
+            MRA_TRY(gemm2(a, b));
+        }
+        return 0;
+    };
+    static const bool pair_ffn = [] { const char* e = getenv("MRA_BWD_PAIR_FFN"); return e == nullptr || atoi(e) != 0; }();
+
     // ---- llm_proj
     const __nv_bfloat16* dl = reinterpret_cast<const __nv_bfloat16*>(d_llm);
     if (int e = wgrad(dl, D, ws.layer[c.layers].xb, H, Mq, D, H, g->w_proj, H, g->b_proj)) return e;
@@ -765,6 +810,11 @@ extern "C" int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, 
         const bool last = l == c.layers - 1;
         const bool cross = h->cross_slot[l] >= 0;
         // ---- FFN_query (rows < Mq) and FFN_text
+        const bool text_ffn = Mt > 0 && !(last && skip_dead);
+        if (pair_ffn && text_ffn && Mt == Mq) {
+            MRA_REQUIRE(LT.w_ft1 && LT.w_ft2 && G.w_ft1 && G.w_ft2, "layer %d: text FFN weights / grads missing", l);
+            if (int e = ffn_bwd_pair(B, cross ? B.ab2 : B.ab, L, G, l)) return e;
+        } else {
         if (int e = ffn_bwd(B, cross ? B.ab2 : B.ab, 0, Mq, LT.w_fq1, LT.w_fq2, L.ln_fq_g, G.w_fq1, G.b_fq1, G.w_fq2, G.b_fq2,
                             G.ln_fq_g, G.ln_fq_b, l)) return e;
         if (Mt > 0) {
@@ -777,6 +827,7 @@ extern "C" int mra_qformer_backward(mra_qformer_t* h, const mra_qformer_io* io, 
                 if (int e = ffn_bwd(B, B.ab, Mq, Mt, LT.w_ft1, LT.w_ft2, L.ln_ft_g, G.w_ft1, G.b_ft1, G.w_ft2, G.b_ft2,
                                     G.ln_ft_g, G.ln_ft_b, l)) return e;
             }
+        }
         }
         // ---- cross-attention block (query rows): g_a[:Mq] is the gradient w.r.t. LN_c's output
         if (cross) {
