@@ -22,6 +22,7 @@ do not finish).
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -290,11 +291,14 @@ def run_b200(args):
 
     def timed(fn, steps):
         barrier()
+        gc.collect()
+        gc.disable()     # (as timeit does) no generational collection pause of the host thread inside a timed region
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             fn()
         e1.record()
+        gc.enable()
         barrier()
         return max_over_ranks(e0.elapsed_time(e1)) / steps
 
@@ -316,9 +320,14 @@ def run_b200(args):
     pipe = model.host_pipeline(B, F, {m: v[0] for m, v in MODAL.items()}, T, slots=int(os.environ.get("MRA_BENCH_SLOTS", "2")))
     set_profile(_lib.PROFILE_OFF)
 
+    submit_ms = []     # host time of every submit of the last e2e_steps() call (diagnosis: MRA_BENCH_TRACE=1 prints it)
+
     def e2e_steps(n):
+        submit_ms.clear()
         for i in range(n):
+            t0 = time.perf_counter()
             pipe.submit(host_feats, ids_h, mask_h)
+            submit_ms.append((time.perf_counter() - t0) * 1e3)
         pipe.drain()
 
     # PCIe / host-memory probes: pinned host -> device and back.  "solo" = this rank alone on the bus (ranks take turns);
@@ -372,10 +381,17 @@ def run_b200(args):
 
     e2e_steps(max(2, args.warmup))
     barrier()
+    gc.collect()
+    gc.disable()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t_host0 = time.perf_counter()
     e2e_steps(args.steps)          # drain() makes the current stream wait for the last D2H copy
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps
+    if os.environ.get("MRA_BENCH_TRACE") and rank == 0:
+        print("[bench trace] host ms per submit:", " ".join(f"{x:.1f}" for x in submit_ms), file=sys.stderr)
     e1.record()
+    gc.enable()
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     t_clock1 = time.time()
@@ -469,7 +485,7 @@ def run_b200(args):
                 "copy_bound_ms_per_step": copy_bound_solo,
                 "copy_bound_ms_per_step_concurrent": copy_bound_conc,
                 "bound_ms_per_step": e2e_bound,
-                "frac_of_bound": e2e_bound / ms_e2e,
+                "frac_of_bound": e2e_bound / ms_e2e, "host_enqueue_ms_per_step": host_enqueue_ms,
                 "bound_note": "lower bound of an end-to-end step = max(device step, bytes / concurrent copy bandwidth of the slower "
                               "direction with both directions active on all ranks)",
                 "host_cpu_binding": numa,

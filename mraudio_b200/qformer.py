@@ -294,9 +294,11 @@ class BertModelB200(nn.Module):
     # ------------------------------------------------------------------------------------------------------- forward
     def prepare(self, input_ids=None, attention_mask=None, position_ids=None, query_embeds=None, encoder_hidden_states=None,
                 encoder_attention_mask=None, llm_proj: nn.Linear = None, need_last_hidden: bool = True,
-                skip_dead_text_ffn: bool = False, llm_scatter=None):
+                skip_dead_text_ffn: bool = False, llm_scatter=None, llm_out=None):
         """``llm_scatter = (view [bs, F, Nq, D] into inputs_embeds)``: llm_proj writes each frame's tokens into that strided
         view (4-D TMA store, see ``mraudio_b200/prompt.py``) instead of a dense ``[rows*Nq, D]`` tensor.
+        ``llm_out``: caller-owned bf16 ``[rows*Nq, D]`` buffer for the projected tokens (streaming callers that reuse their
+        buffers: no allocation per call, see ``HostPipeline``).
 
         Validate the arguments of one ``Qformer.bert(...)`` call and stage everything the C-ABI needs (handle, packed
         weights, io struct, workspace, output tensors) without launching.  ``launch_prepared`` enqueues one or two such
@@ -363,7 +365,13 @@ class BertModelB200(nn.Module):
             llm_out, llm_view = v, v
             scatter = dict(llm_frames=v.shape[1], llm_ld=v.stride(2), llm_frame_stride=v.stride(1), llm_video_stride=v.stride(0))
         else:
-            llm_out = torch.empty(rows * Nq, llm_dim, device=dev, dtype=torch.bfloat16) if llm_proj is not None else None
+            if llm_out is not None:
+                if llm_proj is None or llm_out.dtype != torch.bfloat16 or llm_out.device != dev or not llm_out.is_contiguous() or \
+                        llm_out.numel() != rows * Nq * llm_dim:
+                    raise ValueError(f"llm_out must be a contiguous bf16 buffer of {rows * Nq} x {llm_dim} elements on {dev}")
+                llm_out = llm_out.view(rows * Nq, llm_dim)
+            else:
+                llm_out = torch.empty(rows * Nq, llm_dim, device=dev, dtype=torch.bfloat16) if llm_proj is not None else None
             llm_view = llm_out.view(rows, Nq, llm_dim) if llm_out is not None else None
         io = _lib.QFormerIO(enc=enc_b.data_ptr(), input_ids=_lib.ptr(ids), attn_mask=_lib.ptr(tmask), enc_mask=_lib.ptr(emask),
                             query_embeds=qe.data_ptr(), q_rows=q_rows, rows=rows, T=T, Nk=Nk, flags=flags,

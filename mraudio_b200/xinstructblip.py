@@ -183,7 +183,7 @@ class XInstructBLIPQFormers(nn.Module):
     def encode_modalities(self, feats: Dict[str, Features], input_ids: torch.Tensor, attention_mask: torch.Tensor,
                           apply_ln: bool = False, match_reference_text_tiling: bool = True,
                           need_last_hidden: bool = False, prompt: Optional["prompt_mod.PromptPieces"] = None,
-                          scatter_epilogue: bool = True):
+                          scatter_epilogue: bool = True, out: Optional[Dict[str, torch.Tensor]] = None):
         """Returns ``(inputs_llm, atts_llm)`` dicts exactly as :296-306 builds them.
 
         input_ids / attention_mask: ``text_Qformer.input_ids`` / ``.attention_mask`` ``[bs, T]`` (:233-239).
@@ -192,6 +192,9 @@ class XInstructBLIPQFormers(nn.Module):
         ``(inputs_embeds [bs, L, D], attention_mask [bs, L])`` -- what :388-392 hands to ``llm_model.generate``: the
         llm_proj epilogue writes the query tokens straight into their slots (``scatter_epilogue``; off = dense outputs +
         copy, kept for the parity test) and one more launch copies the text pieces.
+
+        ``out``: per-modality caller-owned bf16 buffers ``[bs, F*32, D]`` the projected tokens are written into (streaming
+        callers; the returned ``inputs_llm`` are views of them).
         """
         inputs_llm, atts_llm = {}, {}
         todo = [m for m in self.modalities if m in feats]
@@ -225,7 +228,8 @@ class XInstructBLIPQFormers(nn.Module):
                                               encoder_hidden_states=enc, encoder_attention_mask=None, llm_proj=proj,
                                               need_last_hidden=need_last_hidden, skip_dead_text_ffn=not need_last_hidden,
                                               llm_scatter=prompt_mod.query_slot_view(embeds, lay, modality)
-                                              if lay is not None and scatter_epilogue else None))
+                                              if lay is not None and scatter_epilogue else None,
+                                              llm_out=out[modality] if out is not None and lay is None else None))
             shapes.append((bs, num))
         # Both Q-Formers share the layer geometry: run them in lockstep, every Linear as ONE grouped GEMM launch over
         # (video queries, video text, audio queries, audio text) -- see mra_qformer_forward_multi.
@@ -275,10 +279,11 @@ class HostPipeline:
         nq, D = model.num_query_token, model.llm_hidden_size
         for _ in range(slots):
             sl = HostPipeline._Slot()
-            sl.feats, sl.out_host = {}, {}
+            sl.feats, sl.out_dev, sl.out_host = {}, {}, {}
             for m in model.modalities:
                 W = getattr(model, f"{m}_Qformer").config.encoder_width
                 sl.feats[m] = torch.empty(bs, frames, tokens[m], W, device=dev, dtype=torch.bfloat16)
+                sl.out_dev[m] = torch.empty(bs, frames * nq, D, device=dev, dtype=torch.bfloat16)
                 sl.out_host[m] = torch.empty(bs, frames * nq, D, dtype=torch.bfloat16).pin_memory()
             sl.ids = torch.empty(bs, text_len, device=dev, dtype=torch.long)
             sl.mask = torch.empty(bs, text_len, device=dev, dtype=torch.long)
@@ -296,7 +301,7 @@ class HostPipeline:
         main = torch.cuda.current_stream(self.dev)
         if sl.used:
             self.copy_in.wait_event(sl.compute_done)   # the previous batch in this slot has been consumed
-            self.copy_out.wait_event(sl.out_done)
+            main.wait_event(sl.out_done)               # ... and its projected tokens have left the slot's device buffers
         with torch.cuda.stream(self.copy_in):
             for m, t in host_feats.items():
                 sl.feats[m].copy_(t, non_blocking=True)
@@ -305,13 +310,15 @@ class HostPipeline:
             sl.in_done.record(self.copy_in)
         main.wait_event(sl.in_done)
         with torch.no_grad():
-            inputs_llm, _ = self.model.encode_modalities(sl.feats, sl.ids, sl.mask)
+            # the projections write into this slot's own device buffers: no output allocation per batch (fresh tensors handed
+            # to another stream keep their blocks reserved until that stream catches up, and a host that runs ahead of the
+            # device then sends the caching allocator to cudaMalloc in the middle of the stream: stalls of 10-80 ms per call)
+            inputs_llm, _ = self.model.encode_modalities(sl.feats, sl.ids, sl.mask, out=sl.out_dev)
         sl.compute_done.record(main)
         self.copy_out.wait_event(sl.compute_done)
         with torch.cuda.stream(self.copy_out):
             for m, y in inputs_llm.items():
                 sl.out_host[m].copy_(y, non_blocking=True)
-                y.record_stream(self.copy_out)
             sl.out_done.record(self.copy_out)
         sl.used = True
         return sl

@@ -173,6 +173,49 @@ def test_fused_qkv_attention_forward_equals_unfused_forward(monkeypatch, rows):
     assert _rel(outs[("1", "1")][0][:, :32], ref32[:, :32]) < TOL_FP32_REF
 
 
+def test_host_pipeline_streams_batches_through_reused_slots():
+    """``HostPipeline`` (pinned host features -> H2D -> both Q-Formers -> D2H into pinned host buffers, three streams, two
+    slots whose device buffers are reused without per-batch allocation): five different batches submitted back to back --
+    more than there are slots, the host far ahead of the device -- each come out equal to ``encode_modalities`` on the same
+    batch, and nothing is allocated on the device after the first round through the slots."""
+    from mraudio_b200.xinstructblip import XInstructBLIPQFormers
+    torch.manual_seed(0)
+    widths = {"video": 1408, "audio": 768}
+    model = XInstructBLIPQFormers(modalities=("video", "audio"), encoder_num_features=widths, llm_hidden_size=512,
+                                  num_hidden_layers=2).cuda().eval()
+    bs, Fr, T = 2, 4, 32
+    tokens = {"video": 257, "audio": 64}
+    pipe = model.host_pipeline(bs, Fr, tokens, T, slots=2)
+    g = torch.Generator().manual_seed(9)
+    batches = []
+    for i in range(5):
+        feats = {m: torch.randn(bs, Fr, tokens[m], widths[m], generator=g).to(torch.bfloat16).pin_memory() for m in tokens}
+        ids = torch.randint(1000, 30000, (bs, T), generator=g).pin_memory()
+        mask = torch.ones(bs, T, dtype=torch.long)
+        mask[i % bs, 7 + i:] = 0
+        batches.append((feats, ids, mask.pin_memory()))
+    outs, allocated = [], []
+    for feats, ids, mask in batches:
+        sl = pipe.submit(feats, ids, mask)
+        allocated.append(torch.cuda.memory_allocated())
+        # a consumer reads a slot's pinned output once that slot's D2H event has completed (before the slot comes round again)
+        sl.out_done.synchronize()
+        outs.append({m: t.clone() for m, t in sl.out_host.items()})
+    assert allocated[2] == allocated[3] == allocated[4]          # steady state: no device allocation per batch
+    assert pipe.h2d_bytes == sum(t.numel() * 2 for t in batches[0][0].values()) + 2 * bs * T * 8
+    assert pipe.d2h_bytes == 2 * bs * Fr * 32 * 512 * 2
+    for (feats, ids, mask), out in zip(batches, outs):
+        with torch.no_grad():
+            ref, _ = model.encode_modalities({m: t.cuda() for m, t in feats.items()}, ids.cuda(), mask.cuda())
+        for m in ref:
+            assert torch.equal(out[m], ref[m].cpu()), m
+    # without waiting in between: the slots' events alone order reuse (batch i + 2 overwrites slot i only after its D2H)
+    last = [pipe.submit(*b) for b in batches]
+    torch.cuda.synchronize()
+    for m in outs[4]:
+        assert torch.equal(last[4].out_host[m], outs[4][m]) and torch.equal(last[3].out_host[m], outs[3][m])
+
+
 def test_forward_is_deterministic_and_linear_in_projection():
     cfg = qo.QFormerOracleConfig(encoder_width=768, num_hidden_layers=2)
     w = qo.init_qformer_weights(cfg, seed=0, llm_dim=256)
