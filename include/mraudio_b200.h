@@ -118,6 +118,11 @@ typedef struct mra_qformer_io {
     float dropout_p;
     uint32_t reserved1;
     uint64_t dropout_seed;
+    /* Optional cudaEvent_t: `enc` is still being produced (e.g. copied from the host on another stream) when the call is
+     * made; the forward makes its stream wait for the event in front of the first kernel that reads `enc` (the stacked
+     * cross-attention K/V projection), so the embeddings and -- in a lockstep call -- the other Q-Former's projection need
+     * not wait for it.  NULL = `enc` is ready in stream order. */
+    void* enc_ready;
 } mra_qformer_io;
 
 /* Replaces `{modality}_Qformer.bert(input_ids, attention_mask=, query_embeds=, encoder_hidden_states=,

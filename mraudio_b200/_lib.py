@@ -61,7 +61,8 @@ class QFormerIO(C.Structure):
                 ("query_embeds", C.c_void_p), ("q_rows", C.c_int32), ("rows", C.c_int32), ("T", C.c_int32),
                 ("Nk", C.c_int32), ("flags", C.c_uint32), ("last_hidden", C.c_void_p), ("llm_out", C.c_void_p),
                 ("llm_frames", C.c_int32), ("reserved0", C.c_int32), ("llm_ld", C.c_int64), ("llm_frame_stride", C.c_int64),
-                ("llm_video_stride", C.c_int64), ("dropout_p", C.c_float), ("reserved1", C.c_uint32), ("dropout_seed", C.c_uint64)]
+                ("llm_video_stride", C.c_int64), ("dropout_p", C.c_float), ("reserved1", C.c_uint32), ("dropout_seed", C.c_uint64),
+                ("enc_ready", C.c_void_p)]
 
 
 MAX_PROMPT_SEGMENTS = 16

@@ -444,6 +444,8 @@ int forward_multi(int n, mra_qformer_t* const* hs, const mra_qformer_io* const* 
             x.enc_mask = x.ws.enc_mask;
         }
         const int Wd = x.h->cfg.enc_width;
+        // first reader of the encoder tokens: they may still be on their way (mra_qformer_io::enc_ready)
+        if (x.io->enc_ready) MRA_CHECK_CUDA(cudaStreamWaitEvent(s, reinterpret_cast<cudaEvent_t>(x.io->enc_ready), 0));
         add(x.io->enc, Wd, W.w_ckv, Wd, W.b_ckv, nullptr, 0, x.ws.kv, x.kv_ld, x.rows * x.Nk, x.kv_ld, Wd, 0, 0);
         if (hm && ng > 0) ga[ng - 1].c_head_major = 1;
         MRA_TRY(flush(MRA_CAT_GEMM_CROSS_KV));

@@ -294,11 +294,12 @@ class BertModelB200(nn.Module):
     # ------------------------------------------------------------------------------------------------------- forward
     def prepare(self, input_ids=None, attention_mask=None, position_ids=None, query_embeds=None, encoder_hidden_states=None,
                 encoder_attention_mask=None, llm_proj: nn.Linear = None, need_last_hidden: bool = True,
-                skip_dead_text_ffn: bool = False, llm_scatter=None, llm_out=None):
+                skip_dead_text_ffn: bool = False, llm_scatter=None, llm_out=None, enc_ready=None):
         """``llm_scatter = (view [bs, F, Nq, D] into inputs_embeds)``: llm_proj writes each frame's tokens into that strided
         view (4-D TMA store, see ``mraudio_b200/prompt.py``) instead of a dense ``[rows*Nq, D]`` tensor.
         ``llm_out``: caller-owned bf16 ``[rows*Nq, D]`` buffer for the projected tokens (streaming callers that reuse their
-        buffers: no allocation per call, see ``HostPipeline``).
+        buffers: no allocation per call, see ``HostPipeline``).  ``enc_ready``: a recorded ``torch.cuda.Event`` after which
+        ``encoder_hidden_states`` is valid (it is being copied in on another stream): only the kernels that read it wait.
 
         Validate the arguments of one ``Qformer.bert(...)`` call and stage everything the C-ABI needs (handle, packed
         weights, io struct, workspace, output tensors) without launching.  ``launch_prepared`` enqueues one or two such
@@ -319,6 +320,9 @@ class BertModelB200(nn.Module):
         Nq = query_embeds.shape[1]
         if Nq != cfg.query_length:
             raise ValueError(f"query_embeds has {Nq} tokens, config.query_length is {cfg.query_length}")
+        if enc_ready is not None and (enc.dtype != torch.bfloat16 or not enc.is_contiguous()):
+            torch.cuda.current_stream(dev).wait_event(enc_ready)    # the conversion below reads it: wait here instead
+            enc_ready = None
         enc_b = enc.to(torch.bfloat16).contiguous()
         q_rows = query_embeds.shape[0]
         # ``query_tokens.expand(bs,-1,-1).repeat(F,1,1)`` (:229,289) materialises identical rows: detect the broadcast
@@ -375,9 +379,10 @@ class BertModelB200(nn.Module):
             llm_view = llm_out.view(rows, Nq, llm_dim) if llm_out is not None else None
         io = _lib.QFormerIO(enc=enc_b.data_ptr(), input_ids=_lib.ptr(ids), attn_mask=_lib.ptr(tmask), enc_mask=_lib.ptr(emask),
                             query_embeds=qe.data_ptr(), q_rows=q_rows, rows=rows, T=T, Nk=Nk, flags=flags,
-                            last_hidden=_lib.ptr(last_hidden), llm_out=_lib.ptr(llm_out), **scatter)
+                            last_hidden=_lib.ptr(last_hidden), llm_out=_lib.ptr(llm_out),
+                            enc_ready=enc_ready.cuda_event if enc_ready is not None else None, **scatter)
         out = QFormerOutput(last_hidden_state=last_hidden, llm_inputs=llm_view)
-        return _Prepared(self, h, io, self._workspace, out, (enc_b, qe, ids, tmask, emask))
+        return _Prepared(self, h, io, self._workspace, out, (enc_b, qe, ids, tmask, emask))   # (enc_ready: owned by the caller)
 
     def forward(self, input_ids=None, attention_mask=None, position_ids=None, query_embeds=None,
                 encoder_hidden_states=None, encoder_attention_mask=None, return_dict=True, llm_proj: nn.Linear = None,

@@ -183,7 +183,8 @@ class XInstructBLIPQFormers(nn.Module):
     def encode_modalities(self, feats: Dict[str, Features], input_ids: torch.Tensor, attention_mask: torch.Tensor,
                           apply_ln: bool = False, match_reference_text_tiling: bool = True,
                           need_last_hidden: bool = False, prompt: Optional["prompt_mod.PromptPieces"] = None,
-                          scatter_epilogue: bool = True, out: Optional[Dict[str, torch.Tensor]] = None):
+                          scatter_epilogue: bool = True, out: Optional[Dict[str, torch.Tensor]] = None,
+                          ready: Optional[Dict[str, torch.cuda.Event]] = None):
         """Returns ``(inputs_llm, atts_llm)`` dicts exactly as :296-306 builds them.
 
         input_ids / attention_mask: ``text_Qformer.input_ids`` / ``.attention_mask`` ``[bs, T]`` (:233-239).
@@ -194,7 +195,8 @@ class XInstructBLIPQFormers(nn.Module):
         copy, kept for the parity test) and one more launch copies the text pieces.
 
         ``out``: per-modality caller-owned bf16 buffers ``[bs, F*32, D]`` the projected tokens are written into (streaming
-        callers; the returned ``inputs_llm`` are views of them).
+        callers; the returned ``inputs_llm`` are views of them).  ``ready``: per-modality recorded events after which that
+        modality's features are valid (copied in on another stream): only the kernels that read them wait.
         """
         inputs_llm, atts_llm = {}, {}
         todo = [m for m in self.modalities if m in feats]
@@ -210,6 +212,10 @@ class XInstructBLIPQFormers(nn.Module):
         preps, shapes = [], []
         extra = 0
         for modality in todo:
+            ev = ready.get(modality) if ready is not None else None
+            if ev is not None and (apply_ln or isinstance(feats[modality], (list, tuple))):
+                torch.cuda.current_stream(input_ids.device).wait_event(ev)    # the fold below launches kernels that read them
+                ev = None
             enc = self.fold_frames(modality, feats[modality], apply_ln)
             extra += 1 if apply_ln else 0
             bs = input_ids.shape[0]
@@ -229,7 +235,8 @@ class XInstructBLIPQFormers(nn.Module):
                                               need_last_hidden=need_last_hidden, skip_dead_text_ffn=not need_last_hidden,
                                               llm_scatter=prompt_mod.query_slot_view(embeds, lay, modality)
                                               if lay is not None and scatter_epilogue else None,
-                                              llm_out=out[modality] if out is not None and lay is None else None))
+                                              llm_out=out[modality] if out is not None and lay is None else None,
+                                              enc_ready=ev))
             shapes.append((bs, num))
         # Both Q-Formers share the layer geometry: run them in lockstep, every Linear as ONE grouped GEMM launch over
         # (video queries, video text, audio queries, audio text) -- see mra_qformer_forward_multi.
@@ -288,6 +295,8 @@ class HostPipeline:
             sl.ids = torch.empty(bs, text_len, device=dev, dtype=torch.long)
             sl.mask = torch.empty(bs, text_len, device=dev, dtype=torch.long)
             sl.in_done, sl.compute_done, sl.out_done = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+            sl.text_done = torch.cuda.Event()
+            sl.feat_done = {m: torch.cuda.Event() for m in model.modalities}
             sl.used = False
             self.slots.append(sl)
         s0 = self.slots[0]
@@ -303,17 +312,23 @@ class HostPipeline:
             self.copy_in.wait_event(sl.compute_done)   # the previous batch in this slot has been consumed
             main.wait_event(sl.out_done)               # ... and its projected tokens have left the slot's device buffers
         with torch.cuda.stream(self.copy_in):
-            for m, t in host_feats.items():
-                sl.feats[m].copy_(t, non_blocking=True)
+            # prompt tokens first (tiny), then the modalities in the order the forward reads them; one event each, so that the
+            # first Q-Former's cross-K/V projection starts while the second one's features are still on the bus
             sl.ids.copy_(input_ids, non_blocking=True)
             sl.mask.copy_(attention_mask, non_blocking=True)
+            sl.text_done.record(self.copy_in)
+            for m in self.model.modalities:
+                if m in host_feats:
+                    sl.feats[m].copy_(host_feats[m], non_blocking=True)
+                    sl.feat_done[m].record(self.copy_in)
             sl.in_done.record(self.copy_in)
-        main.wait_event(sl.in_done)
+        main.wait_event(sl.text_done)
+        ready = {m: sl.feat_done[m] for m in self.model.modalities if m in host_feats}
         with torch.no_grad():
             # the projections write into this slot's own device buffers: no output allocation per batch (fresh tensors handed
             # to another stream keep their blocks reserved until that stream catches up, and a host that runs ahead of the
             # device then sends the caching allocator to cudaMalloc in the middle of the stream: stalls of 10-80 ms per call)
-            inputs_llm, _ = self.model.encode_modalities(sl.feats, sl.ids, sl.mask, out=sl.out_dev)
+            inputs_llm, _ = self.model.encode_modalities({m: sl.feats[m] for m in ready}, sl.ids, sl.mask, out=sl.out_dev, ready=ready)
         sl.compute_done.record(main)
         self.copy_out.wait_event(sl.compute_done)
         with torch.cuda.stream(self.copy_out):
