@@ -35,6 +35,36 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.QFormerWeights) == 8 * 8 + _lib.MRA_MAX_LAYERS * 24 * 8
 
 
+def test_ctypes_mirror_matches_the_header_compiled_by_gcc(tmp_path):
+    """The binding a reference maintainer would write is a ctypes mirror of include/mraudio_b200.h: compile the header as
+    plain C (it must stay C: no torch / CUDA types in the boundary) and compare struct sizes and the offsets of the io
+    struct's fields with mraudio_b200/_lib.py."""
+    import shutil
+    import subprocess
+    from mraudio_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    io_fields = [n for n, _ in _lib.QFormerIO._fields_]
+    prog = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', 'int main(void) {',
+            '  printf("cfg %zu\\n", sizeof(mra_qformer_config));', '  printf("layer %zu\\n", sizeof(mra_qformer_layer_weights));',
+            '  printf("weights %zu\\n", sizeof(mra_qformer_weights));', '  printf("grads %zu\\n", sizeof(mra_qformer_grads));',
+            '  printf("io %zu\\n", sizeof(mra_qformer_io));']
+    prog += [f'  printf("io.{n} %zu\\n", offsetof(mra_qformer_io, {n}));' for n in io_fields]
+    prog += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(prog))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-o", str(exe), str(src)], check=True)
+    out = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    assert int(out["cfg"]) == ctypes.sizeof(_lib.QFormerConfig)
+    assert int(out["layer"]) == ctypes.sizeof(_lib.QFormerLayerWeights)
+    assert int(out["weights"]) == ctypes.sizeof(_lib.QFormerWeights)
+    assert int(out["grads"]) == ctypes.sizeof(_lib.QFormerGrads)
+    assert int(out["io"]) == ctypes.sizeof(_lib.QFormerIO)
+    for n in io_fields:
+        assert int(out[f"io.{n}"]) == getattr(_lib.QFormerIO, n).offset, n
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU error path")
 def test_no_cpu_fallback():
     from mraudio_b200 import _lib, ops, mr_eval
